@@ -1,0 +1,344 @@
+/*
+ * chain.c -- MPS/MPO chain operations composed from the device primitives.
+ *
+ * Every function mirrors one reference routine (same contraction order, same
+ * sector conventions) but runs on device-resident tensors, with the transposes
+ * that separate the reference's contractions folded into the GEMM epilogues:
+ *   ctb_heff_*            <- apply_local_hamiltonian            src/algorithm/chain_ops.c:353-390
+ *   ctb_env_step_right    <- contraction_operator_step_right    src/algorithm/chain_ops.c:116-165
+ *   ctb_env_step_left     <- contraction_operator_step_left     src/algorithm/chain_ops.c:196-245
+ *   ctb_dummy_block_*     <- create_dummy_operator_block_*      src/algorithm/chain_ops.c:14-87
+ *   ctb_split_matrix_svd  <- split_block_sparse_matrix_svd      src/algorithm/bond_ops.c:15-138
+ *   ctb_mps_merge_pair    <- mps_merge_tensor_pair              src/state/mps.c:1166-1178
+ *   ctb_mps_split_svd     <- mps_split_tensor_svd               src/state/mps.c:1119-1159
+ *   ctb_mps_local_qr/rq   <- mps_local_orthonormalize_qr/rq     src/state/mps.c:513-602
+ *   ctb_mpo_merge_pair    <- mpo_merge_tensor_pair              src/operator/mpo.c:255-277
+ */
+#include "ctb_internal.h"
+
+struct ctb_stats ctb_global_stats;
+
+/* metadata copy that shares the device buffer, with all axis directions reversed */
+static struct ctb_tensor* view_reversed_dirs(const struct ctb_tensor* t)
+{
+	struct ctb_axis axes[CTB_MAXDIM];
+	for (int i = 0; i < t->ndim; i++) {
+		ctb_axis_copy(&axes[i], &t->ax[i]);
+		axes[i].dir = -axes[i].dir;
+	}
+	struct ctb_tensor* v = ctb_tensor_from_axes(t->dtype, t->ndim, axes, 0);
+	CTB_REQUIRE(v->nstore == t->nstore);
+	v->d = t->d;
+	v->borrowed = 1;
+	return v;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+
+int ctb_split_matrix_svd(struct ctb_tensor* a, double tol, bool relative_thresh, ct_long max_vdim, bool renormalize,
+	int svd_distr, struct ctb_tensor** a0, struct ctb_tensor** a1, struct trunc_info* info)
+{
+	CTB_REQUIRE(a->ndim == 2);
+	struct ctb_tensor *u = NULL, *vh = NULL;
+	double* s_dev = NULL;
+	ct_long ns = 0;
+	int rc = ctb_svd(a, &u, &s_dev, &ns, &vh);
+	if (rc < 0) { return rc; }
+
+	/* only the singular values cross to the host; the selection rule is integer/ordering logic */
+	double* sigma = ctb_malloc((size_t)ns * sizeof(double));
+	CTB_CHECK(ctbd_d2h(sigma, s_dev, (size_t)ns * sizeof(double)));
+	struct index_list retained;
+	ctb_retained_bond_indices(sigma, ns, tol, relative_thresh, max_vdim, &retained, info);
+
+	ct_long nret = retained.num;
+	double* s_ret = NULL;
+	const ct_long ind0[1] = { 0 };
+	const ct_long* ind = retained.ind;
+	if (nret == 0)
+	{
+		/* dummy bond of dimension 1 carrying a zero singular value (reference bond_ops.c:50-84) */
+		nret = 1;
+		ind = ind0;
+		s_ret = ctb_calloc(1, sizeof(double));
+	}
+	else
+	{
+		s_ret = ctb_malloc((size_t)nret * sizeof(double));
+		for (ct_long i = 0; i < nret; i++) { s_ret[i] = sigma[ind[i]]; }
+		if (renormalize)
+		{
+			double nrm_all = 0;
+			for (ct_long i = 0; i < ns; i++) { nrm_all += sigma[i] * sigma[i]; }
+			nrm_all = sqrt(nrm_all);
+			const double scale = nrm_all / info->norm_sigma;
+			for (ct_long i = 0; i < nret; i++) { s_ret[i] *= scale; }
+		}
+	}
+	struct ctb_tensor* us  = ctb_slice(u, 1, ind, nret);
+	struct ctb_tensor* vhs = ctb_slice(vh, 0, ind, nret);
+	ctb_tensor_free(u);
+	ctb_tensor_free(vh);
+	CTB_CHECK(ctbd_free(s_dev));
+
+	double* s_ret_dev = NULL;
+	CTB_CHECK(ctbd_malloc((void**)&s_ret_dev, (size_t)nret * sizeof(double)));
+	CTB_CHECK(ctbd_h2d(s_ret_dev, s_ret, (size_t)nret * sizeof(double)));
+	if (svd_distr == SVD_DISTR_LEFT) {
+		*a0 = ctb_scale_axis(us, 1, s_ret_dev);
+		ctb_tensor_free(us);
+		*a1 = vhs;
+	}
+	else {
+		*a1 = ctb_scale_axis(vhs, 0, s_ret_dev);
+		ctb_tensor_free(vhs);
+		*a0 = us;
+	}
+	CTB_CHECK(ctbd_free(s_ret_dev));
+	ctb_free(s_ret);
+	ctb_free(sigma);
+	ctb_free(retained.ind);
+	return 0;
+}
+
+struct ctb_tensor* ctb_mps_merge_pair(const struct ctb_tensor* a0, const struct ctb_tensor* a1)
+{
+	CTB_REQUIRE(a0->ndim == 3 && a1->ndim == 3);
+	struct ctb_tensor* t = ctb_dot(a0, TENSOR_AXIS_RANGE_TRAILING, 0, a1, TENSOR_AXIS_RANGE_LEADING, 0, 1, NULL);
+	struct ctb_tensor* a = ctb_flatten_axes(t, 1, TENSOR_AXIS_OUT);
+	ctb_tensor_free(t);
+	return a;
+}
+
+int ctb_mps_split_svd(struct ctb_tensor* a, const ct_long d[2], const qnumber* const new_qsite[2], double tol, ct_long max_vdim,
+	bool renormalize, int svd_distr, struct ctb_tensor** a0, struct ctb_tensor** a1, struct trunc_info* info)
+{
+	CTB_REQUIRE(a->ndim == 3 && d[0] * d[1] == a->ax[1].dim && a->ax[1].dir == TENSOR_AXIS_OUT);
+	const int dirs_out[2] = { TENSOR_AXIS_OUT, TENSOR_AXIS_OUT };
+	struct ctb_tensor* a_twosite = ctb_split_axis(a, 1, d, dirs_out, new_qsite);
+	struct ctb_tensor* tmp = ctb_flatten_axes(a_twosite, 0, TENSOR_AXIS_OUT);
+	struct ctb_tensor* a_mat = ctb_flatten_axes(tmp, 1, TENSOR_AXIS_IN);
+	ctb_tensor_free(tmp);
+
+	struct ctb_tensor *m0 = NULL, *m1 = NULL;
+	int rc = ctb_split_matrix_svd(a_mat, tol, true, max_vdim, renormalize, svd_distr, &m0, &m1, info);
+	ctb_tensor_free(a_mat);
+	if (rc < 0) { ctb_tensor_free(a_twosite); return rc; }
+
+	{
+		const ct_long dl[2] = { a_twosite->ax[0].dim, a_twosite->ax[1].dim };
+		const int dirl[2] = { a_twosite->ax[0].dir, a_twosite->ax[1].dir };
+		const qnumber* ql[2] = { a_twosite->ax[0].qlog, a_twosite->ax[1].qlog };
+		*a0 = ctb_split_axis(m0, 0, dl, dirl, ql);
+		const ct_long dr[2] = { a_twosite->ax[2].dim, a_twosite->ax[3].dim };
+		const int dirr[2] = { a_twosite->ax[2].dir, a_twosite->ax[3].dir };
+		const qnumber* qr[2] = { a_twosite->ax[2].qlog, a_twosite->ax[3].qlog };
+		*a1 = ctb_split_axis(m1, 1, dr, dirr, qr);
+	}
+	ctb_tensor_free(m0);
+	ctb_tensor_free(m1);
+	ctb_tensor_free(a_twosite);
+	return 0;
+}
+
+int ctb_mps_local_qr(struct ctb_tensor** a, struct ctb_tensor** a_next)
+{
+	struct ctb_tensor* t = *a;
+	CTB_REQUIRE(t->ndim == 3 && (*a_next)->ndim == 3);
+	CTB_REQUIRE(t->ax[0].dir == TENSOR_AXIS_OUT && t->ax[1].dir == TENSOR_AXIS_OUT);
+	struct ctb_tensor* a_mat = ctb_flatten_axes(t, 0, TENSOR_AXIS_OUT);
+	struct ctb_tensor *q = NULL, *r = NULL;
+	int rc = ctb_qr(a_mat, &q, &r);
+	ctb_tensor_free(a_mat);
+	if (rc < 0) { return rc; }
+	const ct_long dl[2] = { t->ax[0].dim, t->ax[1].dim };
+	const int dirl[2] = { TENSOR_AXIS_OUT, TENSOR_AXIS_OUT };
+	const qnumber* ql[2] = { t->ax[0].qlog, t->ax[1].qlog };
+	struct ctb_tensor* a_new = ctb_split_axis(q, 0, dl, dirl, ql);
+	ctb_tensor_free(q);
+	ctb_tensor_free(t);
+	*a = a_new;
+	struct ctb_tensor* upd = ctb_dot(r, TENSOR_AXIS_RANGE_TRAILING, 0, *a_next, TENSOR_AXIS_RANGE_LEADING, 0, 1, NULL);
+	ctb_tensor_free(r);
+	ctb_tensor_free(*a_next);
+	*a_next = upd;
+	return 0;
+}
+
+int ctb_mps_local_rq(struct ctb_tensor** a, struct ctb_tensor** a_prev)
+{
+	struct ctb_tensor* t = *a;
+	CTB_REQUIRE(t->ndim == 3 && (*a_prev)->ndim == 3);
+	CTB_REQUIRE(t->ax[1].dir == TENSOR_AXIS_OUT && t->ax[2].dir == TENSOR_AXIS_IN);
+	struct ctb_tensor* a_mat = ctb_flatten_axes(t, 1, TENSOR_AXIS_IN);
+	struct ctb_tensor *q = NULL, *r = NULL;
+	int rc = ctb_rq(a_mat, &r, &q);
+	ctb_tensor_free(a_mat);
+	if (rc < 0) { return rc; }
+	const ct_long dr[2] = { t->ax[1].dim, t->ax[2].dim };
+	const int dirr[2] = { TENSOR_AXIS_OUT, TENSOR_AXIS_IN };
+	const qnumber* qr[2] = { t->ax[1].qlog, t->ax[2].qlog };
+	struct ctb_tensor* a_new = ctb_split_axis(q, 1, dr, dirr, qr);
+	ctb_tensor_free(q);
+	ctb_tensor_free(t);
+	*a = a_new;
+	struct ctb_tensor* upd = ctb_dot(*a_prev, TENSOR_AXIS_RANGE_TRAILING, 0, r, TENSOR_AXIS_RANGE_LEADING, 0, 1, NULL);
+	ctb_tensor_free(r);
+	ctb_tensor_free(*a_prev);
+	*a_prev = upd;
+	return 0;
+}
+
+struct ctb_tensor* ctb_mpo_merge_pair(const struct ctb_tensor* w0, const struct ctb_tensor* w1)
+{
+	CTB_REQUIRE(w0->ndim == 4 && w1->ndim == 4);
+	/* dot + transpose [0,1,3,2,4,5] in one launch, then fuse the physical legs */
+	const int perm[6] = { 0, 1, 3, 2, 4, 5 };
+	struct ctb_tensor* t = ctb_dot(w0, TENSOR_AXIS_RANGE_TRAILING, 0, w1, TENSOR_AXIS_RANGE_LEADING, 0, 1, perm);
+	struct ctb_tensor* tmp = ctb_flatten_axes(t, 1, TENSOR_AXIS_OUT);
+	ctb_tensor_free(t);
+	struct ctb_tensor* w = ctb_flatten_axes(tmp, 2, TENSOR_AXIS_IN);
+	ctb_tensor_free(tmp);
+	return w;
+}
+
+/* 1x1x1x1 identity environments with the boundary quantum numbers of the 6-leg construction */
+static struct ctb_tensor* dummy_block_typed(int dtype, const qnumber* qa, const qnumber* qw, const qnumber* qb, int left)
+{
+	const ct_long dim[6] = { 1, 1, 1, 1, 1, 1 };
+	const int dirs[6] = { TENSOR_AXIS_OUT, TENSOR_AXIS_OUT, TENSOR_AXIS_IN, TENSOR_AXIS_IN, TENSOR_AXIS_IN, TENSOR_AXIS_OUT };
+	const qnumber* qn[6] = { qa, qw, qb, qa, qw, qb };
+	struct ctb_tensor* s = ctb_tensor_create(dtype, 6, dim, dirs, qn, 1);
+	CTB_REQUIRE(s->nblk == 1);
+	CTB_CHECK_ABORT(ctb_set_entry(s, 0, 1.0, 0.0));
+	struct ctb_tensor *t, *r;
+	if (left) {
+		t = ctb_flatten_axes(s, 0, TENSOR_AXIS_OUT);
+		r = ctb_flatten_axes(t, 0, TENSOR_AXIS_OUT);
+	}
+	else {
+		t = ctb_flatten_axes(s, 4, TENSOR_AXIS_IN);
+		r = ctb_flatten_axes(t, 3, TENSOR_AXIS_IN);
+	}
+	ctb_tensor_free(s);
+	ctb_tensor_free(t);
+	return r;
+}
+
+struct ctb_tensor* ctb_dummy_block_right(const struct ctb_tensor* a, const struct ctb_tensor* b, const struct ctb_tensor* w)
+{
+	CTB_REQUIRE(a->ndim == 3 && b->ndim == 3 && w->ndim == 4);
+	CTB_REQUIRE(a->ax[2].dim == 1 && b->ax[2].dim == 1 && w->ax[3].dim == 1);
+	return dummy_block_typed(a->dtype, a->ax[2].qlog, w->ax[3].qlog, b->ax[2].qlog, 0);
+}
+
+struct ctb_tensor* ctb_dummy_block_left(const struct ctb_tensor* a, const struct ctb_tensor* b, const struct ctb_tensor* w)
+{
+	CTB_REQUIRE(a->ndim == 3 && b->ndim == 3 && w->ndim == 4);
+	CTB_REQUIRE(a->ax[0].dim == 1 && b->ax[0].dim == 1 && w->ax[0].dim == 1);
+	return dummy_block_typed(a->dtype, a->ax[0].qlog, w->ax[0].qlog, b->ax[0].qlog, 1);
+}
+
+struct ctb_tensor* ctb_env_step_right(const struct ctb_tensor* a, const struct ctb_tensor* b, const struct ctb_tensor* w, const struct ctb_tensor* r)
+{
+	CTB_REQUIRE(a->ndim == 3 && b->ndim == 3 && w->ndim == 4 && r->ndim == 4);
+	/* a . r, stored as [d, Dw', Dl, Dr', x] */
+	const int perm0[5] = { 1, 2, 0, 3, 4 };
+	struct ctb_dot_plan pl;
+	struct ctb_tensor* s = ctb_dot_prepare(a, TENSOR_AXIS_RANGE_TRAILING, 0, r, TENSOR_AXIS_RANGE_LEADING, 0, 1, perm0, 1, &pl);
+	CTB_CHECK_ABORT(ctb_dot_exec(&pl, a->d, r->d, s->d));
+	ctb_global_stats.env_flops += pl.flops;
+	ctb_dot_plan_free(&pl);
+	/* w . (a r), stored as [x, Dl, Dw, d_out, Dr'] */
+	const int perm1[5] = { 4, 2, 0, 1, 3 };
+	struct ctb_tensor* t = ctb_dot_prepare(w, TENSOR_AXIS_RANGE_TRAILING, 0, s, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1, 1, &pl);
+	CTB_CHECK_ABORT(ctb_dot_exec(&pl, w->d, s->d, t->d));
+	ctb_global_stats.env_flops += pl.flops;
+	ctb_dot_plan_free(&pl);
+	ctb_tensor_free(s);
+	/* contract with conj(b) over (d_out, Dr'); conjugation fused into the operand load; result [Dl, Dw, Dl', x] */
+	struct ctb_tensor* br = view_reversed_dirs(b);
+	const int perm2[4] = { 1, 2, 3, 0 };
+	struct ctb_tensor* r_next = ctb_dot_prepare(t, TENSOR_AXIS_RANGE_TRAILING, 0, br, TENSOR_AXIS_RANGE_TRAILING, ctb_is_complex(b->dtype), 2, perm2, 1, &pl);
+	CTB_CHECK_ABORT(ctb_dot_exec(&pl, t->d, br->d, r_next->d));
+	ctb_global_stats.env_flops += pl.flops;
+	ctb_dot_plan_free(&pl);
+	ctb_tensor_free(br);
+	ctb_tensor_free(t);
+	return r_next;
+}
+
+struct ctb_tensor* ctb_env_step_left(const struct ctb_tensor* a, const struct ctb_tensor* b, const struct ctb_tensor* w, const struct ctb_tensor* l)
+{
+	CTB_REQUIRE(a->ndim == 3 && b->ndim == 3 && w->ndim == 4 && l->ndim == 4);
+	struct ctb_dot_plan pl;
+	/* l . conj(b), stored as [x, Dl, Dr', Dw, d'] */
+	struct ctb_tensor* br = view_reversed_dirs(b);
+	const int perm0[5] = { 0, 1, 4, 2, 3 };
+	struct ctb_tensor* s = ctb_dot_prepare(l, TENSOR_AXIS_RANGE_TRAILING, 0, br, TENSOR_AXIS_RANGE_LEADING, ctb_is_complex(b->dtype), 1, perm0, 1, &pl);
+	CTB_CHECK_ABORT(ctb_dot_exec(&pl, l->d, br->d, s->d));
+	ctb_global_stats.env_flops += pl.flops;
+	ctb_dot_plan_free(&pl);
+	ctb_tensor_free(br);
+	/* (l b*) . w over (Dw, d'), stored as [Dl, d_in, Dw', Dr', x] */
+	const int perm1[5] = { 1, 3, 4, 2, 0 };
+	struct ctb_tensor* t = ctb_dot_prepare(s, TENSOR_AXIS_RANGE_TRAILING, 0, w, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1, 1, &pl);
+	CTB_CHECK_ABORT(ctb_dot_exec(&pl, s->d, w->d, t->d));
+	ctb_global_stats.env_flops += pl.flops;
+	ctb_dot_plan_free(&pl);
+	ctb_tensor_free(s);
+	/* a . (...) over (Dl, d_in), stored as [x, Dr, Dw', Dr'] */
+	const int perm2[4] = { 3, 0, 1, 2 };
+	struct ctb_tensor* l_next = ctb_dot_prepare(a, TENSOR_AXIS_RANGE_LEADING, 0, t, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm2, 1, &pl);
+	CTB_CHECK_ABORT(ctb_dot_exec(&pl, a->d, t->d, l_next->d));
+	ctb_global_stats.env_flops += pl.flops;
+	ctb_dot_plan_free(&pl);
+	ctb_tensor_free(t);
+	return l_next;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* effective Hamiltonian: plans built once per bond, three launches per matvec                     */
+/* ---------------------------------------------------------------------------------------------- */
+
+int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h)
+{
+	CTB_REQUIRE(a->ndim == 3 && w->ndim == 4 && l->ndim == 4 && r->ndim == 4);
+	memset(h, 0, sizeof(*h));
+	h->w = w; h->r = r;
+	/* step 1: a . r  -> t1 [dd, Dw', Dl, Dr', x'] */
+	const int perm0[5] = { 1, 2, 0, 3, 4 };
+	h->t1 = ctb_dot_prepare(a, TENSOR_AXIS_RANGE_TRAILING, 0, r, TENSOR_AXIS_RANGE_LEADING, 0, 1, perm0, 1, &h->p1);
+	/* step 2: w . t1 over (dd_in, Dw') -> t2 [Dl, Dw, dd_out, Dr', x'] */
+	const int perm1[5] = { 2, 0, 1, 3, 4 };
+	h->t2 = ctb_dot_prepare(w, TENSOR_AXIS_RANGE_TRAILING, 0, h->t1, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1, 1, &h->p2);
+	/* step 3: k . t2 over (Dl, Dw), k = transpose(l, [0,3,1,2]) once per bond (the reference redoes it every matvec) */
+	const int perm2[4] = { 0, 3, 1, 2 };
+	h->k = ctb_transpose(l, perm2, 0);
+	struct ctb_tensor* s = ctb_dot_prepare(h->k, TENSOR_AXIS_RANGE_TRAILING, 0, h->t2, TENSOR_AXIS_RANGE_LEADING, 0, 2, NULL, 0, &h->p3);
+	/* tracing out the two dummy bonds leaves the packed layout unchanged */
+	h->b = ctb_drop_dummy_axes(s, 1);
+	ctb_tensor_free(s);
+	CTB_REQUIRE(ctb_tensor_same_structure(h->b, a));
+	h->flops = h->p1.flops + h->p2.flops + h->p3.flops;
+	h->n = a->nelem;
+	h->nstore = a->nstore;
+	return 0;
+}
+
+int ctb_heff_apply(struct ctb_heff* h, const void* a_data, void* b_data)
+{
+	CTB_CHECK(ctb_dot_exec(&h->p1, a_data, h->r->d, h->t1->d));
+	CTB_CHECK(ctb_dot_exec(&h->p2, h->w->d, h->t1->d, h->t2->d));
+	CTB_CHECK(ctb_dot_exec(&h->p3, h->k->d, h->t2->d, b_data));
+	ctb_global_stats.heff_flops += h->flops;
+	ctb_global_stats.heff_calls++;
+	return 0;
+}
+
+void ctb_heff_free(struct ctb_heff* h)
+{
+	ctb_dot_plan_free(&h->p1); ctb_dot_plan_free(&h->p2); ctb_dot_plan_free(&h->p3);
+	ctb_tensor_free(h->t1); ctb_tensor_free(h->t2); ctb_tensor_free(h->k); ctb_tensor_free(h->b);
+	memset(h, 0, sizeof(*h));
+}

@@ -1,0 +1,217 @@
+/*
+ * ctb_internal.h -- host-side (plain C) engine internals.
+ *
+ * The engine keeps every tensor of the DMRG hot path resident on the device in
+ * a PACKED block layout: the stored (quantum-number conserving) blocks are
+ * concatenated in row-major order of the sector grid, each block row-major.
+ * With CTB_BLOCK_ALIGN == 1 this is exactly the order produced by the
+ * reference's block_sparse_tensor_serialize_entries
+ * (src/tensor/block_sparse_tensor.c:3131-3150), so a Lanczos vector IS the
+ * storage of the two-site tensor and no (de)serialisation happens per matvec.
+ *
+ * All sector bookkeeping below is integer-only and reproduces the reference's
+ * structural rules bit-exactly.
+ */
+#ifndef CTB_INTERNAL_H
+#define CTB_INTERNAL_H
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include "ctb_types.h"
+#include "ctb_device.h"
+
+#define CTB_MAXDIM CTBD_MAXDIM
+/* alignment (in elements) of each stored block inside the packed device buffer */
+#define CTB_BLOCK_ALIGN 1
+
+#define CTB_CHECK(call) do { int ctb_rc_ = (call); if (ctb_rc_ < 0) { \
+	fprintf(stderr, "chemtensor_b200: %s failed at %s:%d: %s\n", #call, __FILE__, __LINE__, ctbd_last_error()); \
+	return ctb_rc_; } } while (0)
+
+#define CTB_CHECK_ABORT(call) do { int ctb_rc_ = (call); if (ctb_rc_ < 0) { \
+	fprintf(stderr, "chemtensor_b200: %s failed at %s:%d: %s\n", #call, __FILE__, __LINE__, ctbd_last_error()); \
+	abort(); } } while (0)
+
+#define CTB_REQUIRE(cond) do { if (!(cond)) { \
+	fprintf(stderr, "chemtensor_b200: requirement '%s' violated at %s:%d\n", #cond, __FILE__, __LINE__); \
+	abort(); } } while (0)
+
+static inline size_t ctb_sizeof_dtype(int dtype)
+{
+	switch (dtype) {
+		case CT_SINGLE_REAL:    return 4;
+		case CT_DOUBLE_REAL:    return 8;
+		case CT_SINGLE_COMPLEX: return 8;
+		case CT_DOUBLE_COMPLEX: return 16;
+		default: return 0;
+	}
+}
+
+static inline int ctb_is_complex(int dtype) { return dtype == CT_SINGLE_COMPLEX || dtype == CT_DOUBLE_COMPLEX; }
+
+/* 16-byte aligned host allocation, compatible with the reference's ct_malloc / free() pairing */
+static inline void* ctb_malloc(size_t size)
+{
+	if (size == 0) { size = 1; }
+	return aligned_alloc(16, (size + 15) & ~(size_t)15);
+}
+static inline void* ctb_calloc(size_t num, size_t size)
+{
+	void* p = ctb_malloc(num * size);
+	if (p != NULL) { memset(p, 0, num * size); }
+	return p;
+}
+static inline void ctb_free(void* p) { free(p); }
+
+/* ---- one tensor leg: logical quantum numbers and the derived sector structure ---- */
+struct ctb_axis
+{
+	ct_long dim;        /* logical dimension */
+	int dir;            /* +1 out, -1 in */
+	int nsec;           /* number of sectors = distinct quantum numbers */
+	qnumber* qlog;      /* [dim]    logical quantum numbers */
+	qnumber* qsec;      /* [nsec]   sorted distinct quantum numbers */
+	int32_t* secdim;    /* [nsec]   multiplicities */
+	int32_t* sec_of;    /* [dim]    sector of each logical index */
+	int32_t* pos_of;    /* [dim]    position within the sector (order of appearance) */
+	int32_t* secstart;  /* [nsec+1] prefix sums of secdim */
+	int32_t* log_of;    /* [dim]    logical indices grouped by sector */
+};
+
+/* ---- device-resident block-sparse tensor ---- */
+struct ctb_tensor
+{
+	int dtype;
+	int ndim;
+	struct ctb_axis ax[CTB_MAXDIM];
+	ct_long ngrid;       /* cells of the sector grid */
+	ct_long* grid_off;   /* [ngrid] element offset of the block or -1 */
+	int nblk;            /* stored blocks */
+	ct_long* blk_grid;   /* [nblk] grid cell per stored block, ascending */
+	ct_long* blk_off;    /* [nblk+1] */
+	ct_long nelem;       /* stored entries without padding (reference: num_elements_blocks) */
+	ct_long nstore;      /* elements of the device buffer */
+	void* d;             /* device buffer (owned unless 'borrowed') */
+	int borrowed;
+	void* layout;        /* lazily created device-side layout tables */
+};
+
+/* tensor_meta.c */
+void ctb_axis_init(struct ctb_axis* ax, ct_long dim, int dir, const qnumber* qlog);
+void ctb_axis_copy(struct ctb_axis* dst, const struct ctb_axis* src);
+void ctb_axis_free(struct ctb_axis* ax);
+int  ctb_axis_find_sector(const struct ctb_axis* ax, qnumber q);
+bool ctb_axis_same_qnums(const struct ctb_axis* a, const struct ctb_axis* b);
+
+/* build a tensor from axes (axes are MOVED into the tensor); allocates a zeroed device buffer iff alloc != 0 */
+struct ctb_tensor* ctb_tensor_from_axes(int dtype, int ndim, struct ctb_axis* axes, int alloc);
+struct ctb_tensor* ctb_tensor_create(int dtype, int ndim, const ct_long* dim, const int* dirs, const qnumber* const* qnums, int alloc);
+struct ctb_tensor* ctb_tensor_like(const struct ctb_tensor* t, int alloc);
+struct ctb_tensor* ctb_tensor_clone(const struct ctb_tensor* t);
+void ctb_tensor_free(struct ctb_tensor* t);
+void* ctb_tensor_layout(struct ctb_tensor* t);
+void ctb_grid_unravel(const struct ctb_tensor* t, ct_long cell, int* idx);
+ct_long ctb_grid_ravel(const struct ctb_tensor* t, const int* idx);
+bool ctb_tensor_same_structure(const struct ctb_tensor* a, const struct ctb_tensor* b);
+
+/* host struct <-> device tensor */
+struct ctb_tensor* ctb_upload(const struct block_sparse_tensor* h);
+int  ctb_download(const struct ctb_tensor* t, struct block_sparse_tensor* h);   /* allocates the host payload */
+int  ctb_upload_entries(struct ctb_tensor* t, const void* entries);     /* packed entries, serialize order */
+int  ctb_download_entries(const struct ctb_tensor* t, void* entries);
+int  ctb_set_entry(struct ctb_tensor* t, ct_long offset, double re, double im);
+
+/* host struct helpers (host_structs.c) */
+void ctb_host_allocate_bst(int dtype, int ndim, const ct_long* dim, const enum tensor_axis_direction* axis_dir, const qnumber* const* qnums, struct block_sparse_tensor* t);
+
+/* ---- contraction plans (tensor_ops.c) ---- */
+struct ctb_dot_plan
+{
+	void* dev;          /* device-resident plan (ctbd_gemm_plan_create) */
+	double flops;       /* algorithmic flops per execution */
+	int ntiles, nouts, nsegs;
+};
+
+/* r = transpose(dot(s, t), perm); perm == NULL means identity.  conj_s/conj_t conjugate an operand on load. */
+struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, int conj_s,
+	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm,
+	int alloc_result, struct ctb_dot_plan* plan);
+int  ctb_dot_exec(const struct ctb_dot_plan* plan, const void* s_data, const void* t_data, void* r_data);
+void ctb_dot_plan_free(struct ctb_dot_plan* plan);
+struct ctb_tensor* ctb_dot(const struct ctb_tensor* s, int axrange_s, int conj_s,
+	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm);
+
+/* logical-index remaps */
+struct ctb_tensor* ctb_transpose(struct ctb_tensor* t, const int* perm, int conj);
+struct ctb_tensor* ctb_flatten_axes(struct ctb_tensor* t, int i_ax, int new_dir);
+struct ctb_tensor* ctb_split_axis(struct ctb_tensor* t, int i_ax, const ct_long new_dim[2], const int new_dir[2], const qnumber* const new_qnums[2]);
+struct ctb_tensor* ctb_slice(struct ctb_tensor* t, int i_ax, const ct_long* ind, ct_long nind);
+struct ctb_tensor* ctb_scale_axis(struct ctb_tensor* t, int i_ax, const double* scale_dev);
+/* drop 'ntrace' leading and trailing axes, all of logical dimension 1 (cyclic partial trace of dummy bonds) */
+struct ctb_tensor* ctb_drop_dummy_axes(const struct ctb_tensor* t, int ntrace);
+
+/* block-wise factorizations of a block-sparse matrix */
+int ctb_svd(struct ctb_tensor* a, struct ctb_tensor** u, double** s_dev, ct_long* ns, struct ctb_tensor** vh);
+int ctb_qr(struct ctb_tensor* a, struct ctb_tensor** q, struct ctb_tensor** r);
+int ctb_rq(struct ctb_tensor* a, struct ctb_tensor** r, struct ctb_tensor** q);
+
+/* ---- algorithms on device tensors (chain.c, krylov.c, dmrg.c) ---- */
+int ctb_split_matrix_svd(struct ctb_tensor* a, double tol, bool relative_thresh, ct_long max_vdim, bool renormalize,
+	int svd_distr, struct ctb_tensor** a0, struct ctb_tensor** a1, struct trunc_info* info);
+struct ctb_tensor* ctb_mps_merge_pair(const struct ctb_tensor* a0, const struct ctb_tensor* a1);
+int ctb_mps_split_svd(struct ctb_tensor* a, const ct_long d[2], const qnumber* const new_qsite[2], double tol, ct_long max_vdim,
+	bool renormalize, int svd_distr, struct ctb_tensor** a0, struct ctb_tensor** a1, struct trunc_info* info);
+int ctb_mps_local_qr(struct ctb_tensor** a, struct ctb_tensor** a_next);
+int ctb_mps_local_rq(struct ctb_tensor** a, struct ctb_tensor** a_prev);
+struct ctb_tensor* ctb_mpo_merge_pair(const struct ctb_tensor* w0, const struct ctb_tensor* w1);
+struct ctb_tensor* ctb_dummy_block_right(const struct ctb_tensor* a, const struct ctb_tensor* b, const struct ctb_tensor* w);
+struct ctb_tensor* ctb_dummy_block_left(const struct ctb_tensor* a, const struct ctb_tensor* b, const struct ctb_tensor* w);
+struct ctb_tensor* ctb_env_step_right(const struct ctb_tensor* a, const struct ctb_tensor* b, const struct ctb_tensor* w, const struct ctb_tensor* r);
+struct ctb_tensor* ctb_env_step_left(const struct ctb_tensor* a, const struct ctb_tensor* b, const struct ctb_tensor* w, const struct ctb_tensor* l);
+
+/* effective Hamiltonian of one bond: three cached grouped-GEMM plans + workspaces */
+struct ctb_heff
+{
+	struct ctb_dot_plan p1, p2, p3;
+	struct ctb_tensor* t1;   /* [dd, Dw', Dl, Dr', 1] */
+	struct ctb_tensor* t2;   /* [Dl, Dw, dd, Dr', 1]  */
+	struct ctb_tensor* k;    /* transpose(l, [0,3,1,2]) computed once per bond */
+	struct ctb_tensor* b;    /* structure of the result (no buffer) */
+	const struct ctb_tensor* w;
+	const struct ctb_tensor* r;
+	double flops;            /* algorithmic flops per matvec */
+	ct_long n;               /* logical number of entries of a (Lanczos vector length) */
+	ct_long nstore;
+};
+int  ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h);
+int  ctb_heff_apply(struct ctb_heff* h, const void* a_data, void* b_data);
+void ctb_heff_free(struct ctb_heff* h);
+
+/* symmetric tridiagonal eigen-decomposition (implicit QL); eigenvalues ascending in d, vectors in columns of z (row-major n x n) */
+int ctb_tridiag_eig(int n, double* d, double* e, double* z);
+/* Lanczos ground state of Heff on the device: a_opt has the structure of a_start */
+int ctb_lanczos_min(struct ctb_heff* h, const struct ctb_tensor* a_start, int maxiter, double* en_min, struct ctb_tensor** a_opt, int* numiter_out);
+
+/* truncation.c */
+double ctb_von_neumann_entropy(const double* sigma, ct_long n);
+void ctb_retained_bond_indices(const double* sigma, ct_long n, double tol, bool relative_thresh, ct_long max_vdim,
+	struct index_list* list, struct trunc_info* info);
+
+/* statistics of the last dmrg call (read by bench through ctb_get_stats) */
+struct ctb_stats
+{
+	double heff_flops;       /* algorithmic flops spent in Heff matvecs */
+	long long heff_calls;
+	double heff_ms;          /* device time in Heff matvecs (only when CTB_PROFILE=1: adds event syncs) */
+	double env_flops;
+	double svd_ms, lanczos_ms, env_ms, total_ms;   /* host wall-clock per phase (includes device sync at phase end) */
+	long long max_vector_len;
+	long long max_bond_dim;
+};
+extern struct ctb_stats ctb_global_stats;
+
+double ctb_wall_ms(void);
+
+#endif

@@ -1,0 +1,512 @@
+/*
+ * tensor_ops.c -- plan builders (host, integer-only) for the block-sparse primitives.
+ *
+ * Each primitive derives the sector structure of its result exactly as the
+ * reference does and turns the per-block work into ONE device launch:
+ *   ctb_dot_prepare   <- block_sparse_tensor_dot, src/tensor/block_sparse_tensor.c:1826-2001
+ *                        (+ the block_sparse_tensor_transpose :785 that follows it in
+ *                        chain_ops.c, fused as an output permutation)
+ *   ctb_transpose     <- block_sparse_tensor_transpose          :785
+ *   ctb_flatten_axes  <- block_sparse_tensor_flatten_axes        :950
+ *   ctb_split_axis    <- block_sparse_tensor_split_axis          :1123
+ *   ctb_slice         <- block_sparse_tensor_slice               :1446
+ *   ctb_scale_axis    <- block_sparse_tensor_multiply_pointwise_vector :1654
+ *   ctb_svd/qr/rq     <- block_sparse_tensor_svd :2686 / _qr :2402 / _rq :2544
+ */
+#include "ctb_internal.h"
+
+/* ---------------------------------------------------------------------------------------------- */
+/* grouped-GEMM contraction plans                                                                  */
+/* ---------------------------------------------------------------------------------------------- */
+
+struct tile_sort_item { struct ctbd_gemm_tile tile; double weight; };
+
+static int cmp_tile_weight_desc(const void* a, const void* b)
+{
+	const struct tile_sort_item* x = a; const struct tile_sort_item* y = b;
+	if (x->weight > y->weight) { return -1; }
+	if (x->weight < y->weight) { return  1; }
+	/* deterministic tie-break */
+	if (x->tile.out != y->tile.out) { return x->tile.out < y->tile.out ? -1 : 1; }
+	if (x->tile.m0 != y->tile.m0) { return x->tile.m0 < y->tile.m0 ? -1 : 1; }
+	return (x->tile.n0 > y->tile.n0) - (x->tile.n0 < y->tile.n0);
+}
+
+struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, int conj_s,
+	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm,
+	int alloc_result, struct ctb_dot_plan* plan)
+{
+	CTB_REQUIRE(s->dtype == t->dtype);
+	CTB_REQUIRE(ndim_mult >= 1 && s->ndim >= ndim_mult && t->ndim >= ndim_mult);
+	const int nfs = s->ndim - ndim_mult;   /* free axes of s */
+	const int nft = t->ndim - ndim_mult;   /* free axes of t */
+	const int ndimr = nfs + nft;
+	CTB_REQUIRE(ndimr <= CTB_MAXDIM);
+	const int shift_s  = (axrange_s == TENSOR_AXIS_RANGE_LEADING ? 0 : nfs);          /* first contracted axis */
+	const int shift_t  = (axrange_t == TENSOR_AXIS_RANGE_LEADING ? 0 : nft);
+	const int offset_s = (axrange_s == TENSOR_AXIS_RANGE_LEADING ? ndim_mult : 0);    /* first free axis */
+	const int offset_t = (axrange_t == TENSOR_AXIS_RANGE_LEADING ? ndim_mult : 0);
+
+	/* contracted legs must carry identical quantum numbers and opposite directions (reference :1836-1844) */
+	for (int i = 0; i < ndim_mult; i++) {
+		CTB_REQUIRE(s->ax[shift_s + i].dir == -t->ax[shift_t + i].dir);
+		CTB_REQUIRE(ctb_axis_same_qnums(&s->ax[shift_s + i], &t->ax[shift_t + i]));
+	}
+
+	/* "natural" result axes: free axes of s, then free axes of t; result axis i = natural axis perm[i] */
+	const struct ctb_axis* nat[CTB_MAXDIM];
+	for (int i = 0; i < nfs; i++) { nat[i] = &s->ax[offset_s + i]; }
+	for (int i = 0; i < nft; i++) { nat[nfs + i] = &t->ax[offset_t + i]; }
+	int p[CTB_MAXDIM], pos_of_nat[CTB_MAXDIM];
+	for (int i = 0; i < ndimr; i++) { p[i] = (perm != NULL ? perm[i] : i); }
+	for (int i = 0; i < ndimr; i++) { pos_of_nat[p[i]] = i; }
+
+	struct ctb_axis raxes[CTB_MAXDIM];
+	for (int i = 0; i < ndimr; i++) { ctb_axis_copy(&raxes[i], nat[p[i]]); }
+	struct ctb_tensor* r = ctb_tensor_from_axes(s->dtype, ndimr, raxes, alloc_result);
+
+	const int a_kcontig = (axrange_s == TENSOR_AXIS_RANGE_TRAILING);
+	const int b_ncontig = (axrange_t == TENSOR_AXIS_RANGE_LEADING);
+
+	int tile_m = 64, tile_n = 64;
+	CTB_CHECK_ABORT(ctbd_gemm_tile_shape(s->dtype, &tile_m, &tile_n));
+
+	/* growable host arrays */
+	size_t cap_seg = 1024, nseg = 0;
+	struct ctbd_gemm_seg* segs = malloc(cap_seg * sizeof(*segs));
+	struct ctbd_gemm_out* outs = malloc((r->nblk > 0 ? r->nblk : 1) * sizeof(*outs));
+	size_t cap_tab = 4096, ntab = 0;
+	int32_t* tab = malloc(cap_tab * sizeof(int32_t));
+	size_t cap_tile = 1024, ntile = 0;
+	struct tile_sort_item* tiles = malloc(cap_tile * sizeof(*tiles));
+	double flops = 0;
+	const double flop_factor = ctb_is_complex(s->dtype) ? 8.0 : 2.0;
+
+	/* contracted sector grid */
+	ct_long ncontract = 1;
+	for (int i = 0; i < ndim_mult; i++) { ncontract *= s->ax[shift_s + i].nsec; }
+
+	for (int b = 0; b < r->nblk; b++)
+	{
+		int idx_r[CTB_MAXDIM], nat_sec[CTB_MAXDIM];
+		ctb_grid_unravel(r, r->blk_grid[b], idx_r);
+		for (int i = 0; i < ndimr; i++) { nat_sec[p[i]] = idx_r[i]; }
+
+		ct_long M = 1, N = 1;
+		for (int i = 0; i < nfs; i++) { M *= nat[i]->secdim[nat_sec[i]]; }
+		for (int i = 0; i < nft; i++) { N *= nat[nfs + i]->secdim[nat_sec[nfs + i]]; }
+
+		struct ctbd_gemm_out* o = &outs[b];
+		o->c_off = r->blk_off[b];
+		o->m = (int32_t)M; o->n = (int32_t)N;
+		o->seg_begin = (int32_t)nseg;
+
+		/* enumerate contracted sector tuples in row-major order (reference :1951-1953) */
+		int idx_s[CTB_MAXDIM], idx_t[CTB_MAXDIM], kap[CTB_MAXDIM] = { 0 };
+		for (int i = 0; i < nfs; i++) { idx_s[offset_s + i] = nat_sec[i]; }
+		for (int i = 0; i < nft; i++) { idx_t[offset_t + i] = nat_sec[nfs + i]; }
+		double ktot = 0;
+		for (ct_long c = 0; c < ncontract; c++)
+		{
+			for (int i = 0; i < ndim_mult; i++) { idx_s[shift_s + i] = kap[i]; idx_t[shift_t + i] = kap[i]; }
+			const ct_long a_off = s->grid_off[ctb_grid_ravel(s, idx_s)];
+			if (a_off >= 0)
+			{
+				const ct_long b_off = t->grid_off[ctb_grid_ravel(t, idx_t)];
+				CTB_REQUIRE(b_off >= 0);   /* conservation in t follows from s and r (reference :1976-1984) */
+				ct_long K = 1;
+				for (int i = 0; i < ndim_mult; i++) { K *= s->ax[shift_s + i].secdim[kap[i]]; }
+				if (nseg == cap_seg) { cap_seg *= 2; segs = realloc(segs, cap_seg * sizeof(*segs)); }
+				struct ctbd_gemm_seg* g = &segs[nseg++];
+				g->a_off = a_off; g->b_off = b_off; g->k = (int32_t)K;
+				g->lda = (int32_t)(a_kcontig ? K : M);
+				g->ldb = (int32_t)(b_ncontig ? N : K);
+				g->pad_ = 0;
+				flops += flop_factor * (double)M * (double)N * (double)K;
+				ktot += (double)K;
+			}
+			for (int i = ndim_mult - 1; i >= 0; i--) {
+				if (++kap[i] < s->ax[shift_s + i].nsec) { break; }
+				kap[i] = 0;
+			}
+		}
+		o->seg_end = (int32_t)nseg;
+
+		/* row/column offset tables: where element (i, j) of the natural block lands in the permuted block */
+		ct_long stride_r[CTB_MAXDIM];
+		{
+			ct_long st = 1;
+			for (int i = ndimr - 1; i >= 0; i--) { stride_r[i] = st; st *= r->ax[i].secdim[idx_r[i]]; }
+			CTB_REQUIRE(st < ((ct_long)1 << 31));
+		}
+		while (ntab + (size_t)(M + N) > cap_tab) { cap_tab *= 2; tab = realloc(tab, cap_tab * sizeof(int32_t)); }
+		o->row_tab = (int32_t)ntab;
+		{
+			int dig[CTB_MAXDIM] = { 0 };
+			for (ct_long i = 0; i < M; i++)
+			{
+				ct_long off = 0;
+				for (int a = 0; a < nfs; a++) { off += dig[a] * stride_r[pos_of_nat[a]]; }
+				tab[ntab++] = (int32_t)off;
+				for (int a = nfs - 1; a >= 0; a--) {
+					if (++dig[a] < nat[a]->secdim[nat_sec[a]]) { break; }
+					dig[a] = 0;
+				}
+			}
+		}
+		o->col_tab = (int32_t)ntab;
+		{
+			int dig[CTB_MAXDIM] = { 0 };
+			for (ct_long j = 0; j < N; j++)
+			{
+				ct_long off = 0;
+				for (int a = 0; a < nft; a++) { off += dig[a] * stride_r[pos_of_nat[nfs + a]]; }
+				tab[ntab++] = (int32_t)off;
+				for (int a = nft - 1; a >= 0; a--) {
+					if (++dig[a] < nat[nfs + a]->secdim[nat_sec[nfs + a]]) { break; }
+					dig[a] = 0;
+				}
+			}
+		}
+		CTB_REQUIRE(ntab < ((size_t)1 << 31));
+
+		/* tiles of this block */
+		for (ct_long m0 = 0; m0 < M; m0 += tile_m) {
+			for (ct_long n0 = 0; n0 < N; n0 += tile_n) {
+				if (ntile == cap_tile) { cap_tile *= 2; tiles = realloc(tiles, cap_tile * sizeof(*tiles)); }
+				tiles[ntile].tile.out = b; tiles[ntile].tile.m0 = (int32_t)m0; tiles[ntile].tile.n0 = (int32_t)n0; tiles[ntile].tile.pad_ = 0;
+				const double tm = (double)((M - m0) < tile_m ? (M - m0) : tile_m);
+				const double tn = (double)((N - n0) < tile_n ? (N - n0) : tile_n);
+				tiles[ntile].weight = ktot * (tm + tn) + tm * tn;   /* ~ load + store cost of the tile */
+				ntile++;
+			}
+		}
+	}
+
+	/* longest-processing-time-first order for the persistent tile scheduler */
+	qsort(tiles, ntile, sizeof(*tiles), cmp_tile_weight_desc);
+	struct ctbd_gemm_tile* tl = malloc((ntile > 0 ? ntile : 1) * sizeof(*tl));
+	for (size_t i = 0; i < ntile; i++) { tl[i] = tiles[i].tile; }
+
+	struct ctbd_gemm_plan_host h;
+	memset(&h, 0, sizeof(h));
+	h.dtype = s->dtype;
+	h.a_kcontig = a_kcontig; h.b_ncontig = b_ncontig;
+	h.conj_a = conj_s; h.conj_b = conj_t;
+	h.ntiles = (int32_t)ntile; h.nouts = r->nblk; h.nsegs = (int32_t)nseg; h.ntab = (int32_t)ntab;
+	h.tiles = tl; h.outs = outs; h.segs = segs; h.tab = tab;
+	h.flops = flops;
+	plan->dev = NULL;
+	CTB_CHECK_ABORT(ctbd_gemm_plan_create(&h, &plan->dev));
+	plan->flops = flops;
+	plan->ntiles = (int)ntile; plan->nouts = r->nblk; plan->nsegs = (int)nseg;
+
+	free(tl); free(tiles); free(tab); free(outs); free(segs);
+	return r;
+}
+
+int ctb_dot_exec(const struct ctb_dot_plan* plan, const void* s_data, const void* t_data, void* r_data)
+{
+	if (plan->ntiles == 0) { return 0; }
+	return ctbd_gemm_run(plan->dev, s_data, t_data, r_data);
+}
+
+void ctb_dot_plan_free(struct ctb_dot_plan* plan)
+{
+	if (plan->dev != NULL) { ctbd_gemm_plan_destroy(plan->dev); plan->dev = NULL; }
+}
+
+struct ctb_tensor* ctb_dot(const struct ctb_tensor* s, int axrange_s, int conj_s,
+	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm)
+{
+	struct ctb_dot_plan plan;
+	struct ctb_tensor* r = ctb_dot_prepare(s, axrange_s, conj_s, t, axrange_t, conj_t, ndim_mult, perm, 1, &plan);
+	CTB_CHECK_ABORT(ctb_dot_exec(&plan, s->d, t->d, r->d));
+	ctb_dot_plan_free(&plan);
+	return r;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* logical-index remaps                                                                            */
+/* ---------------------------------------------------------------------------------------------- */
+
+static void run_remap(struct ctbd_remap_args* args, struct ctb_tensor* dst, struct ctb_tensor* src)
+{
+	if (dst->nstore == 0) { return; }
+	args->dst_layout = ctb_tensor_layout(dst); args->dst = dst->d;
+	args->src_layout = ctb_tensor_layout(src); args->src = src->d;
+	CTB_CHECK_ABORT(ctbd_remap(args));
+}
+
+struct ctb_tensor* ctb_transpose(struct ctb_tensor* t, const int* perm, int conj)
+{
+	struct ctb_axis axes[CTB_MAXDIM];
+	for (int i = 0; i < t->ndim; i++) { ctb_axis_copy(&axes[i], &t->ax[perm[i]]); }
+	struct ctb_tensor* r = ctb_tensor_from_axes(t->dtype, t->ndim, axes, 1);
+	struct ctbd_remap_args args;
+	memset(&args, 0, sizeof(args));
+	args.op = CTBD_REMAP_TRANSPOSE;
+	for (int i = 0; i < t->ndim; i++) { args.perm[i] = perm[i]; }
+	args.conj = conj;
+	args.scale_ax = -1;
+	run_remap(&args, r, t);
+	return r;
+}
+
+struct ctb_tensor* ctb_flatten_axes(struct ctb_tensor* t, int i_ax, int new_dir)
+{
+	CTB_REQUIRE(0 <= i_ax && i_ax + 1 < t->ndim);
+	const struct ctb_axis* a0 = &t->ax[i_ax];
+	const struct ctb_axis* a1 = &t->ax[i_ax + 1];
+	const ct_long dflat = a0->dim * a1->dim;
+	qnumber* qflat = ctb_malloc(dflat * sizeof(qnumber));
+	/* reference :972-979 */
+	for (ct_long j = 0; j < a0->dim; j++) {
+		for (ct_long k = 0; k < a1->dim; k++) {
+			qflat[j * a1->dim + k] = new_dir * (a0->dir * a0->qlog[j] + a1->dir * a1->qlog[k]);
+		}
+	}
+	struct ctb_axis axes[CTB_MAXDIM];
+	for (int i = 0; i < i_ax; i++) { ctb_axis_copy(&axes[i], &t->ax[i]); }
+	ctb_axis_init(&axes[i_ax], dflat, new_dir, qflat);
+	for (int i = i_ax + 2; i < t->ndim; i++) { ctb_axis_copy(&axes[i - 1], &t->ax[i]); }
+	ctb_free(qflat);
+	struct ctb_tensor* r = ctb_tensor_from_axes(t->dtype, t->ndim - 1, axes, 1);
+	struct ctbd_remap_args args;
+	memset(&args, 0, sizeof(args));
+	args.op = CTBD_REMAP_FLATTEN;
+	args.i_ax = i_ax;
+	args.scale_ax = -1;
+	run_remap(&args, r, t);
+	return r;
+}
+
+struct ctb_tensor* ctb_split_axis(struct ctb_tensor* t, int i_ax, const ct_long new_dim[2], const int new_dir[2], const qnumber* const new_qnums[2])
+{
+	CTB_REQUIRE(0 <= i_ax && i_ax < t->ndim && t->ndim + 1 <= CTB_MAXDIM);
+	CTB_REQUIRE(new_dim[0] * new_dim[1] == t->ax[i_ax].dim);
+	/* consistency of the provided quantum numbers (reference asserts :1127-1133) */
+	for (ct_long j = 0; j < new_dim[0]; j++) {
+		for (ct_long k = 0; k < new_dim[1]; k++) {
+			CTB_REQUIRE(t->ax[i_ax].dir * t->ax[i_ax].qlog[j * new_dim[1] + k] == new_dir[0] * new_qnums[0][j] + new_dir[1] * new_qnums[1][k]);
+		}
+	}
+	struct ctb_axis axes[CTB_MAXDIM];
+	for (int i = 0; i < i_ax; i++) { ctb_axis_copy(&axes[i], &t->ax[i]); }
+	ctb_axis_init(&axes[i_ax],     new_dim[0], new_dir[0], new_qnums[0]);
+	ctb_axis_init(&axes[i_ax + 1], new_dim[1], new_dir[1], new_qnums[1]);
+	for (int i = i_ax + 1; i < t->ndim; i++) { ctb_axis_copy(&axes[i + 1], &t->ax[i]); }
+	struct ctb_tensor* r = ctb_tensor_from_axes(t->dtype, t->ndim + 1, axes, 1);
+	struct ctbd_remap_args args;
+	memset(&args, 0, sizeof(args));
+	args.op = CTBD_REMAP_SPLIT;
+	args.i_ax = i_ax;
+	args.scale_ax = -1;
+	run_remap(&args, r, t);
+	return r;
+}
+
+struct ctb_tensor* ctb_slice(struct ctb_tensor* t, int i_ax, const ct_long* ind, ct_long nind)
+{
+	CTB_REQUIRE(0 <= i_ax && i_ax < t->ndim && nind > 0);
+	qnumber* q = ctb_malloc(nind * sizeof(qnumber));
+	for (ct_long j = 0; j < nind; j++) {
+		CTB_REQUIRE(0 <= ind[j] && ind[j] < t->ax[i_ax].dim);
+		q[j] = t->ax[i_ax].qlog[ind[j]];
+	}
+	struct ctb_axis axes[CTB_MAXDIM];
+	for (int i = 0; i < t->ndim; i++) {
+		if (i == i_ax) { ctb_axis_init(&axes[i], nind, t->ax[i].dir, q); }
+		else { ctb_axis_copy(&axes[i], &t->ax[i]); }
+	}
+	ctb_free(q);
+	struct ctb_tensor* r = ctb_tensor_from_axes(t->dtype, t->ndim, axes, 1);
+	struct ctbd_remap_args args;
+	memset(&args, 0, sizeof(args));
+	args.op = CTBD_REMAP_SLICE;
+	args.i_ax = i_ax;
+	args.ind = (const int64_t*)ind;
+	args.scale_ax = -1;
+	run_remap(&args, r, t);
+	return r;
+}
+
+struct ctb_tensor* ctb_scale_axis(struct ctb_tensor* t, int i_ax, const double* scale_dev)
+{
+	struct ctb_tensor* r = ctb_tensor_like(t, 1);
+	struct ctbd_remap_args args;
+	memset(&args, 0, sizeof(args));
+	args.op = CTBD_REMAP_IDENTITY;
+	args.scale_ax = i_ax;
+	args.scale = scale_dev;
+	run_remap(&args, r, t);
+	return r;
+}
+
+struct ctb_tensor* ctb_drop_dummy_axes(const struct ctb_tensor* t, int ntrace)
+{
+	CTB_REQUIRE(t->ndim >= 2 * ntrace);
+	struct ctb_axis axes[CTB_MAXDIM];
+	for (int i = 0; i < ntrace; i++) {
+		/* tracing a pair of dimension-1 legs is a copy; the pair must match (reference dense_tensor.c:269) */
+		CTB_REQUIRE(t->ax[i].dim == 1 && t->ax[t->ndim - ntrace + i].dim == 1);
+		CTB_REQUIRE(t->ax[i].qlog[0] == t->ax[t->ndim - ntrace + i].qlog[0]);
+		CTB_REQUIRE(t->ax[i].dir == -t->ax[t->ndim - ntrace + i].dir);
+	}
+	for (int i = ntrace; i < t->ndim - ntrace; i++) { ctb_axis_copy(&axes[i - ntrace], &t->ax[i]); }
+	struct ctb_tensor* r = ctb_tensor_from_axes(t->dtype, t->ndim - 2 * ntrace, axes, t->d != NULL);
+	/* block order and block contents are unchanged by removing unit axes */
+	CTB_REQUIRE(r->nstore == t->nstore);
+	if (t->nstore > 0 && t->d != NULL) {
+		CTB_CHECK_ABORT(ctbd_d2d(r->d, t->d, (size_t)t->nstore * ctb_sizeof_dtype(t->dtype)));
+	}
+	return r;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* block-wise SVD / QR / RQ                                                                        */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* Connecting-axis quantum numbers (reference :2694-2724 for SVD/QR with column sectors outer and ascending,
+ * :2552-2581 for RQ with row sectors outer).  Returns the number of entries; 'q' has room for max(dim0, dim1). */
+static ct_long interm_qnums(const struct ctb_tensor* a, int by_rows, qnumber* q)
+{
+	ct_long n = 0;
+	const struct ctb_axis* outer = by_rows ? &a->ax[0] : &a->ax[1];
+	const struct ctb_axis* inner = by_rows ? &a->ax[1] : &a->ax[0];
+	for (int jo = 0; jo < outer->nsec; jo++) {
+		for (int ji = 0; ji < inner->nsec; ji++) {
+			if (outer->dir * outer->qsec[jo] + inner->dir * inner->qsec[ji] != 0) { continue; }
+			const ct_long k = outer->secdim[jo] < inner->secdim[ji] ? outer->secdim[jo] : inner->secdim[ji];
+			for (ct_long l = 0; l < k; l++) { q[n + l] = outer->qsec[jo]; }
+			n += k;
+		}
+	}
+	return n;
+}
+
+/* descriptors of all stored blocks of the matrix 'a' with their targets in (o0, o1); o0 = [rows, interm], o1 = [interm, cols] */
+static int build_mat_descs(const struct ctb_tensor* a, const struct ctb_tensor* o0, const struct ctb_tensor* o1, int by_rows, struct ctbd_mat_desc* descs)
+{
+	int n = 0;
+	for (int b = 0; b < a->nblk; b++)
+	{
+		int idx[2];
+		ctb_grid_unravel(a, a->blk_grid[b], idx);
+		const qnumber qc = by_rows ? a->ax[0].qsec[idx[0]] : a->ax[1].qsec[idx[1]];
+		const int kk = ctb_axis_find_sector(&o0->ax[1], qc);
+		CTB_REQUIRE(kk >= 0 && o1->ax[0].qsec[kk] == qc);
+		struct ctbd_mat_desc* d = &descs[n++];
+		d->a_off = a->blk_off[b];
+		d->m = a->ax[0].secdim[idx[0]];
+		d->n = a->ax[1].secdim[idx[1]];
+		const int i0[2] = { idx[0], kk };
+		const int i1[2] = { kk, idx[1] };
+		d->o0_off = o0->grid_off[ctb_grid_ravel(o0, i0)];
+		d->o1_off = o1->grid_off[ctb_grid_ravel(o1, i1)];
+		CTB_REQUIRE(d->o0_off >= 0 && d->o1_off >= 0);
+		const int kmin = d->m < d->n ? d->m : d->n;
+		CTB_REQUIRE(o0->ax[1].secdim[kk] == kmin);
+		/* logical indices of one quantum number on the connecting axis are contiguous (reference :2824-2834) */
+		d->s_off = o0->ax[1].log_of[o0->ax[1].secstart[kk]];
+	}
+	return n;
+}
+
+int ctb_svd(struct ctb_tensor* a, struct ctb_tensor** u, double** s_dev, ct_long* ns, struct ctb_tensor** vh)
+{
+	CTB_REQUIRE(a->ndim == 2);
+	const ct_long maxn = a->ax[0].dim > a->ax[1].dim ? a->ax[0].dim : a->ax[1].dim;
+	qnumber* q = ctb_calloc(maxn, sizeof(qnumber));
+	ct_long dim_interm = interm_qnums(a, 0, q);
+	bool dummy = false;
+	if (dim_interm == 0)
+	{
+		/* no stored block: dummy bond of dimension 1 (reference :2726-2776) */
+		dummy = true;
+		dim_interm = 1;
+		q[0] = -a->ax[0].dir * a->ax[1].dir * a->ax[0].qsec[0];
+	}
+	{
+		const ct_long dim_u[2] = { a->ax[0].dim, dim_interm };
+		const int dir_u[2] = { a->ax[0].dir, a->ax[1].dir };
+		const qnumber* qn_u[2] = { a->ax[0].qlog, q };
+		*u = ctb_tensor_create(a->dtype, 2, dim_u, dir_u, qn_u, 1);
+		const ct_long dim_v[2] = { dim_interm, a->ax[1].dim };
+		const int dir_v[2] = { -a->ax[1].dir, a->ax[1].dir };
+		const qnumber* qn_v[2] = { q, a->ax[1].qlog };
+		*vh = ctb_tensor_create(a->dtype, 2, dim_v, dir_v, qn_v, 1);
+	}
+	ctb_free(q);
+	*ns = dim_interm;
+	CTB_CHECK(ctbd_malloc((void**)s_dev, (size_t)dim_interm * sizeof(double)));
+	if (dummy)
+	{
+		const int iu[2] = { 0, ctb_axis_find_sector(&(*u)->ax[1], (*u)->ax[1].qlog[0]) };
+		const ct_long off = (*u)->grid_off[ctb_grid_ravel(*u, iu)];
+		CTB_REQUIRE(off >= 0);
+		CTB_CHECK(ctb_set_entry(*u, off, 1.0, 0.0));
+		return 0;
+	}
+	struct ctbd_mat_desc* descs = malloc((size_t)a->nblk * sizeof(*descs));
+	const int nmat = build_mat_descs(a, *u, *vh, 0, descs);
+	int rc = ctbd_svd_batched(a->dtype, nmat, descs, a->d, (*u)->d, (*vh)->d, *s_dev);
+	free(descs);
+	if (rc < 0) { fprintf(stderr, "chemtensor_b200: batched SVD failed: %s\n", ctbd_last_error()); return -1; }
+	return 0;
+}
+
+static int qr_common(struct ctb_tensor* a, int rq, struct ctb_tensor** o0, struct ctb_tensor** o1)
+{
+	CTB_REQUIRE(a->ndim == 2);
+	const ct_long maxn = a->ax[0].dim > a->ax[1].dim ? a->ax[0].dim : a->ax[1].dim;
+	qnumber* q = ctb_calloc(maxn, sizeof(qnumber));
+	ct_long dim_interm = interm_qnums(a, rq, q);
+	bool dummy = false;
+	if (dim_interm == 0)
+	{
+		dummy = true;
+		dim_interm = 1;
+		if (!rq) { q[0] = -a->ax[0].dir * a->ax[1].dir * a->ax[0].qsec[0]; }   /* reference :2443-2452 */
+		else     { q[0] = -a->ax[0].dir * a->ax[1].dir * a->ax[1].qsec[0]; }   /* reference :2585-2594 */
+	}
+	{
+		/* QR: q keeps a's directions, r = (-dir1, dir1);  RQ: r = (dir0, -dir0), q keeps a's directions */
+		const ct_long dim0[2] = { a->ax[0].dim, dim_interm };
+		const int dir0[2] = { a->ax[0].dir, rq ? -a->ax[0].dir : a->ax[1].dir };
+		const qnumber* qn0[2] = { a->ax[0].qlog, q };
+		*o0 = ctb_tensor_create(a->dtype, 2, dim0, dir0, qn0, 1);
+		const ct_long dim1[2] = { dim_interm, a->ax[1].dim };
+		const int dir1[2] = { rq ? a->ax[0].dir : -a->ax[1].dir, a->ax[1].dir };
+		const qnumber* qn1[2] = { q, a->ax[1].qlog };
+		*o1 = ctb_tensor_create(a->dtype, 2, dim1, dir1, qn1, 1);
+	}
+	const qnumber q0 = q[0];
+	ctb_free(q);
+	if (dummy)
+	{
+		/* the isometry gets a single entry 1, the triangular factor stays zero */
+		if (!rq) {
+			const int iq[2] = { 0, ctb_axis_find_sector(&(*o0)->ax[1], q0) };
+			const ct_long off = (*o0)->grid_off[ctb_grid_ravel(*o0, iq)];
+			CTB_REQUIRE(off >= 0);
+			CTB_CHECK(ctb_set_entry(*o0, off, 1.0, 0.0));
+		}
+		else {
+			const int iq[2] = { ctb_axis_find_sector(&(*o1)->ax[0], q0), 0 };
+			const ct_long off = (*o1)->grid_off[ctb_grid_ravel(*o1, iq)];
+			CTB_REQUIRE(off >= 0);
+			CTB_CHECK(ctb_set_entry(*o1, off, 1.0, 0.0));
+		}
+		return 0;
+	}
+	struct ctbd_mat_desc* descs = malloc((size_t)a->nblk * sizeof(*descs));
+	const int nmat = build_mat_descs(a, *o0, *o1, rq, descs);
+	int rc = ctbd_qr_batched(a->dtype, rq, nmat, descs, a->d, (*o0)->d, (*o1)->d);
+	free(descs);
+	if (rc < 0) { fprintf(stderr, "chemtensor_b200: batched QR failed: %s\n", ctbd_last_error()); return -1; }
+	return 0;
+}
+
+int ctb_qr(struct ctb_tensor* a, struct ctb_tensor** q, struct ctb_tensor** r) { return qr_common(a, 0, q, r); }
+int ctb_rq(struct ctb_tensor* a, struct ctb_tensor** r, struct ctb_tensor** q) { return qr_common(a, 1, r, q); }

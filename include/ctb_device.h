@@ -1,0 +1,214 @@
+/*
+ * ctb_device.h -- the thin C-ABI CUDA layer ("ctbd_*").
+ *
+ * Everything below is extern "C", plain pointers and sizes: no C++ or torch
+ * types cross this boundary.  The host side of the engine (plain C, see
+ * chemtensor_b200/host/) builds integer-only work lists ("plans") from
+ * quantum-number sector metadata and hands them to this layer, which owns
+ * device memory, the stream and the hand-written sm_100a kernels.
+ *
+ * Implemented by the .cu files under chemtensor_b200/csrc (the product).  A CPU test double
+ * with the same symbols lives in tests/emu/ and is linked ONLY into the
+ * host-logic test library (never into libchemtensor_b200.so).
+ *
+ * What each group replaces in the reference (file:line under the reference tree):
+ *   grouped GEMM   : the per-block cblas_?gemm swarm issued by
+ *                    block_sparse_tensor_dot, src/tensor/block_sparse_tensor.c:1935-1994
+ *                    -> dense_tensor_dot_update, src/tensor/dense_tensor.c:1761-1828;
+ *                    with the output permutation of the following
+ *                    block_sparse_tensor_transpose (:785) fused into the epilogue
+ *   remap          : block_sparse_tensor_transpose :785, _flatten_axes :950,
+ *                    _split_axis :1123, _slice :1446, _multiply_pointwise_vector :1654
+ *   level-1        : cblas_dnrm2/dscal/ddot/zdotc + the axpy loops of
+ *                    lanczos_iteration_d/z, src/util/krylov.c:24-167, and the Ritz
+ *                    vector GEMM at krylov.c:242/:335
+ *   batched SVD/QR : LAPACK ?gesvd / ?geqrf+?orgqr / ?gerqf+?orgrq per block,
+ *                    src/tensor/dense_tensor.c:2253, :2680, :3538
+ *
+ * All functions return 0 on success and a negative value on failure (the
+ * reference's "<0" convention); ctbd_last_error() gives the message.
+ */
+#ifndef CTB_DEVICE_H
+#define CTB_DEVICE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTBD_MAXDIM 8
+
+/* dtype codes follow enum numeric_type; only the double types are computed on */
+#define CTBD_F64 1
+#define CTBD_C128 3
+
+/* ---- runtime ------------------------------------------------------------------------------- */
+
+/* select device (negative: keep current / use CTB_DEVICE env or 0), create the stream; idempotent */
+int ctbd_init(int device);
+int ctbd_shutdown(void);
+/* 1 = CUDA sm_100a kernels, 2 = host test double */
+int ctbd_backend(void);
+const char* ctbd_last_error(void);
+/* number of kernels this layer has launched since start (bench.py's gpu_launches) */
+long long ctbd_launch_count(void);
+/* number of SMs of the active device */
+int ctbd_sm_count(void);
+/* the cudaStream_t all work is enqueued on (opaque), for CUDA-event timing by the caller */
+void* ctbd_stream(void);
+
+/* device timing helpers (CUDA events on the layer's stream) */
+int ctbd_event_create(void** ev);
+int ctbd_event_record(void* ev);
+int ctbd_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms);   /* synchronises on ev_stop */
+int ctbd_event_destroy(void* ev);
+
+/* ---- memory -------------------------------------------------------------------------------- */
+
+int ctbd_malloc(void** dptr, size_t bytes);          /* zero-initialised device memory */
+int ctbd_free(void* dptr);
+int ctbd_memset_zero(void* dptr, size_t bytes);
+int ctbd_h2d(void* dptr, const void* hptr, size_t bytes);
+int ctbd_d2h(void* hptr, const void* dptr, size_t bytes);
+int ctbd_d2d(void* dst, const void* src, size_t bytes);
+int ctbd_sync(void);
+int ctbd_host_alloc(void** hptr, size_t bytes);      /* pinned host staging memory */
+int ctbd_host_free(void* hptr);
+/* bytes currently allocated through ctbd_malloc */
+long long ctbd_bytes_in_use(void);
+
+/* ---- grouped block GEMM -------------------------------------------------------------------- */
+
+/* one contracted sector tuple of one output block: C += op(A_seg) * op(B_seg), inner extent k */
+struct ctbd_gemm_seg
+{
+	int64_t a_off;    /* element offset of the A block in the A buffer */
+	int64_t b_off;    /* element offset of the B block in the B buffer */
+	int32_t k;        /* contracted extent (product of contracted sector multiplicities) */
+	int32_t lda;      /* a_kcontig: A(i,kk) = a[a_off + i*lda + kk];  else A(i,kk) = a[a_off + kk*lda + i] */
+	int32_t ldb;      /* b_ncontig: B(kk,j) = b[b_off + kk*ldb + j];  else B(kk,j) = b[b_off + j*ldb + kk] */
+	int32_t pad_;
+};
+
+/* one output block: m x n, C(i,j) stored at c[c_off + tab[row_tab + i] + tab[col_tab + j]] */
+struct ctbd_gemm_out
+{
+	int64_t c_off;
+	int32_t m, n;
+	int32_t seg_begin, seg_end;   /* [begin,end) into the segment array, accumulated in this order */
+	int32_t row_tab, col_tab;     /* start indices into the int32 offset table */
+};
+
+/* one unit of work: a (tile_m x tile_n) tile of an output block */
+struct ctbd_gemm_tile
+{
+	int32_t out;      /* index into the output-block array */
+	int32_t m0, n0;   /* tile origin inside the block */
+	int32_t pad_;
+};
+
+struct ctbd_gemm_plan_host
+{
+	int32_t dtype;                /* CTBD_F64 or CTBD_C128 */
+	int32_t a_kcontig, b_ncontig; /* operand layouts, see ctbd_gemm_seg */
+	int32_t conj_a, conj_b;       /* complex only: conjugate operand on load */
+	int32_t ntiles, nouts, nsegs, ntab;
+	const struct ctbd_gemm_tile* tiles;   /* host arrays; copied to the device by plan_create */
+	const struct ctbd_gemm_out*  outs;
+	const struct ctbd_gemm_seg*  segs;
+	const int32_t* tab;
+	double flops;                 /* algorithmic flops of one run: sum 2*m*n*k (x4 complex) */
+};
+
+/* tile shape the kernel for 'dtype' works on; the host tiles output blocks with it */
+int ctbd_gemm_tile_shape(int dtype, int* tile_m, int* tile_n);
+int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan);
+int ctbd_gemm_plan_destroy(void* plan);
+/* C (overwritten on every tile of the plan) = sum over segments op(A) op(B); A, B, C device buffers */
+int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C);
+
+/* ---- packed block-sparse layout resident on the device, and logical-index remaps ------------ */
+
+struct ctbd_layout_host
+{
+	int32_t ndim;
+	int32_t dtype;
+	int64_t dim[CTBD_MAXDIM];          /* logical dimension per axis */
+	int32_t nsec[CTBD_MAXDIM];         /* number of sectors per axis */
+	const int32_t* sec_of[CTBD_MAXDIM];   /* [dim]   sector index of a logical index */
+	const int32_t* pos_of[CTBD_MAXDIM];   /* [dim]   position inside its sector */
+	const int32_t* secstart[CTBD_MAXDIM]; /* [nsec+1] prefix sums of sector multiplicities */
+	const int32_t* log_of[CTBD_MAXDIM];   /* [dim]   logical indices grouped by sector */
+	int64_t ngrid;                     /* number of cells of the sector grid */
+	const int64_t* grid_off;           /* [ngrid] element offset of the block, -1 if not conserved */
+	int32_t nblk;                      /* number of stored blocks */
+	const int64_t* blk_grid;           /* [nblk] grid cell of each stored block (ascending) */
+	const int64_t* blk_off;            /* [nblk+1] element offsets (blk_off[nblk] = nstore) */
+	int64_t nstore;                    /* stored elements incl. alignment padding */
+};
+
+int ctbd_layout_create(const struct ctbd_layout_host* h, void** layout);
+int ctbd_layout_destroy(void* layout);
+
+#define CTBD_REMAP_TRANSPOSE 0   /* dst axis i = src axis perm[i] */
+#define CTBD_REMAP_FLATTEN   1   /* dst axis i_ax = src axes (i_ax, i_ax+1) fused row-major */
+#define CTBD_REMAP_SPLIT     2   /* dst axes (i_ax, i_ax+1) = src axis i_ax split row-major */
+#define CTBD_REMAP_SLICE     3   /* dst index j on axis i_ax = src index ind[j] */
+#define CTBD_REMAP_IDENTITY  4   /* same logical index (used with 'scale') */
+
+struct ctbd_remap_args
+{
+	int32_t op;
+	int32_t i_ax;
+	int32_t perm[CTBD_MAXDIM];
+	const int64_t* ind;      /* host array of length dst dim[i_ax] (SLICE) */
+	int32_t conj;            /* complex: conjugate while copying */
+	int32_t scale_ax;        /* >= 0: multiply by scale[logical index on this dst axis] */
+	const double* scale;     /* device vector (real), length dst dim[scale_ax] */
+	void* dst_layout; void* dst;
+	void* src_layout; const void* src;
+};
+
+int ctbd_remap(const struct ctbd_remap_args* args);
+
+/* ---- level-1 kernels for the Lanczos iteration (scalars stay on the device) ----------------- */
+
+/* out[0] = Re sum conj(x_i) y_i, out[1] = Im (0 for real) */
+int ctbd_dotc(int dtype, int64_t n, const void* x, const void* y, double* out_dev);
+/* out[0] = sqrt(sum |x_i|^2) */
+int ctbd_nrm2(int dtype, int64_t n, const void* x, double* out_dev);
+/* y = x / s[0]   (divide != 0) or y = x * s[0]; x may equal y */
+int ctbd_rscale(int dtype, int64_t n, const void* x, const double* s_dev, int divide, void* y);
+/* w -= alpha[0]*vj + beta_prev[0]*vjm1 (vjm1 may be NULL); out[0] = ||w|| afterwards */
+int ctbd_lanczos_update(int dtype, int64_t n, void* w, const void* vj, const void* vjm1,
+	const double* alpha_dev, const double* beta_prev_dev, double* out_dev);
+/* out = sum_{j<m} coef[j] * V[j*ldv ...]; coef is a HOST array of m reals */
+int ctbd_lincomb(int dtype, int64_t n, const void* V, int64_t ldv, int m, const double* coef_host, void* out);
+/* x *= alpha (host scalar, real) */
+int ctbd_scale_host(int dtype, int64_t n, void* x, double alpha);
+
+/* ---- batched dense factorizations of the sector blocks -------------------------------------- */
+
+struct ctbd_mat_desc
+{
+	int64_t a_off;      /* m x n row-major input block */
+	int32_t m, n;
+	int64_t o0_off;     /* SVD: U (m x k);  QR: Q (m x k);  RQ: R (m x k)   [k = min(m,n)] */
+	int64_t o1_off;     /* SVD: Vh (k x n); QR: R (k x n);  RQ: Q (k x n) */
+	int64_t s_off;      /* SVD: index of the first singular value of this block in S */
+};
+
+/* per block: A = U diag(S) Vh, singular values descending */
+int ctbd_svd_batched(int dtype, int nmat, const struct ctbd_mat_desc* descs_host,
+	const void* A, void* U, void* Vh, double* S_dev);
+/* rq == 0: A = Q R (Q: m x k isometry, R upper triangular);  rq != 0: A = R Q (Q: k x n) */
+int ctbd_qr_batched(int dtype, int rq, int nmat, const struct ctbd_mat_desc* descs_host,
+	const void* A, void* O0, void* O1);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,432 @@
+/*
+ * ctbd_emu.c -- TEST DOUBLE for the thin CUDA layer (include/ctb_device.h).
+ *
+ * NOT PART OF THE PRODUCT.  This file implements the ctbd_* C-ABI with plain host loops so that
+ * the host-side plan builders (sector bookkeeping, work lists, offset tables, DMRG driver logic)
+ * can be exercised by `pytest -m "not gpu"` on a machine without a GPU.  It is compiled only into
+ * tests/emu/libctb_hostlogic_emu.so by the test-suite; libchemtensor_b200.so never contains it and
+ * never falls back to it (ctbd_backend() reports 2 here, 1 for the CUDA layer).
+ *
+ * The algorithms mirror the CUDA kernels' formulation (grouped GEMM over segments with offset-table
+ * epilogue, logical-index remap, one-sided Jacobi SVD on rows, Householder QR with the RQ index
+ * transform) so that the mathematics of the kernels is validated independently of the GPU.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <complex.h>
+#include "ctb_device.h"
+
+static char g_err[512] = "";
+static long long g_launches = 0;
+static long long g_bytes = 0;
+
+int ctbd_init(int device) { (void)device; return 0; }
+int ctbd_shutdown(void) { return 0; }
+int ctbd_backend(void) { return 2; }
+const char* ctbd_last_error(void) { return g_err; }
+long long ctbd_launch_count(void) { return g_launches; }
+int ctbd_sm_count(void) { return 1; }
+void* ctbd_stream(void) { return NULL; }
+int ctbd_event_create(void** ev) { *ev = malloc(8); return 0; }
+int ctbd_event_record(void* ev) { (void)ev; return 0; }
+int ctbd_event_elapsed_ms(void* a, void* b, float* ms) { (void)a; (void)b; *ms = 0.f; return 0; }
+int ctbd_event_destroy(void* ev) { free(ev); return 0; }
+
+struct hdr { size_t bytes; size_t pad; };
+int ctbd_malloc(void** dptr, size_t bytes)
+{
+	struct hdr* h = calloc(1, sizeof(struct hdr) + (bytes ? bytes : 1));
+	if (!h) { snprintf(g_err, sizeof g_err, "emu: out of memory"); return -1; }
+	h->bytes = bytes; g_bytes += (long long)bytes;
+	*dptr = h + 1;
+	return 0;
+}
+int ctbd_free(void* dptr) { if (dptr) { struct hdr* h = (struct hdr*)dptr - 1; g_bytes -= (long long)h->bytes; free(h); } return 0; }
+int ctbd_memset_zero(void* dptr, size_t bytes) { memset(dptr, 0, bytes); return 0; }
+int ctbd_h2d(void* d, const void* h, size_t bytes) { memcpy(d, h, bytes); return 0; }
+int ctbd_d2h(void* h, const void* d, size_t bytes) { memcpy(h, d, bytes); return 0; }
+int ctbd_d2d(void* dst, const void* src, size_t bytes) { memmove(dst, src, bytes); return 0; }
+int ctbd_sync(void) { return 0; }
+int ctbd_host_alloc(void** hptr, size_t bytes) { *hptr = malloc(bytes ? bytes : 1); return *hptr ? 0 : -1; }
+int ctbd_host_free(void* hptr) { free(hptr); return 0; }
+long long ctbd_bytes_in_use(void) { return g_bytes; }
+
+/* ---- grouped GEMM ---- */
+struct emu_plan { struct ctbd_gemm_plan_host h; struct ctbd_gemm_tile* tiles; struct ctbd_gemm_out* outs; struct ctbd_gemm_seg* segs; int32_t* tab; };
+
+int ctbd_gemm_tile_shape(int dtype, int* tm, int* tn) { *tm = 64; *tn = (dtype == CTBD_C128) ? 32 : 64; return 0; }
+
+static void* dup_mem(const void* p, size_t n) { void* q = malloc(n ? n : 1); if (n) { memcpy(q, p, n); } return q; }
+
+int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan)
+{
+	struct emu_plan* p = calloc(1, sizeof(*p));
+	p->h = *h;
+	p->tiles = dup_mem(h->tiles, (size_t)h->ntiles * sizeof(*h->tiles));
+	p->outs  = dup_mem(h->outs,  (size_t)h->nouts  * sizeof(*h->outs));
+	p->segs  = dup_mem(h->segs,  (size_t)h->nsegs  * sizeof(*h->segs));
+	p->tab   = dup_mem(h->tab,   (size_t)h->ntab   * sizeof(int32_t));
+	*plan = p;
+	return 0;
+}
+int ctbd_gemm_plan_destroy(void* plan)
+{
+	struct emu_plan* p = plan;
+	free(p->tiles); free(p->outs); free(p->segs); free(p->tab); free(p);
+	return 0;
+}
+
+int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
+{
+	struct emu_plan* p = plan;
+	g_launches++;
+	int tm, tn;
+	ctbd_gemm_tile_shape(p->h.dtype, &tm, &tn);
+	const int cplx = (p->h.dtype == CTBD_C128);
+	for (int t = 0; t < p->h.ntiles; t++)
+	{
+		const struct ctbd_gemm_tile* tl = &p->tiles[t];
+		const struct ctbd_gemm_out* o = &p->outs[tl->out];
+		const int mend = tl->m0 + tm < o->m ? tl->m0 + tm : o->m;
+		const int nend = tl->n0 + tn < o->n ? tl->n0 + tn : o->n;
+		for (int i = tl->m0; i < mend; i++) {
+			for (int j = tl->n0; j < nend; j++)
+			{
+				double complex acc = 0;
+				for (int s = o->seg_begin; s < o->seg_end; s++)
+				{
+					const struct ctbd_gemm_seg* g = &p->segs[s];
+					for (int kk = 0; kk < g->k; kk++)
+					{
+						const int64_t ia = p->h.a_kcontig ? g->a_off + (int64_t)i * g->lda + kk : g->a_off + (int64_t)kk * g->lda + i;
+						const int64_t ib = p->h.b_ncontig ? g->b_off + (int64_t)kk * g->ldb + j : g->b_off + (int64_t)j * g->ldb + kk;
+						if (cplx) {
+							double complex a = ((const double complex*)A)[ia], b = ((const double complex*)B)[ib];
+							if (p->h.conj_a) { a = conj(a); }
+							if (p->h.conj_b) { b = conj(b); }
+							acc += a * b;
+						}
+						else {
+							acc += ((const double*)A)[ia] * ((const double*)B)[ib];
+						}
+					}
+				}
+				const int64_t ic = o->c_off + p->tab[o->row_tab + i] + p->tab[o->col_tab + j];
+				if (cplx) { ((double complex*)C)[ic] = acc; } else { ((double*)C)[ic] = creal(acc); }
+			}
+		}
+	}
+	return 0;
+}
+
+/* ---- layouts and remaps ---- */
+struct emu_layout
+{
+	int ndim, dtype; int64_t dim[CTBD_MAXDIM]; int nsec[CTBD_MAXDIM];
+	int32_t *sec_of[CTBD_MAXDIM], *pos_of[CTBD_MAXDIM], *secstart[CTBD_MAXDIM], *log_of[CTBD_MAXDIM];
+	int64_t ngrid; int64_t* grid_off; int nblk; int64_t* blk_grid; int64_t* blk_off; int64_t nstore;
+};
+
+int ctbd_layout_create(const struct ctbd_layout_host* h, void** layout)
+{
+	struct emu_layout* L = calloc(1, sizeof(*L));
+	L->ndim = h->ndim; L->dtype = h->dtype; L->ngrid = h->ngrid; L->nblk = h->nblk; L->nstore = h->nstore;
+	for (int i = 0; i < h->ndim; i++) {
+		L->dim[i] = h->dim[i]; L->nsec[i] = h->nsec[i];
+		L->sec_of[i]   = dup_mem(h->sec_of[i],   (size_t)h->dim[i] * 4);
+		L->pos_of[i]   = dup_mem(h->pos_of[i],   (size_t)h->dim[i] * 4);
+		L->secstart[i] = dup_mem(h->secstart[i], (size_t)(h->nsec[i] + 1) * 4);
+		L->log_of[i]   = dup_mem(h->log_of[i],   (size_t)h->dim[i] * 4);
+	}
+	L->grid_off = dup_mem(h->grid_off, (size_t)h->ngrid * 8);
+	L->blk_grid = dup_mem(h->blk_grid, (size_t)h->nblk * 8);
+	L->blk_off  = dup_mem(h->blk_off,  (size_t)(h->nblk + 1) * 8);
+	*layout = L;
+	return 0;
+}
+int ctbd_layout_destroy(void* layout)
+{
+	struct emu_layout* L = layout;
+	for (int i = 0; i < L->ndim; i++) { free(L->sec_of[i]); free(L->pos_of[i]); free(L->secstart[i]); free(L->log_of[i]); }
+	free(L->grid_off); free(L->blk_grid); free(L->blk_off); free(L);
+	return 0;
+}
+
+int ctbd_remap(const struct ctbd_remap_args* a)
+{
+	g_launches++;
+	const struct emu_layout* D = a->dst_layout; const struct emu_layout* S = a->src_layout;
+	const int cplx = (D->dtype == CTBD_C128);
+	for (int b = 0; b < D->nblk; b++)
+	{
+		int sec[CTBD_MAXDIM]; int64_t bdim[CTBD_MAXDIM];
+		int64_t cell = D->blk_grid[b];
+		for (int i = D->ndim - 1; i >= 0; i--) { sec[i] = (int)(cell % D->nsec[i]); cell /= D->nsec[i]; }
+		int64_t numel = 1;
+		for (int i = 0; i < D->ndim; i++) { bdim[i] = D->secstart[i][sec[i] + 1] - D->secstart[i][sec[i]]; numel *= bdim[i]; }
+		for (int64_t e = 0; e < numel; e++)
+		{
+			int64_t ld[CTBD_MAXDIM], ls[CTBD_MAXDIM];
+			int64_t r = e;
+			for (int i = D->ndim - 1; i >= 0; i--) { const int64_t pos = r % bdim[i]; r /= bdim[i]; ld[i] = D->log_of[i][D->secstart[i][sec[i]] + pos]; }
+			switch (a->op) {
+				case CTBD_REMAP_TRANSPOSE: for (int i = 0; i < D->ndim; i++) { ls[a->perm[i]] = ld[i]; } break;
+				case CTBD_REMAP_FLATTEN:
+					for (int i = 0; i < a->i_ax; i++) { ls[i] = ld[i]; }
+					ls[a->i_ax] = ld[a->i_ax] / S->dim[a->i_ax + 1]; ls[a->i_ax + 1] = ld[a->i_ax] % S->dim[a->i_ax + 1];
+					for (int i = a->i_ax + 1; i < D->ndim; i++) { ls[i + 1] = ld[i]; }
+					break;
+				case CTBD_REMAP_SPLIT:
+					for (int i = 0; i < a->i_ax; i++) { ls[i] = ld[i]; }
+					ls[a->i_ax] = ld[a->i_ax] * D->dim[a->i_ax + 1] + ld[a->i_ax + 1];
+					for (int i = a->i_ax + 2; i < D->ndim; i++) { ls[i - 1] = ld[i]; }
+					break;
+				case CTBD_REMAP_SLICE: for (int i = 0; i < D->ndim; i++) { ls[i] = (i == a->i_ax) ? a->ind[ld[i]] : ld[i]; } break;
+				default: for (int i = 0; i < D->ndim; i++) { ls[i] = ld[i]; } break;
+			}
+			int64_t scell = 0, soff = 0;
+			int64_t sbd[CTBD_MAXDIM], spos[CTBD_MAXDIM];
+			for (int i = 0; i < S->ndim; i++) {
+				const int s = S->sec_of[i][ls[i]];
+				scell = scell * S->nsec[i] + s;
+				sbd[i] = S->secstart[i][s + 1] - S->secstart[i][s];
+				spos[i] = S->pos_of[i][ls[i]];
+			}
+			for (int i = 0; i < S->ndim; i++) { soff = soff * sbd[i] + spos[i]; }
+			const int64_t sbase = S->grid_off[scell];
+			double complex v = 0;
+			if (sbase >= 0) { v = cplx ? ((const double complex*)a->src)[sbase + soff] : ((const double*)a->src)[sbase + soff]; }
+			if (a->conj) { v = conj(v); }
+			if (a->scale_ax >= 0) { v *= a->scale[ld[a->scale_ax]]; }
+			if (cplx) { ((double complex*)a->dst)[D->blk_off[b] + e] = v; } else { ((double*)a->dst)[D->blk_off[b] + e] = creal(v); }
+		}
+	}
+	return 0;
+}
+
+/* ---- level 1 ---- */
+#define GETC(p, i) (cplx ? ((const double complex*)(p))[i] : (double complex)((const double*)(p))[i])
+#define PUTC(p, i, v) do { if (cplx) { ((double complex*)(p))[i] = (v); } else { ((double*)(p))[i] = creal(v); } } while (0)
+
+int ctbd_dotc(int dtype, int64_t n, const void* x, const void* y, double* out)
+{
+	g_launches++;
+	const int cplx = (dtype == CTBD_C128);
+	double complex s = 0;
+	for (int64_t i = 0; i < n; i++) { s += conj(GETC(x, i)) * GETC(y, i); }
+	out[0] = creal(s); out[1] = cimag(s);
+	return 0;
+}
+int ctbd_nrm2(int dtype, int64_t n, const void* x, double* out)
+{
+	g_launches++;
+	const int cplx = (dtype == CTBD_C128);
+	double s = 0;
+	for (int64_t i = 0; i < n; i++) { const double complex v = GETC(x, i); s += creal(v) * creal(v) + cimag(v) * cimag(v); }
+	out[0] = sqrt(s);
+	return 0;
+}
+int ctbd_rscale(int dtype, int64_t n, const void* x, const double* s, int divide, void* y)
+{
+	g_launches++;
+	const int cplx = (dtype == CTBD_C128);
+	const double f = divide ? 1.0 / s[0] : s[0];
+	for (int64_t i = 0; i < n; i++) { PUTC(y, i, f * GETC(x, i)); }
+	return 0;
+}
+int ctbd_lanczos_update(int dtype, int64_t n, void* w, const void* vj, const void* vjm1, const double* alpha, const double* beta_prev, double* out)
+{
+	g_launches++;
+	const int cplx = (dtype == CTBD_C128);
+	double s = 0;
+	for (int64_t i = 0; i < n; i++) {
+		double complex v = GETC(w, i) - alpha[0] * GETC(vj, i);
+		if (vjm1 != NULL) { v -= beta_prev[0] * GETC(vjm1, i); }
+		PUTC(w, i, v);
+		s += creal(v) * creal(v) + cimag(v) * cimag(v);
+	}
+	out[0] = sqrt(s);
+	return 0;
+}
+int ctbd_lincomb(int dtype, int64_t n, const void* V, int64_t ldv, int m, const double* coef, void* out)
+{
+	g_launches++;
+	const int cplx = (dtype == CTBD_C128);
+	for (int64_t i = 0; i < n; i++) {
+		double complex s = 0;
+		for (int j = 0; j < m; j++) { s += coef[j] * GETC(V, (int64_t)j * ldv + i); }
+		PUTC(out, i, s);
+	}
+	return 0;
+}
+int ctbd_scale_host(int dtype, int64_t n, void* x, double alpha)
+{
+	g_launches++;
+	const int cplx = (dtype == CTBD_C128);
+	for (int64_t i = 0; i < n; i++) { PUTC(x, i, alpha * GETC(x, i)); }
+	return 0;
+}
+
+/* ---- batched SVD: one-sided Jacobi on the rows of the wide orientation ---- */
+static int jacobi_rows(int R, int C, double complex* G /* R x (C+R): [G | W] */)
+{
+	const int ld = C + R;
+	const double tol = 1e-15;
+	for (int sweep = 0; sweep < 60; sweep++)
+	{
+		int rotated = 0;
+		for (int p = 0; p < R - 1; p++) {
+			for (int q = p + 1; q < R; q++)
+			{
+				double alpha = 0, beta = 0; double complex gamma = 0;
+				for (int k = 0; k < C; k++) {
+					const double complex x = G[p * ld + k], y = G[q * ld + k];
+					alpha += creal(x) * creal(x) + cimag(x) * cimag(x);
+					beta  += creal(y) * creal(y) + cimag(y) * cimag(y);
+					gamma += x * conj(y);
+				}
+				const double ag = cabs(gamma);
+				if (ag == 0 || ag <= tol * sqrt(alpha * beta)) { continue; }
+				rotated++;
+				const double complex ph = gamma / ag;          /* e^{i phi} */
+				const double zeta = (beta - alpha) / (2 * ag);
+				const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+				const double c = 1 / sqrt(1 + t * t), s = c * t;
+				for (int k = 0; k < ld; k++) {
+					const double complex x = G[p * ld + k], y = ph * G[q * ld + k];
+					G[p * ld + k] = c * x - s * y;
+					G[q * ld + k] = s * x + c * y;
+				}
+			}
+		}
+		if (rotated == 0) { return 0; }
+	}
+	return 0;   /* best effort, as LAPACK's jacobi drivers */
+}
+
+int ctbd_svd_batched(int dtype, int nmat, const struct ctbd_mat_desc* d, const void* A, void* U, void* Vh, double* S)
+{
+	g_launches++;
+	const int cplx = (dtype == CTBD_C128);
+	for (int b = 0; b < nmat; b++)
+	{
+		const int m = d[b].m, n = d[b].n;
+		const int wide = (m <= n);
+		const int R = wide ? m : n, C = wide ? n : m;
+		const int ld = C + R;
+		double complex* G = calloc((size_t)R * ld, sizeof(double complex));
+		for (int i = 0; i < R; i++) {
+			for (int k = 0; k < C; k++) {
+				/* wide: G = A;  tall: G = A^H */
+				G[i * ld + k] = wide ? GETC(A, d[b].a_off + (int64_t)i * n + k) : conj(GETC(A, d[b].a_off + (int64_t)k * n + i));
+			}
+			G[i * ld + C + i] = 1;
+		}
+		jacobi_rows(R, C, G);
+		/* singular values = row norms, sorted descending */
+		double* sig = malloc((size_t)R * sizeof(double)); int* ord = malloc((size_t)R * sizeof(int));
+		for (int i = 0; i < R; i++) {
+			double s = 0;
+			for (int k = 0; k < C; k++) { const double complex x = G[i * ld + k]; s += creal(x) * creal(x) + cimag(x) * cimag(x); }
+			sig[i] = sqrt(s); ord[i] = i;
+		}
+		for (int i = 0; i < R; i++) { for (int j = i + 1; j < R; j++) { if (sig[ord[j]] > sig[ord[i]]) { int t = ord[i]; ord[i] = ord[j]; ord[j] = t; } } }
+		for (int r = 0; r < R; r++)
+		{
+			const int i = ord[r];
+			S[d[b].s_off + r] = sig[i];
+			const double inv = sig[i] > 0 ? 1.0 / sig[i] : 0.0;
+			if (wide) {
+				/* A = W^H G: Vh[r,:] = G[i,:]/sigma, U[:,r] = conj(W[i,:]) */
+				for (int k = 0; k < n; k++) { PUTC(Vh, d[b].o1_off + (int64_t)r * n + k, inv * G[i * ld + k]); }
+				for (int k = 0; k < m; k++) { PUTC(U, d[b].o0_off + (int64_t)k * R + r, conj(G[i * ld + C + k])); }
+			}
+			else {
+				/* A^H = W^H G  =>  A = G^H W: U[:,r] = conj(G[i,:])/sigma, Vh[r,:] = W[i,:] */
+				for (int k = 0; k < m; k++) { PUTC(U, d[b].o0_off + (int64_t)k * R + r, inv * conj(G[i * ld + k])); }
+				for (int k = 0; k < n; k++) { PUTC(Vh, d[b].o1_off + (int64_t)r * n + k, G[i * ld + C + k]); }
+			}
+		}
+		free(sig); free(ord); free(G);
+	}
+	return 0;
+}
+
+/* ---- batched QR / RQ: Householder on a work matrix X (rows x cols), with the RQ index transform ---- */
+static void householder_qr(int rows, int cols, double complex* X, double complex* Q /* rows x k */, double complex* Rm /* k x cols */)
+{
+	const int k = rows < cols ? rows : cols;
+	double complex* tau = calloc((size_t)k, sizeof(double complex));
+	for (int j = 0; j < k; j++)
+	{
+		double nrm = 0;
+		for (int i = j; i < rows; i++) { const double complex x = X[i * cols + j]; nrm += creal(x) * creal(x) + cimag(x) * cimag(x); }
+		nrm = sqrt(nrm);
+		const double complex x0 = X[j * cols + j];
+		double xn = 0;
+		for (int i = j + 1; i < rows; i++) { const double complex x = X[i * cols + j]; xn += creal(x) * creal(x) + cimag(x) * cimag(x); }
+		if (xn == 0 && cimag(x0) == 0) { tau[j] = 0; continue; }
+		const double beta = -(creal(x0) >= 0 ? 1.0 : -1.0) * nrm;
+		tau[j] = (beta - x0) / beta;
+		const double complex scal = 1.0 / (x0 - beta);
+		for (int i = j + 1; i < rows; i++) { X[i * cols + j] *= scal; }
+		X[j * cols + j] = beta;
+		/* apply H^H = I - conj(tau) v v^H to the trailing columns */
+		for (int c = j + 1; c < cols; c++)
+		{
+			double complex s = X[j * cols + c];
+			for (int i = j + 1; i < rows; i++) { s += conj(X[i * cols + j]) * X[i * cols + c]; }
+			s *= conj(tau[j]);
+			X[j * cols + c] -= s;
+			for (int i = j + 1; i < rows; i++) { X[i * cols + c] -= X[i * cols + j] * s; }
+		}
+	}
+	for (int i = 0; i < k; i++) { for (int c = 0; c < cols; c++) { Rm[i * cols + c] = (c >= i) ? X[i * cols + c] : 0; } }
+	/* Q = H_0 H_1 ... H_{k-1} [I; 0] */
+	for (int i = 0; i < rows; i++) { for (int c = 0; c < k; c++) { Q[i * k + c] = (i == c) ? 1 : 0; } }
+	for (int j = k - 1; j >= 0; j--)
+	{
+		for (int c = j; c < k; c++)
+		{
+			double complex s = Q[j * k + c];
+			for (int i = j + 1; i < rows; i++) { s += conj(X[i * cols + j]) * Q[i * k + c]; }
+			s *= tau[j];
+			Q[j * k + c] -= s;
+			for (int i = j + 1; i < rows; i++) { Q[i * k + c] -= X[i * cols + j] * s; }
+		}
+	}
+	free(tau);
+}
+
+int ctbd_qr_batched(int dtype, int rq, int nmat, const struct ctbd_mat_desc* d, const void* A, void* O0, void* O1)
+{
+	g_launches++;
+	const int cplx = (dtype == CTBD_C128);
+	for (int b = 0; b < nmat; b++)
+	{
+		const int m = d[b].m, n = d[b].n;
+		const int k = m < n ? m : n;
+		const int rows = rq ? n : m, cols = rq ? m : n;
+		double complex* X = malloc((size_t)rows * cols * sizeof(double complex));
+		double complex* Q = malloc((size_t)rows * k * sizeof(double complex));
+		double complex* Rm = malloc((size_t)k * cols * sizeof(double complex));
+		for (int i = 0; i < rows; i++) { for (int j = 0; j < cols; j++) {
+			/* RQ: X = (E A E)^H, i.e. X[i][j] = conj(A[m-1-j][n-1-i]) */
+			X[i * cols + j] = rq ? conj(GETC(A, d[b].a_off + (int64_t)(m - 1 - j) * n + (n - 1 - i))) : GETC(A, d[b].a_off + (int64_t)i * n + j);
+		} }
+		householder_qr(rows, cols, X, Q, Rm);
+		if (!rq) {
+			for (int i = 0; i < m; i++) { for (int c = 0; c < k; c++) { PUTC(O0, d[b].o0_off + (int64_t)i * k + c, Q[i * k + c]); } }
+			for (int i = 0; i < k; i++) { for (int c = 0; c < n; c++) { PUTC(O1, d[b].o1_off + (int64_t)i * n + c, Rm[i * n + c]); } }
+		}
+		else {
+			/* R[i][j] = conj(Rt[k-1-j][m-1-i]) (m x k), Q[i][j] = conj(Qt[n-1-j][k-1-i]) (k x n) */
+			for (int i = 0; i < m; i++) { for (int j = 0; j < k; j++) { PUTC(O0, d[b].o0_off + (int64_t)i * k + j, conj(Rm[(k - 1 - j) * cols + (m - 1 - i)])); } }
+			for (int i = 0; i < k; i++) { for (int j = 0; j < n; j++) { PUTC(O1, d[b].o1_off + (int64_t)i * n + j, conj(Q[(n - 1 - j) * k + (k - 1 - i)])); } }
+		}
+		free(X); free(Q); free(Rm);
+	}
+	return 0;
+}
