@@ -1,0 +1,234 @@
+/*
+ * ctbd_remap.cu -- logical-index remaps between packed block-sparse layouts resident on the device.
+ *
+ * One gather kernel covers the structural primitives of the reference that move entries between
+ * block structures (src/tensor/block_sparse_tensor.c): _transpose :785 (incl. the conjugating
+ * variant :880), _flatten_axes :950, _split_axis :1123, _slice :1446 and
+ * _multiply_pointwise_vector :1654.  Every destination entry computes its logical multi-index,
+ * maps it to the source logical multi-index of the operation and reads the source entry through
+ * the source sector tables; writes are fully coalesced (destination order), reads are coalesced
+ * along the innermost source run.  HBM-bound: 2 x sizeof(T) bytes per stored entry.
+ */
+#include <vector>
+#include "ctbd_common.cuh"
+
+namespace ctbd {
+
+struct LayoutDev
+{
+	int ndim, dtype;
+	int64_t dim[CTBD_MAXDIM];
+	int nsec[CTBD_MAXDIM];
+	const int32_t* sec_of[CTBD_MAXDIM];
+	const int32_t* pos_of[CTBD_MAXDIM];
+	const int32_t* secstart[CTBD_MAXDIM];
+	const int32_t* log_of[CTBD_MAXDIM];
+	int64_t ngrid;
+	const int64_t* grid_off;
+	int nblk;
+	const int64_t* blk_grid;
+	const int64_t* blk_off;
+	int64_t nstore;
+};
+
+struct Layout
+{
+	LayoutDev d;
+	void* arena;    /* one device allocation holding all tables */
+};
+
+struct RemapParams
+{
+	int op, i_ax, conj, scale_ax;
+	int perm[CTBD_MAXDIM];
+	const int64_t* ind;
+	const double* scale;
+};
+
+template <typename T> __device__ __forceinline__ T conj_if(T v, int) { return v; }
+template <> __device__ __forceinline__ double2 conj_if<double2>(double2 v, int c) { if (c) { v.y = -v.y; } return v; }
+__device__ __forceinline__ double  scale_by(double v, double s)  { return v * s; }
+__device__ __forceinline__ double2 scale_by(double2 v, double s) { return make_double2(v.x * s, v.y * s); }
+template <typename T> __device__ __forceinline__ T zero_of();
+template <> __device__ __forceinline__ double zero_of<double>() { return 0.0; }
+template <> __device__ __forceinline__ double2 zero_of<double2>() { return make_double2(0.0, 0.0); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) remap_kernel(const LayoutDev D, const LayoutDev S, const RemapParams p, T* __restrict__ dst, const T* __restrict__ src)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < D.nstore; e += stride)
+	{
+		/* stored block containing entry e */
+		int lo = 0, hi = D.nblk - 1;
+		while (lo < hi) {
+			const int mid = (lo + hi + 1) >> 1;
+			if (D.blk_off[mid] <= e) { lo = mid; } else { hi = mid - 1; }
+		}
+		int64_t cell = D.blk_grid[lo];
+		int64_t r = e - D.blk_off[lo];
+		int sec[CTBD_MAXDIM];
+		#pragma unroll
+		for (int i = CTBD_MAXDIM - 1; i >= 0; i--) {
+			if (i < D.ndim) { sec[i] = (int)(cell % D.nsec[i]); cell /= D.nsec[i]; }
+		}
+		int64_t ld[CTBD_MAXDIM], ls[CTBD_MAXDIM];
+		#pragma unroll
+		for (int i = CTBD_MAXDIM - 1; i >= 0; i--) {
+			if (i < D.ndim) {
+				const int s0 = D.secstart[i][sec[i]];
+				const int bd = D.secstart[i][sec[i] + 1] - s0;
+				const int pos = (int)(r % bd); r /= bd;
+				ld[i] = D.log_of[i][s0 + pos];
+			}
+		}
+		switch (p.op)
+		{
+			case CTBD_REMAP_TRANSPOSE:
+				#pragma unroll
+				for (int i = 0; i < CTBD_MAXDIM; i++) { if (i < D.ndim) { ls[p.perm[i]] = ld[i]; } }
+				break;
+			case CTBD_REMAP_FLATTEN:
+				#pragma unroll
+				for (int i = 0; i < CTBD_MAXDIM; i++) {
+					if (i < D.ndim) {
+						if (i < p.i_ax) { ls[i] = ld[i]; }
+						else if (i == p.i_ax) { ls[i] = ld[i] / S.dim[i + 1]; ls[i + 1] = ld[i] % S.dim[i + 1]; }
+						else { ls[i + 1] = ld[i]; }
+					}
+				}
+				break;
+			case CTBD_REMAP_SPLIT:
+				#pragma unroll
+				for (int i = 0; i < CTBD_MAXDIM; i++) {
+					if (i < D.ndim) {
+						if (i < p.i_ax) { ls[i] = ld[i]; }
+						else if (i == p.i_ax) { ls[i] = ld[i] * D.dim[i + 1]; }
+						else if (i == p.i_ax + 1) { ls[i - 1] += ld[i]; }
+						else { ls[i - 1] = ld[i]; }
+					}
+				}
+				break;
+			case CTBD_REMAP_SLICE:
+				#pragma unroll
+				for (int i = 0; i < CTBD_MAXDIM; i++) { if (i < D.ndim) { ls[i] = (i == p.i_ax) ? p.ind[ld[i]] : ld[i]; } }
+				break;
+			default:
+				#pragma unroll
+				for (int i = 0; i < CTBD_MAXDIM; i++) { if (i < D.ndim) { ls[i] = ld[i]; } }
+				break;
+		}
+		int64_t scell = 0, soff = 0;
+		#pragma unroll
+		for (int i = 0; i < CTBD_MAXDIM; i++) {
+			if (i < S.ndim) {
+				const int s = S.sec_of[i][ls[i]];
+				scell = scell * S.nsec[i] + s;
+				soff = soff * (S.secstart[i][s + 1] - S.secstart[i][s]) + S.pos_of[i][ls[i]];
+			}
+		}
+		const int64_t sbase = S.grid_off[scell];
+		T v = (sbase >= 0) ? src[sbase + soff] : zero_of<T>();
+		v = conj_if<T>(v, p.conj);
+		if (p.scale_ax >= 0) { v = scale_by(v, p.scale[ld[p.scale_ax]]); }
+		dst[e] = v;
+	}
+}
+
+} // namespace ctbd
+
+using namespace ctbd;
+
+extern "C" {
+
+int ctbd_layout_create(const struct ctbd_layout_host* h, void** layout)
+{
+	CTBD_REQUIRE_INIT();
+	Layout* L = new Layout();
+	memset(&L->d, 0, sizeof(L->d));
+	L->arena = nullptr;
+	/* pack all tables into one host buffer (8-byte aligned pieces), upload once */
+	size_t bytes = 0;
+	auto reserve = [&](size_t n) { size_t off = bytes; bytes += (n + 7) & ~(size_t)7; return off; };
+	size_t o_sec[CTBD_MAXDIM], o_pos[CTBD_MAXDIM], o_start[CTBD_MAXDIM], o_log[CTBD_MAXDIM];
+	for (int i = 0; i < h->ndim; i++) {
+		o_sec[i]   = reserve((size_t)h->dim[i] * 4);
+		o_pos[i]   = reserve((size_t)h->dim[i] * 4);
+		o_start[i] = reserve((size_t)(h->nsec[i] + 1) * 4);
+		o_log[i]   = reserve((size_t)h->dim[i] * 4);
+	}
+	const size_t o_grid = reserve((size_t)h->ngrid * 8);
+	const size_t o_bg   = reserve((size_t)(h->nblk > 0 ? h->nblk : 1) * 8);
+	const size_t o_bo   = reserve((size_t)(h->nblk + 1) * 8);
+	std::vector<unsigned char> buf(bytes > 0 ? bytes : 8, 0);
+	for (int i = 0; i < h->ndim; i++) {
+		memcpy(&buf[o_sec[i]],   h->sec_of[i],   (size_t)h->dim[i] * 4);
+		memcpy(&buf[o_pos[i]],   h->pos_of[i],   (size_t)h->dim[i] * 4);
+		memcpy(&buf[o_start[i]], h->secstart[i], (size_t)(h->nsec[i] + 1) * 4);
+		memcpy(&buf[o_log[i]],   h->log_of[i],   (size_t)h->dim[i] * 4);
+	}
+	memcpy(&buf[o_grid], h->grid_off, (size_t)h->ngrid * 8);
+	if (h->nblk > 0) { memcpy(&buf[o_bg], h->blk_grid, (size_t)h->nblk * 8); }
+	memcpy(&buf[o_bo], h->blk_off, (size_t)(h->nblk + 1) * 8);
+	if (upload(buf.data(), buf.size(), &L->arena) < 0) { delete L; return -1; }
+	/* the staging vector dies at return: make sure the copy has been consumed */
+	CTBD_CUDA(cudaStreamSynchronize(rt().stream));
+	unsigned char* base = (unsigned char*)L->arena;
+	LayoutDev& d = L->d;
+	d.ndim = h->ndim; d.dtype = h->dtype; d.ngrid = h->ngrid; d.nblk = h->nblk; d.nstore = h->nstore;
+	for (int i = 0; i < h->ndim; i++) {
+		d.dim[i] = h->dim[i]; d.nsec[i] = h->nsec[i];
+		d.sec_of[i]   = (const int32_t*)(base + o_sec[i]);
+		d.pos_of[i]   = (const int32_t*)(base + o_pos[i]);
+		d.secstart[i] = (const int32_t*)(base + o_start[i]);
+		d.log_of[i]   = (const int32_t*)(base + o_log[i]);
+	}
+	d.grid_off = (const int64_t*)(base + o_grid);
+	d.blk_grid = (const int64_t*)(base + o_bg);
+	d.blk_off  = (const int64_t*)(base + o_bo);
+	*layout = L;
+	return 0;
+}
+
+int ctbd_layout_destroy(void* layout)
+{
+	Layout* L = (Layout*)layout;
+	if (L == nullptr) { return 0; }
+	ctbd_free(L->arena);
+	delete L;
+	return 0;
+}
+
+int ctbd_remap(const struct ctbd_remap_args* a)
+{
+	CTBD_REQUIRE_INIT();
+	const Layout* D = (const Layout*)a->dst_layout;
+	const Layout* S = (const Layout*)a->src_layout;
+	if (D->d.dtype != S->d.dtype) { return fail_msg("remap: dtype mismatch"); }
+	if (D->d.nstore == 0) { return 0; }
+	RemapParams p;
+	memset(&p, 0, sizeof(p));
+	p.op = a->op; p.i_ax = a->i_ax; p.conj = a->conj; p.scale_ax = a->scale_ax; p.scale = a->scale;
+	for (int i = 0; i < CTBD_MAXDIM; i++) { p.perm[i] = a->perm[i]; }
+	void* ind_dev = nullptr;
+	if (a->op == CTBD_REMAP_SLICE) {
+		if (upload(a->ind, (size_t)D->d.dim[a->i_ax] * sizeof(int64_t), &ind_dev) < 0) { return -1; }
+		p.ind = (const int64_t*)ind_dev;
+	}
+	const int threads = 256;
+	int64_t blocks = ceil_div(D->d.nstore, threads);
+	const int64_t maxb = (int64_t)rt().sm_count * 16;
+	if (blocks > maxb) { blocks = maxb; }
+	if (D->d.dtype == CTBD_F64) {
+		remap_kernel<double><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, (double*)a->dst, (const double*)a->src);
+	}
+	else if (D->d.dtype == CTBD_C128) {
+		remap_kernel<double2><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, (double2*)a->dst, (const double2*)a->src);
+	}
+	else { return fail_msg("remap: unsupported dtype"); }
+	CTBD_LAUNCH_CHECK();
+	if (ind_dev != nullptr) { ctbd_free(ind_dev); }
+	return 0;
+}
+
+} // extern "C"

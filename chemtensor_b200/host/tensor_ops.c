@@ -19,19 +19,6 @@
 /* grouped-GEMM contraction plans                                                                  */
 /* ---------------------------------------------------------------------------------------------- */
 
-struct tile_sort_item { struct ctbd_gemm_tile tile; double weight; };
-
-static int cmp_tile_weight_desc(const void* a, const void* b)
-{
-	const struct tile_sort_item* x = a; const struct tile_sort_item* y = b;
-	if (x->weight > y->weight) { return -1; }
-	if (x->weight < y->weight) { return  1; }
-	/* deterministic tie-break */
-	if (x->tile.out != y->tile.out) { return x->tile.out < y->tile.out ? -1 : 1; }
-	if (x->tile.m0 != y->tile.m0) { return x->tile.m0 < y->tile.m0 ? -1 : 1; }
-	return (x->tile.n0 > y->tile.n0) - (x->tile.n0 < y->tile.n0);
-}
-
 struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, int conj_s,
 	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm,
 	int alloc_result, struct ctb_dot_plan* plan)
@@ -68,17 +55,12 @@ struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, in
 	const int a_kcontig = (axrange_s == TENSOR_AXIS_RANGE_TRAILING);
 	const int b_ncontig = (axrange_t == TENSOR_AXIS_RANGE_LEADING);
 
-	int tile_m = 64, tile_n = 64;
-	CTB_CHECK_ABORT(ctbd_gemm_tile_shape(s->dtype, &tile_m, &tile_n));
-
 	/* growable host arrays */
 	size_t cap_seg = 1024, nseg = 0;
 	struct ctbd_gemm_seg* segs = malloc(cap_seg * sizeof(*segs));
 	struct ctbd_gemm_out* outs = malloc((r->nblk > 0 ? r->nblk : 1) * sizeof(*outs));
 	size_t cap_tab = 4096, ntab = 0;
 	int32_t* tab = malloc(cap_tab * sizeof(int32_t));
-	size_t cap_tile = 1024, ntile = 0;
-	struct tile_sort_item* tiles = malloc(cap_tile * sizeof(*tiles));
 	double flops = 0;
 	const double flop_factor = ctb_is_complex(s->dtype) ? 8.0 : 2.0;
 
@@ -105,7 +87,6 @@ struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, in
 		int idx_s[CTB_MAXDIM], idx_t[CTB_MAXDIM], kap[CTB_MAXDIM] = { 0 };
 		for (int i = 0; i < nfs; i++) { idx_s[offset_s + i] = nat_sec[i]; }
 		for (int i = 0; i < nft; i++) { idx_t[offset_t + i] = nat_sec[nfs + i]; }
-		double ktot = 0;
 		for (ct_long c = 0; c < ncontract; c++)
 		{
 			for (int i = 0; i < ndim_mult; i++) { idx_s[shift_s + i] = kap[i]; idx_t[shift_t + i] = kap[i]; }
@@ -123,7 +104,6 @@ struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, in
 				g->ldb = (int32_t)(b_ncontig ? N : K);
 				g->pad_ = 0;
 				flops += flop_factor * (double)M * (double)N * (double)K;
-				ktot += (double)K;
 			}
 			for (int i = ndim_mult - 1; i >= 0; i--) {
 				if (++kap[i] < s->ax[shift_s + i].nsec) { break; }
@@ -170,38 +150,24 @@ struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, in
 		}
 		CTB_REQUIRE(ntab < ((size_t)1 << 31));
 
-		/* tiles of this block */
-		for (ct_long m0 = 0; m0 < M; m0 += tile_m) {
-			for (ct_long n0 = 0; n0 < N; n0 += tile_n) {
-				if (ntile == cap_tile) { cap_tile *= 2; tiles = realloc(tiles, cap_tile * sizeof(*tiles)); }
-				tiles[ntile].tile.out = b; tiles[ntile].tile.m0 = (int32_t)m0; tiles[ntile].tile.n0 = (int32_t)n0; tiles[ntile].tile.pad_ = 0;
-				const double tm = (double)((M - m0) < tile_m ? (M - m0) : tile_m);
-				const double tn = (double)((N - n0) < tile_n ? (N - n0) : tile_n);
-				tiles[ntile].weight = ktot * (tm + tn) + tm * tn;   /* ~ load + store cost of the tile */
-				ntile++;
-			}
-		}
 	}
-
-	/* longest-processing-time-first order for the persistent tile scheduler */
-	qsort(tiles, ntile, sizeof(*tiles), cmp_tile_weight_desc);
-	struct ctbd_gemm_tile* tl = malloc((ntile > 0 ? ntile : 1) * sizeof(*tl));
-	for (size_t i = 0; i < ntile; i++) { tl[i] = tiles[i].tile; }
 
 	struct ctbd_gemm_plan_host h;
 	memset(&h, 0, sizeof(h));
 	h.dtype = s->dtype;
 	h.a_kcontig = a_kcontig; h.b_ncontig = b_ncontig;
 	h.conj_a = conj_s; h.conj_b = conj_t;
-	h.ntiles = (int32_t)ntile; h.nouts = r->nblk; h.nsegs = (int32_t)nseg; h.ntab = (int32_t)ntab;
-	h.tiles = tl; h.outs = outs; h.segs = segs; h.tab = tab;
+	h.nouts = r->nblk; h.nsegs = (int32_t)nseg; h.ntab = (int32_t)ntab;
+	h.outs = outs; h.segs = segs; h.tab = tab;
 	h.flops = flops;
 	plan->dev = NULL;
 	CTB_CHECK_ABORT(ctbd_gemm_plan_create(&h, &plan->dev));
 	plan->flops = flops;
-	plan->ntiles = (int)ntile; plan->nouts = r->nblk; plan->nsegs = (int)nseg;
+	plan->nouts = r->nblk; plan->nsegs = (int)nseg;
+	plan->ntiles = 0;
+	CTB_CHECK_ABORT(ctbd_gemm_plan_info(plan->dev, &plan->ntiles, NULL));
 
-	free(tl); free(tiles); free(tab); free(outs); free(segs);
+	free(tab); free(outs); free(segs);
 	return r;
 }
 

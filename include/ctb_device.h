@@ -101,33 +101,26 @@ struct ctbd_gemm_out
 	int32_t row_tab, col_tab;     /* start indices into the int32 offset table */
 };
 
-/* one unit of work: a (tile_m x tile_n) tile of an output block */
-struct ctbd_gemm_tile
-{
-	int32_t out;      /* index into the output-block array */
-	int32_t m0, n0;   /* tile origin inside the block */
-	int32_t pad_;
-};
-
 struct ctbd_gemm_plan_host
 {
 	int32_t dtype;                /* CTBD_F64 or CTBD_C128 */
 	int32_t a_kcontig, b_ncontig; /* operand layouts, see ctbd_gemm_seg */
 	int32_t conj_a, conj_b;       /* complex only: conjugate operand on load */
-	int32_t ntiles, nouts, nsegs, ntab;
-	const struct ctbd_gemm_tile* tiles;   /* host arrays; copied to the device by plan_create */
-	const struct ctbd_gemm_out*  outs;
+	int32_t nouts, nsegs, ntab;
+	const struct ctbd_gemm_out*  outs;    /* host arrays; copied to the device by plan_create */
 	const struct ctbd_gemm_seg*  segs;
 	const int32_t* tab;
 	double flops;                 /* algorithmic flops of one run: sum 2*m*n*k (x4 complex) */
 };
 
-/* tile shape the kernel for 'dtype' works on; the host tiles output blocks with it */
-int ctbd_gemm_tile_shape(int dtype, int* tile_m, int* tile_n);
+/* builds the device-resident work list: every output block is cut into tiles of the kernel variant that
+ * fits it best (tile classes are an internal matter of the CUDA layer), heaviest tiles first */
 int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan);
 int ctbd_gemm_plan_destroy(void* plan);
-/* C (overwritten on every tile of the plan) = sum over segments op(A) op(B); A, B, C device buffers */
+/* C (every output block of the plan is overwritten) = sum over segments op(A) op(B); A, B, C device buffers */
 int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C);
+/* number of tiles / kernel launches one run of the plan issues */
+int ctbd_gemm_plan_info(void* plan, int* ntiles, int* nlaunches);
 
 /* ---- packed block-sparse layout resident on the device, and logical-index remaps ------------ */
 

@@ -54,9 +54,7 @@ int ctbd_host_free(void* hptr) { free(hptr); return 0; }
 long long ctbd_bytes_in_use(void) { return g_bytes; }
 
 /* ---- grouped GEMM ---- */
-struct emu_plan { struct ctbd_gemm_plan_host h; struct ctbd_gemm_tile* tiles; struct ctbd_gemm_out* outs; struct ctbd_gemm_seg* segs; int32_t* tab; };
-
-int ctbd_gemm_tile_shape(int dtype, int* tm, int* tn) { *tm = 64; *tn = (dtype == CTBD_C128) ? 32 : 64; return 0; }
+struct emu_plan { struct ctbd_gemm_plan_host h; struct ctbd_gemm_out* outs; struct ctbd_gemm_seg* segs; int32_t* tab; };
 
 static void* dup_mem(const void* p, size_t n) { void* q = malloc(n ? n : 1); if (n) { memcpy(q, p, n); } return q; }
 
@@ -64,7 +62,6 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan)
 {
 	struct emu_plan* p = calloc(1, sizeof(*p));
 	p->h = *h;
-	p->tiles = dup_mem(h->tiles, (size_t)h->ntiles * sizeof(*h->tiles));
 	p->outs  = dup_mem(h->outs,  (size_t)h->nouts  * sizeof(*h->outs));
 	p->segs  = dup_mem(h->segs,  (size_t)h->nsegs  * sizeof(*h->segs));
 	p->tab   = dup_mem(h->tab,   (size_t)h->ntab   * sizeof(int32_t));
@@ -74,7 +71,15 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan)
 int ctbd_gemm_plan_destroy(void* plan)
 {
 	struct emu_plan* p = plan;
-	free(p->tiles); free(p->outs); free(p->segs); free(p->tab); free(p);
+	free(p->outs); free(p->segs); free(p->tab); free(p);
+	return 0;
+}
+
+int ctbd_gemm_plan_info(void* plan, int* ntiles, int* nlaunches)
+{
+	struct emu_plan* p = plan;
+	if (ntiles) { *ntiles = p->h.nouts; }
+	if (nlaunches) { *nlaunches = 1; }
 	return 0;
 }
 
@@ -82,17 +87,12 @@ int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
 {
 	struct emu_plan* p = plan;
 	g_launches++;
-	int tm, tn;
-	ctbd_gemm_tile_shape(p->h.dtype, &tm, &tn);
 	const int cplx = (p->h.dtype == CTBD_C128);
-	for (int t = 0; t < p->h.ntiles; t++)
+	for (int t = 0; t < p->h.nouts; t++)
 	{
-		const struct ctbd_gemm_tile* tl = &p->tiles[t];
-		const struct ctbd_gemm_out* o = &p->outs[tl->out];
-		const int mend = tl->m0 + tm < o->m ? tl->m0 + tm : o->m;
-		const int nend = tl->n0 + tn < o->n ? tl->n0 + tn : o->n;
-		for (int i = tl->m0; i < mend; i++) {
-			for (int j = tl->n0; j < nend; j++)
+		const struct ctbd_gemm_out* o = &p->outs[t];
+		for (int i = 0; i < o->m; i++) {
+			for (int j = 0; j < o->n; j++)
 			{
 				double complex acc = 0;
 				for (int s = o->seg_begin; s < o->seg_end; s++)
