@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- Heff matvec FP64 TFLOP/s (and two-site DMRG sweep seconds) of the B200 engine vs the reference's CPU path.
+
+Contract (one JSON line on stdout, rank 0):
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME] [--sweep]
+
+A "step" is one application of the block-sparse two-site effective Hamiltonian (reference apply_local_hamiltonian,
+src/algorithm/chain_ops.c:353) at the centre bond of the named synthetic Hamiltonian:
+  value  : algorithmic FP64 flops of one matvec (sum 2 m n k over the block GEMMs the reference issues at
+           block_sparse_tensor.c:1953-1994; x4 for complex128) / device time per matvec, operands resident in HBM,
+           cached per-bond plans, CUDA events on the engine's stream, L2 flushed between timed matvecs.
+  e2e    : the same metric through the reference-named C-ABI call apply_local_hamiltonian() on HOST structs:
+           host->device copies of (a, w, l, r), plan construction, three grouped-GEMM launches, device->host copy of b.
+  --impl reference : the unmodified reference (oracle/_ref, built by oracle/Makefile) running the same call on the
+           box's host cores (OpenMP over blocks, all cores).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from chemtensor_b200 import cabi, workloads  # noqa: E402
+
+WORKLOADS = {
+    # name: (model, nsites, params, sector, max_vdim, dtype, description)
+    "xxz_L100_D1024": ("xxz", 100, (1.0, 0.8, 0.1), 0, 1024, np.float64,
+                       "Heisenberg XXZ chain L=100 (J=1, D=0.8, h=0.1), U(1) 2Sz=0, bond dim 1024, two-site Heff at the centre bond"),
+    "fh_L64_D4096": ("fermi_hubbard", 64, (1.0, 4.0, 0.0), workloads.encode_qpair(64, 0), 4096, np.float64,
+                     "Fermi-Hubbard chain L=64 (t=1, u=4, mu=0), U(1)xU(1) N=64 2Sz=0, bond dim 4096, two-site Heff at the centre bond"),
+    "fh_L32_D1024": ("fermi_hubbard", 32, (1.0, 4.0, 0.0), workloads.encode_qpair(32, 0), 1024, np.float64,
+                     "Fermi-Hubbard chain L=32, N=32 2Sz=0, bond dim 1024, two-site Heff at the centre bond"),
+    "xxz_L16_D64": ("xxz", 16, (1.0, 0.8, 0.1), 0, 64, np.float64, "small XXZ case for functional checks"),
+}
+DEFAULT_WORKLOAD = "fh_L64_D4096"
+
+CUDA_SO = os.path.join(ROOT, "chemtensor_b200", "libchemtensor_b200.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libchemtensor_ref.so")
+
+
+def load_measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, device: int):
+        self.device = device
+        self.samples = []
+        self.stop = threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = max(float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
+
+
+def measure_fp64_peak(device: int):
+    """cuBLAS DGEMM 8192^3 through torch: the FP64 tensor-pipe roofline denominator (MEASURED_PEAKS.json has no FP64 entry)."""
+    import torch
+    n = 8192
+    with torch.cuda.device(device):
+        a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        del a, b
+        torch.cuda.empty_cache()
+    return best
+
+
+def build_operands(lib, wl_name: str, seed: int = 42):
+    model, L, params, sector, D, dtype, _ = WORKLOADS[wl_name]
+    return workloads.heff_operands(lib, model, L, params, sector, D, dtype=dtype, seed=seed)
+
+
+def dist_setup(n_gpus: int):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the same call, on all host cores, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    if not os.path.exists(REF_SO):
+        subprocess.run(["make", "-s", "-C", ROOT, "oracle"], check=False)
+    ref = cabi.CLibrary(REF_SO)
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    a, w, l, r = build_operands(ref, wl)
+    flops = heff_flops_host(a, w, l, r)
+    # bound the CPU work: cap the number of timed calls so that the arm ends within a few minutes
+    t_probe0 = time.perf_counter()
+    b = cabi.BST(ref)
+    ref.apply_local_hamiltonian(a.ptr, w.ptr, l.ptr, r.ptr, b.ptr)
+    t_probe = time.perf_counter() - t_probe0
+    del b
+    budget_s = 120.0
+    steps = max(1, min(args.steps, int(budget_s / max(t_probe, 1e-6))))
+    warm = 0 if t_probe > 20 else min(args.warmup, 1)
+    for _ in range(warm):
+        b = cabi.BST(ref); ref.apply_local_hamiltonian(a.ptr, w.ptr, l.ptr, r.ptr, b.ptr); del b
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        b = cabi.BST(ref); ref.apply_local_hamiltonian(a.ptr, w.ptr, l.ptr, r.ptr, b.ptr); del b
+    dt = (time.perf_counter() - t0) / steps
+    tf = flops / dt / 1e12
+    line = {
+        "impl": "reference", "metric": "heff_matvec_fp64_tflops", "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl, "description": WORKLOADS[wl][6]},
+        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "reference",
+                         "sample": f"{steps} timed apply_local_hamiltonian calls of the unmodified reference (OpenMP {cores} threads, OpenBLAS 1 thread per GEMM) on the same operands"},
+        "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def heff_flops_host(a, w, l, r) -> float:
+    """Algorithmic flops of one matvec from sector metadata alone (integer exact): the three contractions of chain_ops.c:353-390."""
+    from chemtensor_b200.flops import heff_flops
+    return heff_flops(a, w, l, r)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("CTB_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank, world, local = dist_setup(args.gpus)
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    os.environ["CTB_DEVICE"] = str(local)
+    lib = cabi.CLibrary(CUDA_SO, extensions=True)
+    if lib.ctb_init(local) < 0:
+        raise SystemExit("bench.py: ctb_init failed")
+    wl = args.workload
+    model, L, params, sector, D, dtype, desc = WORKLOADS[wl]
+
+    t_setup0 = time.perf_counter()
+    a, w, l, r = build_operands(lib, wl)
+    n_vec = a.num_elements()
+    t_setup = time.perf_counter() - t_setup0
+
+    peaks, peak_kind = load_measured_peaks()
+    fp64_peak = measure_fp64_peak(local) if rank == 0 else 0.0
+
+    launches0 = lib.ctb_launch_count()
+    ms = C.c_double(0); flops = C.c_double(0)
+    step_ms = (C.c_double * 3)(); step_fl = (C.c_double * 3)()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(); torch.cuda.synchronize()
+    with ClockSampler(local) as clocks:
+        rc = lib.ctb_heff_benchmark(a.ptr, w.ptr, l.ptr, r.ptr, args.warmup, args.steps, 1, C.byref(ms), C.byref(flops), step_ms, step_fl)
+        if rc < 0:
+            raise SystemExit("bench.py: ctb_heff_benchmark failed")
+        if world > 1:
+            torch.cuda.synchronize(); dist.barrier()
+        # e2e through the reference-named C-ABI entry point with host structs
+        e2e = None
+        if not args.no_e2e:
+            esize = np.dtype(dtype).itemsize
+            h2d = sum(x.num_elements() for x in (a, w, l, r)) * esize
+            d2h = n_vec * esize
+            for _ in range(2):
+                b = cabi.BST(lib); lib.apply_local_hamiltonian(a.ptr, w.ptr, l.ptr, r.ptr, b.ptr); del b
+            k_e2e = max(3, min(args.steps, 10))
+            t0 = time.perf_counter()
+            for _ in range(k_e2e):
+                b = cabi.BST(lib); lib.apply_local_hamiltonian(a.ptr, w.ptr, l.ptr, r.ptr, b.ptr); del b
+            dt_e2e = (time.perf_counter() - t0) / k_e2e
+            e2e = {"value": flops.value / dt_e2e / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": dt_e2e * 1e3, "steps": k_e2e,
+                   "what": "apply_local_hamiltonian(a, w, l, r, &b) on host structs: upload, per-bond plan build, 3 grouped GEMM launches, download"}
+    launches = lib.ctb_launch_count() - launches0
+
+    # max over ranks of the device time; all ranks run the same workload shard-free in this round (replicas): value = sum over ranks
+    t_ms = ms.value
+    if world > 1:
+        tt = torch.tensor([t_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms = float(tt.item())
+    value = world * flops.value / (t_ms * 1e-3) / 1e12
+
+    if rank != 0:
+        return
+    kdom = int(np.argmax([step_ms[i] for i in range(3)]))
+    k_tf = step_fl[kdom] / (step_ms[kdom] * 1e-3) / 1e12
+    names = ["A.R (step 1)", "W.(AR) (step 2)", "L.(WAR) (step 3)"]
+    roofline = {"bound": "tensor", "achieved": k_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (k_tf / fp64_peak) if fp64_peak > 0 else None, "traffic": None,
+                "kernel": f"grouped_gemm_kernel<double> of {names[kdom]}", "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "per_step_ms": [step_ms[i] for i in range(3)], "per_step_tflops": [step_fl[i] / (step_ms[i] * 1e-3) / 1e12 if step_ms[i] > 0 else None for i in range(3)],
+                "matvec_frac_of_fp64_peak": (flops.value / (ms.value * 1e-3) / 1e12 / fp64_peak) if fp64_peak > 0 else None}
+    line = {
+        "metric": "heff_matvec_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if dtype == np.float64 else "c128",
+        "data": "synthetic",
+        "config": {"workload": wl, "description": desc, "vector_length": int(n_vec), "flops_per_matvec": flops.value,
+                   "l2": "192 MiB buffer rewritten between timed matvecs", "setup_s": round(t_setup, 2),
+                   "multi_gpu": "independent replicas of the bond (sharded Heff lands with the NCCL exchange step)" if world > 1 else "single GPU"},
+        "roofline": roofline,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(wl, flops.value)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(wl: str, flops: float):
+    """The unmodified reference (oracle/_ref) on the host cores of this box, bounded sample, rank 0 only."""
+    cores = os.cpu_count() or 1
+    code = (
+        "import os,sys,time,json\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bench\n"
+        "from chemtensor_b200 import cabi\n"
+        f"ref = cabi.CLibrary({REF_SO!r})\n"
+        f"a,w,l,r = bench.build_operands(ref, {wl!r})\n"
+        "ts=[]\n"
+        "t_all=time.perf_counter()\n"
+        "while len(ts) < 5 and time.perf_counter()-t_all < 25:\n"
+        "    t0=time.perf_counter(); b=cabi.BST(ref); ref.apply_local_hamiltonian(a.ptr,w.ptr,l.ptr,r.ptr,b.ptr); ts.append(time.perf_counter()-t0); del b\n"
+        "print(json.dumps({'ts': ts}))\n"
+    )
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=1200)
+        ts = json.loads(out.stdout.strip().splitlines()[-1])["ts"]
+        best = min(ts)
+        return {"value": flops / best / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "reference", "ms_per_step": best * 1e3,
+                "sample": f"best of {len(ts)} apply_local_hamiltonian calls of the unmodified reference (oracle/_ref, OpenMP {cores} threads) on the same operands"}
+    except Exception as exc:  # the baseline is a reported number, never a gate
+        return {"value": None, "unit": "TFLOP/s", "cores": cores, "kind": "reference", "sample": f"failed: {exc}"}
+
+
+if __name__ == "__main__":
+    main()

@@ -3,12 +3,15 @@
  *
  * Replaces the per-block cblas_dgemm/zgemm swarm of the reference's block_sparse_tensor_dot
  * (src/tensor/block_sparse_tensor.c:1935-1994 -> dense_tensor_dot_update, src/tensor/dense_tensor.c:1761-1828)
- * by ONE launch per tile class over a device-resident work list:
+ * by ONE persistent launch over a device-resident work list:
  *   - an "output block" C (m x n) is the sum over its "segments" (contracted sector tuples, in the
  *     reference's row-major order) of op(A_seg) op(B_seg);
- *   - a CTA owns one tile of one output block and walks the concatenated K extent of all segments
- *     through a multi-stage cp.async (LDGSTS) shared-memory ring, so that many tiny contracted
- *     sectors still keep the pipeline full;
+ *   - the tiles of all output blocks are packed at plan time into one queue per resident CTA
+ *     (longest-processing-time-first bin packing on the known K extents), so the launch is one wave;
+ *   - a CTA walks its queue with ONE software pipeline that runs across tile and segment boundaries:
+ *     a multi-stage cp.async (LDGSTS) shared-memory ring is always STAGES-1 steps ahead in the flattened
+ *     (tile, segment, k-chunk) sequence, so the many short K extents of small sectors never drain it and the
+ *     epilogue of one tile overlaps the loads of the next;
  *   - the math is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; the larger PTX f64 shapes lower to the same
  *     instruction on sm_100a), complex128 as four real DMMAs on (re, im) fragments with optional
  *     conjugation of either operand fused into the fragment load;
@@ -22,14 +25,7 @@
 
 namespace ctbd {
 
-struct GemmTile { int32_t out, m0, n0, pad_; };
-
-struct GemmClass
-{
-	int cfg = 0;
-	int ntiles = 0;
-	GemmTile* tiles = nullptr;    /* device */
-};
+struct GemmTile { int32_t out, m0, n0, nsteps; };   /* nsteps = sum over segments of ceil(k / BK) */
 
 struct GemmPlan
 {
@@ -38,8 +34,11 @@ struct GemmPlan
 	ctbd_gemm_out* outs = nullptr;     /* device */
 	ctbd_gemm_seg* segs = nullptr;
 	int32_t* tab = nullptr;
-	std::vector<GemmClass> classes;
-	int ntiles_total = 0;
+	int cfg = 0;                       /* tile class of this plan */
+	int ntiles = 0, grid = 0;
+	GemmTile* tiles = nullptr;         /* device: tiles grouped by CTA queue */
+	int32_t* queue = nullptr;          /* device: [grid + 1] queue boundaries */
+	void* a_packed = nullptr;          /* device: optional plan-owned A operand (gathered once at plan creation) */
 };
 
 /* ---- PTX helpers ---- */
@@ -65,11 +64,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 /* ---- tile configuration ---- */
 
-template <typename T, int BM_, int BN_, int WM_, int WN_, int STAGES_>
+template <typename T, int BM_, int BN_, int WM_, int WN_, int STAGES_, int BK_ = 16>
 struct TileCfg
 {
 	static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
-	static constexpr int BK = 16;
+	static constexpr int BK = BK_;
 	static constexpr int NWARP = (BM / WM) * (BN / WN);
 	static constexpr int NT = NWARP * 32;
 	static constexpr bool CPLX = (sizeof(T) == 16);
@@ -168,6 +167,7 @@ __device__ __forceinline__ void load_tile(T* __restrict__ S, const T* __restrict
 struct GemmArgs
 {
 	const GemmTile* tiles;
+	const int32_t* queue;
 	const ctbd_gemm_out* outs;
 	const ctbd_gemm_seg* segs;
 	const int32_t* tab;
@@ -188,9 +188,8 @@ __global__ void __launch_bounds__(Cfg::NT) grouped_gemm_kernel(const GemmArgs ar
 	T* As = reinterpret_cast<T*>(smem_raw);
 	T* Bs = As + (size_t)STAGES * Cfg::A_ELEMS;
 
-	const GemmTile tile = args.tiles[blockIdx.x];
-	const ctbd_gemm_out out = args.outs[tile.out];
-	const int M = out.m, N = out.n, m0 = tile.m0, n0 = tile.n0;
+	const int qb = args.queue[blockIdx.x], qe = args.queue[blockIdx.x + 1];
+	if (qb >= qe) { return; }
 	const T* __restrict__ Ag = reinterpret_cast<const T*>(args.A);
 	const T* __restrict__ Bg = reinterpret_cast<const T*>(args.B);
 
@@ -198,152 +197,208 @@ __global__ void __launch_bounds__(Cfg::NT) grouped_gemm_kernel(const GemmArgs ar
 	const int wm0 = (warp / (BN / WN)) * WM, wn0 = (warp % (BN / WN)) * WN;
 	const int lr = lane >> 2, lc = lane & 3;
 
-	double acc[MI][NI][NACC];
-	#pragma unroll
-	for (int i = 0; i < MI; i++) {
-		#pragma unroll
-		for (int j = 0; j < NI; j++) {
-			#pragma unroll
-			for (int c = 0; c < NACC; c++) { acc[i][j][c] = 0.0; }
+	/* ---- producer: iterator over the flattened (tile, segment, k-chunk) sequence of this CTA's queue ---- */
+	int pt = qb, ps = 0, pk0 = 0, p_m0 = 0, p_n0 = 0, p_M = 0, p_N = 0, p_seg_end = 0;
+	ctbd_gemm_seg psg;
+	psg.a_off = 0; psg.b_off = 0; psg.k = 0; psg.lda = 0; psg.ldb = 0; psg.pad_ = 0;
+	auto producer_enter_tile = [&]() {
+		while (pt < qe) {
+			const GemmTile t = args.tiles[pt];
+			if (t.nsteps > 0) {
+				const ctbd_gemm_out o = args.outs[t.out];
+				p_m0 = t.m0; p_n0 = t.n0; p_M = o.m; p_N = o.n; ps = o.seg_begin; p_seg_end = o.seg_end; pk0 = 0;
+				psg = args.segs[ps];
+				return;
+			}
+			pt++;
 		}
-	}
-
-	/* total pipeline steps over the concatenated K extent of all segments */
-	int total = 0;
-	for (int s = out.seg_begin; s < out.seg_end; s++) { total += (args.segs[s].k + BK - 1) / BK; }
-
-	/* producer iterator */
-	int ps = out.seg_begin, pk0 = 0;
+	};
+	producer_enter_tile();
 	auto issue = [&](int stage) {
-		const ctbd_gemm_seg sg = args.segs[ps];
-		const bool va = !CPLX && ((sg.a_off | (int64_t)sg.lda) & 1) == 0;
-		const bool vb = !CPLX && ((sg.b_off | (int64_t)sg.ldb) & 1) == 0;
-		load_tile<T, A_KC,  BM, BK, SK, SXA, NT>(As + (size_t)stage * Cfg::A_ELEMS, Ag, sg.a_off, sg.lda, m0, M, pk0, sg.k, va);
-		load_tile<T, !B_NC, BN, BK, SK, SXB, NT>(Bs + (size_t)stage * Cfg::B_ELEMS, Bg, sg.b_off, sg.ldb, n0, N, pk0, sg.k, vb);
+		const bool va = !CPLX && ((psg.a_off | (int64_t)psg.lda) & 1) == 0;
+		const bool vb = !CPLX && ((psg.b_off | (int64_t)psg.ldb) & 1) == 0;
+		load_tile<T, A_KC,  BM, BK, SK, SXA, NT>(As + (size_t)stage * Cfg::A_ELEMS, Ag, psg.a_off, psg.lda, p_m0, p_M, pk0, psg.k, va);
+		load_tile<T, !B_NC, BN, BK, SK, SXB, NT>(Bs + (size_t)stage * Cfg::B_ELEMS, Bg, psg.b_off, psg.ldb, p_n0, p_N, pk0, psg.k, vb);
 		pk0 += BK;
-		if (pk0 >= sg.k) { ps++; pk0 = 0; }
+		if (pk0 >= psg.k) {
+			pk0 = 0; ps++;
+			if (ps < p_seg_end) { psg = args.segs[ps]; }
+			else { pt++; producer_enter_tile(); }
+		}
 	};
 
 	#pragma unroll
 	for (int st = 0; st < STAGES - 1; st++) {
-		if (st < total) { issue(st); }
+		if (pt < qe) { issue(st); }
 		cp_async_commit();
 	}
 
-	for (int step = 0; step < total; step++)
+	int gstep = 0;   /* consumer position in the flattened sequence */
+	for (int ct = qb; ct < qe; ct++)
 	{
-		cp_async_wait<STAGES - 2>();
-		__syncthreads();
-		if (step + STAGES - 1 < total) { issue((step + STAGES - 1) % STAGES); }
-		cp_async_commit();
-
-		const T* as = As + (size_t)(step % STAGES) * Cfg::A_ELEMS;
-		const T* bs = Bs + (size_t)(step % STAGES) * Cfg::B_ELEMS;
+		const GemmTile tile = args.tiles[ct];
+		double acc[MI][NI][NACC];
 		#pragma unroll
-		for (int kk = 0; kk < BK; kk += 4)
-		{
-			T af[MI], bf[NI];
-			#pragma unroll
-			for (int i = 0; i < MI; i++) {
-				const int row = wm0 + 8 * i + lr, k = kk + lc;
-				af[i] = A_KC ? as[row * SK + k] : as[k * SXA + row];
-			}
+		for (int i = 0; i < MI; i++) {
 			#pragma unroll
 			for (int j = 0; j < NI; j++) {
-				const int col = wn0 + 8 * j + lr, k = kk + lc;
-				bf[j] = B_NC ? bs[k * SXB + col] : bs[col * SK + k];
+				#pragma unroll
+				for (int c = 0; c < NACC; c++) { acc[i][j][c] = 0.0; }
 			}
-			if constexpr (!CPLX)
+		}
+
+		for (int step = 0; step < tile.nsteps; step++, gstep++)
+		{
+			cp_async_wait<STAGES - 2>();
+			__syncthreads();
+			if (pt < qe) { issue((gstep + STAGES - 1) % STAGES); }
+			cp_async_commit();
+
+			const T* as = As + (size_t)(gstep % STAGES) * Cfg::A_ELEMS;
+			const T* bs = Bs + (size_t)(gstep % STAGES) * Cfg::B_ELEMS;
+			#pragma unroll
+			for (int kk = 0; kk < BK; kk += 4)
 			{
+				T af[MI], bf[NI];
 				#pragma unroll
 				for (int i = 0; i < MI; i++) {
-					#pragma unroll
-					for (int j = 0; j < NI; j++) { dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]); }
-				}
-			}
-			else
-			{
-				/* (ar + i ai)(br + i bi): re += ar br - ai bi, im += ar bi + ai br; conjugation flips the sign of ai / bi */
-				double ar[MI], ai[MI], nai[MI];
-				#pragma unroll
-				for (int i = 0; i < MI; i++) {
-					ar[i] = af[i].x;
-					ai[i] = args.conj_a ? -af[i].y : af[i].y;
-					nai[i] = -ai[i];
+					const int row = wm0 + 8 * i + lr, k = kk + lc;
+					af[i] = A_KC ? as[row * SK + k] : as[k * SXA + row];
 				}
 				#pragma unroll
 				for (int j = 0; j < NI; j++) {
-					const double br = bf[j].x;
-					const double bi = args.conj_b ? -bf[j].y : bf[j].y;
+					const int col = wn0 + 8 * j + lr, k = kk + lc;
+					bf[j] = B_NC ? bs[k * SXB + col] : bs[col * SK + k];
+				}
+				if constexpr (!CPLX)
+				{
 					#pragma unroll
 					for (int i = 0; i < MI; i++) {
-						dmma884(acc[i][j][0], acc[i][j][1], ar[i],  br);
-						dmma884(acc[i][j][0], acc[i][j][1], nai[i], bi);
-						dmma884(acc[i][j][2], acc[i][j][3], ar[i],  bi);
-						dmma884(acc[i][j][2], acc[i][j][3], ai[i],  br);
+						#pragma unroll
+						for (int j = 0; j < NI; j++) { dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]); }
 					}
+				}
+				else
+				{
+					/* (ar + i ai)(br + i bi): re += ar br - ai bi, im += ar bi + ai br; conjugation flips the sign of ai / bi */
+					double ar[MI], ai[MI], nai[MI];
+					#pragma unroll
+					for (int i = 0; i < MI; i++) {
+						ar[i] = af[i].x;
+						ai[i] = args.conj_a ? -af[i].y : af[i].y;
+						nai[i] = -ai[i];
+					}
+					#pragma unroll
+					for (int j = 0; j < NI; j++) {
+						const double br = bf[j].x;
+						const double bi = args.conj_b ? -bf[j].y : bf[j].y;
+						#pragma unroll
+						for (int i = 0; i < MI; i++) {
+							dmma884(acc[i][j][0], acc[i][j][1], ar[i],  br);
+							dmma884(acc[i][j][0], acc[i][j][1], nai[i], bi);
+							dmma884(acc[i][j][2], acc[i][j][3], ar[i],  bi);
+							dmma884(acc[i][j][2], acc[i][j][3], ai[i],  br);
+						}
+					}
+				}
+			}
+		}
+
+		/* epilogue (overlaps the in-flight loads of the next tile):
+		 *   standard  C(i, j) -> c[c_off + rowtab[i] + coltab[j]]                      (output permutation fused)
+		 *   merged    C(i, j) -> c[c_off + rowtab[i] + tab[rowcol[i] + j]], col_tab < 0 (rows of several output blocks) */
+		const ctbd_gemm_out out = args.outs[tile.out];
+		const int M = out.m, N = out.n, m0 = tile.m0, n0 = tile.n0;
+		T* __restrict__ Cg = reinterpret_cast<T*>(args.C) + out.c_off;
+		const int32_t* __restrict__ rowtab = args.tab + out.row_tab;
+		const bool merged = (out.col_tab < 0);
+		#pragma unroll
+		for (int i = 0; i < MI; i++)
+		{
+			const int gr = m0 + wm0 + 8 * i + lr;
+			if (gr >= M) { continue; }
+			const int64_t ro = rowtab[gr];
+			const int32_t* __restrict__ coltab = args.tab + (merged ? rowtab[M + gr] : out.col_tab);
+			#pragma unroll
+			for (int j = 0; j < NI; j++)
+			{
+				const int gc = n0 + wn0 + 8 * j + 2 * lc;
+				if constexpr (!CPLX) {
+					if (gc < N)     { Cg[ro + coltab[gc]]     = acc[i][j][0]; }
+					if (gc + 1 < N) { Cg[ro + coltab[gc + 1]] = acc[i][j][1]; }
+				}
+				else {
+					if (gc < N)     { Cg[ro + coltab[gc]]     = make_double2(acc[i][j][0], acc[i][j][2]); }
+					if (gc + 1 < N) { Cg[ro + coltab[gc + 1]] = make_double2(acc[i][j][1], acc[i][j][3]); }
 				}
 			}
 		}
 	}
 	cp_async_wait<0>();
+}
 
-	/* epilogue: C(i, j) -> c[c_off + rowtab[i] + coltab[j]] (output permutation fused) */
-	T* __restrict__ Cg = reinterpret_cast<T*>(args.C) + out.c_off;
-	const int32_t* __restrict__ rowtab = args.tab + out.row_tab;
-	const int32_t* __restrict__ coltab = args.tab + out.col_tab;
-	#pragma unroll
-	for (int i = 0; i < MI; i++)
-	{
-		const int gr = m0 + wm0 + 8 * i + lr;
-		if (gr >= M) { continue; }
-		const int64_t ro = rowtab[gr];
-		#pragma unroll
-		for (int j = 0; j < NI; j++)
-		{
-			const int gc = n0 + wn0 + 8 * j + 2 * lc;
-			if constexpr (!CPLX) {
-				if (gc < N)     { Cg[ro + coltab[gc]]     = acc[i][j][0]; }
-				if (gc + 1 < N) { Cg[ro + coltab[gc + 1]] = acc[i][j][1]; }
-			}
-			else {
-				if (gc < N)     { Cg[ro + coltab[gc]]     = make_double2(acc[i][j][0], acc[i][j][2]); }
-				if (gc + 1 < N) { Cg[ro + coltab[gc + 1]] = make_double2(acc[i][j][1], acc[i][j][3]); }
-			}
-		}
+/* dst[i] = idx[i] >= 0 ? src[idx[i]] : 0  (packs a small operand once per plan) */
+template <typename T>
+__global__ void gather_kernel(int64_t n, const int64_t* __restrict__ idx, const T* __restrict__ src, T* __restrict__ dst)
+{
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t k = idx[i];
+		T v; memset(&v, 0, sizeof(T));
+		if (k >= 0) { v = src[k]; }
+		dst[i] = v;
 	}
 }
 
-/* ---- tile classes ---- */
+/* ---- tile classes: one class per plan, chosen for the least padded work ---- */
 
-/* real: 0 = 64x64 (4 warps of 32x32), 1 = 32x32 (4 warps of 16x16), 2 = 128x128 (8 warps of 64x32)
- * complex: 0 = 64x32 (4 warps of 32x16), 1 = 32x32 (4 warps of 16x16) */
-typedef TileCfg<double, 64, 64, 32, 32, 4>   CfgD0;
-typedef TileCfg<double, 32, 32, 16, 16, 4>   CfgD1;
-typedef TileCfg<double, 128, 128, 64, 32, 3> CfgD2;
-typedef TileCfg<double2, 64, 32, 32, 16, 3>  CfgZ0;
-typedef TileCfg<double2, 32, 32, 16, 16, 3>  CfgZ1;
+/* real:    0 = 64x64 (4 warps of 32x32), 1 = 32x32 (4 warps of 16x16), 2 = 128x128 (8 warps of 64x32),
+ *          3 = 64x128 (8 warps of 32x32, the shape cuBLAS picks for large DGEMM), 4 = 32x128 (4 warps of 32x32, BK 8) for skinny M
+ * complex: 0 = 64x32 (4 warps of 32x16), 1 = 32x32 (4 warps of 16x16), 2 = 32x64 (4 warps of 32x16, BK 8) */
+typedef TileCfg<double, 64, 64, 32, 32, 4>      CfgD0;
+typedef TileCfg<double, 32, 32, 16, 16, 4>      CfgD1;
+typedef TileCfg<double, 128, 128, 64, 32, 3>    CfgD2;
+typedef TileCfg<double, 64, 128, 32, 32, 3>     CfgD3;
+typedef TileCfg<double, 32, 128, 32, 32, 4, 8>  CfgD4;
+typedef TileCfg<double2, 64, 32, 32, 16, 3>     CfgZ0;
+typedef TileCfg<double2, 32, 32, 16, 16, 3>     CfgZ1;
+typedef TileCfg<double2, 32, 64, 32, 16, 4, 8>  CfgZ2;
 
-struct ClassShape { int bm, bn; double eff; };
-static const ClassShape g_shapes_d[3] = { { 64, 64, 1.0 }, { 32, 32, 1.35 }, { 128, 128, 0.9 } };
-static const ClassShape g_shapes_z[2] = { { 64, 32, 1.0 }, { 32, 32, 1.25 } };
+/* eff: relative cost per padded multiply-add of the class */
+struct ClassShape { int bm, bn, bk; double eff; };
+static const ClassShape g_shapes_d[5] = { { 64, 64, 16, 1.0 }, { 32, 32, 16, 1.5 }, { 128, 128, 16, 0.85 }, { 64, 128, 16, 0.9 }, { 32, 128, 8, 1.2 } };
+static const ClassShape g_shapes_z[3] = { { 64, 32, 16, 1.0 }, { 32, 32, 16, 1.3 }, { 32, 64, 8, 1.1 } };
 
 template <typename T, typename Cfg>
-static int launch_cfg(const GemmPlan* p, const GemmClass& cl, const GemmArgs& args)
+static void (*select_kernel(const GemmPlan* p))(const GemmArgs)
 {
-	void (*kern)(const GemmArgs) = nullptr;
-	if (p->a_kcontig) { kern = p->b_ncontig ? grouped_gemm_kernel<T, Cfg, true, true>  : grouped_gemm_kernel<T, Cfg, true, false>; }
-	else              { kern = p->b_ncontig ? grouped_gemm_kernel<T, Cfg, false, true> : grouped_gemm_kernel<T, Cfg, false, false>; }
-	static bool attr_set[4] = { false, false, false, false };
-	const int v = (p->a_kcontig ? 2 : 0) + (p->b_ncontig ? 1 : 0);
-	if (!attr_set[v]) {
-		CTBD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-		attr_set[v] = true;
-	}
-	kern<<<cl.ntiles, Cfg::NT, Cfg::SMEM, rt().stream>>>(args);
+	if (p->a_kcontig) { return p->b_ncontig ? grouped_gemm_kernel<T, Cfg, true, true>  : grouped_gemm_kernel<T, Cfg, true, false>; }
+	return p->b_ncontig ? grouped_gemm_kernel<T, Cfg, false, true> : grouped_gemm_kernel<T, Cfg, false, false>;
+}
+
+/* resident CTAs per SM of the plan's kernel (also opts the kernel into its dynamic shared memory size) */
+template <typename T, typename Cfg>
+static int occupancy_cfg(const GemmPlan* p, int* occ)
+{
+	auto kern = select_kernel<T, Cfg>(p);
+	CTBD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+	CTBD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, Cfg::NT, Cfg::SMEM));
+	return 0;
+}
+
+template <typename T, typename Cfg>
+static int launch_cfg(const GemmPlan* p, const GemmArgs& args)
+{
+	auto kern = select_kernel<T, Cfg>(p);
+	kern<<<p->grid, Cfg::NT, Cfg::SMEM, rt().stream>>>(args);
 	CTBD_LAUNCH_CHECK();
 	return 0;
 }
+
+#define CTBD_GEMM_DISPATCH(FN, ...) \
+	(p->dtype == CTBD_F64 \
+		? (p->cfg == 0 ? FN<double, CfgD0>(__VA_ARGS__) : p->cfg == 1 ? FN<double, CfgD1>(__VA_ARGS__) : p->cfg == 2 ? FN<double, CfgD2>(__VA_ARGS__) \
+			: p->cfg == 3 ? FN<double, CfgD3>(__VA_ARGS__) : FN<double, CfgD4>(__VA_ARGS__)) \
+		: (p->cfg == 0 ? FN<double2, CfgZ0>(__VA_ARGS__) : p->cfg == 1 ? FN<double2, CfgZ1>(__VA_ARGS__) : FN<double2, CfgZ2>(__VA_ARGS__)))
 
 } // namespace ctbd
 
@@ -361,54 +416,102 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 
 	const bool cplx = (h->dtype == CTBD_C128);
 	const ClassShape* shapes = cplx ? g_shapes_z : g_shapes_d;
-	const int nshapes = cplx ? 2 : 3;
-	const char* force = getenv("CTB_GEMM_CLASS");   /* tuning/debug knob: force one tile class */
-	const int forced = force != nullptr ? atoi(force) : -1;
+	const int nshapes = cplx ? 3 : 5;
+
+	/* class with the least padded work over the whole plan (+ a per-tile overhead of about two k-steps) */
+	int best = 0; double best_cost = 0;
+	for (int c = 0; c < nshapes; c++)
+	{
+		double cost = 0;
+		for (int b = 0; b < h->nouts; b++) {
+			const ctbd_gemm_out& o = h->outs[b];
+			if (o.m <= 0 || o.n <= 0) { continue; }
+			double steps = 0;
+			for (int s = o.seg_begin; s < o.seg_end; s++) { steps += (double)ceil_div(h->segs[s].k, shapes[c].bk); }
+			const double nt = (double)ceil_div(o.m, shapes[c].bm) * (double)ceil_div(o.n, shapes[c].bn);
+			cost += nt * (steps * shapes[c].bk + 32.0) * shapes[c].bm * shapes[c].bn * shapes[c].eff;
+		}
+		if (c == 0 || cost < best_cost) { best = c; best_cost = cost; }
+	}
+	const char* force = getenv("CTB_GEMM_CLASS");   /* tuning knob: force one tile class */
+	if (force != nullptr && atoi(force) >= 0 && atoi(force) < nshapes) { best = atoi(force); }
+	p->cfg = best;
+	const int bm = shapes[best].bm, bn = shapes[best].bn, bk = shapes[best].bk;
 
 	struct Item { GemmTile t; double w; };
-	std::vector<std::vector<Item>> items(nshapes);
+	std::vector<Item> items;
 	for (int b = 0; b < h->nouts; b++)
 	{
 		const ctbd_gemm_out& o = h->outs[b];
 		if (o.m <= 0 || o.n <= 0) { continue; }
-		double ktot = 0;
-		for (int s = o.seg_begin; s < o.seg_end; s++) { ktot += h->segs[s].k; }
-		/* pick the class with the least padded work (scaled by its relative efficiency) */
-		int best = 0; double best_cost = 0;
-		for (int c = 0; c < nshapes; c++)
-		{
-			const double pm = (double)ceil_div(o.m, shapes[c].bm) * shapes[c].bm;
-			const double pn = (double)ceil_div(o.n, shapes[c].bn) * shapes[c].bn;
-			const double cost = pm * pn * shapes[c].eff;
-			if (c == 0 || cost < best_cost) { best = c; best_cost = cost; }
-		}
-		if (forced >= 0 && forced < nshapes) { best = forced; }
-		const int bm = shapes[best].bm, bn = shapes[best].bn;
+		int nsteps = 0;
+		for (int s = o.seg_begin; s < o.seg_end; s++) { nsteps += (int)ceil_div(h->segs[s].k, bk); }
 		for (int m0 = 0; m0 < o.m; m0 += bm) {
 			for (int n0 = 0; n0 < o.n; n0 += bn) {
-				const double tm = std::min(bm, o.m - m0), tn = std::min(bn, o.n - n0);
-				Item it; it.t.out = b; it.t.m0 = m0; it.t.n0 = n0; it.t.pad_ = 0;
-				it.w = ktot * (double)(bm * bn) + tm * tn;
-				items[best].push_back(it);
+				Item it; it.t.out = b; it.t.m0 = m0; it.t.n0 = n0; it.t.nsteps = nsteps;
+				it.w = (double)nsteps + 2.0;
+				items.push_back(it);
 			}
 		}
 	}
+	p->ntiles = (int)items.size();
 	int rc = 0;
 	rc |= upload(h->outs, (size_t)h->nouts * sizeof(ctbd_gemm_out), (void**)&p->outs);
 	rc |= upload(h->segs, (size_t)h->nsegs * sizeof(ctbd_gemm_seg), (void**)&p->segs);
 	rc |= upload(h->tab,  (size_t)h->ntab * sizeof(int32_t), (void**)&p->tab);
-	for (int c = 0; c < nshapes && rc == 0; c++)
+	if (rc == 0 && p->ntiles > 0)
 	{
-		if (items[c].empty()) { continue; }
-		/* heaviest first: the hardware block scheduler then acts as a longest-processing-time list scheduler */
-		std::stable_sort(items[c].begin(), items[c].end(), [](const Item& a, const Item& b) { return a.w > b.w; });
-		std::vector<GemmTile> tl(items[c].size());
-		for (size_t i = 0; i < tl.size(); i++) { tl[i] = items[c][i].t; }
-		GemmClass cl;
-		cl.cfg = c; cl.ntiles = (int)tl.size();
-		rc |= upload(tl.data(), tl.size() * sizeof(GemmTile), (void**)&cl.tiles);
-		p->classes.push_back(cl);
-		p->ntiles_total += cl.ntiles;
+		int occ = 1;
+		rc = CTBD_GEMM_DISPATCH(occupancy_cfg, p, &occ);
+		if (occ < 1) { occ = 1; }
+		const int grid = std::min(p->ntiles, rt().sm_count * occ);
+		p->grid = grid;
+		/* longest-processing-time-first packing of the tiles into one queue per resident CTA */
+		std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.w > b.w; });
+		std::vector<double> load(grid, 0.0);
+		std::vector<std::vector<int>> bins(grid);
+		/* binary heap of (load, bin) */
+		std::vector<std::pair<double, int>> heap(grid);
+		for (int g = 0; g < grid; g++) { heap[g] = std::make_pair(0.0, g); }
+		auto cmp = [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first || (a.first == b.first && a.second > b.second); };
+		std::make_heap(heap.begin(), heap.end(), cmp);
+		for (int i = 0; i < p->ntiles; i++) {
+			std::pop_heap(heap.begin(), heap.end(), cmp);
+			std::pair<double, int>& top = heap.back();
+			bins[top.second].push_back(i);
+			top.first += items[i].w;
+			std::push_heap(heap.begin(), heap.end(), cmp);
+		}
+		std::vector<GemmTile> tl; tl.reserve(p->ntiles);
+		std::vector<int32_t> queue(grid + 1, 0);
+		for (int g = 0; g < grid; g++) {
+			/* inside a queue: ascending output order for L2 locality of the operand blocks */
+			std::sort(bins[g].begin(), bins[g].end(), [&](int a, int b) {
+				const GemmTile& x = items[a].t; const GemmTile& y = items[b].t;
+				if (x.out != y.out) { return x.out < y.out; }
+				if (x.m0 != y.m0) { return x.m0 < y.m0; }
+				return x.n0 < y.n0; });
+			for (int i : bins[g]) { tl.push_back(items[i].t); }
+			queue[g + 1] = (int32_t)tl.size();
+		}
+		rc |= upload(tl.data(), tl.size() * sizeof(GemmTile), (void**)&p->tiles);
+		rc |= upload(queue.data(), queue.size() * sizeof(int32_t), (void**)&p->queue);
+	}
+	if (rc == 0 && h->a_gather != nullptr && h->n_a_gather > 0)
+	{
+		/* plan-owned packed A operand: gathered once from the (constant) source operand */
+		const size_t esize = cplx ? 16 : 8;
+		void* idx = nullptr;
+		rc |= upload(h->a_gather, (size_t)h->n_a_gather * sizeof(int64_t), &idx);
+		rc |= ctbd_malloc(&p->a_packed, (size_t)h->n_a_gather * esize);
+		if (rc == 0) {
+			const int blocks = (int)std::min<int64_t>(ceil_div(h->n_a_gather, 256), 1024);
+			if (cplx) { gather_kernel<double2><<<blocks, 256, 0, rt().stream>>>(h->n_a_gather, (const int64_t*)idx, (const double2*)h->a_src, (double2*)p->a_packed); }
+			else      { gather_kernel<double><<<blocks, 256, 0, rt().stream>>>(h->n_a_gather, (const int64_t*)idx, (const double*)h->a_src, (double*)p->a_packed); }
+			rt().launches++;
+			if (cudaGetLastError() != cudaSuccess) { rc = -1; }
+		}
+		ctbd_free(idx);
 	}
 	if (rc < 0) { ctbd_gemm_plan_destroy(p); return -1; }
 	*plan_out = p;
@@ -419,7 +522,7 @@ int ctbd_gemm_plan_destroy(void* plan)
 {
 	GemmPlan* p = (GemmPlan*)plan;
 	if (p == nullptr) { return 0; }
-	for (auto& cl : p->classes) { ctbd_free(cl.tiles); }
+	ctbd_free(p->tiles); ctbd_free(p->queue); ctbd_free(p->a_packed);
 	ctbd_free(p->outs); ctbd_free(p->segs); ctbd_free(p->tab);
 	delete p;
 	return 0;
@@ -428,38 +531,21 @@ int ctbd_gemm_plan_destroy(void* plan)
 int ctbd_gemm_plan_info(void* plan, int* ntiles, int* nlaunches)
 {
 	GemmPlan* p = (GemmPlan*)plan;
-	if (ntiles != nullptr) { *ntiles = p->ntiles_total; }
-	if (nlaunches != nullptr) { *nlaunches = (int)p->classes.size(); }
+	if (ntiles != nullptr) { *ntiles = p->ntiles; }
+	if (nlaunches != nullptr) { *nlaunches = p->ntiles > 0 ? 1 : 0; }
 	return 0;
 }
 
 int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
 {
 	GemmPlan* p = (GemmPlan*)plan;
+	if (p->ntiles == 0) { return 0; }
 	GemmArgs args;
+	args.tiles = p->tiles; args.queue = p->queue;
 	args.outs = p->outs; args.segs = p->segs; args.tab = p->tab;
-	args.A = A; args.B = B; args.C = C;
+	args.A = (p->a_packed != nullptr) ? p->a_packed : A; args.B = B; args.C = C;
 	args.conj_a = p->conj_a; args.conj_b = p->conj_b;
-	for (const GemmClass& cl : p->classes)
-	{
-		args.tiles = cl.tiles;
-		int rc = 0;
-		if (p->dtype == CTBD_F64) {
-			switch (cl.cfg) {
-				case 0: rc = launch_cfg<double, CfgD0>(p, cl, args); break;
-				case 1: rc = launch_cfg<double, CfgD1>(p, cl, args); break;
-				default: rc = launch_cfg<double, CfgD2>(p, cl, args); break;
-			}
-		}
-		else {
-			switch (cl.cfg) {
-				case 0: rc = launch_cfg<double2, CfgZ0>(p, cl, args); break;
-				default: rc = launch_cfg<double2, CfgZ1>(p, cl, args); break;
-			}
-		}
-		if (rc < 0) { return rc; }
-	}
-	return 0;
+	return CTBD_GEMM_DISPATCH(launch_cfg, p, args);
 }
 
 } // extern "C"

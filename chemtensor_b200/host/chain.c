@@ -251,7 +251,7 @@ struct ctb_tensor* ctb_env_step_right(const struct ctb_tensor* a, const struct c
 	ctb_dot_plan_free(&pl);
 	/* w . (a r), stored as [x, Dl, Dw, d_out, Dr'] */
 	const int perm1[5] = { 4, 2, 0, 1, 3 };
-	struct ctb_tensor* t = ctb_dot_prepare(w, TENSOR_AXIS_RANGE_TRAILING, 0, s, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1, 1, &pl);
+	struct ctb_tensor* t = ctb_dot_prepare_ex(w, TENSOR_AXIS_RANGE_TRAILING, 0, s, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1, 1, CTB_DOT_MERGE_ROWS, &pl);
 	CTB_CHECK_ABORT(ctb_dot_exec(&pl, w->d, s->d, t->d));
 	ctb_global_stats.env_flops += pl.flops;
 	ctb_dot_plan_free(&pl);
@@ -311,7 +311,7 @@ int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, str
 	h->t1 = ctb_dot_prepare(a, TENSOR_AXIS_RANGE_TRAILING, 0, r, TENSOR_AXIS_RANGE_LEADING, 0, 1, perm0, 1, &h->p1);
 	/* step 2: w . t1 over (dd_in, Dw') -> t2 [Dl, Dw, dd_out, Dr', x'] */
 	const int perm1[5] = { 2, 0, 1, 3, 4 };
-	h->t2 = ctb_dot_prepare(w, TENSOR_AXIS_RANGE_TRAILING, 0, h->t1, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1, 1, &h->p2);
+	h->t2 = ctb_dot_prepare_ex(w, TENSOR_AXIS_RANGE_TRAILING, 0, h->t1, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1, 1, CTB_DOT_MERGE_ROWS, &h->p2);
 	/* step 3: k . t2 over (Dl, Dw), k = transpose(l, [0,3,1,2]) once per bond (the reference redoes it every matvec) */
 	const int perm2[4] = { 0, 3, 1, 2 };
 	h->k = ctb_transpose(l, perm2, 0);

@@ -138,6 +138,12 @@ struct ctb_dot_plan
 struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, int conj_s,
 	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm,
 	int alloc_result, struct ctb_dot_plan* plan);
+/* flags of ctb_dot_prepare_ex */
+#define CTB_DOT_MERGE_ROWS 1   /* s is small and constant for the life of the plan: all result blocks that share the free sectors of t
+                                  become ONE tall-skinny GEMM against a packed copy of s, so every block of t is read once */
+struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s, int conj_s,
+	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm,
+	int alloc_result, int flags, struct ctb_dot_plan* plan);
 int  ctb_dot_exec(const struct ctb_dot_plan* plan, const void* s_data, const void* t_data, void* r_data);
 void ctb_dot_plan_free(struct ctb_dot_plan* plan);
 struct ctb_tensor* ctb_dot(const struct ctb_tensor* s, int axrange_s, int conj_s,

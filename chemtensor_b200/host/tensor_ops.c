@@ -19,9 +19,53 @@
 /* grouped-GEMM contraction plans                                                                  */
 /* ---------------------------------------------------------------------------------------------- */
 
-struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, int conj_s,
+/* growable int32 table */
+struct i32vec { int32_t* v; size_t n, cap; };
+static void i32vec_reserve(struct i32vec* t, size_t extra)
+{
+	while (t->n + extra > t->cap) { t->cap = t->cap ? 2 * t->cap : 4096; t->v = realloc(t->v, t->cap * sizeof(int32_t)); }
+}
+
+/* element offsets of the rows (free axes of s, 'first' = 0) or columns (free axes of t, 'first' = nfs) of a natural
+ * result block inside the permuted result block */
+static void append_offset_table(struct i32vec* tab, int first, int count, const struct ctb_axis* const* nat, const int* nat_sec,
+	const int* pos_of_nat, const ct_long* stride_r, ct_long base)
+{
+	ct_long total = 1;
+	for (int a = 0; a < count; a++) { total *= nat[first + a]->secdim[nat_sec[first + a]]; }
+	i32vec_reserve(tab, (size_t)total);
+	int dig[CTB_MAXDIM] = { 0 };
+	for (ct_long i = 0; i < total; i++)
+	{
+		ct_long off = base;
+		for (int a = 0; a < count; a++) { off += dig[a] * stride_r[pos_of_nat[first + a]]; }
+		CTB_REQUIRE(off < ((ct_long)1 << 31));
+		tab->v[tab->n++] = (int32_t)off;
+		for (int a = count - 1; a >= 0; a--) {
+			if (++dig[a] < nat[first + a]->secdim[nat_sec[first + a]]) { break; }
+			dig[a] = 0;
+		}
+	}
+}
+
+struct merge_key { ct_long key; int blk; };
+static int cmp_merge_key(const void* a, const void* b)
+{
+	const struct merge_key* x = a; const struct merge_key* y = b;
+	if (x->key != y->key) { return x->key < y->key ? -1 : 1; }
+	return (x->blk > y->blk) - (x->blk < y->blk);
+}
+
+static uint64_t hash_i64(const int64_t* v, size_t n)
+{
+	uint64_t h = 1469598103934665603ull;
+	for (size_t i = 0; i < n; i++) { h ^= (uint64_t)v[i]; h *= 1099511628211ull; h ^= h >> 29; }
+	return h;
+}
+
+struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s, int conj_s,
 	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm,
-	int alloc_result, struct ctb_dot_plan* plan)
+	int alloc_result, int flags, struct ctb_dot_plan* plan)
 {
 	CTB_REQUIRE(s->dtype == t->dtype);
 	CTB_REQUIRE(ndim_mult >= 1 && s->ndim >= ndim_mult && t->ndim >= ndim_mult);
@@ -54,13 +98,14 @@ struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, in
 
 	const int a_kcontig = (axrange_s == TENSOR_AXIS_RANGE_TRAILING);
 	const int b_ncontig = (axrange_t == TENSOR_AXIS_RANGE_LEADING);
+	const bool merge = (flags & CTB_DOT_MERGE_ROWS) != 0 && s->d != NULL && nft > 0 && r->nblk > 0;
 
 	/* growable host arrays */
 	size_t cap_seg = 1024, nseg = 0;
 	struct ctbd_gemm_seg* segs = malloc(cap_seg * sizeof(*segs));
 	struct ctbd_gemm_out* outs = malloc((r->nblk > 0 ? r->nblk : 1) * sizeof(*outs));
-	size_t cap_tab = 4096, ntab = 0;
-	int32_t* tab = malloc(cap_tab * sizeof(int32_t));
+	int nouts = 0;
+	struct i32vec tab = { NULL, 0, 0 };
 	double flops = 0;
 	const double flop_factor = ctb_is_complex(s->dtype) ? 8.0 : 2.0;
 
@@ -68,107 +113,225 @@ struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, in
 	ct_long ncontract = 1;
 	for (int i = 0; i < ndim_mult; i++) { ncontract *= s->ax[shift_s + i].nsec; }
 
-	for (int b = 0; b < r->nblk; b++)
+	/* merged form: packed copy of the (small) s operand, one dense M' x K' matrix per distinct group content */
+	int64_t* gather = NULL; size_t ngather = 0, cap_gather = 0;
+	struct merge_key* mk = NULL;
+	struct { uint64_t h; size_t base, len; }* packed = NULL; size_t npacked = 0, cap_packed = 0;
+	if (merge)
 	{
-		int idx_r[CTB_MAXDIM], nat_sec[CTB_MAXDIM];
-		ctb_grid_unravel(r, r->blk_grid[b], idx_r);
-		for (int i = 0; i < ndimr; i++) { nat_sec[p[i]] = idx_r[i]; }
+		CTB_REQUIRE(r->nstore < ((ct_long)1 << 31));
+		mk = malloc((size_t)r->nblk * sizeof(*mk));
+		for (int b = 0; b < r->nblk; b++) {
+			int idx_r[CTB_MAXDIM];
+			ctb_grid_unravel(r, r->blk_grid[b], idx_r);
+			ct_long key = 0;
+			for (int i = 0; i < nft; i++) { key = key * nat[nfs + i]->nsec + idx_r[pos_of_nat[nfs + i]]; }
+			mk[b].key = key; mk[b].blk = b;
+		}
+		qsort(mk, (size_t)r->nblk, sizeof(*mk), cmp_merge_key);
+	}
 
-		ct_long M = 1, N = 1;
-		for (int i = 0; i < nfs; i++) { M *= nat[i]->secdim[nat_sec[i]]; }
+	for (int b0 = 0; b0 < r->nblk; )
+	{
+		/* members of this output: one result block, or all result blocks sharing the free sectors of t */
+		int b1 = b0 + 1;
+		if (merge) { while (b1 < r->nblk && mk[b1].key == mk[b0].key) { b1++; } }
+
+		int idx_r[CTB_MAXDIM], nat_sec[CTB_MAXDIM];
+		ctb_grid_unravel(r, r->blk_grid[merge ? mk[b0].blk : b0], idx_r);
+		for (int i = 0; i < ndimr; i++) { nat_sec[p[i]] = idx_r[i]; }
+		ct_long N = 1;
 		for (int i = 0; i < nft; i++) { N *= nat[nfs + i]->secdim[nat_sec[nfs + i]]; }
 
-		struct ctbd_gemm_out* o = &outs[b];
-		o->c_off = r->blk_off[b];
-		o->m = (int32_t)M; o->n = (int32_t)N;
+		struct ctbd_gemm_out* o = &outs[nouts++];
+		o->n = (int32_t)N;
 		o->seg_begin = (int32_t)nseg;
 
-		/* enumerate contracted sector tuples in row-major order (reference :1951-1953) */
-		int idx_s[CTB_MAXDIM], idx_t[CTB_MAXDIM], kap[CTB_MAXDIM] = { 0 };
-		for (int i = 0; i < nfs; i++) { idx_s[offset_s + i] = nat_sec[i]; }
-		for (int i = 0; i < nft; i++) { idx_t[offset_t + i] = nat_sec[nfs + i]; }
-		for (ct_long c = 0; c < ncontract; c++)
+		if (!merge)
 		{
-			for (int i = 0; i < ndim_mult; i++) { idx_s[shift_s + i] = kap[i]; idx_t[shift_t + i] = kap[i]; }
-			const ct_long a_off = s->grid_off[ctb_grid_ravel(s, idx_s)];
-			if (a_off >= 0)
+			const int b = b0;
+			ct_long M = 1;
+			for (int i = 0; i < nfs; i++) { M *= nat[i]->secdim[nat_sec[i]]; }
+			o->c_off = r->blk_off[b];
+			o->m = (int32_t)M;
+			/* enumerate contracted sector tuples in row-major order (reference :1951-1953) */
+			int idx_s[CTB_MAXDIM], idx_t[CTB_MAXDIM], kap[CTB_MAXDIM] = { 0 };
+			for (int i = 0; i < nfs; i++) { idx_s[offset_s + i] = nat_sec[i]; }
+			for (int i = 0; i < nft; i++) { idx_t[offset_t + i] = nat_sec[nfs + i]; }
+			for (ct_long c = 0; c < ncontract; c++)
 			{
-				const ct_long b_off = t->grid_off[ctb_grid_ravel(t, idx_t)];
-				CTB_REQUIRE(b_off >= 0);   /* conservation in t follows from s and r (reference :1976-1984) */
-				ct_long K = 1;
-				for (int i = 0; i < ndim_mult; i++) { K *= s->ax[shift_s + i].secdim[kap[i]]; }
-				if (nseg == cap_seg) { cap_seg *= 2; segs = realloc(segs, cap_seg * sizeof(*segs)); }
-				struct ctbd_gemm_seg* g = &segs[nseg++];
-				g->a_off = a_off; g->b_off = b_off; g->k = (int32_t)K;
-				g->lda = (int32_t)(a_kcontig ? K : M);
-				g->ldb = (int32_t)(b_ncontig ? N : K);
-				g->pad_ = 0;
-				flops += flop_factor * (double)M * (double)N * (double)K;
+				for (int i = 0; i < ndim_mult; i++) { idx_s[shift_s + i] = kap[i]; idx_t[shift_t + i] = kap[i]; }
+				const ct_long a_off = s->grid_off[ctb_grid_ravel(s, idx_s)];
+				if (a_off >= 0)
+				{
+					const ct_long b_off = t->grid_off[ctb_grid_ravel(t, idx_t)];
+					CTB_REQUIRE(b_off >= 0);   /* conservation in t follows from s and r (reference :1976-1984) */
+					ct_long K = 1;
+					for (int i = 0; i < ndim_mult; i++) { K *= s->ax[shift_s + i].secdim[kap[i]]; }
+					if (nseg == cap_seg) { cap_seg *= 2; segs = realloc(segs, cap_seg * sizeof(*segs)); }
+					struct ctbd_gemm_seg* g = &segs[nseg++];
+					g->a_off = a_off; g->b_off = b_off; g->k = (int32_t)K;
+					g->lda = (int32_t)(a_kcontig ? K : M);
+					g->ldb = (int32_t)(b_ncontig ? N : K);
+					g->pad_ = 0;
+					flops += flop_factor * (double)M * (double)N * (double)K;
+				}
+				for (int i = ndim_mult - 1; i >= 0; i--) {
+					if (++kap[i] < s->ax[shift_s + i].nsec) { break; }
+					kap[i] = 0;
+				}
 			}
-			for (int i = ndim_mult - 1; i >= 0; i--) {
-				if (++kap[i] < s->ax[shift_s + i].nsec) { break; }
-				kap[i] = 0;
-			}
-		}
-		o->seg_end = (int32_t)nseg;
-
-		/* row/column offset tables: where element (i, j) of the natural block lands in the permuted block */
-		ct_long stride_r[CTB_MAXDIM];
-		{
+			o->seg_end = (int32_t)nseg;
+			/* row/column offset tables: where element (i, j) of the natural block lands in the permuted block */
+			ct_long stride_r[CTB_MAXDIM];
 			ct_long st = 1;
 			for (int i = ndimr - 1; i >= 0; i--) { stride_r[i] = st; st *= r->ax[i].secdim[idx_r[i]]; }
 			CTB_REQUIRE(st < ((ct_long)1 << 31));
+			o->row_tab = (int32_t)tab.n;
+			append_offset_table(&tab, 0, nfs, nat, nat_sec, pos_of_nat, stride_r, 0);
+			o->col_tab = (int32_t)tab.n;
+			append_offset_table(&tab, nfs, nft, nat, nat_sec, pos_of_nat, stride_r, 0);
 		}
-		while (ntab + (size_t)(M + N) > cap_tab) { cap_tab *= 2; tab = realloc(tab, cap_tab * sizeof(int32_t)); }
-		o->row_tab = (int32_t)ntab;
+		else
 		{
-			int dig[CTB_MAXDIM] = { 0 };
-			for (ct_long i = 0; i < M; i++)
+			/* contracted tuples present in t for these free sectors: the common K' of all members */
+			int idx_t[CTB_MAXDIM], kap[CTB_MAXDIM] = { 0 };
+			for (int i = 0; i < nft; i++) { idx_t[offset_t + i] = nat_sec[nfs + i]; }
+			ct_long Ktot = 0;
+			const size_t seg_first = nseg;
+			for (ct_long c = 0; c < ncontract; c++)
 			{
-				ct_long off = 0;
-				for (int a = 0; a < nfs; a++) { off += dig[a] * stride_r[pos_of_nat[a]]; }
-				tab[ntab++] = (int32_t)off;
-				for (int a = nfs - 1; a >= 0; a--) {
-					if (++dig[a] < nat[a]->secdim[nat_sec[a]]) { break; }
-					dig[a] = 0;
+				for (int i = 0; i < ndim_mult; i++) { idx_t[shift_t + i] = kap[i]; }
+				const ct_long b_off = t->grid_off[ctb_grid_ravel(t, idx_t)];
+				if (b_off >= 0)
+				{
+					ct_long K = 1;
+					for (int i = 0; i < ndim_mult; i++) { K *= s->ax[shift_s + i].secdim[kap[i]]; }
+					if (nseg == cap_seg) { cap_seg *= 2; segs = realloc(segs, cap_seg * sizeof(*segs)); }
+					struct ctbd_gemm_seg* g = &segs[nseg++];
+					g->a_off = Ktot;          /* column start inside the packed matrix; base added below */
+					g->b_off = b_off; g->k = (int32_t)K;
+					g->ldb = (int32_t)(b_ncontig ? N : K);
+					g->pad_ = (int32_t)c;     /* contracted grid cell, consumed below */
+					Ktot += K;
+				}
+				for (int i = ndim_mult - 1; i >= 0; i--) {
+					if (++kap[i] < s->ax[shift_s + i].nsec) { break; }
+					kap[i] = 0;
 				}
 			}
-		}
-		o->col_tab = (int32_t)ntab;
-		{
-			int dig[CTB_MAXDIM] = { 0 };
-			for (ct_long j = 0; j < N; j++)
+			o->seg_end = (int32_t)nseg;
+			/* stacked rows of all members */
+			ct_long Mtot = 0;
+			for (int q = b0; q < b1; q++) {
+				int ir[CTB_MAXDIM];
+				ctb_grid_unravel(r, r->blk_grid[mk[q].blk], ir);
+				ct_long M = 1;
+				for (int i = 0; i < nfs; i++) { M *= nat[i]->secdim[ir[pos_of_nat[i]]]; }
+				Mtot += M;
+			}
+			o->c_off = 0;
+			o->m = (int32_t)Mtot;
+			flops += flop_factor * (double)Mtot * (double)N * (double)Ktot;
+			o->row_tab = (int32_t)tab.n;
+			o->col_tab = -1;
+			i32vec_reserve(&tab, (size_t)(2 * Mtot));
+			tab.n += (size_t)(2 * Mtot);
+			const size_t rowtab0 = (size_t)o->row_tab, rowcol0 = rowtab0 + (size_t)Mtot;
+			/* gather list of the packed Mtot x Ktot matrix (k contiguous) */
+			const size_t glen = (size_t)(Mtot * Ktot);
+			while (ngather + glen > cap_gather) { cap_gather = cap_gather ? 2 * cap_gather : 65536; gather = realloc(gather, cap_gather * sizeof(int64_t)); }
+			int64_t* gl = gather + ngather;
+			ct_long row0 = 0;
+			for (int q = b0; q < b1; q++)
 			{
-				ct_long off = 0;
-				for (int a = 0; a < nft; a++) { off += dig[a] * stride_r[pos_of_nat[nfs + a]]; }
-				tab[ntab++] = (int32_t)off;
-				for (int a = nft - 1; a >= 0; a--) {
-					if (++dig[a] < nat[nfs + a]->secdim[nat_sec[nfs + a]]) { break; }
-					dig[a] = 0;
+				const int b = mk[q].blk;
+				int ir[CTB_MAXDIM], ns[CTB_MAXDIM], idx_s[CTB_MAXDIM];
+				ctb_grid_unravel(r, r->blk_grid[b], ir);
+				for (int i = 0; i < ndimr; i++) { ns[p[i]] = ir[i]; }
+				ct_long M = 1;
+				for (int i = 0; i < nfs; i++) { M *= nat[i]->secdim[ns[i]]; idx_s[offset_s + i] = ns[i]; }
+				ct_long stride_r[CTB_MAXDIM];
+				ct_long st = 1;
+				for (int i = ndimr - 1; i >= 0; i--) { stride_r[i] = st; st *= r->ax[i].secdim[ir[i]]; }
+				/* absolute row offsets and the column table of this member */
+				const size_t coltab_idx = tab.n + (size_t)M;
+				{
+					struct i32vec rows = { NULL, 0, 0 };
+					append_offset_table(&rows, 0, nfs, nat, ns, pos_of_nat, stride_r, r->blk_off[b]);
+					for (ct_long i = 0; i < M; i++) {
+						tab.v[rowtab0 + (size_t)(row0 + i)] = rows.v[i];
+						CTB_REQUIRE(coltab_idx < ((size_t)1 << 31));
+					}
+					free(rows.v);
 				}
+				/* member column table */
+				const size_t ct0 = tab.n;
+				append_offset_table(&tab, nfs, nft, nat, ns, pos_of_nat, stride_r, 0);
+				for (ct_long i = 0; i < M; i++) { tab.v[rowcol0 + (size_t)(row0 + i)] = (int32_t)ct0; }
+				/* packed entries of this member's rows */
+				for (size_t sg = seg_first; sg < nseg; sg++)
+				{
+					ct_long cell = segs[sg].pad_;
+					for (int i = ndim_mult - 1; i >= 0; i--) { idx_s[shift_s + i] = (int)(cell % s->ax[shift_s + i].nsec); cell /= s->ax[shift_s + i].nsec; }
+					const ct_long a_off = s->grid_off[ctb_grid_ravel(s, idx_s)];
+					CTB_REQUIRE(a_off >= 0);   /* conservation in s follows from r and t */
+					const ct_long K = segs[sg].k, kcol = segs[sg].a_off;
+					for (ct_long i = 0; i < M; i++) {
+						for (ct_long kk = 0; kk < K; kk++) {
+							gl[(row0 + i) * Ktot + kcol + kk] = a_kcontig ? a_off + i * K + kk : a_off + kk * M + i;
+						}
+					}
+				}
+				row0 += M;
+			}
+			/* reuse an identical packed matrix if one exists */
+			const uint64_t hsh = hash_i64(gl, glen) ^ (uint64_t)glen;
+			size_t base = ngather;
+			bool found = false;
+			for (size_t q = 0; q < npacked; q++) {
+				if (packed[q].h == hsh && packed[q].len == glen && memcmp(gather + packed[q].base, gl, glen * sizeof(int64_t)) == 0) { base = packed[q].base; found = true; break; }
+			}
+			if (!found) {
+				if (npacked == cap_packed) { cap_packed = cap_packed ? 2 * cap_packed : 256; packed = realloc(packed, cap_packed * sizeof(*packed)); }
+				packed[npacked].h = hsh; packed[npacked].base = base; packed[npacked].len = glen; npacked++;
+				ngather += glen;
+			}
+			for (size_t sg = seg_first; sg < nseg; sg++) {
+				segs[sg].a_off += (int64_t)base;
+				segs[sg].lda = (int32_t)Ktot;
+				segs[sg].pad_ = 0;
 			}
 		}
-		CTB_REQUIRE(ntab < ((size_t)1 << 31));
-
+		CTB_REQUIRE(tab.n < ((size_t)1 << 31));
+		b0 = b1;
 	}
 
 	struct ctbd_gemm_plan_host h;
 	memset(&h, 0, sizeof(h));
 	h.dtype = s->dtype;
-	h.a_kcontig = a_kcontig; h.b_ncontig = b_ncontig;
+	h.a_kcontig = merge ? 1 : a_kcontig; h.b_ncontig = b_ncontig;
 	h.conj_a = conj_s; h.conj_b = conj_t;
-	h.nouts = r->nblk; h.nsegs = (int32_t)nseg; h.ntab = (int32_t)ntab;
-	h.outs = outs; h.segs = segs; h.tab = tab;
+	h.nouts = nouts; h.nsegs = (int32_t)nseg; h.ntab = (int32_t)tab.n;
+	h.outs = outs; h.segs = segs; h.tab = tab.v;
 	h.flops = flops;
+	if (merge) { h.a_gather = gather; h.n_a_gather = (int64_t)ngather; h.a_src = s->d; }
 	plan->dev = NULL;
 	CTB_CHECK_ABORT(ctbd_gemm_plan_create(&h, &plan->dev));
 	plan->flops = flops;
-	plan->nouts = r->nblk; plan->nsegs = (int)nseg;
+	plan->nouts = nouts; plan->nsegs = (int)nseg;
 	plan->ntiles = 0;
 	CTB_CHECK_ABORT(ctbd_gemm_plan_info(plan->dev, &plan->ntiles, NULL));
 
-	free(tab); free(outs); free(segs);
+	free(tab.v); free(outs); free(segs); free(gather); free(mk); free(packed);
 	return r;
+}
+
+struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, int conj_s,
+	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm,
+	int alloc_result, struct ctb_dot_plan* plan)
+{
+	return ctb_dot_prepare_ex(s, axrange_s, conj_s, t, axrange_t, conj_t, ndim_mult, perm, alloc_result, 0, plan);
 }
 
 int ctb_dot_exec(const struct ctb_dot_plan* plan, const void* s_data, const void* t_data, void* r_data)

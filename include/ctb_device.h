@@ -92,7 +92,8 @@ struct ctbd_gemm_seg
 	int32_t pad_;
 };
 
-/* one output block: m x n, C(i,j) stored at c[c_off + tab[row_tab + i] + tab[col_tab + j]] */
+/* one output block: m x n, C(i,j) stored at c[c_off + tab[row_tab + i] + tab[col_tab + j]];
+ * merged-row form (col_tab < 0): rows of several result blocks stacked, C(i,j) at c[c_off + tab[row_tab + i] + tab[tab[row_tab + m + i] + j]] */
 struct ctbd_gemm_out
 {
 	int64_t c_off;
@@ -111,6 +112,11 @@ struct ctbd_gemm_plan_host
 	const struct ctbd_gemm_seg*  segs;
 	const int32_t* tab;
 	double flops;                 /* algorithmic flops of one run: sum 2*m*n*k (x4 complex) */
+	/* optional: the plan owns a packed copy of the (constant) A operand, a_packed[i] = a_gather[i] >= 0 ? a_src[a_gather[i]] : 0,
+	 * built once at plan creation; segment a_off then index a_packed and the A argument of ctbd_gemm_run is ignored */
+	const int64_t* a_gather;      /* host array or NULL */
+	int64_t n_a_gather;
+	const void* a_src;            /* device buffer the gather reads from */
 };
 
 /* builds the device-resident work list: every output block is cut into tiles of the kernel variant that

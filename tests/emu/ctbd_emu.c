@@ -54,7 +54,7 @@ int ctbd_host_free(void* hptr) { free(hptr); return 0; }
 long long ctbd_bytes_in_use(void) { return g_bytes; }
 
 /* ---- grouped GEMM ---- */
-struct emu_plan { struct ctbd_gemm_plan_host h; struct ctbd_gemm_out* outs; struct ctbd_gemm_seg* segs; int32_t* tab; };
+struct emu_plan { struct ctbd_gemm_plan_host h; struct ctbd_gemm_out* outs; struct ctbd_gemm_seg* segs; int32_t* tab; void* a_packed; };
 
 static void* dup_mem(const void* p, size_t n) { void* q = malloc(n ? n : 1); if (n) { memcpy(q, p, n); } return q; }
 
@@ -65,13 +65,21 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan)
 	p->outs  = dup_mem(h->outs,  (size_t)h->nouts  * sizeof(*h->outs));
 	p->segs  = dup_mem(h->segs,  (size_t)h->nsegs  * sizeof(*h->segs));
 	p->tab   = dup_mem(h->tab,   (size_t)h->ntab   * sizeof(int32_t));
+	p->a_packed = NULL;
+	if (h->a_gather != NULL && h->n_a_gather > 0) {
+		const size_t es = (h->dtype == CTBD_C128) ? 16 : 8;
+		p->a_packed = calloc((size_t)h->n_a_gather, es);
+		for (int64_t i = 0; i < h->n_a_gather; i++) {
+			if (h->a_gather[i] >= 0) { memcpy((char*)p->a_packed + (size_t)i * es, (const char*)h->a_src + (size_t)h->a_gather[i] * es, es); }
+		}
+	}
 	*plan = p;
 	return 0;
 }
 int ctbd_gemm_plan_destroy(void* plan)
 {
 	struct emu_plan* p = plan;
-	free(p->outs); free(p->segs); free(p->tab); free(p);
+	free(p->outs); free(p->segs); free(p->tab); free(p->a_packed); free(p);
 	return 0;
 }
 
@@ -88,6 +96,7 @@ int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
 	struct emu_plan* p = plan;
 	g_launches++;
 	const int cplx = (p->h.dtype == CTBD_C128);
+	if (p->a_packed != NULL) { A = p->a_packed; }
 	for (int t = 0; t < p->h.nouts; t++)
 	{
 		const struct ctbd_gemm_out* o = &p->outs[t];
@@ -113,7 +122,8 @@ int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
 						}
 					}
 				}
-				const int64_t ic = o->c_off + p->tab[o->row_tab + i] + p->tab[o->col_tab + j];
+				const int64_t ic = (o->col_tab >= 0) ? o->c_off + p->tab[o->row_tab + i] + p->tab[o->col_tab + j]
+					: o->c_off + p->tab[o->row_tab + i] + p->tab[p->tab[o->row_tab + o->m + i] + j];
 				if (cplx) { ((double complex*)C)[ic] = acc; } else { ((double*)C)[ic] = creal(acc); }
 			}
 		}
