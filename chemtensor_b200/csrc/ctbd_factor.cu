@@ -16,7 +16,10 @@
 #include <vector>
 #include <algorithm>
 #include <float.h>
+#include <cooperative_groups.h>
 #include "ctbd_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ctbd {
 
@@ -43,6 +46,44 @@ template <> __device__ __forceinline__ double2 from_real<double2>(double r) { re
 __device__ __forceinline__ double  shfl_xor(double v, int o)  { return __shfl_xor_sync(0xffffffffu, v, o); }
 __device__ __forceinline__ double2 shfl_xor(double2 v, int o) { return make_double2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o)); }
 
+__device__ __forceinline__ double absmax_of(double a)  { return fabs(a); }
+__device__ __forceinline__ double absmax_of(double2 a) { return fmax(fabs(a.x), fabs(a.y)); }
+
+/* power-of-two factor that brings a block with largest entry 'amax' to O(1), as LAPACK's ?lascl-based drivers do:
+ * the factorizations square entries (norms, Gram entries), which would under- or overflow for |a| ~ 1e+-160 */
+__device__ __forceinline__ double pow2_scale(double amax)
+{
+	if (!(amax > 0.0) || !isfinite(amax)) { return 1.0; }
+	int e; frexp(amax, &e);
+	return ldexp(1.0, -e);
+}
+
+/* block-wide maximum; result valid in all threads; 'red' has blockDim.x / 32 entries */
+__device__ __forceinline__ double block_max(double v, double* red)
+{
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o)); }
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = v; }
+	__syncthreads();
+	double r = red[0];
+	for (int w = 1; w < (int)(blockDim.x >> 5); w++) { r = fmax(r, red[w]); }
+	__syncthreads();
+	return r;
+}
+
+/* one CTA per matrix: scale[b] = power-of-two normalisation of block b (m x n entries at a_off) */
+template <typename T>
+__global__ void __launch_bounds__(256) absmax_scale_kernel(const int64_t* __restrict__ a_off, const int64_t* __restrict__ numel, const T* __restrict__ A, double* __restrict__ scale)
+{
+	__shared__ double red[8];
+	const T* a = A + a_off[blockIdx.x];
+	double v = 0;
+	for (int64_t e = threadIdx.x; e < numel[blockIdx.x]; e += blockDim.x) { v = fmax(v, absmax_of(a[e])); }
+	const double amax = block_max(v, red);
+	if (threadIdx.x == 0) { scale[blockIdx.x] = pow2_scale(amax); }
+}
+
 /* ============================================================================================== */
 /* SVD                                                                                              */
 /* ============================================================================================== */
@@ -55,11 +96,13 @@ struct SvdMat
 	int32_t pair_begin;   /* first work item (row pair slot) of this matrix in a round */
 	int32_t npair;        /* pair slots per round: ceil(R / 2) */
 };
+/* note: blocks are normalised by a power of two on load (scale[b]) and the singular values scaled back */
 
 template <typename T>
-__global__ void __launch_bounds__(256) svd_init_kernel(int nmat, const SvdMat* __restrict__ mats, const T* __restrict__ A, T* __restrict__ G)
+__global__ void __launch_bounds__(256) svd_init_kernel(int nmat, const SvdMat* __restrict__ mats, const double* __restrict__ scale, const T* __restrict__ A, T* __restrict__ G)
 {
 	const SvdMat mt = mats[blockIdx.y];
+	const double sc = scale[blockIdx.y];
 	const int ld = mt.C + mt.R;
 	const int64_t total = (int64_t)mt.R * ld;
 	const bool wide = (mt.m <= mt.n);
@@ -69,7 +112,7 @@ __global__ void __launch_bounds__(256) svd_init_kernel(int nmat, const SvdMat* _
 	{
 		const int i = (int)(e / ld), k = (int)(e % ld);
 		T v;
-		if (k < mt.C) { v = wide ? a[(int64_t)i * mt.n + k] : cj(a[(int64_t)k * mt.n + i]); }
+		if (k < mt.C) { v = smul(sc, wide ? a[(int64_t)i * mt.n + k] : cj(a[(int64_t)k * mt.n + i])); }
 		else { v = from_real<T>((k - mt.C) == i ? 1.0 : 0.0); }
 		g[e] = v;
 	}
@@ -133,6 +176,184 @@ __global__ void __launch_bounds__(256) svd_round_kernel(int nmat, const SvdMat* 
 	}
 }
 
+/* ---- blocks beyond shared memory: cooperative block Jacobi ----
+ * The rows of [G | W] are cut into row blocks of b rows (b chosen so that two blocks fit into shared memory).
+ * One persistent cooperative grid runs the whole iteration: per sweep, first every row block is orthogonalised
+ * internally, then the block pairs of a tournament over the blocks are processed, one pair per CTA: the CTA pulls the
+ * 2b rows from L2 into shared memory, rotates all b x b cross pairs there (one warp per pair, b pairs in flight,
+ * cached squared norms) and writes the rows back; a grid barrier separates the rounds.  Compared with one pair per
+ * launch this cuts both the number of grid-wide steps and the L2 traffic by the factor b. */
+struct SvdBlkMat
+{
+	int64_t g_off;
+	int32_t R, C, b, nb;       /* nb row blocks of b rows (the last may be shorter) */
+	int32_t blk_begin;         /* first item of this matrix in the intra-block phase */
+	int32_t pair_begin;        /* first item of this matrix in a tournament round (nbp / 2 items) */
+};
+
+/* one plane rotation of rows x, y (length ld, dot product over the first C entries); returns true if rotated */
+template <typename T>
+__device__ __forceinline__ bool jacobi_rotate_rows(T* x, T* y, double* sqx, double* sqy, int C, int ld, double thresh, int lane)
+{
+	T gamma = from_real<T>(0.0);
+	for (int k = lane; k < C; k += 32) { gamma = add(gamma, mul(x[k], cj(y[k]))); }
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { gamma = add(gamma, shfl_xor(gamma, o)); }
+	const double alpha = *sqx, beta = *sqy;
+	const double ag = sqrt(abs2(gamma));
+	if (ag == 0.0 || ag <= thresh * sqrt(alpha * beta)) { return false; }
+	const T ph = smul(1.0 / ag, gamma);
+	const double zeta = (beta - alpha) / (2.0 * ag);
+	const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+	const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+	for (int k = lane; k < ld; k += 32) {
+		const T xa = x[k], yb = mul(ph, y[k]);
+		x[k] = sub(smul(c, xa), smul(s, yb));
+		y[k] = add(smul(s, xa), smul(c, yb));
+	}
+	__syncwarp();
+	if (lane == 0) {
+		*sqx = fmax(alpha - t * ag, 0.0);
+		*sqy = beta + t * ag;
+	}
+	return true;
+}
+
+static constexpr int SVD_BLK_THREADS = 512;
+
+template <typename T>
+__global__ void __launch_bounds__(SVD_BLK_THREADS, 1) svd_block_kernel(int nmat, const SvdBlkMat* __restrict__ mats, int items_intra, int items_round, int max_rounds,
+	double tol, int max_sweeps, T* __restrict__ G, int* __restrict__ rot /* [max_sweeps][nmat] */)
+{
+	cg::grid_group grid = cg::this_grid();
+	extern __shared__ __align__(16) unsigned char svd_blk_raw[];
+	__shared__ double sq[64];
+	__shared__ int s_rot;
+	T* rows = reinterpret_cast<T*>(svd_blk_raw);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = SVD_BLK_THREADS / 32;
+
+	auto find = [&](int item, bool intra) {
+		int lo = 0, hi = nmat - 1;
+		while (lo < hi) {
+			const int mid = (lo + hi + 1) >> 1;
+			const int beg = intra ? mats[mid].blk_begin : mats[mid].pair_begin;
+			if (beg <= item) { lo = mid; } else { hi = mid - 1; }
+		}
+		return lo;
+	};
+	/* copy rows [r0, r0 + nr) of a matrix to / from shared memory slot 'slot0'; squared norms on load */
+	auto load_rows = [&](const SvdBlkMat& mt, int r0, int nr, int slot0) {
+		const int ld = mt.C + mt.R;
+		const T* src = G + mt.g_off + (int64_t)r0 * ld;
+		T* dst = rows + (size_t)slot0 * ld;
+		for (int e = tid; e < nr * ld; e += SVD_BLK_THREADS) { dst[e] = __ldcg(src + e); }
+	};
+	auto store_rows = [&](const SvdBlkMat& mt, int r0, int nr, int slot0) {
+		const int ld = mt.C + mt.R;
+		T* dst = G + mt.g_off + (int64_t)r0 * ld;
+		const T* src = rows + (size_t)slot0 * ld;
+		for (int e = tid; e < nr * ld; e += SVD_BLK_THREADS) { __stcg(dst + e, src[e]); }
+	};
+	auto norms = [&](const SvdBlkMat& mt, int nr) {
+		const int ld = mt.C + mt.R;
+		for (int i = warp; i < nr; i += nwarp) {
+			double s = 0;
+			for (int k = lane; k < mt.C; k += 32) { s += abs2(rows[(size_t)i * ld + k]); }
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); }
+			if (lane == 0) { sq[i] = s; }
+		}
+	};
+
+	for (int sweep = 0; sweep < max_sweeps; sweep++)
+	{
+		int* rot_now = rot + (size_t)sweep * nmat;
+		const int* rot_prev = rot + (size_t)(sweep > 0 ? sweep - 1 : 0) * nmat;
+		if (sweep > 0) {
+			bool any = false;
+			for (int mm = 0; mm < nmat; mm++) { any = any || (__ldcg(rot_prev + mm) != 0); }
+			if (!any) { break; }     /* uniform over the grid: every CTA reads the same counters after the barrier */
+		}
+
+		/* ---- phase 0: pairs inside each row block ---- */
+		for (int item = blockIdx.x; item < items_intra; item += gridDim.x)
+		{
+			const int mi = find(item, true);
+			const SvdBlkMat mt = mats[mi];
+			if (sweep > 0 && __ldcg(rot_prev + mi) == 0) { continue; }
+			const int I = item - mt.blk_begin;
+			const int r0 = I * mt.b, nr = min(mt.b, mt.R - r0);
+			if (nr < 2) { continue; }
+			const int ld = mt.C + mt.R;
+			const double thresh = tol * sqrt((double)mt.C);
+			if (tid == 0) { s_rot = 0; }
+			load_rows(mt, r0, nr, 0);
+			__syncthreads();
+			norms(mt, nr);
+			__syncthreads();
+			const int N = nr + (nr & 1);
+			for (int r = 0; r < N - 1; r++) {
+				for (int i = warp; i < N / 2; i += nwarp) {
+					int p, q;
+					if (i == 0) { p = N - 1; q = r; }
+					else { p = (r + i) % (N - 1); q = (r - i + (N - 1)) % (N - 1); }
+					if (p >= nr || q >= nr) { continue; }
+					if (p > q) { const int t = p; p = q; q = t; }
+					if (jacobi_rotate_rows<T>(rows + (size_t)p * ld, rows + (size_t)q * ld, &sq[p], &sq[q], mt.C, ld, thresh, lane) && lane == 0) { atomicAdd(&s_rot, 1); }
+				}
+				__syncthreads();
+			}
+			store_rows(mt, r0, nr, 0);
+			if (tid == 0 && s_rot > 0) { atomicAdd(&rot_now[mi], s_rot); }
+			__syncthreads();
+		}
+		grid.sync();
+
+		/* ---- tournament over the row blocks ---- */
+		for (int round = 0; round < max_rounds; round++)
+		{
+			for (int item = blockIdx.x; item < items_round; item += gridDim.x)
+			{
+				const int mi = find(item, false);
+				const SvdBlkMat mt = mats[mi];
+				if (mt.nb < 2 || (sweep > 0 && __ldcg(rot_prev + mi) == 0)) { continue; }
+				const int N = mt.nb + (mt.nb & 1);
+				const int r = round % (N - 1);
+				const int i = item - mt.pair_begin;
+				int I, J;
+				if (i == 0) { I = N - 1; J = r; }
+				else { I = (r + i) % (N - 1); J = (r - i + (N - 1)) % (N - 1); }
+				if (I >= mt.nb || J >= mt.nb) { continue; }
+				if (I > J) { const int t = I; I = J; J = t; }
+				const int ri = I * mt.b, ni = min(mt.b, mt.R - ri);
+				const int rj = J * mt.b, nj = min(mt.b, mt.R - rj);
+				const int ld = mt.C + mt.R;
+				const double thresh = tol * sqrt((double)mt.C);
+				if (tid == 0) { s_rot = 0; }
+				load_rows(mt, ri, ni, 0);
+				load_rows(mt, rj, nj, ni);
+				__syncthreads();
+				norms(mt, ni + nj);
+				__syncthreads();
+				const int bm = max(ni, nj);
+				for (int rr = 0; rr < bm; rr++) {
+					for (int x = warp; x < bm; x += nwarp) {
+						const int y = (x + rr) % bm;
+						if (x >= ni || y >= nj) { continue; }
+						if (jacobi_rotate_rows<T>(rows + (size_t)x * ld, rows + (size_t)(ni + y) * ld, &sq[x], &sq[ni + y], mt.C, ld, thresh, lane) && lane == 0) { atomicAdd(&s_rot, 1); }
+					}
+					__syncthreads();
+				}
+				store_rows(mt, ri, ni, 0);
+				store_rows(mt, rj, nj, ni);
+				if (tid == 0 && s_rot > 0) { atomicAdd(&rot_now[mi], s_rot); }
+				__syncthreads();
+			}
+			grid.sync();
+		}
+	}
+}
+
 /* after a window of rounds: a matrix without any rotation in a window that covered at least one full sweep is converged */
 __global__ void svd_mark_kernel(int nmat, const SvdMat* __restrict__ mats, int window, int* rot_count, int* done, int* pending)
 {
@@ -149,10 +370,11 @@ __global__ void svd_mark_kernel(int nmat, const SvdMat* __restrict__ mats, int w
 
 /* singular values (row norms, sorted descending) and vectors; one CTA per matrix */
 template <typename T>
-__global__ void __launch_bounds__(256) svd_finish_kernel(const SvdMat* __restrict__ mats, const T* __restrict__ G, double* __restrict__ sig_work, int* __restrict__ ord_work,
+__global__ void __launch_bounds__(256) svd_finish_kernel(const SvdMat* __restrict__ mats, const double* __restrict__ scale, const T* __restrict__ G, double* __restrict__ sig_work, int* __restrict__ ord_work,
 	T* __restrict__ U, T* __restrict__ Vh, double* __restrict__ S)
 {
 	const SvdMat mt = mats[blockIdx.x];
+	const double unscale = 1.0 / scale[blockIdx.x];
 	const int R = mt.R, C = mt.C, ld = C + R;
 	const T* g = G + mt.g_off;
 	double* sig = sig_work + mt.s_off;
@@ -178,7 +400,7 @@ __global__ void __launch_bounds__(256) svd_finish_kernel(const SvdMat* __restric
 	const int m = mt.m, n = mt.n;
 	T* u = U + mt.u_off;
 	T* vh = Vh + mt.vh_off;
-	for (int r = threadIdx.x; r < R; r += blockDim.x) { S[mt.s_off + r] = sig[ord[r]]; }
+	for (int r = threadIdx.x; r < R; r += blockDim.x) { S[mt.s_off + r] = unscale * sig[ord[r]]; }
 	/* Vh: R x n row-major, coalesced along the row */
 	for (int64_t e = threadIdx.x; e < (int64_t)R * n; e += blockDim.x) {
 		const int r = (int)(e / n), k = (int)(e % n);
@@ -195,9 +417,170 @@ __global__ void __launch_bounds__(256) svd_finish_kernel(const SvdMat* __restric
 	}
 }
 
+/* ---- blocks that fit into shared memory: the whole Jacobi iteration in ONE CTA, no global round trips ----
+ * [G | W] (R x (C + R)) lives in shared memory; warps take the R/2 disjoint row pairs of a tournament round, one block
+ * barrier per round.  Squared row norms are cached and updated by the rotation formulas (recomputed once per sweep), so a
+ * pair costs one dot product instead of three. */
+static constexpr int SVD_SMEM_THREADS = 512;
+static constexpr size_t SVD_SMEM_LIMIT = 220 * 1024;
+
 template <typename T>
-static int svd_batched_impl(int nmat, const ctbd_mat_desc* descs, const void* A, void* U, void* Vh, double* S)
+__global__ void __launch_bounds__(SVD_SMEM_THREADS) svd_smem_kernel(const SvdMat* __restrict__ mats, const int* __restrict__ sel, double tol, int max_sweeps,
+	const T* __restrict__ A, T* __restrict__ U, T* __restrict__ Vh, double* __restrict__ S)
 {
+	extern __shared__ __align__(16) unsigned char svd_smem_raw[];
+	const SvdMat mt = mats[sel[blockIdx.x]];
+	const int R = mt.R, C = mt.C, ld = C + R, m = mt.m, n = mt.n;
+	const bool wide = (m <= n);
+	T* g = reinterpret_cast<T*>(svd_smem_raw);
+	double* sq = reinterpret_cast<double*>(g + (size_t)R * ld);
+	int* ord = reinterpret_cast<int*>(sq + R);
+	__shared__ int s_rot;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = SVD_SMEM_THREADS / 32;
+	const T* a = A + mt.a_off;
+
+	__shared__ double s_red[SVD_SMEM_THREADS / 32];
+	double vmax = 0;
+	for (int e = tid; e < m * n; e += SVD_SMEM_THREADS) { vmax = fmax(vmax, absmax_of(a[e])); }
+	const double sc = pow2_scale(block_max(vmax, s_red));
+	for (int e = tid; e < R * ld; e += SVD_SMEM_THREADS) {
+		const int i = e / ld, k = e % ld;
+		T v;
+		if (k < C) { v = smul(sc, wide ? a[(int64_t)i * n + k] : cj(a[(int64_t)k * n + i])); }
+		else { v = from_real<T>((k - C) == i ? 1.0 : 0.0); }
+		g[e] = v;
+	}
+	__syncthreads();
+
+	const int N = R + (R & 1);
+	const double thresh = tol * sqrt((double)C);
+	for (int sweep = 0; sweep < max_sweeps && R >= 2; sweep++)
+	{
+		if (tid == 0) { s_rot = 0; }
+		for (int i = warp; i < R; i += nwarp) {
+			double s = 0;
+			for (int k = lane; k < C; k += 32) { s += abs2(g[i * ld + k]); }
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); }
+			if (lane == 0) { sq[i] = s; }
+		}
+		__syncthreads();
+		for (int r = 0; r < N - 1; r++)
+		{
+			for (int i = warp; i < N / 2; i += nwarp)
+			{
+				int p, q;
+				if (i == 0) { p = N - 1; q = r; }
+				else { p = (r + i) % (N - 1); q = (r - i + (N - 1)) % (N - 1); }
+				if (p >= R || q >= R) { continue; }
+				if (p > q) { const int t = p; p = q; q = t; }
+				T* x = g + p * ld;
+				T* y = g + q * ld;
+				T gamma = from_real<T>(0.0);
+				for (int k = lane; k < C; k += 32) { gamma = add(gamma, mul(x[k], cj(y[k]))); }
+				#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) { gamma = add(gamma, shfl_xor(gamma, o)); }
+				const double alpha = sq[p], beta = sq[q];
+				const double ag = sqrt(abs2(gamma));
+				if (ag == 0.0 || ag <= thresh * sqrt(alpha * beta)) { continue; }
+				const T ph = smul(1.0 / ag, gamma);
+				const double zeta = (beta - alpha) / (2.0 * ag);
+				const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+				const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+				for (int k = lane; k < ld; k += 32) {
+					const T xa = x[k], yb = mul(ph, y[k]);
+					x[k] = sub(smul(c, xa), smul(s, yb));
+					y[k] = add(smul(s, xa), smul(c, yb));
+				}
+				if (lane == 0) {
+					sq[p] = fmax(alpha - t * ag, 0.0);
+					sq[q] = beta + t * ag;
+					atomicAdd(&s_rot, 1);
+				}
+			}
+			__syncthreads();
+		}
+		const int nrot = s_rot;
+		__syncthreads();
+		if (nrot == 0) { break; }
+	}
+
+	/* singular values = exact final row norms, sorted descending (ties by index) */
+	for (int i = warp; i < R; i += nwarp) {
+		double s = 0;
+		for (int k = lane; k < C; k += 32) { s += abs2(g[i * ld + k]); }
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); }
+		if (lane == 0) { sq[i] = sqrt(s); }
+	}
+	__syncthreads();
+	for (int i = tid; i < R; i += SVD_SMEM_THREADS) {
+		const double si = sq[i];
+		int rank = 0;
+		for (int j = 0; j < R; j++) { const double sj = sq[j]; rank += (sj > si || (sj == si && j < i)) ? 1 : 0; }
+		ord[rank] = i;
+	}
+	__syncthreads();
+	T* u = U + mt.u_off;
+	T* vh = Vh + mt.vh_off;
+	for (int r = tid; r < R; r += SVD_SMEM_THREADS) { S[mt.s_off + r] = sq[ord[r]] / sc; }
+	for (int e = tid; e < R * n; e += SVD_SMEM_THREADS) {
+		const int r = e / n, k = e % n;
+		const int i = ord[r];
+		if (wide) { const double s = sq[i]; vh[e] = smul(s > 0 ? 1.0 / s : 0.0, g[i * ld + k]); }
+		else      { vh[e] = g[i * ld + C + k]; }
+	}
+	for (int e = tid; e < m * R; e += SVD_SMEM_THREADS) {
+		const int k = e / R, r = e % R;
+		const int i = ord[r];
+		if (wide) { u[e] = cj(g[i * ld + C + k]); }
+		else      { const double s = sq[i]; u[e] = smul(s > 0 ? 1.0 / s : 0.0, cj(g[i * ld + k])); }
+	}
+}
+
+template <typename T>
+static int svd_batched_impl(int nmat_all, const ctbd_mat_desc* descs_all, const void* A, void* U, void* Vh, double* S)
+{
+	if (nmat_all == 0) { return 0; }
+	/* blocks whose [G | W] fits into shared memory take the single-CTA path, the rest the global tournament below */
+	std::vector<SvdMat> small_mats;
+	std::vector<ctbd_mat_desc> big;
+	size_t smem_max = 0;
+	for (int b = 0; b < nmat_all; b++)
+	{
+		const int R = std::min(descs_all[b].m, descs_all[b].n), C = std::max(descs_all[b].m, descs_all[b].n);
+		const size_t need = (size_t)R * (C + R) * sizeof(T) + (size_t)R * (sizeof(double) + sizeof(int)) + 16;
+		if (need <= SVD_SMEM_LIMIT && getenv("CTB_SVD_NO_SMEM") == nullptr) {
+			SvdMat mt; memset(&mt, 0, sizeof(mt));
+			mt.a_off = descs_all[b].a_off; mt.u_off = descs_all[b].o0_off; mt.vh_off = descs_all[b].o1_off; mt.s_off = descs_all[b].s_off;
+			mt.m = descs_all[b].m; mt.n = descs_all[b].n; mt.R = R; mt.C = C;
+			small_mats.push_back(mt);
+			smem_max = std::max(smem_max, need);
+		}
+		else { big.push_back(descs_all[b]); }
+	}
+	if (!small_mats.empty())
+	{
+		/* heaviest first */
+		std::stable_sort(small_mats.begin(), small_mats.end(), [](const SvdMat& x, const SvdMat& y) {
+			return (double)x.R * x.R * (x.C + x.R) > (double)y.R * y.R * (y.C + y.R); });
+		std::vector<int> sel(small_mats.size());
+		for (size_t i = 0; i < sel.size(); i++) { sel[i] = (int)i; }
+		void *d_small = nullptr, *d_sel = nullptr;
+		if (upload(small_mats.data(), small_mats.size() * sizeof(SvdMat), &d_small) < 0) { return -1; }
+		if (upload(sel.data(), sel.size() * sizeof(int), &d_sel) < 0) { return -1; }
+		static bool attr_done = false;
+		if (!attr_done) {
+			CTBD_CUDA(cudaFuncSetAttribute(svd_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVD_SMEM_LIMIT));
+			attr_done = true;
+		}
+		svd_smem_kernel<T><<<(int)small_mats.size(), SVD_SMEM_THREADS, smem_max, rt().stream>>>((const SvdMat*)d_small, (const int*)d_sel, DBL_EPSILON, 40,
+			(const T*)A, (T*)U, (T*)Vh, S);
+		CTBD_LAUNCH_CHECK();
+		ctbd_free(d_sel); ctbd_free(d_small);
+	}
+	const int nmat = (int)big.size();
+	const ctbd_mat_desc* descs = big.data();
 	if (nmat == 0) { return 0; }
 	std::vector<SvdMat> mats(nmat);
 	int64_t g_total = 0; int total_pairs = 0; int Rmax = 0; int64_t smax = 0;
@@ -222,13 +605,64 @@ static int svd_batched_impl(int nmat, const ctbd_mat_desc* descs, const void* A,
 
 	int64_t maxel = 0;
 	for (int b = 0; b < nmat; b++) { maxel = std::max(maxel, (int64_t)mats[b].R * (mats[b].C + mats[b].R)); }
+	void *d_aoff = nullptr, *d_numel = nullptr, *d_scale = nullptr;
 	{
+		std::vector<int64_t> aoff(nmat), numel(nmat);
+		for (int b = 0; b < nmat; b++) { aoff[b] = mats[b].a_off; numel[b] = (int64_t)mats[b].m * mats[b].n; }
+		if (upload(aoff.data(), (size_t)nmat * sizeof(int64_t), &d_aoff) < 0) { return -1; }
+		if (upload(numel.data(), (size_t)nmat * sizeof(int64_t), &d_numel) < 0) { return -1; }
+		if (ctbd_malloc(&d_scale, (size_t)nmat * sizeof(double)) < 0) { return -1; }
+		absmax_scale_kernel<T><<<nmat, 256, 0, rt().stream>>>((const int64_t*)d_aoff, (const int64_t*)d_numel, (const T*)A, (double*)d_scale);
+		CTBD_LAUNCH_CHECK();
 		dim3 grid((unsigned)std::min<int64_t>(ceil_div(maxel, 256), 64), (unsigned)nmat);
-		svd_init_kernel<T><<<grid, 256, 0, rt().stream>>>(nmat, (const SvdMat*)d_mats, (const T*)A, (T*)d_G);
+		svd_init_kernel<T><<<grid, 256, 0, rt().stream>>>(nmat, (const SvdMat*)d_mats, (const double*)d_scale, (const T*)A, (T*)d_G);
 		CTBD_LAUNCH_CHECK();
 	}
 	int rc = 0;
-	if (Rmax >= 2)
+	/* rows per block such that two row blocks fit into shared memory */
+	const size_t blk_budget = 208 * 1024;
+	bool use_block = (getenv("CTB_SVD_TOURNAMENT") == nullptr);
+	std::vector<SvdBlkMat> bm(nmat);
+	int items_intra = 0, items_round = 0, max_rounds = 0; size_t blk_smem = 0;
+	for (int b = 0; b < nmat && use_block; b++)
+	{
+		const size_t ld = (size_t)(mats[b].C + mats[b].R);
+		int rows_fit = (int)(blk_budget / (2 * ld * sizeof(T)));
+		if (rows_fit < 1) { use_block = false; break; }
+		if (rows_fit > 32) { rows_fit = 32; }
+		SvdBlkMat& x = bm[b];
+		x.g_off = mats[b].g_off; x.R = mats[b].R; x.C = mats[b].C; x.b = rows_fit;
+		x.nb = (int)ceil_div(x.R, x.b);
+		x.blk_begin = items_intra; items_intra += x.nb;
+		const int nbp = x.nb + (x.nb & 1);
+		x.pair_begin = items_round; items_round += nbp / 2;
+		max_rounds = std::max(max_rounds, x.nb >= 2 ? nbp - 1 : 0);
+		blk_smem = std::max(blk_smem, (size_t)2 * x.b * ld * sizeof(T));
+	}
+	if (Rmax >= 2 && use_block)
+	{
+		const int max_sweeps = 40;
+		void *d_bm = nullptr, *d_rot = nullptr;
+		if (upload(bm.data(), (size_t)nmat * sizeof(SvdBlkMat), &d_bm) < 0) { return -1; }
+		if (ctbd_malloc(&d_rot, (size_t)max_sweeps * nmat * sizeof(int)) < 0) { return -1; }
+		static bool attr_done = false;
+		if (!attr_done) {
+			CTBD_CUDA(cudaFuncSetAttribute(svd_block_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(216 * 1024)));
+			attr_done = true;
+		}
+		int occ = 0;
+		CTBD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, svd_block_kernel<T>, SVD_BLK_THREADS, blk_smem));
+		if (occ < 1) { occ = 1; }
+		int grid = std::min(rt().sm_count * occ, std::max(items_intra, items_round));
+		if (grid < 1) { grid = 1; }
+		int a_nmat = nmat, a_mr = max_rounds, a_ms = max_sweeps; double a_tol = DBL_EPSILON;
+		const SvdBlkMat* a_mats = (const SvdBlkMat*)d_bm; T* a_G = (T*)d_G; int* a_rot = (int*)d_rot;
+		void* kargs[] = { &a_nmat, &a_mats, &items_intra, &items_round, &a_mr, &a_tol, &a_ms, &a_G, &a_rot };
+		CTBD_CUDA(cudaLaunchCooperativeKernel((void*)svd_block_kernel<T>, dim3(grid), dim3(SVD_BLK_THREADS), kargs, blk_smem, rt().stream));
+		rt().launches++;
+		ctbd_free(d_rot); ctbd_free(d_bm);
+	}
+	else if (Rmax >= 2)
 	{
 		const int Nmax = Rmax + (Rmax & 1);
 		const int window = Nmax - 1;            /* rounds per global sweep */
@@ -251,11 +685,12 @@ static int svd_batched_impl(int nmat, const ctbd_mat_desc* descs, const void* A,
 	}
 	if (rc == 0)
 	{
-		svd_finish_kernel<T><<<nmat, 256, 0, rt().stream>>>((const SvdMat*)d_mats, (const T*)d_G, (double*)d_sig, ord, (T*)U, (T*)Vh, S);
+		svd_finish_kernel<T><<<nmat, 256, 0, rt().stream>>>((const SvdMat*)d_mats, (const double*)d_scale, (const T*)d_G, (double*)d_sig, ord, (T*)U, (T*)Vh, S);
 		rt().launches++;
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) { rc = fail("svd_finish_kernel", e, __FILE__, __LINE__); }
 	}
+	ctbd_free(d_scale); ctbd_free(d_numel); ctbd_free(d_aoff);
 	ctbd_free(d_sig); ctbd_free(d_int); ctbd_free(d_G); ctbd_free(d_mats);
 	return rc;
 }
@@ -296,10 +731,14 @@ __global__ void __launch_bounds__(QR_THREADS) qr_kernel(const QrMat* __restrict_
 	__shared__ T s_tau;
 	__shared__ double s_beta;
 
-	/* load: X = A, or for RQ X = (E A E)^H, i.e. X[i][j] = conj(A[m-1-j][n-1-i]) */
+	/* load: X = A, or for RQ X = (E A E)^H, i.e. X[i][j] = conj(A[m-1-j][n-1-i]); normalised by a power of two */
+	double vmax = 0;
+	for (int64_t e = tid; e < (int64_t)rows * cols; e += QR_THREADS) { vmax = fmax(vmax, absmax_of(a[e])); }
+	const double sc = pow2_scale(block_max(vmax, red));
+	const double unsc = 1.0 / sc;
 	for (int64_t e = tid; e < (int64_t)rows * cols; e += QR_THREADS) {
 		const int i = (int)(e / cols), j = (int)(e % cols);
-		X[e] = rq ? cj(a[(int64_t)(m - 1 - j) * n + (n - 1 - i)]) : a[e];
+		X[e] = smul(sc, rq ? cj(a[(int64_t)(m - 1 - j) * n + (n - 1 - i)]) : a[e]);
 	}
 	__syncthreads();
 
@@ -337,8 +776,9 @@ __global__ void __launch_bounds__(QR_THREADS) qr_kernel(const QrMat* __restrict_
 			/* v = x / (x0 - beta) below the diagonal */
 			const T x0 = X[(int64_t)j * cols + j];
 			const T d = sub(x0, from_real<T>(s_beta));
-			const double dn = abs2(d);
-			const T scal = smul(1.0 / dn, cj(d));     /* 1 / (x0 - beta) */
+			const double dmx = absmax_of(d);
+			const T ds = smul(1.0 / dmx, d);
+			const T scal = smul(1.0 / (abs2(ds) * dmx), cj(ds));     /* 1 / (x0 - beta), safe against underflow of |d|^2 */
 			__syncthreads();
 			for (int i = j + 1 + tid; i < rows; i += QR_THREADS) { X[(int64_t)i * cols + j] = mul(X[(int64_t)i * cols + j], scal); }
 			if (tid == 0) { X[(int64_t)j * cols + j] = from_real<T>(s_beta); }
@@ -426,7 +866,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_kernel(const QrMat* __restrict_
 		for (int64_t e = tid; e < (int64_t)m * k; e += QR_THREADS) { o0[e] = Q[e]; }
 		for (int64_t e = tid; e < (int64_t)k * n; e += QR_THREADS) {
 			const int i = (int)(e / n), c = (int)(e % n);
-			o1[e] = (c >= i) ? X[(int64_t)i * cols + c] : from_real<T>(0.0);
+			o1[e] = (c >= i) ? smul(unsc, X[(int64_t)i * cols + c]) : from_real<T>(0.0);
 		}
 	}
 	else
@@ -435,7 +875,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_kernel(const QrMat* __restrict_
 		for (int64_t e = tid; e < (int64_t)m * k; e += QR_THREADS) {
 			const int i = (int)(e / k), j = (int)(e % k);
 			const int ri = k - 1 - j, rc = m - 1 - i;
-			o0[e] = (rc >= ri) ? cj(X[(int64_t)ri * cols + rc]) : from_real<T>(0.0);
+			o0[e] = (rc >= ri) ? smul(unsc, cj(X[(int64_t)ri * cols + rc])) : from_real<T>(0.0);
 		}
 		for (int64_t e = tid; e < (int64_t)k * n; e += QR_THREADS) {
 			const int i = (int)(e / n), j = (int)(e % n);

@@ -173,6 +173,7 @@ struct GemmArgs
 	const int32_t* tab;
 	const void* A; const void* B; void* C;
 	int conj_a, conj_b;
+	int a_odd, b_odd;     /* operand base pointer is 8 (mod 16): shifts the parity test of the 16-byte copy path */
 };
 
 template <typename T, typename Cfg, bool A_KC, bool B_NC>
@@ -215,8 +216,8 @@ __global__ void __launch_bounds__(Cfg::NT) grouped_gemm_kernel(const GemmArgs ar
 	};
 	producer_enter_tile();
 	auto issue = [&](int stage) {
-		const bool va = !CPLX && ((psg.a_off | (int64_t)psg.lda) & 1) == 0;
-		const bool vb = !CPLX && ((psg.b_off | (int64_t)psg.ldb) & 1) == 0;
+		const bool va = !CPLX && (((psg.a_off + args.a_odd) | (int64_t)psg.lda) & 1) == 0;
+		const bool vb = !CPLX && (((psg.b_off + args.b_odd) | (int64_t)psg.ldb) & 1) == 0;
 		load_tile<T, A_KC,  BM, BK, SK, SXA, NT>(As + (size_t)stage * Cfg::A_ELEMS, Ag, psg.a_off, psg.lda, p_m0, p_M, pk0, psg.k, va);
 		load_tile<T, !B_NC, BN, BK, SK, SXB, NT>(Bs + (size_t)stage * Cfg::B_ELEMS, Bg, psg.b_off, psg.ldb, p_n0, p_N, pk0, psg.k, vb);
 		pk0 += BK;
@@ -545,6 +546,7 @@ int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
 	args.outs = p->outs; args.segs = p->segs; args.tab = p->tab;
 	args.A = (p->a_packed != nullptr) ? p->a_packed : A; args.B = B; args.C = C;
 	args.conj_a = p->conj_a; args.conj_b = p->conj_b;
+	args.a_odd = (int)(((uintptr_t)args.A >> 3) & 1); args.b_odd = (int)(((uintptr_t)args.B >> 3) & 1);
 	return CTBD_GEMM_DISPATCH(launch_cfg, p, args);
 }
 

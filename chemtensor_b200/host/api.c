@@ -520,14 +520,25 @@ void compute_right_operator_blocks(const struct mps* psi, const struct mps* chi,
 void apply_local_hamiltonian(const struct block_sparse_tensor* a, const struct block_sparse_tensor* w, const struct block_sparse_tensor* l, const struct block_sparse_tensor* r, struct block_sparse_tensor* b)
 {
 	ensure_init();
+	const bool trace = getenv("CTB_TRACE") != NULL;
+	const double t0 = ctb_wall_ms();
 	struct ctb_tensor* ad = ctb_upload(a); struct ctb_tensor* wd = ctb_upload(w); struct ctb_tensor* ld = ctb_upload(l); struct ctb_tensor* rd = ctb_upload(r);
+	const double t1 = ctb_wall_ms();
 	struct ctb_heff h;
 	CTB_CHECK_ABORT(ctb_heff_prepare(ad, wd, ld, rd, &h));
+	const double t2 = ctb_wall_ms();
 	struct ctb_tensor* bd = ctb_tensor_like(h.b, 1);
 	CTB_CHECK_ABORT(ctb_heff_apply(&h, ad->d, bd->d));
+	if (trace) { ctbd_sync(); }
+	const double t3 = ctb_wall_ms();
 	ctb_heff_free(&h);
 	ctb_tensor_free(ad); ctb_tensor_free(wd); ctb_tensor_free(ld); ctb_tensor_free(rd);
+	const double t4 = ctb_wall_ms();
 	finish(bd, b);
+	if (trace) {
+		fprintf(stderr, "apply_local_hamiltonian: upload %.2f ms, plans %.2f ms, matvec %.2f ms, free %.2f ms, download %.2f ms\n",
+			t1 - t0, t2 - t1, t3 - t2, t4 - t3, ctb_wall_ms() - t4);
+	}
 }
 
 /* ---- measurement ---- */

@@ -146,6 +146,13 @@ int ctb_lanczos_min(struct ctb_heff* h, const struct ctb_tensor* a_start, int ma
 
 	int rc = 0;
 	if (numiter < 1) { rc = -1; }
+	for (int j = 0; j < numiter && rc == 0; j++) {
+		if (!isfinite(alpha[j]) || (j + 1 < numiter && !isfinite(beta[j]))) {
+			fprintf(stderr, "chemtensor_b200: Lanczos produced a non-finite coefficient at iteration %d (alpha = %g, beta = %g, n = %lld)\n",
+				j, alpha[j], j + 1 < numiter ? beta[j] : 0.0, (long long)n);
+			rc = -1;
+		}
+	}
 	if (rc == 0)
 	{
 		double* z = ctb_malloc((size_t)numiter * numiter * sizeof(double));

@@ -207,3 +207,94 @@ def test_mps_orthonormalize_qr(eng, ref, dtype, mode):
     assert abs(ne - nr) <= 1e-13 * nr
     for i in range(6):
         helpers.assert_bst_close(psi_e.site(i), psi_c.site(i), 1e-11)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("path", ["block", "tournament"])
+def test_svd_paths_beyond_shared_memory(ref, rng, dtype, path, monkeypatch):
+    """Blocks too large for the single-CTA shared-memory kernel take the cooperative block-Jacobi kernel (or, for rows
+    that do not fit at all, the one-pair-per-warp tournament): force those paths on a moderate size."""
+    monkeypatch.setenv("CTB_SVD_NO_SMEM", "1")
+    if path == "tournament":
+        monkeypatch.setenv("CTB_SVD_TOURNAMENT", "1")
+    eng = helpers.load("cuda")
+    dense, dirs, qn = _matrix_inputs(rng, dtype, 120, 90, lo=0, hi=2)
+    a = cabi.bst_from_dense(eng, dense, dirs, qn)
+    u, vh = cabi.BST(eng), cabi.BST(eng)
+    s = cabi.DenseTensor()
+    assert eng.block_sparse_tensor_svd(a.ptr, u.ptr, C.byref(s), vh.ptr) == 0
+    ns = int(s.dim[0])
+    sv = np.ctypeslib.as_array(C.cast(s.data, C.POINTER(C.c_double)), shape=(ns,)).copy()
+    U, V = u.to_dense(), vh.to_dense()
+    assert helpers.rel_err((U * sv) @ V, dense) <= 1e-13
+    assert np.linalg.norm(U.conj().T @ U - np.eye(ns)) <= 1e-13 * ns
+    assert np.linalg.norm(V @ V.conj().T - np.eye(ns)) <= 1e-13 * ns
+    eng.delete_dense_tensor(C.byref(s))
+
+
+@pytest.mark.gpu
+def test_svd_large_block_in_shared_memory(ref, rng):
+    """A block close to the shared-memory limit (100 x 140 real) against numpy's LAPACK singular values."""
+    eng = helpers.load("cuda")
+    qn = [np.zeros(100, dtype=np.int32), np.zeros(140, dtype=np.int32)]
+    dense = rng.standard_normal((100, 140))
+    a = cabi.bst_from_dense(eng, dense, [1, -1], qn)
+    u, vh = cabi.BST(eng), cabi.BST(eng)
+    s = cabi.DenseTensor()
+    assert eng.block_sparse_tensor_svd(a.ptr, u.ptr, C.byref(s), vh.ptr) == 0
+    sv = np.ctypeslib.as_array(C.cast(s.data, C.POINTER(C.c_double)), shape=(100,)).copy()
+    assert np.max(np.abs(sv - np.linalg.svd(dense, compute_uv=False))) <= 1e-13 * sv[0]
+    U, V = u.to_dense(), vh.to_dense()
+    assert helpers.rel_err((U * sv) @ V, dense) <= 1e-13
+    assert np.linalg.norm(U.T @ U - np.eye(100)) <= 1e-12
+    eng.delete_dense_tensor(C.byref(s))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,shape", [(np.float64, (300, 260)), (np.float64, (150, 420)), (np.complex128, (180, 200))])
+def test_svd_block_jacobi_single_sector(rng, dtype, shape):
+    """One dense sector block larger than shared memory: cooperative block Jacobi against numpy's LAPACK."""
+    eng = helpers.load("cuda")
+    m, n = shape
+    qn = [np.zeros(m, dtype=np.int32), np.zeros(n, dtype=np.int32)]
+    dense = rng.standard_normal((m, n)).astype(dtype)
+    if np.dtype(dtype).kind == "c":
+        dense = dense + 1j * rng.standard_normal((m, n))
+    # graded columns: singular values spanning many orders of magnitude
+    dense = dense * np.logspace(0, -9, n)[None, :]
+    a = cabi.bst_from_dense(eng, dense, [1, -1], qn)
+    u, vh = cabi.BST(eng), cabi.BST(eng)
+    s = cabi.DenseTensor()
+    assert eng.block_sparse_tensor_svd(a.ptr, u.ptr, C.byref(s), vh.ptr) == 0
+    k = min(m, n)
+    sv = np.ctypeslib.as_array(C.cast(s.data, C.POINTER(C.c_double)), shape=(k,)).copy()
+    ref_sv = np.linalg.svd(dense, compute_uv=False)
+    assert np.max(np.abs(sv - ref_sv)) <= 1e-13 * ref_sv[0]
+    U, V = u.to_dense(), vh.to_dense()
+    assert helpers.rel_err((U * sv) @ V, dense) <= 1e-13
+    assert np.linalg.norm(U.conj().T @ U - np.eye(k)) <= 1e-12
+    assert np.linalg.norm(V @ V.conj().T - np.eye(k)) <= 1e-12
+    eng.delete_dense_tensor(C.byref(s))
+
+
+@pytest.mark.gpu
+def test_factorizations_of_tiny_magnitudes(ref, rng):
+    """Entries around 1e-170 (a long unnormalised random MPS): squares underflow unless blocks are rescaled as LAPACK does."""
+    eng = helpers.load("cuda")
+    qn = [helpers.random_qnums(rng, 40), helpers.random_qnums(rng, 30)]
+    dense = helpers.random_dense(rng, np.float64, (40, 30), [1, -1], qn) * 1e-170
+    a, b = cabi.bst_from_dense(eng, dense, [1, -1], qn), cabi.bst_from_dense(ref, dense, [1, -1], qn)
+    q, r, qr_, rr = cabi.BST(eng), cabi.BST(eng), cabi.BST(ref), cabi.BST(ref)
+    assert eng.block_sparse_tensor_qr(a.ptr, cabi.QR_REDUCED, q.ptr, r.ptr) == 0
+    assert ref.block_sparse_tensor_qr(b.ptr, cabi.QR_REDUCED, qr_.ptr, rr.ptr) == 0
+    assert np.all(np.isfinite(q.to_dense())) and np.all(np.isfinite(r.to_dense()))
+    assert helpers.rel_err(q.to_dense() @ r.to_dense(), dense) <= 1e-13
+    helpers.assert_bst_close(r, rr, 1e-11)
+    u, vh = cabi.BST(eng), cabi.BST(eng)
+    s = cabi.DenseTensor()
+    assert eng.block_sparse_tensor_svd(a.ptr, u.ptr, C.byref(s), vh.ptr) == 0
+    ns = int(s.dim[0])
+    sv = np.ctypeslib.as_array(C.cast(s.data, C.POINTER(C.c_double)), shape=(ns,)).copy()
+    assert helpers.rel_err((u.to_dense() * sv) @ vh.to_dense(), dense) <= 1e-13
+    eng.delete_dense_tensor(C.byref(s))
