@@ -32,6 +32,12 @@ sys.path.insert(0, ROOT)
 
 from chemtensor_b200 import cabi, workloads  # noqa: E402
 
+# measured bond structures: name -> (data file, L of the measured chain, scale of the multiplicities)
+MEASURED = {
+    "fh_L64_D4096": ("bonds_fh_L32_D1024.json", 32, 4),
+    "fh_L32_D1024": ("bonds_fh_L32_D1024.json", 32, 1),
+}
+
 WORKLOADS = {
     # name: (model, nsites, params, sector, max_vdim, dtype, description)
     "xxz_L100_D1024": ("xxz", 100, (1.0, 0.8, 0.1), 0, 1024, np.float64,
@@ -115,9 +121,19 @@ def measure_fp64_peak(device: int):
     return best
 
 
-def build_operands(lib, wl_name: str, seed: int = 42):
+def build_operands(lib, wl_name: str, seed: int = 42, structure: str = "converged"):
+    """(a, w, l, r) of the centre pair.  structure = "converged": the sector histogram a converged two-site sweep of this
+    model produced (measured, chemtensor_b200/data), multiplicities scaled to the named bond dimension;
+    "random": the structure of the reference's construct_random_mps (uniformly sub-sampled sectors, many tiny blocks)."""
     model, L, params, sector, D, dtype, _ = WORKLOADS[wl_name]
-    return workloads.heff_operands(lib, model, L, params, sector, D, dtype=dtype, seed=seed)
+    bonds = None
+    if structure == "converged" and wl_name in MEASURED:
+        data, L0, scale = MEASURED[wl_name]
+        site0 = L0 // 2 - 1
+        dN = (L - L0) // 2      # same filling: the particle number left of the centre grows with half the extra sites
+        shift = workloads.encode_qpair(dN, 0) if model == "fermi_hubbard" else 0
+        bonds = (workloads.measured_bond_qnums(data, site0, scale, shift, D), workloads.measured_bond_qnums(data, site0 + 2, scale, shift, D))
+    return workloads.heff_operands(lib, model, L, params, sector, D, dtype=dtype, seed=seed, bonds=bonds)
 
 
 def dist_setup(n_gpus: int):
@@ -143,7 +159,7 @@ def run_reference(args):
     ref = cabi.CLibrary(REF_SO)
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    a, w, l, r = build_operands(ref, wl)
+    a, w, l, r = build_operands(ref, wl, structure=args.structure)
     flops = heff_flops_host(a, w, l, r)
     # bound the CPU work: cap the number of timed calls so that the arm ends within a few minutes
     t_probe0 = time.perf_counter()
@@ -164,7 +180,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "heff_matvec_fp64_tflops", "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl, "description": WORKLOADS[wl][6]},
+        "config": {"workload": wl, "description": WORKLOADS[wl][6], "structure": args.structure},
         "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "reference",
                          "sample": f"{steps} timed apply_local_hamiltonian calls of the unmodified reference (OpenMP {cores} threads, OpenBLAS 1 thread per GEMM) on the same operands"},
         "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,6 +201,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("CTB_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
+    ap.add_argument("--structure", default="converged", choices=["converged", "random"],
+                    help="sector structure of the synthetic operands: measured from converged sweeps (default) or the random-MPS rule")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -206,7 +224,7 @@ def main():
     model, L, params, sector, D, dtype, desc = WORKLOADS[wl]
 
     t_setup0 = time.perf_counter()
-    a, w, l, r = build_operands(lib, wl)
+    a, w, l, r = build_operands(lib, wl, structure=args.structure)
     n_vec = a.num_elements()
     t_setup = time.perf_counter() - t_setup0
 
@@ -264,7 +282,7 @@ def main():
         "metric": "heff_matvec_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if dtype == np.float64 else "c128",
         "data": "synthetic",
-        "config": {"workload": wl, "description": desc, "vector_length": int(n_vec), "flops_per_matvec": flops.value,
+        "config": {"workload": wl, "description": desc, "structure": args.structure, "vector_length": int(n_vec), "flops_per_matvec": flops.value,
                    "l2": "192 MiB buffer rewritten between timed matvecs", "setup_s": round(t_setup, 2),
                    "multi_gpu": "independent replicas of the bond (sharded Heff lands with the NCCL exchange step)" if world > 1 else "single GPU"},
         "roofline": roofline,
@@ -273,11 +291,11 @@ def main():
         "clocks": clocks.summary(),
     }
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(wl, flops.value)
+        line["cpu_baseline"] = cpu_baseline(wl, flops.value, args.structure)
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(wl: str, flops: float):
+def cpu_baseline(wl: str, flops: float, structure: str = "converged"):
     """The unmodified reference (oracle/_ref) on the host cores of this box, bounded sample, rank 0 only."""
     cores = os.cpu_count() or 1
     code = (
@@ -286,7 +304,7 @@ def cpu_baseline(wl: str, flops: float):
         "import bench\n"
         "from chemtensor_b200 import cabi\n"
         f"ref = cabi.CLibrary({REF_SO!r})\n"
-        f"a,w,l,r = bench.build_operands(ref, {wl!r})\n"
+        f"a,w,l,r = bench.build_operands(ref, {wl!r}, structure={structure!r})\n"
         "ts=[]\n"
         "t_all=time.perf_counter()\n"
         "while len(ts) < 5 and time.perf_counter()-t_all < 25:\n"

@@ -118,6 +118,7 @@ _EXT_SIGNATURES = {
     "ctb_backend": (C.c_int, []),
     "ctb_launch_count": (C.c_longlong, []),
     "ctb_heff_benchmark": (C.c_int, [_P_BST, _P_BST, _P_BST, _P_BST, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ctb_dot_benchmark": (C.c_int, [_P_BST, C.c_int, _P_BST, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ctb_get_stats": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
 }
 

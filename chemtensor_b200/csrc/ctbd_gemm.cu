@@ -39,6 +39,7 @@ struct GemmPlan
 	GemmTile* tiles = nullptr;         /* device: tiles grouped by CTA queue */
 	int32_t* queue = nullptr;          /* device: [grid + 1] queue boundaries */
 	void* a_packed = nullptr;          /* device: optional plan-owned A operand (gathered once at plan creation) */
+	int64_t* b_rowtab = nullptr;       /* device: optional row table of the B operand */
 };
 
 /* ---- PTX helpers ---- */
@@ -87,9 +88,44 @@ struct TileCfg
  * KIN: global elem(x,k) = g[base + x*ld + k], shared S[x*SK + k];  else global g[base + k*ld + x], shared S[k*SX + x] */
 template <typename T, bool KIN, int BX, int BK, int SK, int SX, int NT>
 __device__ __forceinline__ void load_tile(T* __restrict__ S, const T* __restrict__ g, const int64_t base, const int ld,
-	const int x0, const int X, const int k0, const int K, const bool vec2)
+	const int x0, const int X, const int k0, const int K, const bool vec2, const int64_t* __restrict__ rowtab = nullptr, const int odd = 0)
 {
 	const int tid = threadIdx.x;
+	if constexpr (!KIN)
+	{
+		if (rowtab != nullptr)
+		{
+			/* row-table form: row kk of the operand starts at g[rowtab[base + kk]] (rows gathered from many small blocks) */
+			if constexpr (sizeof(T) == 16) {
+				#pragma unroll
+				for (int c = tid; c < BX * BK; c += NT) {
+					const int k = c / BX, x = c % BX;
+					const bool ok = (x0 + x < X) && (k0 + k < K);
+					const T* src = ok ? g + rowtab[base + k0 + k] + (x0 + x) : g;
+					cp_async16(&S[k * SX + x], src, ok ? 16 : 0);
+				}
+			}
+			else {
+				constexpr int CPR = BX / 2;
+				const T* g16 = reinterpret_cast<const T*>(reinterpret_cast<uintptr_t>(g) & ~(uintptr_t)15);   /* aligned dummy source of zero-fill copies */
+				#pragma unroll
+				for (int c = tid; c < BK * CPR; c += NT) {
+					const int k = c / CPR, x = (c % CPR) * 2;
+					if (k0 + k < K && x0 + x < X) {
+						const int64_t ro = rowtab[base + k0 + k] + (x0 + x);
+						const bool two = (x0 + x + 1 < X);
+						if (((ro + odd) & 1) == 0) { cp_async16(&S[k * SX + x], g + ro, two ? 16 : 8); }
+						else {
+							cp_async8(&S[k * SX + x], g + ro, 8);
+							cp_async8(&S[k * SX + x + 1], two ? g + ro + 1 : g, two ? 8 : 0);
+						}
+					}
+					else { cp_async16(&S[k * SX + x], g16, 0); }
+				}
+			}
+			return;
+		}
+	}
 	if constexpr (sizeof(T) == 16)
 	{
 		/* complex128: one 16-byte element per copy */
@@ -174,6 +210,7 @@ struct GemmArgs
 	const void* A; const void* B; void* C;
 	int conj_a, conj_b;
 	int a_odd, b_odd;     /* operand base pointer is 8 (mod 16): shifts the parity test of the 16-byte copy path */
+	const int64_t* b_rowtab;   /* optional: B rows gathered through a row table, seg.b_off indexes it (merged-row plans) */
 };
 
 template <typename T, typename Cfg, bool A_KC, bool B_NC>
@@ -219,7 +256,8 @@ __global__ void __launch_bounds__(Cfg::NT) grouped_gemm_kernel(const GemmArgs ar
 		const bool va = !CPLX && (((psg.a_off + args.a_odd) | (int64_t)psg.lda) & 1) == 0;
 		const bool vb = !CPLX && (((psg.b_off + args.b_odd) | (int64_t)psg.ldb) & 1) == 0;
 		load_tile<T, A_KC,  BM, BK, SK, SXA, NT>(As + (size_t)stage * Cfg::A_ELEMS, Ag, psg.a_off, psg.lda, p_m0, p_M, pk0, psg.k, va);
-		load_tile<T, !B_NC, BN, BK, SK, SXB, NT>(Bs + (size_t)stage * Cfg::B_ELEMS, Bg, psg.b_off, psg.ldb, p_n0, p_N, pk0, psg.k, vb);
+		if constexpr (B_NC) { load_tile<T, false, BN, BK, SK, SXB, NT>(Bs + (size_t)stage * Cfg::B_ELEMS, Bg, psg.b_off, psg.ldb, p_n0, p_N, pk0, psg.k, vb, args.b_rowtab, args.b_odd); }
+		else                { load_tile<T, true,  BN, BK, SK, SXB, NT>(Bs + (size_t)stage * Cfg::B_ELEMS, Bg, psg.b_off, psg.ldb, p_n0, p_N, pk0, psg.k, vb); }
 		pk0 += BK;
 		if (pk0 >= psg.k) {
 			pk0 = 0; ps++;
@@ -353,20 +391,23 @@ __global__ void gather_kernel(int64_t n, const int64_t* __restrict__ idx, const 
 /* ---- tile classes: one class per plan, chosen for the least padded work ---- */
 
 /* real:    0 = 64x64 (4 warps of 32x32), 1 = 32x32 (4 warps of 16x16), 2 = 128x128 (8 warps of 64x32),
- *          3 = 64x128 (8 warps of 32x32, the shape cuBLAS picks for large DGEMM), 4 = 32x128 (4 warps of 32x32, BK 8) for skinny M
+ *          3 = 64x128 (8 warps of 32x32), 4 = 32x128 (4 warps of 32x32, BK 8) for skinny M,
+ *          5 = 64x128 (4 warps of 32x64: tile and warp shape of cuBLAS' cutlass_80_tensorop_d884gemm_64x128_16x3)
  * complex: 0 = 64x32 (4 warps of 32x16), 1 = 32x32 (4 warps of 16x16), 2 = 32x64 (4 warps of 32x16, BK 8) */
 typedef TileCfg<double, 64, 64, 32, 32, 4>      CfgD0;
 typedef TileCfg<double, 32, 32, 16, 16, 4>      CfgD1;
 typedef TileCfg<double, 128, 128, 64, 32, 3>    CfgD2;
 typedef TileCfg<double, 64, 128, 32, 32, 3>     CfgD3;
 typedef TileCfg<double, 32, 128, 32, 32, 4, 8>  CfgD4;
+typedef TileCfg<double, 64, 128, 32, 64, 3>     CfgD5;
 typedef TileCfg<double2, 64, 32, 32, 16, 3>     CfgZ0;
 typedef TileCfg<double2, 32, 32, 16, 16, 3>     CfgZ1;
 typedef TileCfg<double2, 32, 64, 32, 16, 4, 8>  CfgZ2;
 
 /* eff: relative cost per padded multiply-add of the class */
 struct ClassShape { int bm, bn, bk; double eff; };
-static const ClassShape g_shapes_d[5] = { { 64, 64, 16, 1.0 }, { 32, 32, 16, 1.5 }, { 128, 128, 16, 0.85 }, { 64, 128, 16, 0.9 }, { 32, 128, 8, 1.2 } };
+/* eff from the measured large-block throughput of each class (tools/gemm_sweep.py, profiles/) */
+static const ClassShape g_shapes_d[6] = { { 64, 64, 16, 1.0 }, { 32, 32, 16, 1.05 }, { 128, 128, 16, 0.88 }, { 64, 128, 16, 0.82 }, { 32, 128, 8, 0.95 }, { 64, 128, 16, 0.80 } };
 static const ClassShape g_shapes_z[3] = { { 64, 32, 16, 1.0 }, { 32, 32, 16, 1.3 }, { 32, 64, 8, 1.1 } };
 
 template <typename T, typename Cfg>
@@ -398,7 +439,7 @@ static int launch_cfg(const GemmPlan* p, const GemmArgs& args)
 #define CTBD_GEMM_DISPATCH(FN, ...) \
 	(p->dtype == CTBD_F64 \
 		? (p->cfg == 0 ? FN<double, CfgD0>(__VA_ARGS__) : p->cfg == 1 ? FN<double, CfgD1>(__VA_ARGS__) : p->cfg == 2 ? FN<double, CfgD2>(__VA_ARGS__) \
-			: p->cfg == 3 ? FN<double, CfgD3>(__VA_ARGS__) : FN<double, CfgD4>(__VA_ARGS__)) \
+			: p->cfg == 3 ? FN<double, CfgD3>(__VA_ARGS__) : p->cfg == 4 ? FN<double, CfgD4>(__VA_ARGS__) : FN<double, CfgD5>(__VA_ARGS__)) \
 		: (p->cfg == 0 ? FN<double2, CfgZ0>(__VA_ARGS__) : p->cfg == 1 ? FN<double2, CfgZ1>(__VA_ARGS__) : FN<double2, CfgZ2>(__VA_ARGS__)))
 
 } // namespace ctbd
@@ -417,7 +458,7 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 
 	const bool cplx = (h->dtype == CTBD_C128);
 	const ClassShape* shapes = cplx ? g_shapes_z : g_shapes_d;
-	const int nshapes = cplx ? 3 : 5;
+	const int nshapes = cplx ? 3 : 6;
 
 	/* class with the least padded work over the whole plan (+ a per-tile overhead of about two k-steps) */
 	int best = 0; double best_cost = 0;
@@ -460,6 +501,10 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 	rc |= upload(h->outs, (size_t)h->nouts * sizeof(ctbd_gemm_out), (void**)&p->outs);
 	rc |= upload(h->segs, (size_t)h->nsegs * sizeof(ctbd_gemm_seg), (void**)&p->segs);
 	rc |= upload(h->tab,  (size_t)h->ntab * sizeof(int32_t), (void**)&p->tab);
+	if (h->b_rowtab != nullptr && h->n_b_rowtab > 0) {
+		if (!h->b_ncontig) { ctbd_gemm_plan_destroy(p); return fail_msg("grouped GEMM: the B row table needs an n-contiguous B operand"); }
+		rc |= upload(h->b_rowtab, (size_t)h->n_b_rowtab * sizeof(int64_t), (void**)&p->b_rowtab);
+	}
 	if (rc == 0 && p->ntiles > 0)
 	{
 		int occ = 1;
@@ -523,7 +568,7 @@ int ctbd_gemm_plan_destroy(void* plan)
 {
 	GemmPlan* p = (GemmPlan*)plan;
 	if (p == nullptr) { return 0; }
-	ctbd_free(p->tiles); ctbd_free(p->queue); ctbd_free(p->a_packed);
+	ctbd_free(p->tiles); ctbd_free(p->queue); ctbd_free(p->a_packed); ctbd_free(p->b_rowtab);
 	ctbd_free(p->outs); ctbd_free(p->segs); ctbd_free(p->tab);
 	delete p;
 	return 0;
@@ -547,6 +592,7 @@ int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
 	args.A = (p->a_packed != nullptr) ? p->a_packed : A; args.B = B; args.C = C;
 	args.conj_a = p->conj_a; args.conj_b = p->conj_b;
 	args.a_odd = (int)(((uintptr_t)args.A >> 3) & 1); args.b_odd = (int)(((uintptr_t)args.B >> 3) & 1);
+	args.b_rowtab = p->b_rowtab;
 	return CTBD_GEMM_DISPATCH(launch_cfg, p, args);
 }
 

@@ -587,6 +587,39 @@ int ctb_heff_benchmark(const struct block_sparse_tensor* a, const struct block_s
 	return 0;
 }
 
+/* one contraction r = dot(s, t), device-resident, plan built once: mean device time per execution (CUDA events) */
+int ctb_dot_benchmark(const struct block_sparse_tensor* s, const int axrange_s, const struct block_sparse_tensor* t, const int axrange_t, const int ndim_mult,
+	int warmup, int reps, int flush_l2, double* ms_per_run, double* flops_per_run)
+{
+	CTB_CHECK(ctbd_init(-1));
+	struct ctb_tensor* sd = ctb_upload(s); struct ctb_tensor* td = ctb_upload(t);
+	struct ctb_dot_plan pl;
+	struct ctb_tensor* rd = ctb_dot_prepare(sd, axrange_s, 0, td, axrange_t, 0, ndim_mult, NULL, 1, &pl);
+	void* flush = NULL;
+	const size_t flush_bytes = (size_t)192 << 20;
+	if (flush_l2) { CTB_CHECK(ctbd_malloc(&flush, flush_bytes)); }
+	for (int i = 0; i < warmup; i++) { CTB_CHECK(ctb_dot_exec(&pl, sd->d, td->d, rd->d)); }
+	void *e0 = NULL, *e1 = NULL;
+	CTB_CHECK(ctbd_event_create(&e0)); CTB_CHECK(ctbd_event_create(&e1));
+	double tot = 0;
+	for (int i = 0; i < reps; i++)
+	{
+		if (flush_l2) { CTB_CHECK(ctbd_memset_zero(flush, flush_bytes)); }
+		CTB_CHECK(ctbd_event_record(e0));
+		CTB_CHECK(ctb_dot_exec(&pl, sd->d, td->d, rd->d));
+		CTB_CHECK(ctbd_event_record(e1));
+		float ms;
+		CTB_CHECK(ctbd_event_elapsed_ms(e0, e1, &ms)); tot += ms;
+	}
+	*ms_per_run = tot / (reps > 0 ? reps : 1);
+	*flops_per_run = pl.flops;
+	ctbd_event_destroy(e0); ctbd_event_destroy(e1);
+	if (flush != NULL) { CTB_CHECK(ctbd_free(flush)); }
+	ctb_dot_plan_free(&pl);
+	ctb_tensor_free(rd); ctb_tensor_free(sd); ctb_tensor_free(td);
+	return 0;
+}
+
 int ctb_get_stats(double* out, int n)
 {
 	const double v[9] = {

@@ -115,6 +115,10 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 
 	/* merged form: packed copy of the (small) s operand, one dense M' x K' matrix per distinct group content */
 	int64_t* gather = NULL; size_t ngather = 0, cap_gather = 0;
+	/* merged form with an n-contiguous t: the rows of all contracted tuples of one output are addressed through a row table,
+	 * so the output is ONE segment of extent K' (a pipeline step of the kernel then spans many of the 1-4 row blocks) */
+	const bool use_rowtab = merge && b_ncontig;
+	int64_t* browtab = NULL; size_t nbrow = 0, cap_brow = 0;
 	struct merge_key* mk = NULL;
 	struct { uint64_t h; size_t base, len; }* packed = NULL; size_t npacked = 0, cap_packed = 0;
 	if (merge)
@@ -302,6 +306,19 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 				segs[sg].lda = (int32_t)Ktot;
 				segs[sg].pad_ = 0;
 			}
+			if (use_rowtab && nseg > seg_first)
+			{
+				while (nbrow + (size_t)Ktot > cap_brow) { cap_brow = cap_brow ? 2 * cap_brow : 16384; browtab = realloc(browtab, cap_brow * sizeof(int64_t)); }
+				const size_t row0_idx = nbrow;
+				for (size_t sg = seg_first; sg < nseg; sg++) {
+					for (ct_long kk = 0; kk < segs[sg].k; kk++) { browtab[nbrow++] = segs[sg].b_off + kk * N; }
+				}
+				CTB_REQUIRE(nbrow - row0_idx == (size_t)Ktot);
+				struct ctbd_gemm_seg* g = &segs[seg_first];
+				g->a_off = (int64_t)base; g->b_off = (int64_t)row0_idx; g->k = (int32_t)Ktot; g->lda = (int32_t)Ktot; g->ldb = (int32_t)N; g->pad_ = 0;
+				nseg = seg_first + 1;
+				o->seg_end = (int32_t)nseg;
+			}
 		}
 		CTB_REQUIRE(tab.n < ((size_t)1 << 31));
 		b0 = b1;
@@ -316,6 +333,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	h.outs = outs; h.segs = segs; h.tab = tab.v;
 	h.flops = flops;
 	if (merge) { h.a_gather = gather; h.n_a_gather = (int64_t)ngather; h.a_src = s->d; }
+	if (use_rowtab && nbrow > 0) { h.b_rowtab = browtab; h.n_b_rowtab = (int64_t)nbrow; }
 	plan->dev = NULL;
 	CTB_CHECK_ABORT(ctbd_gemm_plan_create(&h, &plan->dev));
 	plan->flops = flops;
@@ -323,7 +341,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	plan->ntiles = 0;
 	CTB_CHECK_ABORT(ctbd_gemm_plan_info(plan->dev, &plan->ntiles, NULL));
 
-	free(tab.v); free(outs); free(segs); free(gather); free(mk); free(packed);
+	free(tab.v); free(outs); free(segs); free(gather); free(mk); free(packed); free(browtab);
 	return r;
 }
 

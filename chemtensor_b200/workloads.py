@@ -154,8 +154,30 @@ def random_mps(lib: cabi.CLibrary, dtype, nsites: int, qsite, qnum_sector: int, 
 # operands of one two-site effective-Hamiltonian application
 # ------------------------------------------------------------------------------------------------
 
+def measured_bond_qnums(data_file: str, bond: int, scale: int = 1, shift_q: int = 0, max_vdim: int | None = None):
+    """Bond quantum numbers with the sector histogram a converged two-site sweep produced (chemtensor_b200/data/bonds_*.json,
+    recorded by tools/measure_bond_structure.py on the GPU), every multiplicity multiplied by `scale` and every quantum
+    number shifted by `shift_q` (a longer chain at the same filling).  Ordering as the SVD split leaves it: sectors
+    ascending, all entries of a sector contiguous (reference block_sparse_tensor.c:2694-2724)."""
+    import json
+    import os
+    path = data_file if os.path.isabs(data_file) else os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", data_file)
+    with open(path) as f:
+        rec = json.load(f)
+    hist = {int(q) + shift_q: int(m) * scale for q, m in rec["bonds"][bond]["sectors"].items()}
+    if max_vdim is not None:
+        # trim the largest sectors proportionally if integer scaling overshoots the bond dimension
+        tot = sum(hist.values())
+        while tot > max_vdim:
+            q = max(hist, key=hist.get)
+            hist[q] -= 1
+            tot -= 1
+    qs = sorted(hist)
+    return np.concatenate([np.full(hist[q], q, dtype=np.int32) for q in qs if hist[q] > 0])
+
+
 def heff_operands(lib: cabi.CLibrary, model: str, nsites: int, params, qnum_sector: int, max_vdim: int, site: int | None = None,
-                  dtype=np.float64, seed: int = 42):
+                  dtype=np.float64, seed: int = 42, bonds=None):
     """(a, w, l, r) for the pair (site, site+1): the merged two-site MPS tensor a[Dl, d^2, Dr], the merged MPO tensor
     w[Dw, d^2, d^2, Dw'] (real Hamiltonian entries), and environments l[1, Dl, Dw, Dl], r[Dr, Dw', Dr, 1] with the
     structure of the reference's contraction_operator_step_left/right outputs (chain_ops.c:116, :196) and random entries."""
@@ -163,7 +185,11 @@ def heff_operands(lib: cabi.CLibrary, model: str, nsites: int, params, qnum_sect
     tensors, qwb, qsite = MODELS[model](nsites, *params)
     if site is None:
         site = nsites // 2 - 1
-    qb = random_bond_qnums(nsites, qsite, qnum_sector, max_vdim, rng)
+    if bonds is None:
+        qb = random_bond_qnums(nsites, qsite, qnum_sector, max_vdim, rng)
+    else:
+        # measured (converged) sector structure of the two bonds around the pair: (q_left, q_right)
+        qb = {site: np.asarray(bonds[0], dtype=np.int32), site + 2: np.asarray(bonds[1], dtype=np.int32)}
     OUT, IN = cabi.TENSOR_AXIS_OUT, cabi.TENSOR_AXIS_IN
     # merged physical leg: logical index j*d + k, quantum number q_j + q_k (flatten_axes with both legs OUT)
     q2 = (np.asarray(qsite, dtype=np.int64)[:, None] + np.asarray(qsite, dtype=np.int64)[None, :]).reshape(-1).astype(np.int32)

@@ -118,6 +118,9 @@ long long ctb_launch_count(void);
  * receives the mean time of each of the three grouped-GEMM launches. */
 int ctb_heff_benchmark(const struct block_sparse_tensor* a, const struct block_sparse_tensor* w, const struct block_sparse_tensor* l, const struct block_sparse_tensor* r,
 	int warmup, int reps, int flush_l2, double* ms_per_matvec, double* flops_per_matvec, double* per_step_ms, double* per_step_flops);
+/* micro-benchmark of one contraction r = dot(s, t) (one grouped-GEMM launch), operands device-resident, plan built once */
+int ctb_dot_benchmark(const struct block_sparse_tensor* s, const int axrange_s, const struct block_sparse_tensor* t, const int axrange_t, const int ndim_mult,
+	int warmup, int reps, int flush_l2, double* ms_per_run, double* flops_per_run);
 /* statistics of the last dmrg_* call: fills up to 'n' doubles:
  * [0] heff flops, [1] heff calls, [2] env flops, [3] lanczos ms, [4] svd ms, [5] env ms, [6] total ms,
  * [7] longest Lanczos vector, [8] largest bond dimension */

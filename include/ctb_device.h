@@ -117,6 +117,10 @@ struct ctbd_gemm_plan_host
 	const int64_t* a_gather;      /* host array or NULL */
 	int64_t n_a_gather;
 	const void* a_src;            /* device buffer the gather reads from */
+	/* optional (needs b_ncontig): the rows of B are gathered through a row table, B(kk, j) = b[b_rowtab[seg.b_off + kk] + j];
+	 * lets ONE pipeline step span the rows of many small blocks (the MPO-mixing contraction has 1-4 rows per block) */
+	const int64_t* b_rowtab;      /* host array or NULL */
+	int64_t n_b_rowtab;
 };
 
 /* builds the device-resident work list: every output block is cut into tiles of the kernel variant that

@@ -54,7 +54,7 @@ int ctbd_host_free(void* hptr) { free(hptr); return 0; }
 long long ctbd_bytes_in_use(void) { return g_bytes; }
 
 /* ---- grouped GEMM ---- */
-struct emu_plan { struct ctbd_gemm_plan_host h; struct ctbd_gemm_out* outs; struct ctbd_gemm_seg* segs; int32_t* tab; void* a_packed; };
+struct emu_plan { struct ctbd_gemm_plan_host h; struct ctbd_gemm_out* outs; struct ctbd_gemm_seg* segs; int32_t* tab; void* a_packed; int64_t* b_rowtab; };
 
 static void* dup_mem(const void* p, size_t n) { void* q = malloc(n ? n : 1); if (n) { memcpy(q, p, n); } return q; }
 
@@ -65,6 +65,8 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan)
 	p->outs  = dup_mem(h->outs,  (size_t)h->nouts  * sizeof(*h->outs));
 	p->segs  = dup_mem(h->segs,  (size_t)h->nsegs  * sizeof(*h->segs));
 	p->tab   = dup_mem(h->tab,   (size_t)h->ntab   * sizeof(int32_t));
+	p->b_rowtab = NULL;
+	if (h->b_rowtab != NULL && h->n_b_rowtab > 0) { p->b_rowtab = dup_mem(h->b_rowtab, (size_t)h->n_b_rowtab * sizeof(int64_t)); }
 	p->a_packed = NULL;
 	if (h->a_gather != NULL && h->n_a_gather > 0) {
 		const size_t es = (h->dtype == CTBD_C128) ? 16 : 8;
@@ -79,7 +81,7 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan)
 int ctbd_gemm_plan_destroy(void* plan)
 {
 	struct emu_plan* p = plan;
-	free(p->outs); free(p->segs); free(p->tab); free(p->a_packed); free(p);
+	free(p->outs); free(p->segs); free(p->tab); free(p->a_packed); free(p->b_rowtab); free(p);
 	return 0;
 }
 
@@ -110,7 +112,8 @@ int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
 					for (int kk = 0; kk < g->k; kk++)
 					{
 						const int64_t ia = p->h.a_kcontig ? g->a_off + (int64_t)i * g->lda + kk : g->a_off + (int64_t)kk * g->lda + i;
-						const int64_t ib = p->h.b_ncontig ? g->b_off + (int64_t)kk * g->ldb + j : g->b_off + (int64_t)j * g->ldb + kk;
+						const int64_t ib = (p->b_rowtab != NULL) ? p->b_rowtab[g->b_off + kk] + j
+							: (p->h.b_ncontig ? g->b_off + (int64_t)kk * g->ldb + j : g->b_off + (int64_t)j * g->ldb + kk);
 						if (cplx) {
 							double complex a = ((const double complex*)A)[ia], b = ((const double complex*)B)[ib];
 							if (p->h.conj_a) { a = conj(a); }
