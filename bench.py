@@ -34,8 +34,9 @@ from chemtensor_b200 import cabi, workloads  # noqa: E402
 
 # measured bond structures: name -> (data file, L of the measured chain, scale of the multiplicities)
 MEASURED = {
-    "fh_L64_D4096": ("bonds_fh_L32_D1024.json", 32, 4),
+    "fh_L64_D4096": ("bonds_fh_L32_D2048.json", 32, 2),
     "fh_L32_D1024": ("bonds_fh_L32_D1024.json", 32, 1),
+    "xxz_L100_D1024": ("bonds_xxz_L100_D1024.json", 100, 1),
 }
 
 WORKLOADS = {
@@ -179,7 +180,7 @@ def run_reference(args):
     tf = flops / dt / 1e12
     line = {
         "impl": "reference", "metric": "heff_matvec_fp64_tflops", "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl, "description": WORKLOADS[wl][6], "structure": args.structure},
         "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "reference",
                          "sample": f"{steps} timed apply_local_hamiltonian calls of the unmodified reference (OpenMP {cores} threads, OpenBLAS 1 thread per GEMM) on the same operands"},
@@ -220,6 +221,17 @@ def main():
     lib = cabi.CLibrary(CUDA_SO, extensions=True)
     if lib.ctb_init(local) < 0:
         raise SystemExit("bench.py: ctb_init failed")
+    if world > 1:
+        # one process per GPU: NCCL communicator inside the C layer; rank 0 creates the unique id, torch.distributed carries it
+        import torch.distributed as dist
+        uid = (C.c_uint8 * 128)()
+        if rank == 0 and lib.ctb_dist_unique_id(uid) < 0:
+            raise SystemExit("bench.py: ctb_dist_unique_id failed")
+        t_uid = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t_uid, 0)
+        uid = (C.c_uint8 * 128)(*t_uid.cpu().tolist())
+        if lib.ctb_dist_init(rank, world, uid) < 0:
+            raise SystemExit("bench.py: ctb_dist_init failed")
     wl = args.workload
     model, L, params, sector, D, dtype, desc = WORKLOADS[wl]
 
@@ -243,6 +255,12 @@ def main():
             raise SystemExit("bench.py: ctb_heff_benchmark failed")
         if world > 1:
             torch.cuda.synchronize(); dist.barrier()
+        # whole-job algorithmic flops: the shards partition the block GEMMs column-wise, so their flops add up exactly
+        flops_total = flops.value
+        if world > 1:
+            tf_ = torch.tensor([flops.value], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tf_, op=dist.ReduceOp.SUM)
+            flops_total = float(tf_.item())
         # e2e through the reference-named C-ABI entry point with host structs
         e2e = None
         if not args.no_e2e:
@@ -256,18 +274,23 @@ def main():
             for _ in range(k_e2e):
                 b = cabi.BST(lib); lib.apply_local_hamiltonian(a.ptr, w.ptr, l.ptr, r.ptr, b.ptr); del b
             dt_e2e = (time.perf_counter() - t0) / k_e2e
-            e2e = {"value": flops.value / dt_e2e / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            if world > 1:
+                te = torch.tensor([dt_e2e], dtype=torch.float64, device="cuda")
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+                dt_e2e = float(te.item())
+            e2e = {"value": flops_total / dt_e2e / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": dt_e2e * 1e3, "steps": k_e2e,
                    "what": "apply_local_hamiltonian(a, w, l, r, &b) on host structs: upload, per-bond plan build, 3 grouped GEMM launches, download"}
     launches = lib.ctb_launch_count() - launches0
 
-    # max over ranks of the device time; all ranks run the same workload shard-free in this round (replicas): value = sum over ranks
+    # strong scaling: ONE matvec sharded over the ranks (bra bond of the right environment cut into balanced index sets, one
+    # NCCL all-gather per application); time = max over ranks of the device time, value = whole-job flops / that time
     t_ms = ms.value
     if world > 1:
         tt = torch.tensor([t_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_ms = float(tt.item())
-    value = world * flops.value / (t_ms * 1e-3) / 1e12
+    value = flops_total / (t_ms * 1e-3) / 1e12
 
     if rank != 0:
         return
@@ -277,21 +300,22 @@ def main():
     roofline = {"bound": "tensor", "achieved": k_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (k_tf / fp64_peak) if fp64_peak > 0 else None, "traffic": None,
                 "kernel": f"grouped_gemm_kernel<double> of {names[kdom]}", "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "per_step_ms": [step_ms[i] for i in range(3)], "per_step_tflops": [step_fl[i] / (step_ms[i] * 1e-3) / 1e12 if step_ms[i] > 0 else None for i in range(3)],
-                "matvec_frac_of_fp64_peak": (flops.value / (ms.value * 1e-3) / 1e12 / fp64_peak) if fp64_peak > 0 else None}
+                "matvec_frac_of_fp64_peak": (flops_total / world / (t_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak > 0 else None}
     line = {
         "metric": "heff_matvec_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if dtype == np.float64 else "c128",
+        "ms_per_step": t_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if dtype == np.float64 else "c128",
         "data": "synthetic",
-        "config": {"workload": wl, "description": desc, "structure": args.structure, "vector_length": int(n_vec), "flops_per_matvec": flops.value,
+        "config": {"workload": wl, "description": desc, "structure": args.structure, "vector_length": int(n_vec), "flops_per_matvec": flops_total,
                    "l2": "192 MiB buffer rewritten between timed matvecs", "setup_s": round(t_setup, 2),
-                   "multi_gpu": "independent replicas of the bond (sharded Heff lands with the NCCL exchange step)" if world > 1 else "single GPU"},
+                   "multi_gpu": (f"one matvec sharded over {world} GPUs by balanced index sets of the bra bond of the right environment; "
+                                 "per application one NCCL all-gather of the result slices + scatter") if world > 1 else "single GPU"},
         "roofline": roofline,
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }
-    if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(wl, flops.value, args.structure)
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(wl, flops_total, args.structure)
     print(json.dumps(line), flush=True)
 
 

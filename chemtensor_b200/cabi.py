@@ -64,6 +64,8 @@ class MPOStruct(C.Structure):
 
 
 LANCZOS_FUNC = C.CFUNCTYPE(None, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p)
+# int fn(void* ctx, const void* sendbuf, void* recvbuf, size_t bytes_per_rank, void* stream)
+ALLGATHER_FUNC = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
 _P_BST = C.POINTER(BlockSparseTensor)
 _P_DT = C.POINTER(DenseTensor)
@@ -120,6 +122,10 @@ _EXT_SIGNATURES = {
     "ctb_heff_benchmark": (C.c_int, [_P_BST, _P_BST, _P_BST, _P_BST, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ctb_dot_benchmark": (C.c_int, [_P_BST, C.c_int, _P_BST, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ctb_get_stats": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
+    "ctb_dist_unique_id": (C.c_int, [C.c_void_p]),
+    "ctb_dist_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "ctb_dist_set_allgather": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ctb_dist_finalize": (C.c_int, []),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES) + tuple(_EXT_SIGNATURES) + ("allocate_zero_dense_tensor", "allocate_block_sparse_tensor_like",

@@ -40,7 +40,17 @@ struct GemmPlan
 	int32_t* queue = nullptr;          /* device: [grid + 1] queue boundaries */
 	void* a_packed = nullptr;          /* device: optional plan-owned A operand (gathered once at plan creation) */
 	int64_t* b_rowtab = nullptr;       /* device: optional row table of the B operand */
+	/* mixing form (see ctbd_mix_group in ctb_device.h) */
+	int n_mix_groups = 0, n_mix_rows = 0, n_mix_tiles = 0;
+	ctbd_mix_group* mix_groups = nullptr;
+	ctbd_mix_row* mix_rows = nullptr;
+	struct MixTile* mix_tiles = nullptr;
+	int32_t* mix_nzk = nullptr;        /* [n_a_gather] compacted column indices of the non-zero packed entries, per row at row.a_off */
+	void* mix_nzv = nullptr;           /* [n_a_gather] their values */
+	int32_t* mix_cnt = nullptr;        /* [n_mix_rows] number of non-zeros of each row */
 };
+
+struct MixTile { int32_t group, col0; };
 
 /* ---- PTX helpers ---- */
 
@@ -388,6 +398,105 @@ __global__ void gather_kernel(int64_t n, const int64_t* __restrict__ idx, const 
 	}
 }
 
+
+/* ============================================================================================== */
+/* mixing form: C rows = (small sparse constant matrix) x (gathered B rows), streamed at HBM speed   */
+/* ============================================================================================== */
+
+static constexpr int MIX_THREADS = 256;
+static constexpr int MIX_U = 4;                       /* columns per thread */
+static constexpr int MIX_COLS = MIX_THREADS * MIX_U;  /* columns per tile */
+
+__device__ __forceinline__ void mix_fma(double& acc, const double v, const double b, int, int) { acc = fma(v, b, acc); }
+__device__ __forceinline__ void mix_fma(double2& acc, const double2 v, const double2 b, int conj_a, int conj_b)
+{
+	const double vi = conj_a ? -v.y : v.y, bi = conj_b ? -b.y : b.y;
+	acc.x = fma(v.x, b.x, acc.x); acc.x = fma(-vi, bi, acc.x);
+	acc.y = fma(v.x, bi, acc.y);  acc.y = fma(vi, b.x, acc.y);
+}
+__device__ __forceinline__ bool mix_nonzero(const double v)  { return v != 0.0; }
+__device__ __forceinline__ bool mix_nonzero(const double2 v) { return v.x != 0.0 || v.y != 0.0; }
+
+/* one thread per row: compact the non-zero entries of the packed operand row (run once per plan) */
+template <typename T>
+__global__ void mix_compact_kernel(int nrows, const ctbd_mix_row* __restrict__ rows, const int32_t* __restrict__ row_kp,
+	const T* __restrict__ apacked, int32_t* __restrict__ nzk, T* __restrict__ nzv, int32_t* __restrict__ cnt)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nrows) { return; }
+	const int64_t a0 = rows[r].a_off;
+	const int kp = row_kp[r];
+	int c = 0;
+	for (int k = 0; k < kp; k++) {
+		const T v = apacked[a0 + k];
+		if (mix_nonzero(v)) { nzk[a0 + c] = k; nzv[a0 + c] = v; c++; }
+	}
+	cnt[r] = c;
+}
+
+struct MixArgs
+{
+	const MixTile* tiles; int ntiles;
+	const ctbd_mix_group* groups;
+	const ctbd_mix_row* rows;
+	const int64_t* brow;
+	const int32_t* nzk; const void* nzv; const int32_t* cnt;
+	const void* B; void* C;
+	int conj_a, conj_b;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(MIX_THREADS) mix_kernel(const MixArgs args)
+{
+	const T* __restrict__ Bg = reinterpret_cast<const T*>(args.B);
+	T* __restrict__ Cg = reinterpret_cast<T*>(args.C);
+	const T* __restrict__ nzv = reinterpret_cast<const T*>(args.nzv);
+	for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x)
+	{
+		const MixTile t = args.tiles[tile];
+		const ctbd_mix_group g = args.groups[t.group];
+		/* this thread's columns and their digits over the free axes of the right operand */
+		int jc[MIX_U]; bool ok[MIX_U]; int dig[MIX_U][4];
+		#pragma unroll
+		for (int u = 0; u < MIX_U; u++) {
+			const int j = t.col0 + (int)threadIdx.x + u * MIX_THREADS;
+			ok[u] = (j < g.n);
+			jc[u] = ok[u] ? j : 0;
+			int rem = jc[u];
+			#pragma unroll
+			for (int a = 3; a >= 0; a--) {
+				if (a < g.ndig) { dig[u][a] = rem % g.dig_dim[a]; rem /= g.dig_dim[a]; } else { dig[u][a] = 0; }
+			}
+		}
+		const int64_t* __restrict__ brow = args.brow + g.brow_begin;
+		for (int r = g.row_begin; r < g.row_end; r++)
+		{
+			const ctbd_mix_row rw = args.rows[r];
+			const int cnt = args.cnt[r];
+			T acc[MIX_U];
+			#pragma unroll
+			for (int u = 0; u < MIX_U; u++) { memset(&acc[u], 0, sizeof(T)); }
+			for (int q = 0; q < cnt; q++)
+			{
+				const T v = nzv[rw.a_off + q];
+				const T* __restrict__ b = Bg + brow[args.nzk[rw.a_off + q]];
+				T bv[MIX_U];
+				#pragma unroll
+				for (int u = 0; u < MIX_U; u++) { bv[u] = b[jc[u]]; }
+				#pragma unroll
+				for (int u = 0; u < MIX_U; u++) { mix_fma(acc[u], v, bv[u], args.conj_a, args.conj_b); }
+			}
+			#pragma unroll
+			for (int u = 0; u < MIX_U; u++) {
+				if (ok[u]) {
+					const int64_t off = rw.c_off + (int64_t)dig[u][0] * rw.cs[0] + (int64_t)dig[u][1] * rw.cs[1] + (int64_t)dig[u][2] * rw.cs[2] + (int64_t)dig[u][3] * rw.cs[3];
+					Cg[off] = acc[u];
+				}
+			}
+		}
+	}
+}
+
 /* ---- tile classes: one class per plan, chosen for the least padded work ---- */
 
 /* real:    0 = 64x64 (4 warps of 32x32), 1 = 32x32 (4 warps of 16x16), 2 = 128x128 (8 warps of 64x32),
@@ -457,6 +566,58 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 	p->nouts = h->nouts; p->nsegs = h->nsegs; p->ntab = h->ntab;
 
 	const bool cplx = (h->dtype == CTBD_C128);
+	if (h->mix_groups != nullptr && h->n_mix_groups > 0)
+	{
+		/* mixing form: upload the group / row descriptors, gather the packed operand, compact its non-zeros, list the column tiles */
+		if (h->a_gather == nullptr || h->b_rowtab == nullptr) { delete p; return fail_msg("mixing plan needs a packed left operand and a B row table"); }
+		const size_t esize = cplx ? 16 : 8;
+		p->n_mix_groups = h->n_mix_groups; p->n_mix_rows = h->n_mix_rows;
+		int rc = 0;
+		rc |= upload(h->mix_groups, (size_t)h->n_mix_groups * sizeof(ctbd_mix_group), (void**)&p->mix_groups);
+		rc |= upload(h->mix_rows, (size_t)h->n_mix_rows * sizeof(ctbd_mix_row), (void**)&p->mix_rows);
+		rc |= upload(h->b_rowtab, (size_t)h->n_b_rowtab * sizeof(int64_t), (void**)&p->b_rowtab);
+		std::vector<MixTile> tiles;
+		std::vector<int32_t> row_kp((size_t)h->n_mix_rows, 0);
+		std::vector<std::pair<double, int>> order((size_t)h->n_mix_groups);
+		for (int g = 0; g < h->n_mix_groups; g++) {
+			const ctbd_mix_group& mg = h->mix_groups[g];
+			order[g] = std::make_pair((double)(mg.row_end - mg.row_begin) * mg.kp, g);
+			for (int r = mg.row_begin; r < mg.row_end; r++) { row_kp[r] = mg.kp; }
+		}
+		std::stable_sort(order.begin(), order.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first; });
+		for (const auto& og : order) {
+			const ctbd_mix_group& mg = h->mix_groups[og.second];
+			for (int c0 = 0; c0 < mg.n; c0 += MIX_COLS) { MixTile t; t.group = og.second; t.col0 = c0; tiles.push_back(t); }
+		}
+		p->n_mix_tiles = (int)tiles.size();
+		p->ntiles = p->n_mix_tiles;
+		rc |= upload(tiles.data(), tiles.size() * sizeof(MixTile), (void**)&p->mix_tiles);
+		void* idx = nullptr; void* d_kp = nullptr;
+		rc |= upload(h->a_gather, (size_t)h->n_a_gather * sizeof(int64_t), &idx);
+		rc |= upload(row_kp.data(), row_kp.size() * sizeof(int32_t), &d_kp);
+		rc |= ctbd_malloc(&p->a_packed, (size_t)h->n_a_gather * esize);
+		rc |= ctbd_malloc((void**)&p->mix_nzk, (size_t)h->n_a_gather * sizeof(int32_t));
+		rc |= ctbd_malloc(&p->mix_nzv, (size_t)h->n_a_gather * esize);
+		rc |= ctbd_malloc((void**)&p->mix_cnt, (size_t)h->n_mix_rows * sizeof(int32_t));
+		if (rc == 0 && h->n_a_gather > 0 && h->n_mix_rows > 0) {
+			const int blocks = (int)std::min<int64_t>(ceil_div(h->n_a_gather, 256), 1024);
+			const int rblocks = (int)ceil_div(h->n_mix_rows, 128);
+			if (cplx) {
+				gather_kernel<double2><<<blocks, 256, 0, rt().stream>>>(h->n_a_gather, (const int64_t*)idx, (const double2*)h->a_src, (double2*)p->a_packed);
+				mix_compact_kernel<double2><<<rblocks, 128, 0, rt().stream>>>(h->n_mix_rows, p->mix_rows, (const int32_t*)d_kp, (const double2*)p->a_packed, p->mix_nzk, (double2*)p->mix_nzv, p->mix_cnt);
+			}
+			else {
+				gather_kernel<double><<<blocks, 256, 0, rt().stream>>>(h->n_a_gather, (const int64_t*)idx, (const double*)h->a_src, (double*)p->a_packed);
+				mix_compact_kernel<double><<<rblocks, 128, 0, rt().stream>>>(h->n_mix_rows, p->mix_rows, (const int32_t*)d_kp, (const double*)p->a_packed, p->mix_nzk, (double*)p->mix_nzv, p->mix_cnt);
+			}
+			rt().launches += 2;
+			if (cudaGetLastError() != cudaSuccess) { rc = -1; }
+		}
+		ctbd_free(idx); ctbd_free(d_kp);
+		if (rc < 0) { ctbd_gemm_plan_destroy(p); return -1; }
+		*plan_out = p;
+		return 0;
+	}
 	const ClassShape* shapes = cplx ? g_shapes_z : g_shapes_d;
 	const int nshapes = cplx ? 3 : 6;
 
@@ -569,6 +730,7 @@ int ctbd_gemm_plan_destroy(void* plan)
 	GemmPlan* p = (GemmPlan*)plan;
 	if (p == nullptr) { return 0; }
 	ctbd_free(p->tiles); ctbd_free(p->queue); ctbd_free(p->a_packed); ctbd_free(p->b_rowtab);
+	ctbd_free(p->mix_groups); ctbd_free(p->mix_rows); ctbd_free(p->mix_tiles); ctbd_free(p->mix_nzk); ctbd_free(p->mix_nzv); ctbd_free(p->mix_cnt);
 	ctbd_free(p->outs); ctbd_free(p->segs); ctbd_free(p->tab);
 	delete p;
 	return 0;
@@ -586,6 +748,17 @@ int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
 {
 	GemmPlan* p = (GemmPlan*)plan;
 	if (p->ntiles == 0) { return 0; }
+	if (p->n_mix_tiles > 0)
+	{
+		MixArgs ma;
+		ma.tiles = p->mix_tiles; ma.ntiles = p->n_mix_tiles; ma.groups = p->mix_groups; ma.rows = p->mix_rows; ma.brow = p->b_rowtab;
+		ma.nzk = p->mix_nzk; ma.nzv = p->mix_nzv; ma.cnt = p->mix_cnt; ma.B = B; ma.C = C; ma.conj_a = p->conj_a; ma.conj_b = p->conj_b;
+		const int grid = std::min(p->n_mix_tiles, rt().sm_count * 32);
+		if (p->dtype == CTBD_C128) { mix_kernel<double2><<<grid, MIX_THREADS, 0, rt().stream>>>(ma); }
+		else                       { mix_kernel<double><<<grid, MIX_THREADS, 0, rt().stream>>>(ma); }
+		CTBD_LAUNCH_CHECK();
+		return 0;
+	}
 	GemmArgs args;
 	args.tiles = p->tiles; args.queue = p->queue;
 	args.outs = p->outs; args.segs = p->segs; args.tab = p->tab;

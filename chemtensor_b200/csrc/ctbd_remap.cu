@@ -10,6 +10,7 @@
  * along the innermost source run.  HBM-bound: 2 x sizeof(T) bytes per stored entry.
  */
 #include <vector>
+#include <algorithm>
 #include "ctbd_common.cuh"
 
 namespace ctbd {
@@ -135,6 +136,51 @@ __global__ void __launch_bounds__(256) remap_kernel(const LayoutDev D, const Lay
 	}
 }
 
+/* scatter form (CTBD_REMAP_UNSLICE): every SOURCE entry is written to the destination entry whose index on axis i_ax is
+ * ind[source index]; used to merge the column slices computed by different GPUs back into the full tensor */
+template <typename T>
+__global__ void __launch_bounds__(256) unslice_kernel(const LayoutDev D, const LayoutDev S, const RemapParams p, T* __restrict__ dst, const T* __restrict__ src)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < S.nstore; e += stride)
+	{
+		int lo = 0, hi = S.nblk - 1;
+		while (lo < hi) {
+			const int mid = (lo + hi + 1) >> 1;
+			if (S.blk_off[mid] <= e) { lo = mid; } else { hi = mid - 1; }
+		}
+		int64_t cell = S.blk_grid[lo];
+		int64_t r = e - S.blk_off[lo];
+		int sec[CTBD_MAXDIM];
+		#pragma unroll
+		for (int i = CTBD_MAXDIM - 1; i >= 0; i--) {
+			if (i < S.ndim) { sec[i] = (int)(cell % S.nsec[i]); cell /= S.nsec[i]; }
+		}
+		int64_t ld[CTBD_MAXDIM];
+		#pragma unroll
+		for (int i = CTBD_MAXDIM - 1; i >= 0; i--) {
+			if (i < S.ndim) {
+				const int s0 = S.secstart[i][sec[i]];
+				const int bd = S.secstart[i][sec[i] + 1] - s0;
+				const int pos = (int)(r % bd); r /= bd;
+				const int64_t ls = S.log_of[i][s0 + pos];
+				ld[i] = (i == p.i_ax) ? p.ind[ls] : ls;
+			}
+		}
+		int64_t dcell = 0, doff = 0;
+		#pragma unroll
+		for (int i = 0; i < CTBD_MAXDIM; i++) {
+			if (i < D.ndim) {
+				const int s = D.sec_of[i][ld[i]];
+				dcell = dcell * D.nsec[i] + s;
+				doff = doff * (D.secstart[i][s + 1] - D.secstart[i][s]) + D.pos_of[i][ld[i]];
+			}
+		}
+		const int64_t dbase = D.grid_off[dcell];
+		if (dbase >= 0) { dst[dbase + doff] = src[e]; }
+	}
+}
+
 } // namespace ctbd
 
 using namespace ctbd;
@@ -206,6 +252,23 @@ int ctbd_remap(const struct ctbd_remap_args* a)
 	const Layout* S = (const Layout*)a->src_layout;
 	if (D->d.dtype != S->d.dtype) { return fail_msg("remap: dtype mismatch"); }
 	if (D->d.nstore == 0) { return 0; }
+	if (a->op == CTBD_REMAP_UNSLICE)
+	{
+		if (S->d.nstore == 0) { return 0; }
+		RemapParams p;
+		memset(&p, 0, sizeof(p));
+		p.op = a->op; p.i_ax = a->i_ax; p.scale_ax = -1;
+		void* ind_dev = nullptr;
+		if (upload(a->ind, (size_t)S->d.dim[a->i_ax] * sizeof(int64_t), &ind_dev) < 0) { return -1; }
+		p.ind = (const int64_t*)ind_dev;
+		int64_t blocks = std::min<int64_t>(ceil_div(S->d.nstore, 256), (int64_t)rt().sm_count * 16);
+		if (D->d.dtype == CTBD_F64) { unslice_kernel<double><<<(int)blocks, 256, 0, rt().stream>>>(D->d, S->d, p, (double*)a->dst, (const double*)a->src); }
+		else if (D->d.dtype == CTBD_C128) { unslice_kernel<double2><<<(int)blocks, 256, 0, rt().stream>>>(D->d, S->d, p, (double2*)a->dst, (const double2*)a->src); }
+		else { return fail_msg("remap: unsupported dtype"); }
+		CTBD_LAUNCH_CHECK();
+		ctbd_free(ind_dev);
+		return 0;
+	}
 	RemapParams p;
 	memset(&p, 0, sizeof(p));
 	p.op = a->op; p.i_ax = a->i_ax; p.conj = a->conj; p.scale_ax = a->scale_ax; p.scale = a->scale;

@@ -3,8 +3,11 @@
  * Implements the "runtime" and "memory" groups of include/ctb_device.h.
  */
 #include <stdlib.h>
+#include <dlfcn.h>
 #include <unordered_map>
 #include <mutex>
+#include <vector>
+#include <algorithm>
 #include "ctbd_common.cuh"
 
 namespace ctbd {
@@ -38,6 +41,38 @@ int upload(const void* host, size_t bytes, void** dev)
 } // namespace ctbd
 
 using namespace ctbd;
+
+/* ---- block-wise host <-> device transfers through a persistent pinned staging ring ------------------------------
+ * Host tensors are thousands of separately allocated (pageable) blocks; the device layout is one packed buffer.  The blocks
+ * are streamed through two pinned chunks: while chunk c is in flight on the copy engine the host packs (or unpacks) chunk
+ * c+1, so a transfer costs about max(host memcpy, PCIe) instead of pinned allocation + pack + copy in sequence. */
+struct ncclUniqueIdBytes { char internal[CTBD_UNIQUE_ID_BYTES]; };   /* layout of ncclUniqueId (nccl.h), passed by value */
+
+namespace {
+constexpr size_t STAGE_CHUNK = (size_t)32 << 20;
+struct StageRing
+{
+	void* buf[2] = { nullptr, nullptr };
+	cudaEvent_t ev[2] = { nullptr, nullptr };
+	bool busy[2] = { false, false };
+};
+StageRing g_ring;
+
+int ring_init()
+{
+	if (g_ring.buf[0] != nullptr) { return 0; }
+	for (int i = 0; i < 2; i++) {
+		CTBD_CUDA(cudaMallocHost(&g_ring.buf[i], STAGE_CHUNK));
+		CTBD_CUDA(cudaEventCreateWithFlags(&g_ring.ev[i], cudaEventDisableTiming));
+	}
+	return 0;
+}
+int ring_wait(int i)
+{
+	if (g_ring.busy[i]) { CTBD_CUDA(cudaEventSynchronize(g_ring.ev[i])); g_ring.busy[i] = false; }
+	return 0;
+}
+} // namespace
 
 extern "C" {
 
@@ -90,6 +125,11 @@ int ctbd_shutdown(void)
 	Runtime& r = rt();
 	if (!r.ready) { return 0; }
 	cudaStreamSynchronize(r.stream);
+	for (int i = 0; i < 2; i++) {
+		if (g_ring.buf[i] != nullptr) { cudaFreeHost(g_ring.buf[i]); g_ring.buf[i] = nullptr; }
+		if (g_ring.ev[i] != nullptr) { cudaEventDestroy(g_ring.ev[i]); g_ring.ev[i] = nullptr; }
+		g_ring.busy[i] = false;
+	}
 	cudaStreamDestroy(r.stream);
 	r.stream = nullptr;
 	r.ready = false;
@@ -164,6 +204,168 @@ int ctbd_d2h(void* hptr, const void* dptr, size_t bytes)
 	CTBD_CUDA(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, rt().stream));
 	CTBD_CUDA(cudaStreamSynchronize(rt().stream));
 	return 0;
+}
+
+
+int ctbd_h2d_blocks(void* dptr, int nblk, const void* const* hptrs, const int64_t* dst_off, const int64_t* nbytes)
+{
+	CTBD_REQUIRE_INIT();
+	if (ring_init() < 0) { return -1; }
+	int cur = 0;
+	if (ring_wait(cur) < 0) { return -1; }
+	size_t fill = 0;            /* bytes packed into the current chunk */
+	int64_t chunk_dst = -1;     /* device offset the current chunk starts at */
+	auto flush = [&]() -> int {
+		if (fill == 0) { return 0; }
+		CTBD_CUDA(cudaMemcpyAsync((char*)dptr + chunk_dst, g_ring.buf[cur], fill, cudaMemcpyHostToDevice, rt().stream));
+		CTBD_CUDA(cudaEventRecord(g_ring.ev[cur], rt().stream));
+		g_ring.busy[cur] = true;
+		cur ^= 1; fill = 0; chunk_dst = -1;
+		return ring_wait(cur);
+	};
+	for (int b = 0; b < nblk; b++)
+	{
+		int64_t done = 0;
+		while (done < nbytes[b])
+		{
+			/* a chunk holds a contiguous device range: start a new one when the next piece is not adjacent */
+			if (fill > 0 && chunk_dst + (int64_t)fill != dst_off[b] + done) { if (flush() < 0) { return -1; } }
+			if (fill == 0) { chunk_dst = dst_off[b] + done; }
+			const size_t n = std::min<size_t>((size_t)(nbytes[b] - done), STAGE_CHUNK - fill);
+			memcpy((char*)g_ring.buf[cur] + fill, (const char*)hptrs[b] + done, n);
+			fill += n; done += (int64_t)n;
+			if (fill == STAGE_CHUNK) { if (flush() < 0) { return -1; } }
+		}
+	}
+	if (flush() < 0) { return -1; }
+	/* the ring stays owned by this layer, so the copies may complete asynchronously */
+	return 0;
+}
+
+int ctbd_d2h_blocks(const void* dptr, int nblk, void* const* hptrs, const int64_t* src_off, const int64_t* nbytes)
+{
+	CTBD_REQUIRE_INIT();
+	if (ring_init() < 0) { return -1; }
+	/* list of chunks (contiguous device ranges of at most STAGE_CHUNK bytes), each covering pieces of consecutive blocks */
+	struct Piece { int b; int64_t boff, n; };
+	struct Chunk { int64_t src, len; size_t p0, p1; };
+	std::vector<Piece> pieces; std::vector<Chunk> chunks;
+	{
+		Chunk c; c.src = -1; c.len = 0; c.p0 = 0; c.p1 = 0;
+		for (int b = 0; b < nblk; b++) {
+			int64_t done = 0;
+			while (done < nbytes[b]) {
+				if (c.len > 0 && (c.src + c.len != src_off[b] + done || (size_t)c.len == STAGE_CHUNK)) { c.p1 = pieces.size(); chunks.push_back(c); c.len = 0; }
+				if (c.len == 0) { c.src = src_off[b] + done; c.p0 = pieces.size(); }
+				const int64_t n = std::min<int64_t>(nbytes[b] - done, (int64_t)STAGE_CHUNK - c.len);
+				Piece pc; pc.b = b; pc.boff = done; pc.n = n; pieces.push_back(pc);
+				c.len += n; done += n;
+			}
+		}
+		if (c.len > 0) { c.p1 = pieces.size(); chunks.push_back(c); }
+	}
+	auto issue = [&](size_t ci) -> int {
+		const int slot = (int)(ci & 1);
+		if (ring_wait(slot) < 0) { return -1; }
+		CTBD_CUDA(cudaMemcpyAsync(g_ring.buf[slot], (const char*)dptr + chunks[ci].src, (size_t)chunks[ci].len, cudaMemcpyDeviceToHost, rt().stream));
+		CTBD_CUDA(cudaEventRecord(g_ring.ev[slot], rt().stream));
+		g_ring.busy[slot] = true;
+		return 0;
+	};
+	if (!chunks.empty() && issue(0) < 0) { return -1; }
+	for (size_t ci = 0; ci < chunks.size(); ci++)
+	{
+		const int slot = (int)(ci & 1);
+		if (ci + 1 < chunks.size() && issue(ci + 1) < 0) { return -1; }
+		if (ring_wait(slot) < 0) { return -1; }
+		size_t pos = 0;
+		for (size_t q = chunks[ci].p0; q < chunks[ci].p1; q++) {
+			memcpy((char*)hptrs[pieces[q].b] + pieces[q].boff, (const char*)g_ring.buf[slot] + pos, (size_t)pieces[q].n);
+			pos += (size_t)pieces[q].n;
+		}
+	}
+	return 0;
+}
+
+/* ---- distributed exchange: NCCL bound at run time, or a host callback ---- */
+namespace {
+struct NcclApi
+{
+	void* lib = nullptr;
+	int (*GetUniqueId)(void*) = nullptr;
+	int (*CommInitRank)(void**, int, ncclUniqueIdBytes, int) = nullptr;
+	int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+	int (*CommDestroy)(void*) = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+void* g_comm = nullptr;
+int g_rank = 0, g_world = 1;
+ctbd_allgather_fn g_ag_fn = nullptr;
+void* g_ag_ctx = nullptr;
+
+int nccl_load()
+{
+	if (g_nccl.lib != nullptr) { return 0; }
+	const char* names[] = { "libnccl.so.2", "libnccl.so" };
+	for (const char* n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib != nullptr) { break; } }
+	if (g_nccl.lib == nullptr) { return fail_msg("NCCL: libnccl.so.2 not found (needed for more than one GPU)"); }
+	g_nccl.GetUniqueId    = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+	g_nccl.CommInitRank   = (int (*)(void**, int, ncclUniqueIdBytes, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+	g_nccl.AllGather      = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
+	g_nccl.CommDestroy    = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+	g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+	if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) { return fail_msg("NCCL: missing symbols in libnccl"); }
+	return 0;
+}
+int nccl_fail(const char* what, int rc)
+{
+	snprintf(rt().err, sizeof(rt().err), "%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error");
+	return -1;
+}
+} // namespace
+
+int ctbd_dist_unique_id(void* id_out)
+{
+	if (nccl_load() < 0) { return -1; }
+	const int rc = g_nccl.GetUniqueId(id_out);
+	return rc == 0 ? 0 : nccl_fail("ncclGetUniqueId", rc);
+}
+
+int ctbd_dist_init(int rank, int world, const void* unique_id)
+{
+	CTBD_REQUIRE_INIT();
+	if (world < 1 || rank < 0 || rank >= world) { return fail_msg("dist: bad rank / world"); }
+	g_rank = rank; g_world = world;
+	if (world == 1 || unique_id == nullptr) { return 0; }      /* single rank, or the host supplies the collective by callback */
+	if (nccl_load() < 0) { return -1; }
+	ncclUniqueIdBytes id;
+	memcpy(&id, unique_id, sizeof(id));
+	CTBD_CUDA(cudaSetDevice(rt().device));
+	const int rc = g_nccl.CommInitRank(&g_comm, world, id, rank);
+	return rc == 0 ? 0 : nccl_fail("ncclCommInitRank", rc);
+}
+
+int ctbd_dist_set_allgather(ctbd_allgather_fn fn, void* ctx) { g_ag_fn = fn; g_ag_ctx = ctx; return 0; }
+
+int ctbd_dist_finalize(void)
+{
+	if (g_comm != nullptr) { cudaStreamSynchronize(rt().stream); g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
+	g_rank = 0; g_world = 1; g_ag_fn = nullptr; g_ag_ctx = nullptr;
+	return 0;
+}
+
+int ctbd_allgather(const void* sendbuf, void* recvbuf, size_t bytes_per_rank)
+{
+	if (g_world == 1) {
+		if (sendbuf != recvbuf) { CTBD_CUDA(cudaMemcpyAsync(recvbuf, sendbuf, bytes_per_rank, cudaMemcpyDeviceToDevice, rt().stream)); }
+		return 0;
+	}
+	if (g_ag_fn != nullptr) { return g_ag_fn(g_ag_ctx, sendbuf, recvbuf, bytes_per_rank, (void*)rt().stream); }
+	if (g_comm == nullptr) { return fail_msg("dist: no communicator (call ctbd_dist_init with the NCCL unique id, or register a callback)"); }
+	const int rc = g_nccl.AllGather(sendbuf, recvbuf, bytes_per_rank, /* ncclUint8 */ 1, g_comm, rt().stream);
+	rt().launches++;
+	return rc == 0 ? 0 : nccl_fail("ncclAllGather", rc);
 }
 
 int ctbd_d2d(void* dst, const void* src, size_t bytes)

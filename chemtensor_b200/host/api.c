@@ -14,6 +14,18 @@
 static void ensure_init(void) { CTB_CHECK_ABORT(ctbd_init(-1)); }
 
 int ctb_init(int device) { return ctbd_init(device); }
+
+/* ---- one process per GPU ---- */
+int ctb_dist_unique_id(void* id_out) { return ctbd_dist_unique_id(id_out); }
+int ctb_dist_init(int rank, int world, const void* unique_id)
+{
+	CTB_CHECK(ctbd_init(-1));
+	CTB_CHECK(ctbd_dist_init(rank, world, unique_id));
+	ctb_dist_rank = rank; ctb_dist_world = world;
+	return 0;
+}
+int ctb_dist_set_allgather(ctbd_allgather_fn fn, void* ctx) { return ctbd_dist_set_allgather(fn, ctx); }
+int ctb_dist_finalize(void) { ctb_dist_rank = 0; ctb_dist_world = 1; return ctbd_dist_finalize(); }
 int ctb_backend(void) { return ctbd_backend(); }
 long long ctb_launch_count(void) { return ctbd_launch_count(); }
 
@@ -556,21 +568,23 @@ int ctb_heff_benchmark(const struct block_sparse_tensor* a, const struct block_s
 	const size_t flush_bytes = (size_t)192 << 20;
 	if (flush_l2) { CTB_CHECK(ctbd_malloc(&flush, flush_bytes)); }
 	for (int i = 0; i < warmup; i++) { CTB_CHECK(ctb_heff_apply(&h, ad->d, bd->d)); }
-	void *e0 = NULL, *e1 = NULL, *e2 = NULL, *e3 = NULL;
-	CTB_CHECK(ctbd_event_create(&e0)); CTB_CHECK(ctbd_event_create(&e1)); CTB_CHECK(ctbd_event_create(&e2)); CTB_CHECK(ctbd_event_create(&e3));
+	void *e0 = NULL, *e1 = NULL, *e2 = NULL, *e3 = NULL, *e4 = NULL;
+	CTB_CHECK(ctbd_event_create(&e0)); CTB_CHECK(ctbd_event_create(&e1)); CTB_CHECK(ctbd_event_create(&e2)); CTB_CHECK(ctbd_event_create(&e3)); CTB_CHECK(ctbd_event_create(&e4));
 	double tot = 0, t1 = 0, t2 = 0, t3 = 0;
 	for (int i = 0; i < reps; i++)
 	{
 		if (flush_l2) { CTB_CHECK(ctbd_memset_zero(flush, flush_bytes)); }
 		CTB_CHECK(ctbd_event_record(e0));
-		CTB_CHECK(ctb_dot_exec(&h.p1, ad->d, rd->d, h.t1->d));
+		CTB_CHECK(ctb_dot_exec(&h.p1, ad->d, h.r->d, h.t1->d));
 		CTB_CHECK(ctbd_event_record(e1));
 		CTB_CHECK(ctb_dot_exec(&h.p2, wd->d, h.t1->d, h.t2->d));
 		CTB_CHECK(ctbd_event_record(e2));
-		CTB_CHECK(ctb_dot_exec(&h.p3, h.k->d, h.t2->d, bd->d));
+		CTB_CHECK(ctb_dot_exec(&h.p3, h.k->d, h.t2->d, h.world > 1 ? h.send : bd->d));
 		CTB_CHECK(ctbd_event_record(e3));
+		CTB_CHECK(ctb_heff_exchange(&h, bd->d));
+		CTB_CHECK(ctbd_event_record(e4));
 		float ms;
-		CTB_CHECK(ctbd_event_elapsed_ms(e0, e3, &ms)); tot += ms;
+		CTB_CHECK(ctbd_event_elapsed_ms(e0, e4, &ms)); tot += ms;
 		CTB_CHECK(ctbd_event_elapsed_ms(e0, e1, &ms)); t1 += ms;
 		CTB_CHECK(ctbd_event_elapsed_ms(e1, e2, &ms)); t2 += ms;
 		CTB_CHECK(ctbd_event_elapsed_ms(e2, e3, &ms)); t3 += ms;
@@ -579,7 +593,7 @@ int ctb_heff_benchmark(const struct block_sparse_tensor* a, const struct block_s
 	*flops_per_matvec = h.flops;
 	if (per_step_ms != NULL) { per_step_ms[0] = t1 / reps; per_step_ms[1] = t2 / reps; per_step_ms[2] = t3 / reps; }
 	if (per_step_flops != NULL) { per_step_flops[0] = h.p1.flops; per_step_flops[1] = h.p2.flops; per_step_flops[2] = h.p3.flops; }
-	ctbd_event_destroy(e0); ctbd_event_destroy(e1); ctbd_event_destroy(e2); ctbd_event_destroy(e3);
+	ctbd_event_destroy(e0); ctbd_event_destroy(e1); ctbd_event_destroy(e2); ctbd_event_destroy(e3); ctbd_event_destroy(e4);
 	if (flush != NULL) { CTB_CHECK(ctbd_free(flush)); }
 	ctb_heff_free(&h);
 	ctb_tensor_free(bd);

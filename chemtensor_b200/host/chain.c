@@ -17,6 +17,7 @@
 #include "ctb_internal.h"
 
 struct ctb_stats ctb_global_stats;
+int ctb_dist_rank = 0, ctb_dist_world = 1;
 
 /* metadata copy that shares the device buffer, with all axis directions reversed */
 static struct ctb_tensor* view_reversed_dirs(const struct ctb_tensor* t)
@@ -301,14 +302,73 @@ struct ctb_tensor* ctb_env_step_left(const struct ctb_tensor* a, const struct ct
 /* effective Hamiltonian: plans built once per bond, three launches per matvec                     */
 /* ---------------------------------------------------------------------------------------------- */
 
+/* balanced split of a bond among 'world' ranks: the entries of every sector (in order of appearance) are cut into
+ * 'world' nearly equal contiguous ranges; rank p gets range p of every sector.  Returns 0 if some rank would stay empty. */
+static int split_bond(const struct ctb_axis* ax, int world, ct_long** ind, ct_long* nind)
+{
+	for (int p = 0; p < world; p++) { ind[p] = ctb_malloc((size_t)(ax->dim > 0 ? ax->dim : 1) * sizeof(ct_long)); nind[p] = 0; }
+	unsigned char* owner = ctb_malloc((size_t)(ax->dim > 0 ? ax->dim : 1));
+	for (int s = 0; s < ax->nsec; s++) {
+		const ct_long m = ax->secdim[s];
+		for (ct_long j = 0; j < m; j++) {
+			/* position j of the sector belongs to the rank p with floor(m p / W) <= j < floor(m (p + 1) / W) */
+			int p = (int)(((j + 1) * world - 1) / m);
+			while (p > 0 && (m * p) / world > j) { p--; }
+			while (p + 1 < world && (m * (p + 1)) / world <= j) { p++; }
+			owner[ax->log_of[ax->secstart[s] + j]] = (unsigned char)p;
+		}
+	}
+	for (ct_long i = 0; i < ax->dim; i++) { const int p = owner[i]; ind[p][nind[p]++] = i; }
+	ctb_free(owner);
+	for (int p = 0; p < world; p++) { if (nind[p] == 0) { return 0; } }
+	return 1;
+}
+
 int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h)
 {
 	CTB_REQUIRE(a->ndim == 3 && w->ndim == 4 && l->ndim == 4 && r->ndim == 4);
 	memset(h, 0, sizeof(*h));
 	h->w = w; h->r = r;
+	h->world = 1; h->rank = 0;
+	if (ctb_dist_world > 1)
+	{
+		const int W = ctb_dist_world;
+		CTB_REQUIRE(W <= 255);
+		h->ind = ctb_calloc((size_t)W, sizeof(ct_long*));
+		h->nind = ctb_calloc((size_t)W, sizeof(ct_long));
+		if (split_bond(&r->ax[2], W, h->ind, h->nind))
+		{
+			h->world = W; h->rank = ctb_dist_rank;
+			h->r_own = ctb_slice((struct ctb_tensor*)r, 2, h->ind[h->rank], h->nind[h->rank]);
+			h->r = h->r_own;
+			h->piece = ctb_calloc((size_t)W, sizeof(struct ctb_tensor*));
+			for (int p = 0; p < W; p++) {
+				qnumber* q = ctb_malloc((size_t)h->nind[p] * sizeof(qnumber));
+				for (ct_long j = 0; j < h->nind[p]; j++) { q[j] = a->ax[2].qlog[h->ind[p][j]]; }
+				struct ctb_axis axes[3];
+				ctb_axis_copy(&axes[0], &a->ax[0]);
+				ctb_axis_copy(&axes[1], &a->ax[1]);
+				ctb_axis_init(&axes[2], h->nind[p], a->ax[2].dir, q);
+				ctb_free(q);
+				h->piece[p] = ctb_tensor_from_axes(a->dtype, 3, axes, 0);
+				if (h->piece[p]->nstore > h->piece_cap) { h->piece_cap = h->piece[p]->nstore; }
+			}
+			if (h->piece_cap == 0) { h->piece_cap = 1; }
+			const size_t esize = ctb_sizeof_dtype(a->dtype);
+			CTB_CHECK(ctbd_malloc(&h->send, (size_t)h->piece_cap * esize));
+			CTB_CHECK(ctbd_malloc(&h->recv, (size_t)h->piece_cap * esize * (size_t)W));
+		}
+		else
+		{
+			/* a bond too small to split (chain ends): every rank computes the whole matvec, no exchange */
+			for (int p = 0; p < W; p++) { ctb_free(h->ind[p]); }
+			ctb_free(h->ind); ctb_free(h->nind); h->ind = NULL; h->nind = NULL;
+		}
+	}
+	const struct ctb_tensor* ru = h->r;
 	/* step 1: a . r  -> t1 [dd, Dw', Dl, Dr', x'] */
 	const int perm0[5] = { 1, 2, 0, 3, 4 };
-	h->t1 = ctb_dot_prepare(a, TENSOR_AXIS_RANGE_TRAILING, 0, r, TENSOR_AXIS_RANGE_LEADING, 0, 1, perm0, 1, &h->p1);
+	h->t1 = ctb_dot_prepare(a, TENSOR_AXIS_RANGE_TRAILING, 0, ru, TENSOR_AXIS_RANGE_LEADING, 0, 1, perm0, 1, &h->p1);
 	/* step 2: w . t1 over (dd_in, Dw') -> t2 [Dl, Dw, dd_out, Dr', x'] */
 	const int perm1[5] = { 2, 0, 1, 3, 4 };
 	h->t2 = ctb_dot_prepare_ex(w, TENSOR_AXIS_RANGE_TRAILING, 0, h->t1, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1, 1, CTB_DOT_MERGE_ROWS, &h->p2);
@@ -317,10 +377,19 @@ int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, str
 	h->k = ctb_transpose(l, perm2, 0);
 	struct ctb_tensor* s = ctb_dot_prepare(h->k, TENSOR_AXIS_RANGE_TRAILING, 0, h->t2, TENSOR_AXIS_RANGE_LEADING, 0, 2, NULL, 0, &h->p3);
 	/* tracing out the two dummy bonds leaves the packed layout unchanged */
-	h->b = ctb_drop_dummy_axes(s, 1);
+	struct ctb_tensor* bs = ctb_drop_dummy_axes(s, 1);
 	ctb_tensor_free(s);
-	CTB_REQUIRE(ctb_tensor_same_structure(h->b, a));
+	if (h->world > 1) {
+		CTB_REQUIRE(ctb_tensor_same_structure(bs, h->piece[h->rank]));
+		ctb_tensor_free(bs);
+		h->b = ctb_tensor_like(a, 0);
+	}
+	else {
+		h->b = bs;
+		CTB_REQUIRE(ctb_tensor_same_structure(h->b, a));
+	}
 	h->flops = h->p1.flops + h->p2.flops + h->p3.flops;
+	h->flops_total = h->flops * h->world;     /* the shards are balanced by construction; exact totals come from flops of world == 1 */
 	h->n = a->nelem;
 	h->nstore = a->nstore;
 	return 0;
@@ -328,11 +397,37 @@ int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, str
 
 int ctb_heff_apply(struct ctb_heff* h, const void* a_data, void* b_data)
 {
+	void* out = (h->world > 1) ? h->send : b_data;
 	CTB_CHECK(ctb_dot_exec(&h->p1, a_data, h->r->d, h->t1->d));
 	CTB_CHECK(ctb_dot_exec(&h->p2, h->w->d, h->t1->d, h->t2->d));
-	CTB_CHECK(ctb_dot_exec(&h->p3, h->k->d, h->t2->d, b_data));
+	CTB_CHECK(ctb_dot_exec(&h->p3, h->k->d, h->t2->d, out));
+	CTB_CHECK(ctb_heff_exchange(h, b_data));
 	ctb_global_stats.heff_flops += h->flops;
 	ctb_global_stats.heff_calls++;
+	return 0;
+}
+
+int ctb_heff_exchange(struct ctb_heff* h, void* b_data)
+{
+	if (h->world > 1)
+	{
+		/* exchange step: all-gather of the result slices over NVLink, then scatter into the packed layout of b */
+		const size_t esize = ctb_sizeof_dtype(h->b->dtype);
+		CTB_CHECK(ctbd_allgather(h->send, h->recv, (size_t)h->piece_cap * esize));
+		for (int p = 0; p < h->world; p++)
+		{
+			if (h->piece[p]->nstore == 0) { continue; }
+			struct ctbd_remap_args args;
+			memset(&args, 0, sizeof(args));
+			args.op = CTBD_REMAP_UNSLICE;
+			args.i_ax = 2;
+			args.ind = (const int64_t*)h->ind[p];
+			args.scale_ax = -1;
+			args.dst_layout = ctb_tensor_layout(h->b); args.dst = b_data;
+			args.src_layout = ctb_tensor_layout(h->piece[p]); args.src = (const char*)h->recv + (size_t)p * (size_t)h->piece_cap * esize;
+			CTB_CHECK(ctbd_remap(&args));
+		}
+	}
 	return 0;
 }
 
@@ -340,5 +435,10 @@ void ctb_heff_free(struct ctb_heff* h)
 {
 	ctb_dot_plan_free(&h->p1); ctb_dot_plan_free(&h->p2); ctb_dot_plan_free(&h->p3);
 	ctb_tensor_free(h->t1); ctb_tensor_free(h->t2); ctb_tensor_free(h->k); ctb_tensor_free(h->b);
+	if (h->piece != NULL) { for (int p = 0; p < h->world; p++) { ctb_tensor_free(h->piece[p]); } ctb_free(h->piece); }
+	if (h->ind != NULL) { for (int p = 0; p < h->world; p++) { ctb_free(h->ind[p]); } ctb_free(h->ind); ctb_free(h->nind); }
+	ctb_tensor_free(h->r_own);
+	if (h->send != NULL) { ctbd_free(h->send); }
+	if (h->recv != NULL) { ctbd_free(h->recv); }
 	memset(h, 0, sizeof(*h));
 }

@@ -26,6 +26,9 @@
 /* alignment (in elements) of each stored block inside the packed device buffer */
 #define CTB_BLOCK_ALIGN 1
 
+/* largest total contracted extent for which a merged-row contraction uses the streaming "mixing" kernel instead of the tensor-pipe GEMM */
+#define CTB_MIX_KMAX 128
+
 #define CTB_CHECK(call) do { int ctb_rc_ = (call); if (ctb_rc_ < 0) { \
 	fprintf(stderr, "chemtensor_b200: %s failed at %s:%d: %s\n", #call, __FILE__, __LINE__, ctbd_last_error()); \
 	return ctb_rc_; } } while (0)
@@ -187,12 +190,26 @@ struct ctb_heff
 	struct ctb_tensor* b;    /* structure of the result (no buffer) */
 	const struct ctb_tensor* w;
 	const struct ctb_tensor* r;
-	double flops;            /* algorithmic flops per matvec */
+	double flops;            /* algorithmic flops per matvec (of this rank's shard when sharded) */
 	ct_long n;               /* logical number of entries of a (Lanczos vector length) */
 	ct_long nstore;
+	/* one process per GPU: the bra bond of r is cut into 'world' balanced index sets (every sector split evenly), rank p
+	 * contracts with its column slice of r and owns the matching slice of the result; one all-gather + scatter rebuilds b */
+	int world, rank;
+	struct ctb_tensor* r_own;     /* slice(r, axis 2, ind[rank]) (owned) */
+	struct ctb_tensor** piece;    /* [world] structure of every rank's result slice (no buffers) */
+	ct_long** ind;                /* [world] logical indices of the bra bond owned by each rank, ascending */
+	ct_long* nind;
+	ct_long piece_cap;            /* elements of one all-gather slot (largest piece) */
+	void* send; void* recv;       /* device: own piece; all pieces */
+	double flops_total;           /* algorithmic flops of the whole matvec (all ranks) */
 };
+/* rank / world of this process (ctb_dist_init); world == 1 means no sharding */
+extern int ctb_dist_rank, ctb_dist_world;
 int  ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h);
 int  ctb_heff_apply(struct ctb_heff* h, const void* a_data, void* b_data);
+/* sharded case: all-gather of the result slices (h->send) and scatter into b_data; no-op on one rank */
+int  ctb_heff_exchange(struct ctb_heff* h, void* b_data);
 void ctb_heff_free(struct ctb_heff* h);
 
 /* symmetric tridiagonal eigen-decomposition (implicit QL); eigenvalues ascending in d, vectors in columns of z (row-major n x n) */

@@ -264,7 +264,15 @@ void* ctb_tensor_layout(struct ctb_tensor* t)
 /* ---- host struct <-> device ---- */
 
 /* allocate a reference-ABI host tensor (all payload with 16-byte aligned malloc; released by delete_block_sparse_tensor) */
+static void host_allocate_bst(int dtype, int ndim, const ct_long* dim, const enum tensor_axis_direction* axis_dir, const qnumber* const* qnums, struct block_sparse_tensor* t, int zero);
+
 void ctb_host_allocate_bst(int dtype, int ndim, const ct_long* dim, const enum tensor_axis_direction* axis_dir, const qnumber* const* qnums, struct block_sparse_tensor* t)
+{
+	host_allocate_bst(dtype, ndim, dim, axis_dir, qnums, t, 1);
+}
+
+/* zero == 0: block payloads are left uninitialised (the caller overwrites every entry) */
+static void host_allocate_bst(int dtype, int ndim, const ct_long* dim, const enum tensor_axis_direction* axis_dir, const qnumber* const* qnums, struct block_sparse_tensor* t, int zero)
 {
 	t->dtype = (enum numeric_type)dtype;
 	t->ndim = ndim;
@@ -314,7 +322,7 @@ void ctb_host_allocate_bst(int dtype, int ndim, const ct_long* dim, const enum t
 			b->dim = ctb_malloc(ndim * sizeof(ct_long));
 			ct_long numel = 1;
 			for (int i = 0; i < ndim; i++) { b->dim[i] = axes[i].secdim[idx[i]]; numel *= b->dim[i]; }
-			b->data = ctb_calloc(numel, esize);
+			b->data = zero ? ctb_calloc(numel, esize) : ctb_malloc((size_t)numel * esize);
 			t->blocks[c] = b;
 		}
 		for (int i = ndim - 1; i >= 0; i--) {
@@ -332,19 +340,20 @@ struct ctb_tensor* ctb_upload(const struct block_sparse_tensor* h)
 	struct ctb_tensor* t = ctb_tensor_create(h->dtype, h->ndim, h->dim_logical, dirs, (const qnumber* const*)h->qnums_logical, 1);
 	if (t->nstore == 0) { return t; }
 	const size_t esize = ctb_sizeof_dtype(t->dtype);
-	void* stage = NULL;
-	CTB_CHECK_ABORT(ctbd_host_alloc(&stage, (size_t)t->nstore * esize));
-	memset(stage, 0, (size_t)t->nstore * esize);
+	/* the separately allocated host blocks stream through the pinned staging ring of the device layer */
+	const void** hptrs = malloc((size_t)t->nblk * sizeof(void*));
+	int64_t* offs = malloc((size_t)t->nblk * sizeof(int64_t));
+	int64_t* lens = malloc((size_t)t->nblk * sizeof(int64_t));
 	for (int b = 0; b < t->nblk; b++)
 	{
 		const struct dense_tensor* hb = h->blocks[t->blk_grid[b]];
 		CTB_REQUIRE(hb != NULL);
 		ct_long numel = 1;
 		for (int i = 0; i < hb->ndim; i++) { numel *= hb->dim[i]; }
-		memcpy((char*)stage + (size_t)t->blk_off[b] * esize, hb->data, (size_t)numel * esize);
+		hptrs[b] = hb->data; offs[b] = (int64_t)t->blk_off[b] * (int64_t)esize; lens[b] = (int64_t)numel * (int64_t)esize;
 	}
-	CTB_CHECK_ABORT(ctbd_h2d(t->d, stage, (size_t)t->nstore * esize));
-	CTB_CHECK_ABORT(ctbd_host_free(stage));
+	CTB_CHECK_ABORT(ctbd_h2d_blocks(t->d, t->nblk, hptrs, offs, lens));
+	free(hptrs); free(offs); free(lens);
 	return t;
 }
 
@@ -358,22 +367,23 @@ int ctb_download(const struct ctb_tensor* t, struct block_sparse_tensor* h)
 		dirs[i] = (enum tensor_axis_direction)t->ax[i].dir;
 		qn[i] = t->ax[i].qlog;
 	}
-	ctb_host_allocate_bst(t->dtype, t->ndim, dim, dirs, qn, h);
+	host_allocate_bst(t->dtype, t->ndim, dim, dirs, qn, h, 0);
 	if (t->nstore == 0) { return 0; }
 	const size_t esize = ctb_sizeof_dtype(t->dtype);
-	void* stage = NULL;
-	CTB_CHECK(ctbd_host_alloc(&stage, (size_t)t->nstore * esize));
-	CTB_CHECK(ctbd_d2h(stage, t->d, (size_t)t->nstore * esize));
+	void** hptrs = malloc((size_t)t->nblk * sizeof(void*));
+	int64_t* offs = malloc((size_t)t->nblk * sizeof(int64_t));
+	int64_t* lens = malloc((size_t)t->nblk * sizeof(int64_t));
 	for (int b = 0; b < t->nblk; b++)
 	{
 		struct dense_tensor* hb = h->blocks[t->blk_grid[b]];
 		CTB_REQUIRE(hb != NULL);
 		ct_long numel = 1;
 		for (int i = 0; i < hb->ndim; i++) { numel *= hb->dim[i]; }
-		memcpy(hb->data, (char*)stage + (size_t)t->blk_off[b] * esize, (size_t)numel * esize);
+		hptrs[b] = hb->data; offs[b] = (int64_t)t->blk_off[b] * (int64_t)esize; lens[b] = (int64_t)numel * (int64_t)esize;
 	}
-	CTB_CHECK(ctbd_host_free(stage));
-	return 0;
+	int rc = ctbd_d2h_blocks(t->d, t->nblk, hptrs, offs, lens);
+	free(hptrs); free(offs); free(lens);
+	return rc;
 }
 
 int ctb_upload_entries(struct ctb_tensor* t, const void* entries)

@@ -119,11 +119,18 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	 * so the output is ONE segment of extent K' (a pipeline step of the kernel then spans many of the 1-4 row blocks) */
 	const bool use_rowtab = merge && b_ncontig;
 	int64_t* browtab = NULL; size_t nbrow = 0, cap_brow = 0;
+	/* mixing form (ctbd_mix_group): chosen when the whole contracted extent is small, i.e. s is an MPO tensor of a short-range
+	 * Hamiltonian; the launch then streams t and the result once, with no per-element offset tables at all */
+	ct_long kfull = 1;
+	for (int i = 0; i < ndim_mult; i++) { kfull *= s->ax[shift_s + i].dim; }
+	const bool mixmode = use_rowtab && nft <= 4 && kfull <= CTB_MIX_KMAX;
+	struct ctbd_mix_group* mgroups = NULL; size_t nmg = 0, cap_mg = 0;
+	struct ctbd_mix_row* mrows = NULL; size_t nmr = 0, cap_mr = 0;
 	struct merge_key* mk = NULL;
 	struct { uint64_t h; size_t base, len; }* packed = NULL; size_t npacked = 0, cap_packed = 0;
 	if (merge)
 	{
-		CTB_REQUIRE(r->nstore < ((ct_long)1 << 31));
+		CTB_REQUIRE(mixmode || r->nstore < ((ct_long)1 << 31));
 		mk = malloc((size_t)r->nblk * sizeof(*mk));
 		for (int b = 0; b < r->nblk; b++) {
 			int idx_r[CTB_MAXDIM];
@@ -147,7 +154,8 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 		ct_long N = 1;
 		for (int i = 0; i < nft; i++) { N *= nat[nfs + i]->secdim[nat_sec[nfs + i]]; }
 
-		struct ctbd_gemm_out* o = &outs[nouts++];
+		struct ctbd_gemm_out o_scratch;
+		struct ctbd_gemm_out* o = mixmode ? &o_scratch : &outs[nouts++];
 		o->n = (int32_t)N;
 		o->seg_begin = (int32_t)nseg;
 
@@ -239,9 +247,15 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 			flops += flop_factor * (double)Mtot * (double)N * (double)Ktot;
 			o->row_tab = (int32_t)tab.n;
 			o->col_tab = -1;
-			i32vec_reserve(&tab, (size_t)(2 * Mtot));
-			tab.n += (size_t)(2 * Mtot);
+			if (!mixmode) {
+				i32vec_reserve(&tab, (size_t)(2 * Mtot));
+				tab.n += (size_t)(2 * Mtot);
+			}
 			const size_t rowtab0 = (size_t)o->row_tab, rowcol0 = rowtab0 + (size_t)Mtot;
+			size_t mrow_first = nmr;
+			if (mixmode) {
+				while (nmr + (size_t)Mtot > cap_mr) { cap_mr = cap_mr ? 2 * cap_mr : 4096; mrows = realloc(mrows, cap_mr * sizeof(*mrows)); }
+			}
 			/* gather list of the packed Mtot x Ktot matrix (k contiguous) */
 			const size_t glen = (size_t)(Mtot * Ktot);
 			while (ngather + glen > cap_gather) { cap_gather = cap_gather ? 2 * cap_gather : 65536; gather = realloc(gather, cap_gather * sizeof(int64_t)); }
@@ -258,6 +272,30 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 				ct_long stride_r[CTB_MAXDIM];
 				ct_long st = 1;
 				for (int i = ndimr - 1; i >= 0; i--) { stride_r[i] = st; st *= r->ax[i].secdim[ir[i]]; }
+				if (mixmode)
+				{
+					/* one row descriptor per stacked row: absolute offset of its first column and the stride of every column digit */
+					int dig[CTB_MAXDIM] = { 0 };
+					for (ct_long i = 0; i < M; i++)
+					{
+						struct ctbd_mix_row* mr = &mrows[nmr++];
+						ct_long off = r->blk_off[b];
+						for (int a = 0; a < nfs; a++) { off += dig[a] * stride_r[pos_of_nat[a]]; }
+						mr->c_off = off;
+						mr->a_off = (row0 + i) * Ktot;      /* base of the packed matrix added below */
+						for (int a = 0; a < 4; a++) { mr->cs[a] = 0; }
+						for (int a = 0; a < nft; a++) {
+							CTB_REQUIRE(stride_r[pos_of_nat[nfs + a]] < ((ct_long)1 << 31));
+							mr->cs[a] = (int32_t)stride_r[pos_of_nat[nfs + a]];
+						}
+						for (int a = nfs - 1; a >= 0; a--) {
+							if (++dig[a] < nat[a]->secdim[ns[a]]) { break; }
+							dig[a] = 0;
+						}
+					}
+				}
+				else
+				{
 				/* absolute row offsets and the column table of this member */
 				const size_t coltab_idx = tab.n + (size_t)M;
 				{
@@ -273,6 +311,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 				const size_t ct0 = tab.n;
 				append_offset_table(&tab, nfs, nft, nat, ns, pos_of_nat, stride_r, 0);
 				for (ct_long i = 0; i < M; i++) { tab.v[rowcol0 + (size_t)(row0 + i)] = (int32_t)ct0; }
+				}
 				/* packed entries of this member's rows */
 				for (size_t sg = seg_first; sg < nseg; sg++)
 				{
@@ -318,7 +357,22 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 				g->a_off = (int64_t)base; g->b_off = (int64_t)row0_idx; g->k = (int32_t)Ktot; g->lda = (int32_t)Ktot; g->ldb = (int32_t)N; g->pad_ = 0;
 				nseg = seg_first + 1;
 				o->seg_end = (int32_t)nseg;
+				if (mixmode)
+				{
+					if (nmg == cap_mg) { cap_mg = cap_mg ? 2 * cap_mg : 1024; mgroups = realloc(mgroups, cap_mg * sizeof(*mgroups)); }
+					struct ctbd_mix_group* mg = &mgroups[nmg++];
+					memset(mg, 0, sizeof(*mg));
+					mg->brow_begin = (int64_t)row0_idx;
+					mg->n = (int32_t)N; mg->kp = (int32_t)Ktot;
+					mg->row_begin = (int32_t)mrow_first; mg->row_end = (int32_t)nmr;
+					mg->ndig = nft;
+					for (int a = 0; a < 4; a++) { mg->dig_dim[a] = 1; }
+					for (int a = 0; a < nft; a++) { mg->dig_dim[a] = nat[nfs + a]->secdim[nat_sec[nfs + a]]; }
+					for (size_t q = mrow_first; q < nmr; q++) { mrows[q].a_off += (int64_t)base; }
+					nseg = seg_first;      /* the mixing form carries no segment list */
+				}
 			}
+			else if (mixmode) { nmr = mrow_first; nseg = seg_first; }
 		}
 		CTB_REQUIRE(tab.n < ((size_t)1 << 31));
 		b0 = b1;
@@ -334,6 +388,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	h.flops = flops;
 	if (merge) { h.a_gather = gather; h.n_a_gather = (int64_t)ngather; h.a_src = s->d; }
 	if (use_rowtab && nbrow > 0) { h.b_rowtab = browtab; h.n_b_rowtab = (int64_t)nbrow; }
+	if (mixmode && nmg > 0) { h.mix_groups = mgroups; h.n_mix_groups = (int32_t)nmg; h.mix_rows = mrows; h.n_mix_rows = (int32_t)nmr; }
 	plan->dev = NULL;
 	CTB_CHECK_ABORT(ctbd_gemm_plan_create(&h, &plan->dev));
 	plan->flops = flops;
@@ -341,7 +396,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	plan->ntiles = 0;
 	CTB_CHECK_ABORT(ctbd_gemm_plan_info(plan->dev, &plan->ntiles, NULL));
 
-	free(tab.v); free(outs); free(segs); free(gather); free(mk); free(packed); free(browtab);
+	free(tab.v); free(outs); free(segs); free(gather); free(mk); free(packed); free(browtab); free(mgroups); free(mrows);
 	return r;
 }
 

@@ -108,6 +108,16 @@ int dmrg_twosite(const struct mpo* hamiltonian, const int num_sweeps, const int 
 /* ---- engine extensions (no reference counterpart; measurement and lifecycle) -------------------------------- */
 /* explicit device selection / start-up; returns <0 when no CUDA device is usable */
 int ctb_init(int device);
+/* one process per GPU: after ctb_dist_init every effective-Hamiltonian application inside dmrg_* / the Lanczos
+ * driver is sharded over the ranks -- the bra bond of the right environment is cut into balanced index sets, each rank
+ * contracts its slice and one NCCL all-gather over NVLink rebuilds the result on every rank; everything else (level-1
+ * Lanczos work, SVD, environment updates) runs replicated and deterministic, so all ranks hold bit-identical states.
+ * unique_id: the 128-byte NCCL id obtained on rank 0 with ctb_dist_unique_id and distributed by the host (MPI, torchrun, ...);
+ * alternatively pass NULL and register the host's own all-gather with ctb_dist_set_allgather. */
+int ctb_dist_unique_id(void* id_out_128_bytes);
+int ctb_dist_init(int rank, int world, const void* unique_id);
+int ctb_dist_set_allgather(int (*fn)(void* ctx, const void* sendbuf, void* recvbuf, size_t bytes_per_rank, void* stream), void* ctx);
+int ctb_dist_finalize(void);
 /* 1 = CUDA kernels, 2 = host test double (tests/emu only) */
 int ctb_backend(void);
 /* kernels launched by the engine so far */

@@ -73,11 +73,28 @@ int ctbd_memset_zero(void* dptr, size_t bytes);
 int ctbd_h2d(void* dptr, const void* hptr, size_t bytes);
 int ctbd_d2h(void* hptr, const void* dptr, size_t bytes);
 int ctbd_d2d(void* dst, const void* src, size_t bytes);
+/* pack 'nblk' separately allocated host blocks into one device buffer (block b -> dptr + dst_off[b], byte units) and back,
+ * streamed through the layer's persistent pinned staging ring; h2d returns once the host blocks have been consumed */
+int ctbd_h2d_blocks(void* dptr, int nblk, const void* const* hptrs, const int64_t* dst_off, const int64_t* nbytes);
+int ctbd_d2h_blocks(const void* dptr, int nblk, void* const* hptrs, const int64_t* src_off, const int64_t* nbytes);
 int ctbd_sync(void);
 int ctbd_host_alloc(void** hptr, size_t bytes);      /* pinned host staging memory */
 int ctbd_host_free(void* hptr);
 /* bytes currently allocated through ctbd_malloc */
 long long ctbd_bytes_in_use(void);
+
+/* ---- one process per GPU: the exchange step of the sharded effective Hamiltonian -------------------------------------
+ * The collective is NCCL (all-gather over NVLink / NVSwitch) enqueued on the layer's stream.  libnccl is bound at run time
+ * (dlopen "libnccl.so.2"), so a single-GPU host never needs it.  A host that owns its own communicator may instead register
+ * a callback; the CPU test double only knows the callback form (gloo in the tests). */
+#define CTBD_UNIQUE_ID_BYTES 128
+typedef int (*ctbd_allgather_fn)(void* ctx, const void* sendbuf, void* recvbuf, size_t bytes_per_rank, void* stream);
+int ctbd_dist_unique_id(void* id_out);                              /* rank 0: ncclGetUniqueId */
+int ctbd_dist_init(int rank, int world, const void* unique_id);     /* ncclCommInitRank on the active device; unique_id may be NULL with a callback */
+int ctbd_dist_set_allgather(ctbd_allgather_fn fn, void* ctx);       /* optional host-provided collective */
+int ctbd_dist_finalize(void);
+/* recv[p * bytes_per_rank ...] = send of rank p, for all ranks p; device buffers; ordered on the layer's stream */
+int ctbd_allgather(const void* sendbuf, void* recvbuf, size_t bytes_per_rank);
 
 /* ---- grouped block GEMM -------------------------------------------------------------------- */
 
@@ -102,6 +119,29 @@ struct ctbd_gemm_out
 	int32_t row_tab, col_tab;     /* start indices into the int32 offset table */
 };
 
+/* ---- "mixing" form of a merged-row contraction with a small constant left operand (the MPO tensor) ----
+ * One group = all result rows that share the free sectors of the right operand t.  For column j of the group
+ * (a multi-index over the free axes of t, row-major, extents dig_dim[]) and row i:
+ *     C[row.c_off + sum_a digit_a(j) * row.cs[a]]  =  sum_k  Apacked[row.a_off + k] * B[b_rowtab[group.brow_begin + k] + j],   k < kp
+ * Exact zeros of the packed operand are skipped (x + 0 * y == x), so the work is proportional to the non-zero operator
+ * entries; the traffic is one read of every B row block and one write of every C row block (HBM-bound by construction). */
+struct ctbd_mix_group
+{
+	int64_t brow_begin;          /* first entry of this group in b_rowtab */
+	int32_t n;                   /* number of columns = product of dig_dim */
+	int32_t kp;                  /* contracted extent K' */
+	int32_t row_begin, row_end;  /* rows of this group in the row array */
+	int32_t ndig;                /* number of column digits (free axes of t), <= 4 */
+	int32_t dig_dim[4];
+	int32_t pad_;
+};
+struct ctbd_mix_row
+{
+	int64_t c_off;               /* element offset of C(i, column 0) */
+	int64_t a_off;               /* start of the kp packed operand entries of this row */
+	int32_t cs[4];               /* stride of each column digit in the result block of this row */
+};
+
 struct ctbd_gemm_plan_host
 {
 	int32_t dtype;                /* CTBD_F64 or CTBD_C128 */
@@ -121,6 +161,11 @@ struct ctbd_gemm_plan_host
 	 * lets ONE pipeline step span the rows of many small blocks (the MPO-mixing contraction has 1-4 rows per block) */
 	const int64_t* b_rowtab;      /* host array or NULL */
 	int64_t n_b_rowtab;
+	/* optional: mixing form (needs a_gather and b_rowtab); when present outs/segs/tab are empty and the run is one mix launch */
+	const struct ctbd_mix_group* mix_groups;
+	int32_t n_mix_groups;
+	const struct ctbd_mix_row* mix_rows;
+	int32_t n_mix_rows;
 };
 
 /* builds the device-resident work list: every output block is cut into tiles of the kernel variant that
@@ -160,6 +205,7 @@ int ctbd_layout_destroy(void* layout);
 #define CTBD_REMAP_SPLIT     2   /* dst axes (i_ax, i_ax+1) = src axis i_ax split row-major */
 #define CTBD_REMAP_SLICE     3   /* dst index j on axis i_ax = src index ind[j] */
 #define CTBD_REMAP_IDENTITY  4   /* same logical index (used with 'scale') */
+#define CTBD_REMAP_UNSLICE   5   /* scatter: dst index ind[j] on axis i_ax = src index j (other dst entries untouched) */
 
 struct ctbd_remap_args
 {

@@ -47,6 +47,28 @@ int ctbd_free(void* dptr) { if (dptr) { struct hdr* h = (struct hdr*)dptr - 1; g
 int ctbd_memset_zero(void* dptr, size_t bytes) { memset(dptr, 0, bytes); return 0; }
 int ctbd_h2d(void* d, const void* h, size_t bytes) { memcpy(d, h, bytes); return 0; }
 int ctbd_d2h(void* h, const void* d, size_t bytes) { memcpy(h, d, bytes); return 0; }
+int ctbd_h2d_blocks(void* dptr, int nblk, const void* const* hptrs, const int64_t* dst_off, const int64_t* nbytes)
+{
+	for (int b = 0; b < nblk; b++) { memcpy((char*)dptr + dst_off[b], hptrs[b], (size_t)nbytes[b]); }
+	return 0;
+}
+int ctbd_d2h_blocks(const void* dptr, int nblk, void* const* hptrs, const int64_t* src_off, const int64_t* nbytes)
+{
+	for (int b = 0; b < nblk; b++) { memcpy(hptrs[b], (const char*)dptr + src_off[b], (size_t)nbytes[b]); }
+	return 0;
+}
+/* exchange step: the test double only knows the host-callback form (gloo in the tests) */
+static ctbd_allgather_fn g_ag_fn = NULL; static void* g_ag_ctx = NULL; static int g_world = 1;
+int ctbd_dist_unique_id(void* id_out) { memset(id_out, 0, CTBD_UNIQUE_ID_BYTES); return 0; }
+int ctbd_dist_init(int rank, int world, const void* unique_id) { (void)rank; (void)unique_id; g_world = world; return 0; }
+int ctbd_dist_set_allgather(ctbd_allgather_fn fn, void* ctx) { g_ag_fn = fn; g_ag_ctx = ctx; return 0; }
+int ctbd_dist_finalize(void) { g_world = 1; g_ag_fn = NULL; g_ag_ctx = NULL; return 0; }
+int ctbd_allgather(const void* sendbuf, void* recvbuf, size_t bytes_per_rank)
+{
+	if (g_world == 1) { if (sendbuf != recvbuf) { memmove(recvbuf, sendbuf, bytes_per_rank); } return 0; }
+	if (g_ag_fn == NULL) { snprintf(g_err, sizeof(g_err), "dist: no all-gather callback registered"); return -1; }
+	return g_ag_fn(g_ag_ctx, sendbuf, recvbuf, bytes_per_rank, NULL);
+}
 int ctbd_d2d(void* dst, const void* src, size_t bytes) { memmove(dst, src, bytes); return 0; }
 int ctbd_sync(void) { return 0; }
 int ctbd_host_alloc(void** hptr, size_t bytes) { *hptr = malloc(bytes ? bytes : 1); return *hptr ? 0 : -1; }
@@ -54,7 +76,8 @@ int ctbd_host_free(void* hptr) { free(hptr); return 0; }
 long long ctbd_bytes_in_use(void) { return g_bytes; }
 
 /* ---- grouped GEMM ---- */
-struct emu_plan { struct ctbd_gemm_plan_host h; struct ctbd_gemm_out* outs; struct ctbd_gemm_seg* segs; int32_t* tab; void* a_packed; int64_t* b_rowtab; };
+struct emu_plan { struct ctbd_gemm_plan_host h; struct ctbd_gemm_out* outs; struct ctbd_gemm_seg* segs; int32_t* tab; void* a_packed; int64_t* b_rowtab;
+	struct ctbd_mix_group* mix_groups; struct ctbd_mix_row* mix_rows; };
 
 static void* dup_mem(const void* p, size_t n) { void* q = malloc(n ? n : 1); if (n) { memcpy(q, p, n); } return q; }
 
@@ -67,6 +90,11 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan)
 	p->tab   = dup_mem(h->tab,   (size_t)h->ntab   * sizeof(int32_t));
 	p->b_rowtab = NULL;
 	if (h->b_rowtab != NULL && h->n_b_rowtab > 0) { p->b_rowtab = dup_mem(h->b_rowtab, (size_t)h->n_b_rowtab * sizeof(int64_t)); }
+	p->mix_groups = NULL; p->mix_rows = NULL;
+	if (h->mix_groups != NULL && h->n_mix_groups > 0) {
+		p->mix_groups = dup_mem(h->mix_groups, (size_t)h->n_mix_groups * sizeof(*h->mix_groups));
+		p->mix_rows = dup_mem(h->mix_rows, (size_t)h->n_mix_rows * sizeof(*h->mix_rows));
+	}
 	p->a_packed = NULL;
 	if (h->a_gather != NULL && h->n_a_gather > 0) {
 		const size_t es = (h->dtype == CTBD_C128) ? 16 : 8;
@@ -81,14 +109,14 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan)
 int ctbd_gemm_plan_destroy(void* plan)
 {
 	struct emu_plan* p = plan;
-	free(p->outs); free(p->segs); free(p->tab); free(p->a_packed); free(p->b_rowtab); free(p);
+	free(p->outs); free(p->segs); free(p->tab); free(p->a_packed); free(p->b_rowtab); free(p->mix_groups); free(p->mix_rows); free(p);
 	return 0;
 }
 
 int ctbd_gemm_plan_info(void* plan, int* ntiles, int* nlaunches)
 {
 	struct emu_plan* p = plan;
-	if (ntiles) { *ntiles = p->h.nouts; }
+	if (ntiles) { *ntiles = p->h.nouts + p->h.n_mix_groups; }
 	if (nlaunches) { *nlaunches = 1; }
 	return 0;
 }
@@ -99,6 +127,30 @@ int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
 	g_launches++;
 	const int cplx = (p->h.dtype == CTBD_C128);
 	if (p->a_packed != NULL) { A = p->a_packed; }
+	for (int gi = 0; gi < (p->mix_groups != NULL ? p->h.n_mix_groups : 0); gi++)
+	{
+		/* mixing form, straight from its definition in ctb_device.h */
+		const struct ctbd_mix_group* g = &p->mix_groups[gi];
+		for (int r = g->row_begin; r < g->row_end; r++) {
+			const struct ctbd_mix_row* rw = &p->mix_rows[r];
+			for (int j = 0; j < g->n; j++) {
+				double complex acc = 0;
+				for (int k = 0; k < g->kp; k++) {
+					const int64_t ib = p->b_rowtab[g->brow_begin + k] + j;
+					if (cplx) {
+						double complex a = ((const double complex*)A)[rw->a_off + k], b = ((const double complex*)B)[ib];
+						if (p->h.conj_a) { a = conj(a); }
+						if (p->h.conj_b) { b = conj(b); }
+						acc += a * b;
+					}
+					else { acc += ((const double*)A)[rw->a_off + k] * ((const double*)B)[ib]; }
+				}
+				int64_t off = rw->c_off; int rem = j;
+				for (int a = g->ndig - 1; a >= 0; a--) { off += (int64_t)(rem % g->dig_dim[a]) * rw->cs[a]; rem /= g->dig_dim[a]; }
+				if (cplx) { ((double complex*)C)[off] = acc; } else { ((double*)C)[off] = creal(acc); }
+			}
+		}
+	}
 	for (int t = 0; t < p->h.nouts; t++)
 	{
 		const struct ctbd_gemm_out* o = &p->outs[t];
@@ -172,6 +224,39 @@ int ctbd_remap(const struct ctbd_remap_args* a)
 	g_launches++;
 	const struct emu_layout* D = a->dst_layout; const struct emu_layout* S = a->src_layout;
 	const int cplx = (D->dtype == CTBD_C128);
+	if (a->op == CTBD_REMAP_UNSLICE)
+	{
+		/* scatter: every source entry goes to the destination entry with index ind[.] on axis i_ax */
+		for (int b = 0; b < S->nblk; b++)
+		{
+			int sec[CTBD_MAXDIM]; int64_t bdim[CTBD_MAXDIM];
+			int64_t cell = S->blk_grid[b];
+			for (int i = S->ndim - 1; i >= 0; i--) { sec[i] = (int)(cell % S->nsec[i]); cell /= S->nsec[i]; }
+			int64_t numel = 1;
+			for (int i = 0; i < S->ndim; i++) { bdim[i] = S->secstart[i][sec[i] + 1] - S->secstart[i][sec[i]]; numel *= bdim[i]; }
+			for (int64_t e = 0; e < numel; e++)
+			{
+				int64_t ld[CTBD_MAXDIM];
+				int64_t r = e;
+				for (int i = S->ndim - 1; i >= 0; i--) {
+					const int64_t pos = r % bdim[i]; r /= bdim[i];
+					const int64_t ls = S->log_of[i][S->secstart[i][sec[i]] + pos];
+					ld[i] = (i == a->i_ax) ? a->ind[ls] : ls;
+				}
+				int64_t dcell = 0, doff = 0;
+				for (int i = 0; i < D->ndim; i++) {
+					const int sc = D->sec_of[i][ld[i]];
+					dcell = dcell * D->nsec[i] + sc;
+					doff = doff * (D->secstart[i][sc + 1] - D->secstart[i][sc]) + D->pos_of[i][ld[i]];
+				}
+				const int64_t dbase = D->grid_off[dcell];
+				if (dbase < 0) { continue; }
+				if (cplx) { ((double complex*)a->dst)[dbase + doff] = ((const double complex*)a->src)[S->blk_off[b] + e]; }
+				else { ((double*)a->dst)[dbase + doff] = ((const double*)a->src)[S->blk_off[b] + e]; }
+			}
+		}
+		return 0;
+	}
 	for (int b = 0; b < D->nblk; b++)
 	{
 		int sec[CTBD_MAXDIM]; int64_t bdim[CTBD_MAXDIM];
