@@ -10,7 +10,7 @@
 NVCC     ?= /usr/local/cuda/bin/nvcc
 CC       ?= gcc
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Ichemtensor_b200/csrc --expt-relaxed-constexpr
+NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fopenmp -Iinclude -Ichemtensor_b200/csrc --expt-relaxed-constexpr
 CFLAGS   := -std=gnu11 -O2 -fPIC -Wall -Wno-unused-function -Iinclude -Ichemtensor_b200/host
 BUILD    := build_tmp
 
@@ -35,19 +35,23 @@ $(BUILD)/csrc/%.o: chemtensor_b200/csrc/%.cu chemtensor_b200/csrc/ctbd_common.cu
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(HOST_OBJ) $(CUDA_OBJ)
-	$(NVCC) $(ARCH) -shared -Xlinker -Bsymbolic -o $@ $^ -lm
+	$(NVCC) $(ARCH) -shared -Xlinker -Bsymbolic -Xlinker -soname=libchemtensor_b200.so -Xlinker --no-undefined -o $@ $^ -lm -lgomp -ldl
 
 $(BUILD)/emu/ctbd_emu.o: tests/emu/ctbd_emu.c include/ctb_device.h
 	@mkdir -p $(dir $@)
 	$(CC) $(CFLAGS) -c $< -o $@
 
 $(EMU): $(HOST_OBJ) $(BUILD)/emu/ctbd_emu.o
-	$(CC) -shared -Wl,-Bsymbolic -o $@ $^ -lm
+	$(CC) -shared -Wl,-Bsymbolic -Wl,-soname,libctb_hostlogic_emu.so -Wl,--no-undefined -o $@ $^ -lm
 
 oracle:
 	@if [ -d /root/reference/src ]; then $(MAKE) -C oracle; else echo "reference sources absent: using prebuilt oracle/_ref"; fi
 
+# the reference relinked against the engine; needs lib, emu and the oracle objects
+dropin: lib emu oracle
+	@if [ -d /root/reference/src ]; then $(MAKE) -C oracle dropin; else echo "reference sources absent: using prebuilt oracle/_ref"; fi
+
 clean:
 	rm -rf $(BUILD) $(LIB) $(EMU)
 
-.PHONY: all lib emu oracle clean
+.PHONY: all lib emu oracle dropin clean

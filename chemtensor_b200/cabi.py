@@ -122,6 +122,7 @@ _EXT_SIGNATURES = {
     "ctb_heff_benchmark": (C.c_int, [_P_BST, _P_BST, _P_BST, _P_BST, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ctb_dot_benchmark": (C.c_int, [_P_BST, C.c_int, _P_BST, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ctb_get_stats": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
+    "ctb_heff_plan_info": (C.c_int, [_P_BST, _P_BST, _P_BST, _P_BST, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "ctb_dist_unique_id": (C.c_int, [C.c_void_p]),
     "ctb_dist_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
     "ctb_dist_set_allgather": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -621,19 +621,46 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 	const ClassShape* shapes = cplx ? g_shapes_z : g_shapes_d;
 	const int nshapes = cplx ? 3 : 6;
 
-	/* class with the least padded work over the whole plan (+ a per-tile overhead of about two k-steps) */
+	/* tile class with the shortest estimated launch: for every class the tiles are packed longest-processing-time-first into
+	 * the resident CTA slots (sm_count x occupancy) and the makespan is priced with the class' measured cost per multiply-add;
+	 * this accounts for padding, the per-tile overhead AND wave quantisation (few huge tiles leave SMs idle) */
 	int best = 0; double best_cost = 0;
+	static int occ_cache[2][8] = { { 0 } };
 	for (int c = 0; c < nshapes; c++)
 	{
-		double cost = 0;
+		if (occ_cache[cplx][c] == 0) {
+			int occ = 1;
+			p->cfg = c;
+			if (CTBD_GEMM_DISPATCH(occupancy_cfg, p, &occ) < 0) { occ = 1; }
+			occ_cache[cplx][c] = occ < 1 ? 1 : occ;
+		}
+		const int slots = rt().sm_count * occ_cache[cplx][c];
+		std::vector<double> tw;      /* tile weights in k-steps */
+		double total = 0, wmax = 0;
 		for (int b = 0; b < h->nouts; b++) {
 			const ctbd_gemm_out& o = h->outs[b];
 			if (o.m <= 0 || o.n <= 0) { continue; }
 			double steps = 0;
 			for (int s = o.seg_begin; s < o.seg_end; s++) { steps += (double)ceil_div(h->segs[s].k, shapes[c].bk); }
-			const double nt = (double)ceil_div(o.m, shapes[c].bm) * (double)ceil_div(o.n, shapes[c].bn);
-			cost += nt * (steps * shapes[c].bk + 32.0) * shapes[c].bm * shapes[c].bn * shapes[c].eff;
+			const int64_t nt = ceil_div(o.m, shapes[c].bm) * ceil_div(o.n, shapes[c].bn);
+			const double w = steps + 32.0 / shapes[c].bk;
+			total += w * (double)nt; wmax = std::max(wmax, w);
+			if (tw.size() < 40000) { for (int64_t i = 0; i < nt && tw.size() < 40000; i++) { tw.push_back(w); } }
 		}
+		const int64_t ntl = (int64_t)tw.size();
+		if (ntl == 0) { continue; }
+		const int grid = (int)std::min<int64_t>(ntl, slots);
+		double makespan;
+		if (ntl < 40000) {
+			std::sort(tw.begin(), tw.end(), [](double a, double b) { return a > b; });
+			std::vector<double> heap(grid, 0.0);     /* min-heap of slot loads */
+			auto cmpd = [](double a, double b) { return a > b; };
+			for (double w : tw) { std::pop_heap(heap.begin(), heap.end(), cmpd); heap.back() += w; std::push_heap(heap.begin(), heap.end(), cmpd); }
+			makespan = *std::max_element(heap.begin(), heap.end());
+		}
+		else { makespan = std::max(total / grid, wmax); }
+		const int per_sm = (int)ceil_div(grid, rt().sm_count);      /* CTAs sharing the tensor pipe of one SM */
+		const double cost = makespan * shapes[c].bk * shapes[c].bm * shapes[c].bn * shapes[c].eff * per_sm;
 		if (c == 0 || cost < best_cost) { best = c; best_cost = cost; }
 	}
 	const char* force = getenv("CTB_GEMM_CLASS");   /* tuning knob: force one tile class */

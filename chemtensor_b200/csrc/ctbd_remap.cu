@@ -181,6 +181,29 @@ __global__ void __launch_bounds__(256) unslice_kernel(const LayoutDev D, const L
 	}
 }
 
+/* ---- batched strided 2-d copy ---- */
+struct CopyTile { int32_t desc, row0; };
+struct CopyPlan { int dtype; int ndesc, ntiles; ctbd_copy2d* descs; CopyTile* tiles; };
+static constexpr int COPY_ROWS = 16;      /* rows per tile: 8 warps x 2 rows */
+
+template <typename T>
+__global__ void __launch_bounds__(256) copy2d_kernel(int ntiles, const CopyTile* __restrict__ tiles, const ctbd_copy2d* __restrict__ descs,
+	const T* __restrict__ src, T* __restrict__ dst)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+	{
+		const CopyTile tl = tiles[t];
+		const ctbd_copy2d d = descs[tl.desc];
+		const int r1 = min(tl.row0 + COPY_ROWS, d.rows);
+		for (int i = tl.row0 + warp; i < r1; i += 8) {
+			const T* __restrict__ s = src + d.src_off + (int64_t)i * d.src_ld;
+			T* __restrict__ o = dst + d.dst_off + (int64_t)i * d.dst_ld;
+			for (int j = lane; j < d.cols; j += 32) { o[j] = s[j]; }
+		}
+	}
+}
+
 } // namespace ctbd
 
 using namespace ctbd;
@@ -242,6 +265,45 @@ int ctbd_layout_destroy(void* layout)
 	if (L == nullptr) { return 0; }
 	ctbd_free(L->arena);
 	delete L;
+	return 0;
+}
+
+int ctbd_copy_plan_create(int dtype, int n, const struct ctbd_copy2d* descs_host, void** plan)
+{
+	CTBD_REQUIRE_INIT();
+	if (dtype != CTBD_F64 && dtype != CTBD_C128) { return fail_msg("copy plan: unsupported dtype"); }
+	CopyPlan* p = new CopyPlan();
+	p->dtype = dtype; p->ndesc = n; p->descs = nullptr; p->tiles = nullptr;
+	std::vector<CopyTile> tiles;
+	for (int i = 0; i < n; i++) {
+		if (descs_host[i].cols <= 0) { continue; }
+		for (int r0 = 0; r0 < descs_host[i].rows; r0 += COPY_ROWS) { CopyTile t; t.desc = i; t.row0 = r0; tiles.push_back(t); }
+	}
+	p->ntiles = (int)tiles.size();
+	int rc = upload(descs_host, (size_t)n * sizeof(ctbd_copy2d), (void**)&p->descs);
+	rc |= upload(tiles.data(), tiles.size() * sizeof(CopyTile), (void**)&p->tiles);
+	if (rc < 0) { ctbd_copy_plan_destroy(p); return -1; }
+	*plan = p;
+	return 0;
+}
+
+int ctbd_copy_plan_run(void* plan, const void* src, void* dst)
+{
+	CopyPlan* p = (CopyPlan*)plan;
+	if (p == nullptr || p->ntiles == 0) { return 0; }
+	const int grid = std::min(p->ntiles, rt().sm_count * 16);
+	if (p->dtype == CTBD_F64) { copy2d_kernel<double><<<grid, 256, 0, rt().stream>>>(p->ntiles, p->tiles, p->descs, (const double*)src, (double*)dst); }
+	else                      { copy2d_kernel<double2><<<grid, 256, 0, rt().stream>>>(p->ntiles, p->tiles, p->descs, (const double2*)src, (double2*)dst); }
+	CTBD_LAUNCH_CHECK();
+	return 0;
+}
+
+int ctbd_copy_plan_destroy(void* plan)
+{
+	CopyPlan* p = (CopyPlan*)plan;
+	if (p == nullptr) { return 0; }
+	ctbd_free(p->descs); ctbd_free(p->tiles);
+	delete p;
 	return 0;
 }
 

@@ -4,6 +4,7 @@
  */
 #include <stdlib.h>
 #include <dlfcn.h>
+#include <omp.h>
 #include <unordered_map>
 #include <mutex>
 #include <vector>
@@ -207,37 +208,60 @@ int ctbd_d2h(void* hptr, const void* dptr, size_t bytes)
 }
 
 
+/* pieces of host blocks laid out in consecutive staging chunks (each chunk = one contiguous device range) */
+namespace {
+struct Piece { int b; int64_t boff, n; size_t pos; };          /* block, byte offset inside the block, bytes, position in the chunk */
+struct Chunk { int64_t dev, len; size_t p0, p1; };
+constexpr int64_t PIECE_MAX = (int64_t)1 << 20;                /* split large blocks so that the host copy parallelises */
+
+void plan_chunks(int nblk, const int64_t* dev_off, const int64_t* nbytes, std::vector<Piece>& pieces, std::vector<Chunk>& chunks)
+{
+	Chunk c; c.dev = -1; c.len = 0; c.p0 = 0; c.p1 = 0;
+	for (int b = 0; b < nblk; b++) {
+		int64_t done = 0;
+		while (done < nbytes[b]) {
+			if (c.len > 0 && (c.dev + c.len != dev_off[b] + done || (size_t)c.len == STAGE_CHUNK)) { c.p1 = pieces.size(); chunks.push_back(c); c.len = 0; }
+			if (c.len == 0) { c.dev = dev_off[b] + done; c.p0 = pieces.size(); }
+			const int64_t n = std::min<int64_t>(std::min<int64_t>(nbytes[b] - done, (int64_t)STAGE_CHUNK - c.len), PIECE_MAX);
+			Piece pc; pc.b = b; pc.boff = done; pc.n = n; pc.pos = (size_t)c.len; pieces.push_back(pc);
+			c.len += n; done += n;
+		}
+	}
+	if (c.len > 0) { c.p1 = pieces.size(); chunks.push_back(c); }
+}
+
+int host_copy_threads()
+{
+	static int nt = 0;
+	if (nt == 0) {
+		const char* env = getenv("CTB_COPY_THREADS");
+		nt = (env != nullptr) ? atoi(env) : std::min(8, omp_get_num_procs());
+		if (nt < 1) { nt = 1; }
+	}
+	return nt;
+}
+} // namespace
+
 int ctbd_h2d_blocks(void* dptr, int nblk, const void* const* hptrs, const int64_t* dst_off, const int64_t* nbytes)
 {
 	CTBD_REQUIRE_INIT();
 	if (ring_init() < 0) { return -1; }
-	int cur = 0;
-	if (ring_wait(cur) < 0) { return -1; }
-	size_t fill = 0;            /* bytes packed into the current chunk */
-	int64_t chunk_dst = -1;     /* device offset the current chunk starts at */
-	auto flush = [&]() -> int {
-		if (fill == 0) { return 0; }
-		CTBD_CUDA(cudaMemcpyAsync((char*)dptr + chunk_dst, g_ring.buf[cur], fill, cudaMemcpyHostToDevice, rt().stream));
-		CTBD_CUDA(cudaEventRecord(g_ring.ev[cur], rt().stream));
-		g_ring.busy[cur] = true;
-		cur ^= 1; fill = 0; chunk_dst = -1;
-		return ring_wait(cur);
-	};
-	for (int b = 0; b < nblk; b++)
+	std::vector<Piece> pieces; std::vector<Chunk> chunks;
+	plan_chunks(nblk, dst_off, nbytes, pieces, chunks);
+	const int nt = host_copy_threads();
+	for (size_t ci = 0; ci < chunks.size(); ci++)
 	{
-		int64_t done = 0;
-		while (done < nbytes[b])
-		{
-			/* a chunk holds a contiguous device range: start a new one when the next piece is not adjacent */
-			if (fill > 0 && chunk_dst + (int64_t)fill != dst_off[b] + done) { if (flush() < 0) { return -1; } }
-			if (fill == 0) { chunk_dst = dst_off[b] + done; }
-			const size_t n = std::min<size_t>((size_t)(nbytes[b] - done), STAGE_CHUNK - fill);
-			memcpy((char*)g_ring.buf[cur] + fill, (const char*)hptrs[b] + done, n);
-			fill += n; done += (int64_t)n;
-			if (fill == STAGE_CHUNK) { if (flush() < 0) { return -1; } }
-		}
+		const int slot = (int)(ci & 1);
+		if (ring_wait(slot) < 0) { return -1; }
+		char* stage = (char*)g_ring.buf[slot];
+		const long p0 = (long)chunks[ci].p0, p1 = (long)chunks[ci].p1;
+		/* pack: pageable host blocks -> pinned chunk, in parallel (the previous chunk is on the copy engine meanwhile) */
+		#pragma omp parallel for schedule(dynamic, 4) num_threads(nt) if (p1 - p0 > 8)
+		for (long q = p0; q < p1; q++) { memcpy(stage + pieces[q].pos, (const char*)hptrs[pieces[q].b] + pieces[q].boff, (size_t)pieces[q].n); }
+		CTBD_CUDA(cudaMemcpyAsync((char*)dptr + chunks[ci].dev, stage, (size_t)chunks[ci].len, cudaMemcpyHostToDevice, rt().stream));
+		CTBD_CUDA(cudaEventRecord(g_ring.ev[slot], rt().stream));
+		g_ring.busy[slot] = true;
 	}
-	if (flush() < 0) { return -1; }
 	/* the ring stays owned by this layer, so the copies may complete asynchronously */
 	return 0;
 }
@@ -246,28 +270,13 @@ int ctbd_d2h_blocks(const void* dptr, int nblk, void* const* hptrs, const int64_
 {
 	CTBD_REQUIRE_INIT();
 	if (ring_init() < 0) { return -1; }
-	/* list of chunks (contiguous device ranges of at most STAGE_CHUNK bytes), each covering pieces of consecutive blocks */
-	struct Piece { int b; int64_t boff, n; };
-	struct Chunk { int64_t src, len; size_t p0, p1; };
 	std::vector<Piece> pieces; std::vector<Chunk> chunks;
-	{
-		Chunk c; c.src = -1; c.len = 0; c.p0 = 0; c.p1 = 0;
-		for (int b = 0; b < nblk; b++) {
-			int64_t done = 0;
-			while (done < nbytes[b]) {
-				if (c.len > 0 && (c.src + c.len != src_off[b] + done || (size_t)c.len == STAGE_CHUNK)) { c.p1 = pieces.size(); chunks.push_back(c); c.len = 0; }
-				if (c.len == 0) { c.src = src_off[b] + done; c.p0 = pieces.size(); }
-				const int64_t n = std::min<int64_t>(nbytes[b] - done, (int64_t)STAGE_CHUNK - c.len);
-				Piece pc; pc.b = b; pc.boff = done; pc.n = n; pieces.push_back(pc);
-				c.len += n; done += n;
-			}
-		}
-		if (c.len > 0) { c.p1 = pieces.size(); chunks.push_back(c); }
-	}
+	plan_chunks(nblk, src_off, nbytes, pieces, chunks);
+	const int nt = host_copy_threads();
 	auto issue = [&](size_t ci) -> int {
 		const int slot = (int)(ci & 1);
 		if (ring_wait(slot) < 0) { return -1; }
-		CTBD_CUDA(cudaMemcpyAsync(g_ring.buf[slot], (const char*)dptr + chunks[ci].src, (size_t)chunks[ci].len, cudaMemcpyDeviceToHost, rt().stream));
+		CTBD_CUDA(cudaMemcpyAsync(g_ring.buf[slot], (const char*)dptr + chunks[ci].dev, (size_t)chunks[ci].len, cudaMemcpyDeviceToHost, rt().stream));
 		CTBD_CUDA(cudaEventRecord(g_ring.ev[slot], rt().stream));
 		g_ring.busy[slot] = true;
 		return 0;
@@ -278,11 +287,11 @@ int ctbd_d2h_blocks(const void* dptr, int nblk, void* const* hptrs, const int64_
 		const int slot = (int)(ci & 1);
 		if (ci + 1 < chunks.size() && issue(ci + 1) < 0) { return -1; }
 		if (ring_wait(slot) < 0) { return -1; }
-		size_t pos = 0;
-		for (size_t q = chunks[ci].p0; q < chunks[ci].p1; q++) {
-			memcpy((char*)hptrs[pieces[q].b] + pieces[q].boff, (const char*)g_ring.buf[slot] + pos, (size_t)pieces[q].n);
-			pos += (size_t)pieces[q].n;
-		}
+		const char* stage = (const char*)g_ring.buf[slot];
+		const long p0 = (long)chunks[ci].p0, p1 = (long)chunks[ci].p1;
+		/* unpack in parallel: the destination blocks are freshly allocated, so this is where their pages get faulted in */
+		#pragma omp parallel for schedule(dynamic, 4) num_threads(nt) if (p1 - p0 > 8)
+		for (long q = p0; q < p1; q++) { memcpy((char*)hptrs[pieces[q].b] + pieces[q].boff, stage + pieces[q].pos, (size_t)pieces[q].n); }
 	}
 	return 0;
 }

@@ -634,6 +634,28 @@ int ctb_dot_benchmark(const struct block_sparse_tensor* s, const int axrange_s, 
 	return 0;
 }
 
+/* plan-only query of the (sharded) effective Hamiltonian: out[0] = algorithmic flops of rank 'rank' of 'world', out[1..3] = tiles of the
+ * three launches, out[4] = stored entries of this rank's result slice, out[5] = entries of one all-gather slot, out[6] = entries of t1, out[7] = of t2 */
+int ctb_heff_plan_info(const struct block_sparse_tensor* a, const struct block_sparse_tensor* w, const struct block_sparse_tensor* l, const struct block_sparse_tensor* r,
+	int rank, int world, double* out)
+{
+	CTB_CHECK(ctbd_init(-1));
+	const int rank0 = ctb_dist_rank, world0 = ctb_dist_world;
+	struct ctb_tensor* ad = ctb_upload(a); struct ctb_tensor* wd = ctb_upload(w); struct ctb_tensor* ld = ctb_upload(l); struct ctb_tensor* rd = ctb_upload(r);
+	ctb_dist_rank = rank; ctb_dist_world = world;
+	struct ctb_heff h;
+	int rc = ctb_heff_prepare(ad, wd, ld, rd, &h);
+	ctb_dist_rank = rank0; ctb_dist_world = world0;
+	if (rc == 0) {
+		out[0] = h.flops; out[1] = h.p1.ntiles; out[2] = h.p2.ntiles; out[3] = h.p3.ntiles;
+		out[4] = (h.world > 1) ? (double)h.piece[h.rank]->nstore : (double)h.b->nstore;
+		out[5] = (double)h.piece_cap; out[6] = (double)h.t1->nstore; out[7] = (double)h.t2->nstore;
+		ctb_heff_free(&h);
+	}
+	ctb_tensor_free(ad); ctb_tensor_free(wd); ctb_tensor_free(ld); ctb_tensor_free(rd);
+	return rc;
+}
+
 int ctb_get_stats(double* out, int n)
 {
 	const double v[9] = {

@@ -302,24 +302,68 @@ struct ctb_tensor* ctb_env_step_left(const struct ctb_tensor* a, const struct ct
 /* effective Hamiltonian: plans built once per bond, three launches per matvec                     */
 /* ---------------------------------------------------------------------------------------------- */
 
-/* balanced split of a bond among 'world' ranks: the entries of every sector (in order of appearance) are cut into
- * 'world' nearly equal contiguous ranges; rank p gets range p of every sector.  Returns 0 if some rank would stay empty. */
-static int split_bond(const struct ctb_axis* ax, int world, ct_long** ind, ct_long* nind)
+/* Split of the bra bond of r among 'world' ranks.  Every sector is cut into ceil(m / grain) nearly equal contiguous chunks
+ * (grain = one GEMM tile width, so a rank's blocks keep full tiles), each chunk is weighted by the step-1 flops of its
+ * columns (computed from the block structures of a and r), and the chunks are handed out longest-processing-time first.
+ * Deterministic, identical on every rank.  Returns 0 if some rank would stay empty (bond too small to shard). */
+struct shard_chunk { int sec; ct_long pos0, len; double cost; };
+static int cmp_chunk_desc(const void* x, const void* y)
 {
-	for (int p = 0; p < world; p++) { ind[p] = ctb_malloc((size_t)(ax->dim > 0 ? ax->dim : 1) * sizeof(ct_long)); nind[p] = 0; }
-	unsigned char* owner = ctb_malloc((size_t)(ax->dim > 0 ? ax->dim : 1));
+	const struct shard_chunk* a = x; const struct shard_chunk* b = y;
+	if (a->cost != b->cost) { return a->cost > b->cost ? -1 : 1; }
+	if (a->sec != b->sec) { return a->sec < b->sec ? -1 : 1; }
+	return (a->pos0 > b->pos0) - (a->pos0 < b->pos0);
+}
+
+static int split_bond(const struct ctb_tensor* a, const struct ctb_tensor* r, int world, ct_long** ind, ct_long* nind)
+{
+	const struct ctb_axis* ax = &r->ax[2];
+	ct_long grain = 128;
+	const char* env = getenv("CTB_SHARD_GRAIN");
+	if (env != NULL && atol(env) > 0) { grain = atol(env); }
+	/* flops per column of each bra sector: sum over blocks r[Dr, w', Dr' = s] of (rows of a with that Dr sector) * nDr * mw' */
+	double* rows_a = ctb_calloc((size_t)a->ax[2].nsec, sizeof(double));
+	for (int b = 0; b < a->nblk; b++) {
+		int idx[CTB_MAXDIM];
+		ctb_grid_unravel(a, a->blk_grid[b], idx);
+		rows_a[idx[2]] += (double)a->ax[0].secdim[idx[0]] * (double)a->ax[1].secdim[idx[1]];
+	}
+	double* wcol = ctb_calloc((size_t)ax->nsec, sizeof(double));
+	for (int b = 0; b < r->nblk; b++) {
+		int idx[CTB_MAXDIM];
+		ctb_grid_unravel(r, r->blk_grid[b], idx);
+		const int sa = ctb_axis_find_sector(&a->ax[2], r->ax[0].qsec[idx[0]]);
+		if (sa < 0) { continue; }
+		wcol[idx[2]] += rows_a[sa] * (double)r->ax[0].secdim[idx[0]] * (double)r->ax[1].secdim[idx[1]];
+	}
+	/* the balanced chunks */
+	size_t nch = 0, cap = 64;
+	struct shard_chunk* ch = malloc(cap * sizeof(*ch));
 	for (int s = 0; s < ax->nsec; s++) {
 		const ct_long m = ax->secdim[s];
-		for (ct_long j = 0; j < m; j++) {
-			/* position j of the sector belongs to the rank p with floor(m p / W) <= j < floor(m (p + 1) / W) */
-			int p = (int)(((j + 1) * world - 1) / m);
-			while (p > 0 && (m * p) / world > j) { p--; }
-			while (p + 1 < world && (m * (p + 1)) / world <= j) { p++; }
-			owner[ax->log_of[ax->secstart[s] + j]] = (unsigned char)p;
+		ct_long parts = (m + grain - 1) / grain;
+		/* never fewer chunks in total than ranks: small bonds are cut finer */
+		if (ax->dim < grain * world) { parts = (m * world + ax->dim - 1) / ax->dim; if (parts > m) { parts = m; } if (parts < 1) { parts = 1; } }
+		for (ct_long c = 0; c < parts; c++) {
+			const ct_long p0 = (m * c) / parts, p1 = (m * (c + 1)) / parts;
+			if (p1 <= p0) { continue; }
+			if (nch == cap) { cap *= 2; ch = realloc(ch, cap * sizeof(*ch)); }
+			ch[nch].sec = s; ch[nch].pos0 = p0; ch[nch].len = p1 - p0; ch[nch].cost = (double)(p1 - p0) * (wcol[s] > 0 ? wcol[s] : 1.0);
+			nch++;
 		}
 	}
+	qsort(ch, nch, sizeof(*ch), cmp_chunk_desc);
+	double* load = ctb_calloc((size_t)world, sizeof(double));
+	unsigned char* owner = ctb_malloc((size_t)(ax->dim > 0 ? ax->dim : 1));
+	for (size_t c = 0; c < nch; c++) {
+		int best = 0;
+		for (int p = 1; p < world; p++) { if (load[p] < load[best]) { best = p; } }
+		load[best] += ch[c].cost;
+		for (ct_long j = 0; j < ch[c].len; j++) { owner[ax->log_of[ax->secstart[ch[c].sec] + ch[c].pos0 + j]] = (unsigned char)best; }
+	}
+	for (int p = 0; p < world; p++) { ind[p] = ctb_malloc((size_t)(ax->dim > 0 ? ax->dim : 1) * sizeof(ct_long)); nind[p] = 0; }
 	for (ct_long i = 0; i < ax->dim; i++) { const int p = owner[i]; ind[p][nind[p]++] = i; }
-	ctb_free(owner);
+	ctb_free(owner); ctb_free(load); ctb_free(wcol); ctb_free(rows_a); free(ch);
 	for (int p = 0; p < world; p++) { if (nind[p] == 0) { return 0; } }
 	return 1;
 }
@@ -336,7 +380,7 @@ int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, str
 		CTB_REQUIRE(W <= 255);
 		h->ind = ctb_calloc((size_t)W, sizeof(ct_long*));
 		h->nind = ctb_calloc((size_t)W, sizeof(ct_long));
-		if (split_bond(&r->ax[2], W, h->ind, h->nind))
+		if (split_bond(a, r, W, h->ind, h->nind))
 		{
 			h->world = W; h->rank = ctb_dist_rank;
 			h->r_own = ctb_slice((struct ctb_tensor*)r, 2, h->ind[h->rank], h->nind[h->rank]);
@@ -357,6 +401,49 @@ int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, str
 			const size_t esize = ctb_sizeof_dtype(a->dtype);
 			CTB_CHECK(ctbd_malloc(&h->send, (size_t)h->piece_cap * esize));
 			CTB_CHECK(ctbd_malloc(&h->recv, (size_t)h->piece_cap * esize * (size_t)W));
+			/* scatter plan: every stored block of every piece is a set of strided 2-d copies into the matching block of b, one per
+			 * maximal run of consecutive sector positions owned by that rank */
+			{
+				size_t cap = 1024, nd = 0;
+				struct ctbd_copy2d* descs = malloc(cap * sizeof(*descs));
+				for (int p = 0; p < W; p++)
+				{
+					const struct ctb_tensor* pc = h->piece[p];
+					for (int blk = 0; blk < pc->nblk; blk++)
+					{
+						int idx[CTB_MAXDIM];
+						ctb_grid_unravel(pc, pc->blk_grid[blk], idx);
+						const int sfull = ctb_axis_find_sector(&a->ax[2], pc->ax[2].qsec[idx[2]]);
+						CTB_REQUIRE(sfull >= 0);
+						const int ifull[3] = { idx[0], idx[1], sfull };
+						const ct_long dst_blk = a->grid_off[ctb_grid_ravel(a, ifull)];
+						CTB_REQUIRE(dst_blk >= 0);
+						const int rows = pc->ax[0].secdim[idx[0]] * pc->ax[1].secdim[idx[1]];
+						const int np = pc->ax[2].secdim[idx[2]], nfull = a->ax[2].secdim[sfull];
+						int j = 0;
+						while (j < np)
+						{
+							/* position inside the full sector of the j-th piece column of this sector */
+							const ct_long lg0 = h->ind[p][pc->ax[2].log_of[pc->ax[2].secstart[idx[2]] + j]];
+							const int pos0 = a->ax[2].pos_of[lg0];
+							int len = 1;
+							while (j + len < np) {
+								const ct_long lg = h->ind[p][pc->ax[2].log_of[pc->ax[2].secstart[idx[2]] + j + len]];
+								if (a->ax[2].pos_of[lg] != pos0 + len) { break; }
+								len++;
+							}
+							if (nd == cap) { cap *= 2; descs = realloc(descs, cap * sizeof(*descs)); }
+							struct ctbd_copy2d* d = &descs[nd++];
+							d->src_off = (int64_t)p * h->piece_cap + pc->blk_off[blk] + j;
+							d->dst_off = dst_blk + pos0;
+							d->rows = rows; d->cols = len; d->src_ld = np; d->dst_ld = nfull;
+							j += len;
+						}
+					}
+				}
+				CTB_CHECK(ctbd_copy_plan_create(a->dtype, (int)nd, descs, &h->scatter));
+				free(descs);
+			}
 		}
 		else
 		{
@@ -414,19 +501,7 @@ int ctb_heff_exchange(struct ctb_heff* h, void* b_data)
 		/* exchange step: all-gather of the result slices over NVLink, then scatter into the packed layout of b */
 		const size_t esize = ctb_sizeof_dtype(h->b->dtype);
 		CTB_CHECK(ctbd_allgather(h->send, h->recv, (size_t)h->piece_cap * esize));
-		for (int p = 0; p < h->world; p++)
-		{
-			if (h->piece[p]->nstore == 0) { continue; }
-			struct ctbd_remap_args args;
-			memset(&args, 0, sizeof(args));
-			args.op = CTBD_REMAP_UNSLICE;
-			args.i_ax = 2;
-			args.ind = (const int64_t*)h->ind[p];
-			args.scale_ax = -1;
-			args.dst_layout = ctb_tensor_layout(h->b); args.dst = b_data;
-			args.src_layout = ctb_tensor_layout(h->piece[p]); args.src = (const char*)h->recv + (size_t)p * (size_t)h->piece_cap * esize;
-			CTB_CHECK(ctbd_remap(&args));
-		}
+		CTB_CHECK(ctbd_copy_plan_run(h->scatter, h->recv, b_data));
 	}
 	return 0;
 }
@@ -438,6 +513,7 @@ void ctb_heff_free(struct ctb_heff* h)
 	if (h->piece != NULL) { for (int p = 0; p < h->world; p++) { ctb_tensor_free(h->piece[p]); } ctb_free(h->piece); }
 	if (h->ind != NULL) { for (int p = 0; p < h->world; p++) { ctb_free(h->ind[p]); } ctb_free(h->ind); ctb_free(h->nind); }
 	ctb_tensor_free(h->r_own);
+	if (h->scatter != NULL) { ctbd_copy_plan_destroy(h->scatter); }
 	if (h->send != NULL) { ctbd_free(h->send); }
 	if (h->recv != NULL) { ctbd_free(h->recv); }
 	memset(h, 0, sizeof(*h));

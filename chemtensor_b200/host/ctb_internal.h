@@ -202,6 +202,7 @@ struct ctb_heff
 	ct_long* nind;
 	ct_long piece_cap;            /* elements of one all-gather slot (largest piece) */
 	void* send; void* recv;       /* device: own piece; all pieces */
+	void* scatter;                /* device copy plan: gathered pieces -> packed layout of b */
 	double flops_total;           /* algorithmic flops of the whole matvec (all ranks) */
 };
 /* rank / world of this process (ctb_dist_init); world == 1 means no sharding */

@@ -131,6 +131,10 @@ int ctb_heff_benchmark(const struct block_sparse_tensor* a, const struct block_s
 /* micro-benchmark of one contraction r = dot(s, t) (one grouped-GEMM launch), operands device-resident, plan built once */
 int ctb_dot_benchmark(const struct block_sparse_tensor* s, const int axrange_s, const struct block_sparse_tensor* t, const int axrange_t, const int ndim_mult,
 	int warmup, int reps, int flush_l2, double* ms_per_run, double* flops_per_run);
+/* plan-only query of the effective Hamiltonian as rank 'rank' of 'world' would build it (no communicator needed): out[0] flops of the
+ * shard, out[1..3] tiles of the three launches, out[4] entries of the result slice, out[5] entries of an all-gather slot, out[6..7] entries of t1, t2 */
+int ctb_heff_plan_info(const struct block_sparse_tensor* a, const struct block_sparse_tensor* w, const struct block_sparse_tensor* l, const struct block_sparse_tensor* r,
+	int rank, int world, double* out);
 /* statistics of the last dmrg_* call: fills up to 'n' doubles:
  * [0] heff flops, [1] heff calls, [2] env flops, [3] lanczos ms, [4] svd ms, [5] env ms, [6] total ms,
  * [7] longest Lanczos vector, [8] largest bond dimension */

@@ -222,6 +222,18 @@ struct ctbd_remap_args
 
 int ctbd_remap(const struct ctbd_remap_args* args);
 
+/* batched strided 2-d copies with a device-resident descriptor list (built once, run many times):
+ * dst[d.dst_off + i * d.dst_ld + j] = src[d.src_off + i * d.src_ld + j], i < rows, j < cols.
+ * Used to scatter the all-gathered column slices of the sharded effective Hamiltonian into the packed result. */
+struct ctbd_copy2d
+{
+	int64_t src_off, dst_off;
+	int32_t rows, cols, src_ld, dst_ld;
+};
+int ctbd_copy_plan_create(int dtype, int n, const struct ctbd_copy2d* descs_host, void** plan);
+int ctbd_copy_plan_run(void* plan, const void* src, void* dst);
+int ctbd_copy_plan_destroy(void* plan);
+
 /* ---- level-1 kernels for the Lanczos iteration (scalars stay on the device) ----------------- */
 
 /* out[0] = Re sum conj(x_i) y_i, out[1] = Im (0 for real) */

@@ -219,6 +219,29 @@ int ctbd_layout_destroy(void* layout)
 	return 0;
 }
 
+struct emu_copy_plan { int dtype, n; struct ctbd_copy2d* descs; };
+int ctbd_copy_plan_create(int dtype, int n, const struct ctbd_copy2d* descs_host, void** plan)
+{
+	struct emu_copy_plan* p = calloc(1, sizeof(*p));
+	p->dtype = dtype; p->n = n; p->descs = dup_mem(descs_host, (size_t)n * sizeof(*descs_host));
+	*plan = p;
+	return 0;
+}
+int ctbd_copy_plan_run(void* plan, const void* src, void* dst)
+{
+	const struct emu_copy_plan* p = plan;
+	g_launches++;
+	const size_t es = (p->dtype == CTBD_C128) ? 16 : 8;
+	for (int k = 0; k < p->n; k++) {
+		const struct ctbd_copy2d* d = &p->descs[k];
+		for (int i = 0; i < d->rows; i++) {
+			memcpy((char*)dst + (size_t)(d->dst_off + (int64_t)i * d->dst_ld) * es, (const char*)src + (size_t)(d->src_off + (int64_t)i * d->src_ld) * es, (size_t)d->cols * es);
+		}
+	}
+	return 0;
+}
+int ctbd_copy_plan_destroy(void* plan) { struct emu_copy_plan* p = plan; if (p) { free(p->descs); free(p); } return 0; }
+
 int ctbd_remap(const struct ctbd_remap_args* a)
 {
 	g_launches++;
