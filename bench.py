@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("CTB_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
     ap.add_argument("--structure", default="converged", choices=["converged", "random"],
                     help="sector structure of the synthetic operands: measured from converged sweeps (default) or the random-MPS rule")
+    ap.add_argument("--sweep", action="store_true", help="also report two-site DMRG sweep seconds (engine, and reference on the small case)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -314,9 +315,59 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }
+    if args.sweep and world == 1:
+        line["sweep"] = sweep_report(lib)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(wl, flops_total, args.structure)
     print(json.dumps(line), flush=True)
+
+
+def sweep_seconds(lib, model, L, params, sector, D, sweeps=2, lanczos=10, tol=0.0):
+    """Wall seconds per two-site DMRG sweep (the other half of BASELINE.json's metric) through the public dmrg_twosite() on host structs,
+    from the seeded random MPS; also returns the energies so that both arms can be compared."""
+    mpo = workloads.mpo_chain(lib, model, L, params)
+    psi = workloads.random_mps(lib, np.float64, L, mpo.qsite, sector, D, seed=42)
+    en = np.zeros(sweeps); ent = np.zeros(L - 1)
+    t0 = time.perf_counter()
+    rc = lib.dmrg_twosite(mpo.ptr, sweeps, lanczos, tol, D, psi.ptr, en.ctypes.data_as(C.POINTER(C.c_double)), ent.ctypes.data_as(C.POINTER(C.c_double)))
+    dt = time.perf_counter() - t0
+    if rc != 0:
+        return None
+    return {"s_per_sweep": dt / sweeps, "energies": [float(x) for x in en], "max_bond": int(max(psi.bond_dims()))}
+
+
+SWEEP_CASES = [
+    # (name, model, L, params, sector, D, time the reference too?)
+    ("fh_L16_D256", "fermi_hubbard", 16, (1.0, 4.0, 0.0), workloads.encode_qpair(16, 0), 256, True),
+    ("fh_L32_D1024", "fermi_hubbard", 32, (1.0, 4.0, 0.0), workloads.encode_qpair(32, 0), 1024, False),
+]
+
+
+def sweep_report(lib):
+    """Two-site sweep seconds of the engine (and of the unmodified reference on the small case) -- reported, not the headline."""
+    out = []
+    for name, model, L, params, sector, D, with_ref in SWEEP_CASES:
+        rec = {"config": name, "sweeps": 2, "lanczos_iterations": 10, "tol_split": 0.0}
+        ours = sweep_seconds(lib, model, L, params, sector, D)
+        rec["b200"] = ours
+        if with_ref and os.path.exists(REF_SO):
+            code = (
+                "import sys, json\n"
+                f"sys.path.insert(0, {ROOT!r})\n"
+                "import bench\n"
+                "from chemtensor_b200 import cabi\n"
+                f"ref = cabi.CLibrary({REF_SO!r})\n"
+                f"print(json.dumps(bench.sweep_seconds(ref, {model!r}, {L}, {params!r}, {sector}, {D})))\n"
+            )
+            env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+            try:
+                r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
+                rec["reference_cpu"] = json.loads(r.stdout.strip().splitlines()[-1])
+                rec["reference_cpu"]["cores"] = os.cpu_count()
+            except Exception as exc:
+                rec["reference_cpu"] = {"failed": str(exc)}
+        out.append(rec)
+    return out
 
 
 def cpu_baseline(wl: str, flops: float, structure: str = "converged"):

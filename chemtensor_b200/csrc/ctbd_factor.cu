@@ -370,7 +370,7 @@ __global__ void svd_mark_kernel(int nmat, const SvdMat* __restrict__ mats, int w
 
 /* singular values (row norms, sorted descending) and vectors; one CTA per matrix */
 template <typename T>
-__global__ void __launch_bounds__(256) svd_finish_kernel(const SvdMat* __restrict__ mats, const double* __restrict__ scale, const T* __restrict__ G, double* __restrict__ sig_work, int* __restrict__ ord_work,
+__global__ void __launch_bounds__(256) svd_finish_kernel(const SvdMat* __restrict__ mats, const double* __restrict__ scale, const T* __restrict__ G, double* __restrict__ sig_work, double* __restrict__ wn_work, int* __restrict__ ord_work,
 	T* __restrict__ U, T* __restrict__ Vh, double* __restrict__ S)
 {
 	const SvdMat mt = mats[blockIdx.x];
@@ -378,14 +378,16 @@ __global__ void __launch_bounds__(256) svd_finish_kernel(const SvdMat* __restric
 	const int R = mt.R, C = mt.C, ld = C + R;
 	const T* g = G + mt.g_off;
 	double* sig = sig_work + mt.s_off;
+	double* wn = wn_work + mt.s_off;      /* 1 / norm of the accumulated-rotation rows: removes the O(#rotations) eps drift of their length */
 	int* ord = ord_work + mt.s_off;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
 	for (int i = warp; i < R; i += nwarp) {
-		double s = 0;
+		double s = 0, w = 0;
 		for (int k = lane; k < C; k += 32) { s += abs2(g[(int64_t)i * ld + k]); }
+		for (int k = lane; k < R; k += 32) { w += abs2(g[(int64_t)i * ld + C + k]); }
 		#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); }
-		if (lane == 0) { sig[i] = sqrt(s); }
+		for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); w += __shfl_xor_sync(0xffffffffu, w, o); }
+		if (lane == 0) { sig[i] = sqrt(s); wn[i] = (w > 0) ? 1.0 / sqrt(w) : 1.0; }
 	}
 	__syncthreads();
 	/* rank sort, descending, ties by index */
@@ -406,13 +408,13 @@ __global__ void __launch_bounds__(256) svd_finish_kernel(const SvdMat* __restric
 		const int r = (int)(e / n), k = (int)(e % n);
 		const int i = ord[r];
 		if (wide) { const double s = sig[i]; vh[e] = smul(s > 0 ? 1.0 / s : 0.0, g[(int64_t)i * ld + k]); }
-		else      { vh[e] = g[(int64_t)i * ld + C + k]; }
+		else      { vh[e] = smul(wn[i], g[(int64_t)i * ld + C + k]); }
 	}
 	/* U: m x R row-major; U[k][r] */
 	for (int64_t e = threadIdx.x; e < (int64_t)m * R; e += blockDim.x) {
 		const int k = (int)(e / R), r = (int)(e % R);
 		const int i = ord[r];
-		if (wide) { u[e] = cj(g[(int64_t)i * ld + C + k]); }
+		if (wide) { u[e] = smul(wn[i], cj(g[(int64_t)i * ld + C + k])); }
 		else      { const double s = sig[i]; u[e] = smul(s > 0 ? 1.0 / s : 0.0, cj(g[(int64_t)i * ld + k])); }
 	}
 }
@@ -434,7 +436,8 @@ __global__ void __launch_bounds__(SVD_SMEM_THREADS) svd_smem_kernel(const SvdMat
 	const bool wide = (m <= n);
 	T* g = reinterpret_cast<T*>(svd_smem_raw);
 	double* sq = reinterpret_cast<double*>(g + (size_t)R * ld);
-	int* ord = reinterpret_cast<int*>(sq + R);
+	double* wn = sq + R;
+	int* ord = reinterpret_cast<int*>(wn + R);
 	__shared__ int s_rot;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = SVD_SMEM_THREADS / 32;
 	const T* a = A + mt.a_off;
@@ -505,13 +508,14 @@ __global__ void __launch_bounds__(SVD_SMEM_THREADS) svd_smem_kernel(const SvdMat
 		if (nrot == 0) { break; }
 	}
 
-	/* singular values = exact final row norms, sorted descending (ties by index) */
+	/* singular values = exact final row norms, sorted descending (ties by index); the accumulated-rotation rows are re-normalised */
 	for (int i = warp; i < R; i += nwarp) {
-		double s = 0;
+		double s = 0, w = 0;
 		for (int k = lane; k < C; k += 32) { s += abs2(g[i * ld + k]); }
+		for (int k = lane; k < R; k += 32) { w += abs2(g[i * ld + C + k]); }
 		#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); }
-		if (lane == 0) { sq[i] = sqrt(s); }
+		for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); w += __shfl_xor_sync(0xffffffffu, w, o); }
+		if (lane == 0) { sq[i] = sqrt(s); wn[i] = (w > 0) ? 1.0 / sqrt(w) : 1.0; }
 	}
 	__syncthreads();
 	for (int i = tid; i < R; i += SVD_SMEM_THREADS) {
@@ -528,12 +532,12 @@ __global__ void __launch_bounds__(SVD_SMEM_THREADS) svd_smem_kernel(const SvdMat
 		const int r = e / n, k = e % n;
 		const int i = ord[r];
 		if (wide) { const double s = sq[i]; vh[e] = smul(s > 0 ? 1.0 / s : 0.0, g[i * ld + k]); }
-		else      { vh[e] = g[i * ld + C + k]; }
+		else      { vh[e] = smul(wn[i], g[i * ld + C + k]); }
 	}
 	for (int e = tid; e < m * R; e += SVD_SMEM_THREADS) {
 		const int k = e / R, r = e % R;
 		const int i = ord[r];
-		if (wide) { u[e] = cj(g[i * ld + C + k]); }
+		if (wide) { u[e] = smul(wn[i], cj(g[i * ld + C + k])); }
 		else      { const double s = sq[i]; u[e] = smul(s > 0 ? 1.0 / s : 0.0, cj(g[i * ld + k])); }
 	}
 }
@@ -549,7 +553,7 @@ static int svd_batched_impl(int nmat_all, const ctbd_mat_desc* descs_all, const 
 	for (int b = 0; b < nmat_all; b++)
 	{
 		const int R = std::min(descs_all[b].m, descs_all[b].n), C = std::max(descs_all[b].m, descs_all[b].n);
-		const size_t need = (size_t)R * (C + R) * sizeof(T) + (size_t)R * (sizeof(double) + sizeof(int)) + 16;
+		const size_t need = (size_t)R * (C + R) * sizeof(T) + (size_t)R * (2 * sizeof(double) + sizeof(int)) + 16;
 		if (need <= SVD_SMEM_LIMIT && getenv("CTB_SVD_NO_SMEM") == nullptr) {
 			SvdMat mt; memset(&mt, 0, sizeof(mt));
 			mt.a_off = descs_all[b].a_off; mt.u_off = descs_all[b].o0_off; mt.vh_off = descs_all[b].o1_off; mt.s_off = descs_all[b].s_off;
@@ -600,7 +604,7 @@ static int svd_batched_impl(int nmat_all, const ctbd_mat_desc* descs_all, const 
 	if (ctbd_malloc(&d_G, (size_t)g_total * sizeof(T)) < 0) { return -1; }
 	/* ints: rot_count[nmat], done[nmat], pending[1], ord[smax] */
 	if (ctbd_malloc(&d_int, (size_t)(2 * nmat + 1 + smax) * sizeof(int)) < 0) { return -1; }
-	if (ctbd_malloc(&d_sig, (size_t)smax * sizeof(double)) < 0) { return -1; }
+	if (ctbd_malloc(&d_sig, (size_t)2 * smax * sizeof(double)) < 0) { return -1; }
 	int* rot_count = (int*)d_int; int* done = rot_count + nmat; int* pending = done + nmat; int* ord = pending + 1;
 
 	int64_t maxel = 0;
@@ -685,7 +689,7 @@ static int svd_batched_impl(int nmat_all, const ctbd_mat_desc* descs_all, const 
 	}
 	if (rc == 0)
 	{
-		svd_finish_kernel<T><<<nmat, 256, 0, rt().stream>>>((const SvdMat*)d_mats, (const double*)d_scale, (const T*)d_G, (double*)d_sig, ord, (T*)U, (T*)Vh, S);
+		svd_finish_kernel<T><<<nmat, 256, 0, rt().stream>>>((const SvdMat*)d_mats, (const double*)d_scale, (const T*)d_G, (double*)d_sig, (double*)d_sig + smax, ord, (T*)U, (T*)Vh, S);
 		rt().launches++;
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) { rc = fail("svd_finish_kernel", e, __FILE__, __LINE__); }

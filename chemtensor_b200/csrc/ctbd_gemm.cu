@@ -210,6 +210,69 @@ __device__ __forceinline__ void load_tile(T* __restrict__ S, const T* __restrict
 	}
 }
 
+
+/* Fast operand copy for one pipeline step: every thread owns a FIXED set of 16-byte chunks of the tile, so the per-step work is
+ * one pointer increment, one size clamp and the LDGSTS per chunk (the generic load_tile above recomputes indices and bounds).
+ * Requires 16-byte aligned chunks (complex128 always; real when offsets and leading dimension are even).
+ *   KIN: chunk i of the thread = row xr + i*RP of the tile, columns [kc, kc + EPC): global p + i*RP*ld, valid rows by 'xmask',
+ *        bytes limited by the remaining k extent 'krem';
+ *   XIN: chunk i = k-row kr + i*RP, columns [xc, xc + EPC): global p + i*RP*ld, valid while kr + i*RP < krem, 'xbytes' fixed per tile. */
+template <typename T, bool KIN, int BX, int BK, int SK, int SX, int NT>
+struct FastCopy
+{
+	static constexpr int EPC = 16 / (int)sizeof(T);                 /* elements per 16-byte chunk */
+	static constexpr int CPR = (KIN ? BK : BX) / EPC;               /* chunks per tile row */
+	static constexpr int RP  = NT / CPR;                            /* tile rows covered per pass of the CTA */
+	static constexpr int NC  = (KIN ? BX : BK) / RP;                /* chunks per thread */
+	static_assert(NT % CPR == 0 && (KIN ? BX : BK) % RP == 0 && NC >= 1 && NC <= 32, "tile / thread-count mismatch");
+
+	/* tile-constant part: called when the producer enters a segment */
+	__device__ __forceinline__ static const T* base(const T* g, int64_t off, int ld, int x0, int k0)
+	{
+		const int r = threadIdx.x / CPR, c = (threadIdx.x % CPR) * EPC;
+		return KIN ? g + off + (int64_t)(x0 + r) * ld + (k0 + c) : g + off + (int64_t)(k0 + r) * ld + (x0 + c);
+	}
+	/* KIN: bit i set when row xr + i*RP is inside the block;  XIN: bytes of this thread's column chunk (0, 8 or 16) */
+	__device__ __forceinline__ static unsigned xinfo(int x0, int X)
+	{
+		if constexpr (KIN) {
+			const int r = threadIdx.x / CPR;
+			unsigned m = 0;
+			#pragma unroll
+			for (int i = 0; i < NC; i++) { m |= (x0 + r + i * RP < X) ? (1u << i) : 0u; }
+			return m;
+		}
+		else {
+			const int c = (threadIdx.x % CPR) * EPC;
+			const int rem = X - (x0 + c);
+			return (unsigned)(rem >= EPC ? 16 : (rem > 0 ? rem * (int)sizeof(T) : 0));
+		}
+	}
+	__device__ __forceinline__ static void copy(T* __restrict__ S, const T* __restrict__ p, int ld, unsigned xi, int krem)
+	{
+		const int r = threadIdx.x / CPR, c = (threadIdx.x % CPR) * EPC;
+		const unsigned sbase = (unsigned)__cvta_generic_to_shared(S) + (unsigned)((KIN ? r * SK + c : r * SX + c) * (int)sizeof(T));
+		constexpr unsigned SSTEP = (unsigned)(RP * (KIN ? SK : SX) * (int)sizeof(T));
+		const int64_t gstep = (int64_t)RP * ld;
+		if constexpr (KIN) {
+			const int kb = krem - c;                                    /* elements of this chunk still inside the k extent */
+			const int nb = kb >= EPC ? 16 : (kb > 0 ? kb * (int)sizeof(T) : 0);
+			#pragma unroll
+			for (int i = 0; i < NC; i++) {
+				const int bytes = ((xi >> i) & 1u) ? nb : 0;
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(sbase + i * SSTEP), "l"(p + i * gstep), "r"(bytes));
+			}
+		}
+		else {
+			#pragma unroll
+			for (int i = 0; i < NC; i++) {
+				const int bytes = (r + i * RP < krem) ? (int)xi : 0;
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(sbase + i * SSTEP), "l"(p + i * gstep), "r"(bytes));
+			}
+		}
+	}
+};
+
 struct GemmArgs
 {
 	const GemmTile* tiles;
@@ -262,17 +325,36 @@ __global__ void __launch_bounds__(Cfg::NT) grouped_gemm_kernel(const GemmArgs ar
 		}
 	};
 	producer_enter_tile();
+	/* per-segment state of the fast copy path (16-byte aligned chunks owned by fixed threads) */
+	typedef FastCopy<T, A_KC,  BM, BK, SK, SXA, NT> FcA;
+	typedef FastCopy<T, !B_NC, BN, BK, SK, SXB, NT> FcB;
+	const T* fa_p = nullptr; const T* fb_p = nullptr;
+	unsigned fa_x = 0, fb_x = 0;
+	bool fa_ok = false, fb_ok = false;
+	auto seg_setup = [&]() {
+		fa_ok = CPLX || (((psg.a_off + args.a_odd) | (int64_t)psg.lda) & 1) == 0;
+		fb_ok = (args.b_rowtab == nullptr) && (CPLX || (((psg.b_off + args.b_odd) | (int64_t)psg.ldb) & 1) == 0);
+		if (!A_KC) { fa_ok = fa_ok && (CPLX || ((p_m0 & 1) == 0)); }
+		if (B_NC)  { fb_ok = fb_ok && (CPLX || ((p_n0 & 1) == 0)); }
+		fa_p = FcA::base(Ag, psg.a_off, psg.lda, p_m0, 0); fa_x = FcA::xinfo(p_m0, p_M);
+		fb_p = FcB::base(Bg, psg.b_off, psg.ldb, p_n0, 0); fb_x = FcB::xinfo(p_n0, p_N);
+	};
+	if (pt < qe) { seg_setup(); }
 	auto issue = [&](int stage) {
-		const bool va = !CPLX && (((psg.a_off + args.a_odd) | (int64_t)psg.lda) & 1) == 0;
-		const bool vb = !CPLX && (((psg.b_off + args.b_odd) | (int64_t)psg.ldb) & 1) == 0;
-		load_tile<T, A_KC,  BM, BK, SK, SXA, NT>(As + (size_t)stage * Cfg::A_ELEMS, Ag, psg.a_off, psg.lda, p_m0, p_M, pk0, psg.k, va);
-		if constexpr (B_NC) { load_tile<T, false, BN, BK, SK, SXB, NT>(Bs + (size_t)stage * Cfg::B_ELEMS, Bg, psg.b_off, psg.ldb, p_n0, p_N, pk0, psg.k, vb, args.b_rowtab, args.b_odd); }
-		else                { load_tile<T, true,  BN, BK, SK, SXB, NT>(Bs + (size_t)stage * Cfg::B_ELEMS, Bg, psg.b_off, psg.ldb, p_n0, p_N, pk0, psg.k, vb); }
+		const int krem = psg.k - pk0;
+		if (fa_ok) { FcA::copy(As + (size_t)stage * Cfg::A_ELEMS, fa_p, psg.lda, fa_x, krem); fa_p += A_KC ? (int64_t)BK : (int64_t)BK * psg.lda; }
+		else { load_tile<T, A_KC, BM, BK, SK, SXA, NT>(As + (size_t)stage * Cfg::A_ELEMS, Ag, psg.a_off, psg.lda, p_m0, p_M, pk0, psg.k, false); }
+		if (fb_ok) { FcB::copy(Bs + (size_t)stage * Cfg::B_ELEMS, fb_p, psg.ldb, fb_x, krem); fb_p += B_NC ? (int64_t)BK * psg.ldb : (int64_t)BK; }
+		else {
+			if constexpr (B_NC) { load_tile<T, false, BN, BK, SK, SXB, NT>(Bs + (size_t)stage * Cfg::B_ELEMS, Bg, psg.b_off, psg.ldb, p_n0, p_N, pk0, psg.k, false, args.b_rowtab, args.b_odd); }
+			else                { load_tile<T, true,  BN, BK, SK, SXB, NT>(Bs + (size_t)stage * Cfg::B_ELEMS, Bg, psg.b_off, psg.ldb, p_n0, p_N, pk0, psg.k, false); }
+		}
 		pk0 += BK;
 		if (pk0 >= psg.k) {
 			pk0 = 0; ps++;
 			if (ps < p_seg_end) { psg = args.segs[ps]; }
 			else { pt++; producer_enter_tile(); }
+			if (pt < qe) { seg_setup(); }
 		}
 	};
 
