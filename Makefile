@@ -42,7 +42,7 @@ $(BUILD)/emu/ctbd_emu.o: tests/emu/ctbd_emu.c include/ctb_device.h
 	$(CC) $(CFLAGS) -c $< -o $@
 
 $(EMU): $(HOST_OBJ) $(BUILD)/emu/ctbd_emu.o
-	$(CC) -shared -Wl,-Bsymbolic -Wl,-soname,libctb_hostlogic_emu.so -Wl,--no-undefined -o $@ $^ -lm
+	$(CC) -shared -Wl,-Bsymbolic -Wl,-soname,libctb_hostlogic_emu.so -Wl,--no-undefined -o $@ $^ -lm -lrt
 
 oracle:
 	@if [ -d /root/reference/src ]; then $(MAKE) -C oracle; else echo "reference sources absent: using prebuilt oracle/_ref"; fi

@@ -298,10 +298,27 @@ def main():
     kdom = int(np.argmax([step_ms[i] for i in range(3)]))
     k_tf = step_fl[kdom] / (step_ms[kdom] * 1e-3) / 1e12
     names = ["A.R (step 1)", "W.(AR) (step 2)", "L.(WAR) (step 3)"]
-    roofline = {"bound": "tensor", "achieved": k_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (k_tf / fp64_peak) if fp64_peak > 0 else None, "traffic": None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if world == 1 and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("workload") == wl and tj.get("structure") == args.structure:
+            kk = tj["kernels"][["step1_grouped_gemm", "step2_mix_kernel", "step3_grouped_gemm"][kdom]]
+            traffic = kk["dram_read_bytes"] + kk["dram_write_bytes"]      # bytes per launch of the dominant kernel, from the committed ncu capture
+    roofline = {"bound": "tensor", "achieved": k_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (k_tf / fp64_peak) if fp64_peak > 0 else None, "traffic": traffic,
                 "kernel": f"grouped_gemm_kernel<double> of {names[kdom]}", "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "per_step_ms": [step_ms[i] for i in range(3)], "per_step_tflops": [step_fl[i] / (step_ms[i] * 1e-3) / 1e12 if step_ms[i] > 0 else None for i in range(3)],
-                "matvec_frac_of_fp64_peak": (flops_total / world / (t_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak > 0 else None}
+                "matvec_frac_of_fp64_peak": (flops_total / world / (t_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak > 0 else None,
+                "exchange_ms": (ms.value - sum(step_ms[i] for i in range(3))) if world > 1 else 0.0}
+    info = (C.c_double * 8)()
+    if lib.ctb_heff_plan_info(a.ptr, w.ptr, l.ptr, r.ptr, rank, world, info) == 0 and step_ms[1] > 0:
+        esize_ = np.dtype(dtype).itemsize
+        mix_bytes = (info[6] + info[7]) * esize_      # one read of t1 + one write of t2 (algorithmic bytes of the MPO-mixing launch)
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        roofline["secondary"] = {"kernel": "mix_kernel<double> of W.(AR) (step 2)", "bound": "hbm", "achieved": mix_bytes / (step_ms[1] * 1e-3) / 1e9, "peak": hbm_peak,
+                                 "unit": "GB/s", "frac": mix_bytes / (step_ms[1] * 1e-3) / 1e9 / hbm_peak, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                                 "algorithmic_bytes": mix_bytes}
     line = {
         "metric": "heff_matvec_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if dtype == np.float64 else "c128",

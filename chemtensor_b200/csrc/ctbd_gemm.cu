@@ -284,6 +284,8 @@ struct GemmArgs
 	int conj_a, conj_b;
 	int a_odd, b_odd;     /* operand base pointer is 8 (mod 16): shifts the parity test of the 16-byte copy path */
 	const int64_t* b_rowtab;   /* optional: B rows gathered through a row table, seg.b_off indexes it (merged-row plans) */
+	int ndst;                  /* >= 1: additional destinations of the epilogue (peer-mapped buffers of the other GPUs) follow */
+	void* Cx[7];
 };
 
 template <typename T, typename Cfg, bool A_KC, bool B_NC>
@@ -454,13 +456,19 @@ __global__ void __launch_bounds__(Cfg::NT) grouped_gemm_kernel(const GemmArgs ar
 			for (int j = 0; j < NI; j++)
 			{
 				const int gc = n0 + wn0 + 8 * j + 2 * lc;
-				if constexpr (!CPLX) {
-					if (gc < N)     { Cg[ro + coltab[gc]]     = acc[i][j][0]; }
-					if (gc + 1 < N) { Cg[ro + coltab[gc + 1]] = acc[i][j][1]; }
-				}
-				else {
-					if (gc < N)     { Cg[ro + coltab[gc]]     = make_double2(acc[i][j][0], acc[i][j][2]); }
-					if (gc + 1 < N) { Cg[ro + coltab[gc + 1]] = make_double2(acc[i][j][1], acc[i][j][3]); }
+				T v0, v1;
+				if constexpr (!CPLX) { v0 = acc[i][j][0]; v1 = acc[i][j][1]; }
+				else { v0 = make_double2(acc[i][j][0], acc[i][j][2]); v1 = make_double2(acc[i][j][1], acc[i][j][3]); }
+				const int64_t o0 = out.c_off + ro + (gc < N ? coltab[gc] : 0), o1 = out.c_off + ro + (gc + 1 < N ? coltab[gc + 1] : 0);
+				if (gc < N)     { Cg[o0 - out.c_off] = v0; }
+				if (gc + 1 < N) { Cg[o1 - out.c_off] = v1; }
+				if (args.ndst > 1) {
+					/* fused all-gather: the same element goes to the peer-mapped result buffers of the other GPUs (posted NVLink stores) */
+					for (int d = 0; d < args.ndst - 1; d++) {
+						T* __restrict__ Cp = reinterpret_cast<T*>(args.Cx[d]);
+						if (gc < N)     { Cp[o0] = v0; }
+						if (gc + 1 < N) { Cp[o1] = v1; }
+					}
 				}
 			}
 		}
@@ -583,7 +591,8 @@ __global__ void __launch_bounds__(MIX_THREADS) mix_kernel(const MixArgs args)
 
 /* real:    0 = 64x64 (4 warps of 32x32), 1 = 32x32 (4 warps of 16x16), 2 = 128x128 (8 warps of 64x32),
  *          3 = 64x128 (8 warps of 32x32), 4 = 32x128 (4 warps of 32x32, BK 8) for skinny M,
- *          5 = 64x128 (4 warps of 32x64: tile and warp shape of cuBLAS' cutlass_80_tensorop_d884gemm_64x128_16x3)
+ *          5 = 64x128 (4 warps of 32x64: tile and warp shape of cuBLAS' cutlass_80_tensorop_d884gemm_64x128_16x3),
+ *          6 = 64x64 with 3 stages (4 CTAs per SM instead of 2)
  * complex: 0 = 64x32 (4 warps of 32x16), 1 = 32x32 (4 warps of 16x16), 2 = 32x64 (4 warps of 32x16, BK 8) */
 typedef TileCfg<double, 64, 64, 32, 32, 4>      CfgD0;
 typedef TileCfg<double, 32, 32, 16, 16, 4>      CfgD1;
@@ -591,6 +600,7 @@ typedef TileCfg<double, 128, 128, 64, 32, 3>    CfgD2;
 typedef TileCfg<double, 64, 128, 32, 32, 3>     CfgD3;
 typedef TileCfg<double, 32, 128, 32, 32, 4, 8>  CfgD4;
 typedef TileCfg<double, 64, 128, 32, 64, 3>     CfgD5;
+typedef TileCfg<double, 64, 64, 32, 32, 3>      CfgD6;
 typedef TileCfg<double2, 64, 32, 32, 16, 3>     CfgZ0;
 typedef TileCfg<double2, 32, 32, 16, 16, 3>     CfgZ1;
 typedef TileCfg<double2, 32, 64, 32, 16, 4, 8>  CfgZ2;
@@ -598,8 +608,8 @@ typedef TileCfg<double2, 32, 64, 32, 16, 4, 8>  CfgZ2;
 /* eff: relative cost per padded multiply-add of the class */
 struct ClassShape { int bm, bn, bk; double eff; };
 /* eff from the measured large-block throughput of each class (tools/gemm_sweep.py, profiles/) */
-static const ClassShape g_shapes_d[6] = { { 64, 64, 16, 1.0 }, { 32, 32, 16, 1.05 }, { 128, 128, 16, 0.88 }, { 64, 128, 16, 0.82 }, { 32, 128, 8, 0.95 }, { 64, 128, 16, 0.80 } };
-static const ClassShape g_shapes_z[3] = { { 64, 32, 16, 1.0 }, { 32, 32, 16, 1.3 }, { 32, 64, 8, 1.1 } };
+static const ClassShape g_shapes_d[7] = { { 64, 64, 16, 1.03 }, { 32, 32, 16, 1.22 }, { 128, 128, 16, 1.09 }, { 64, 128, 16, 1.075 }, { 32, 128, 8, 1.08 }, { 64, 128, 16, 1.0 }, { 64, 64, 16, 1.04 } };
+static const ClassShape g_shapes_z[3] = { { 64, 32, 16, 1.0 }, { 32, 32, 16, 1.06 }, { 32, 64, 8, 1.03 } };
 
 template <typename T, typename Cfg>
 static void (*select_kernel(const GemmPlan* p))(const GemmArgs)
@@ -630,7 +640,7 @@ static int launch_cfg(const GemmPlan* p, const GemmArgs& args)
 #define CTBD_GEMM_DISPATCH(FN, ...) \
 	(p->dtype == CTBD_F64 \
 		? (p->cfg == 0 ? FN<double, CfgD0>(__VA_ARGS__) : p->cfg == 1 ? FN<double, CfgD1>(__VA_ARGS__) : p->cfg == 2 ? FN<double, CfgD2>(__VA_ARGS__) \
-			: p->cfg == 3 ? FN<double, CfgD3>(__VA_ARGS__) : p->cfg == 4 ? FN<double, CfgD4>(__VA_ARGS__) : FN<double, CfgD5>(__VA_ARGS__)) \
+			: p->cfg == 3 ? FN<double, CfgD3>(__VA_ARGS__) : p->cfg == 4 ? FN<double, CfgD4>(__VA_ARGS__) : p->cfg == 5 ? FN<double, CfgD5>(__VA_ARGS__) : FN<double, CfgD6>(__VA_ARGS__)) \
 		: (p->cfg == 0 ? FN<double2, CfgZ0>(__VA_ARGS__) : p->cfg == 1 ? FN<double2, CfgZ1>(__VA_ARGS__) : FN<double2, CfgZ2>(__VA_ARGS__)))
 
 } // namespace ctbd
@@ -701,7 +711,7 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 		return 0;
 	}
 	const ClassShape* shapes = cplx ? g_shapes_z : g_shapes_d;
-	const int nshapes = cplx ? 3 : 6;
+	const int nshapes = cplx ? 3 : 7;
 
 	/* tile class with the shortest estimated launch: for every class the tiles are packed longest-processing-time-first into
 	 * the resident CTA slots (sm_count x occupancy) and the makespan is priced with the class' measured cost per multiply-add;
@@ -875,6 +885,25 @@ int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
 	args.conj_a = p->conj_a; args.conj_b = p->conj_b;
 	args.a_odd = (int)(((uintptr_t)args.A >> 3) & 1); args.b_odd = (int)(((uintptr_t)args.B >> 3) & 1);
 	args.b_rowtab = p->b_rowtab;
+	args.ndst = 1;
+	return CTBD_GEMM_DISPATCH(launch_cfg, p, args);
+}
+
+int ctbd_gemm_run_multi(void* plan, const void* A, const void* B, int ndst, void* const* Cs)
+{
+	GemmPlan* p = (GemmPlan*)plan;
+	if (ndst < 1 || ndst > 8) { return fail_msg("grouped GEMM: between 1 and 8 destinations"); }
+	if (p->n_mix_tiles > 0) { return fail_msg("grouped GEMM: the mixing form has a single destination"); }
+	if (p->ntiles == 0) { return 0; }
+	GemmArgs args;
+	args.tiles = p->tiles; args.queue = p->queue;
+	args.outs = p->outs; args.segs = p->segs; args.tab = p->tab;
+	args.A = (p->a_packed != nullptr) ? p->a_packed : A; args.B = B; args.C = Cs[0];
+	args.conj_a = p->conj_a; args.conj_b = p->conj_b;
+	args.a_odd = (int)(((uintptr_t)args.A >> 3) & 1); args.b_odd = (int)(((uintptr_t)args.B >> 3) & 1);
+	args.b_rowtab = p->b_rowtab;
+	args.ndst = ndst;
+	for (int d = 1; d < ndst; d++) { args.Cx[d - 1] = Cs[d]; }
 	return CTBD_GEMM_DISPATCH(launch_cfg, p, args);
 }
 

@@ -377,6 +377,101 @@ int ctbd_allgather(const void* sendbuf, void* recvbuf, size_t bytes_per_rank)
 	return rc == 0 ? 0 : nccl_fail("ncclAllGather", rc);
 }
 
+int ctbd_barrier(void)
+{
+	if (g_world == 1) { return 0; }
+	/* an 8-byte all-gather on the stream: completes on a rank only after every rank has reached it, and kernel boundaries make the
+	 * peer stores issued before it visible system-wide */
+	static void* scratch = nullptr;
+	if (scratch == nullptr) { if (ctbd_malloc(&scratch, (size_t)8 * (size_t)(g_world + 1)) < 0) { return -1; } }
+	return ctbd_allgather(scratch, (char*)scratch + 8, 8);
+}
+
+namespace {
+struct PeerBuffer { void* local = nullptr; std::vector<void*> ptrs; };
+}
+
+int ctbd_peer_buffer_create(size_t bytes, void** handle)
+{
+	CTBD_REQUIRE_INIT();
+	*handle = nullptr;
+	if (g_world == 1 || g_comm == nullptr) { return fail_msg("peer buffer: needs the NCCL communicator of ctbd_dist_init"); }
+	if (getenv("CTB_NO_PEER") != nullptr) { return fail_msg("peer buffer: disabled by CTB_NO_PEER"); }
+	PeerBuffer* pb = new PeerBuffer();
+	pb->ptrs.assign((size_t)g_world, nullptr);
+	/* plain cudaMalloc: pool memory is not exportable through legacy CUDA IPC */
+	cudaError_t e = cudaMalloc(&pb->local, bytes > 0 ? bytes : 256);
+	if (e != cudaSuccess) { delete pb; return fail("cudaMalloc (peer buffer)", e, __FILE__, __LINE__); }
+	cudaIpcMemHandle_t mine;
+	e = cudaIpcGetMemHandle(&mine, pb->local);
+	int ok = (e == cudaSuccess) ? 1 : 0;
+	/* exchange the handles (and the success flags) with the collective itself */
+	const size_t slot = 128;
+	static_assert(sizeof(cudaIpcMemHandle_t) + sizeof(int) <= 128, "handle slot too small");
+	std::vector<unsigned char> hbuf(slot * (size_t)(g_world + 1), 0);
+	memcpy(hbuf.data(), &mine, sizeof(mine));
+	memcpy(hbuf.data() + sizeof(mine), &ok, sizeof(int));
+	void* dbuf = nullptr;
+	if (ctbd_malloc(&dbuf, slot * (size_t)(g_world + 1)) < 0) { cudaFree(pb->local); delete pb; return -1; }
+	int rc = ctbd_h2d(dbuf, hbuf.data(), slot);
+	if (rc == 0) { rc = ctbd_allgather(dbuf, (char*)dbuf + slot, slot); }
+	if (rc == 0) { rc = ctbd_d2h(hbuf.data() + slot, (char*)dbuf + slot, slot * (size_t)g_world); }
+	ctbd_free(dbuf);
+	if (rc < 0) { cudaFree(pb->local); delete pb; return -1; }
+	bool all_ok = true;
+	for (int p = 0; p < g_world; p++) { int f = 0; memcpy(&f, hbuf.data() + slot * (size_t)(p + 1) + sizeof(mine), sizeof(int)); all_ok = all_ok && (f == 1); }
+	for (int p = 0; p < g_world && all_ok; p++) {
+		if (p == g_rank) { pb->ptrs[p] = pb->local; continue; }
+		cudaIpcMemHandle_t hp;
+		memcpy(&hp, hbuf.data() + slot * (size_t)(p + 1), sizeof(hp));
+		e = cudaIpcOpenMemHandle(&pb->ptrs[p], hp, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) { all_ok = false; (void)cudaGetLastError(); }
+	}
+	/* every rank must take the same decision: agree on success with one more tiny all-gather */
+	{
+		int flag = all_ok ? 1 : 0;
+		std::vector<int> flags((size_t)g_world * 2 + 2, 0);
+		void* dflag = nullptr;
+		if (ctbd_malloc(&dflag, 8 * (size_t)(g_world + 1)) < 0) { all_ok = false; }
+		else {
+			long long f64 = flag;
+			std::vector<long long> all((size_t)g_world + 1, 0);
+			all[0] = f64;
+			if (ctbd_h2d(dflag, all.data(), 8) < 0 || ctbd_allgather(dflag, (char*)dflag + 8, 8) < 0 || ctbd_d2h(all.data() + 1, (char*)dflag + 8, 8 * (size_t)g_world) < 0) { all_ok = false; }
+			else { for (int p = 0; p < g_world; p++) { all_ok = all_ok && (all[(size_t)p + 1] == 1); } }
+			ctbd_free(dflag);
+		}
+	}
+	if (!all_ok) {
+		for (int p = 0; p < g_world; p++) { if (p != g_rank && pb->ptrs[p] != nullptr) { cudaIpcCloseMemHandle(pb->ptrs[p]); } }
+		cudaFree(pb->local); delete pb;
+		return fail_msg("peer buffer: CUDA IPC mapping of the peers failed");
+	}
+	*handle = pb;
+	return 0;
+}
+
+int ctbd_peer_buffer_ptrs(void* handle, void** ptrs)
+{
+	PeerBuffer* pb = (PeerBuffer*)handle;
+	for (int p = 0; p < g_world; p++) { ptrs[p] = pb->ptrs[(size_t)p]; }
+	return 0;
+}
+
+int ctbd_peer_buffer_destroy(void* handle)
+{
+	PeerBuffer* pb = (PeerBuffer*)handle;
+	if (pb == nullptr) { return 0; }
+	cudaStreamSynchronize(rt().stream);
+	for (int p = 0; p < (int)pb->ptrs.size(); p++) { if (p != g_rank && pb->ptrs[(size_t)p] != nullptr) { cudaIpcCloseMemHandle(pb->ptrs[(size_t)p]); } }
+	/* peers may still be unmapping: make sure nobody writes any more before the memory goes away */
+	ctbd_barrier();
+	cudaStreamSynchronize(rt().stream);
+	cudaFree(pb->local);
+	delete pb;
+	return 0;
+}
+
 int ctbd_d2d(void* dst, const void* src, size_t bytes)
 {
 	if (bytes == 0) { return 0; }

@@ -25,7 +25,9 @@ int ctb_dist_init(int rank, int world, const void* unique_id)
 	return 0;
 }
 int ctb_dist_set_allgather(ctbd_allgather_fn fn, void* ctx) { return ctbd_dist_set_allgather(fn, ctx); }
-int ctb_dist_finalize(void) { ctb_dist_rank = 0; ctb_dist_world = 1; return ctbd_dist_finalize(); }
+/* out[0] = rank, out[1] = world, out[2] = exchanges done by the fused peer-store path, out[3] = by all-gather + scatter */
+int ctb_dist_info(long long* out) { out[0] = ctb_dist_rank; out[1] = ctb_dist_world; ctb_dist_counters(&out[2], &out[3]); return 0; }
+int ctb_dist_finalize(void) { ctb_dist_release_buffers(); ctb_dist_rank = 0; ctb_dist_world = 1; return ctbd_dist_finalize(); }
 int ctb_backend(void) { return ctbd_backend(); }
 long long ctb_launch_count(void) { return ctbd_launch_count(); }
 
@@ -579,7 +581,7 @@ int ctb_heff_benchmark(const struct block_sparse_tensor* a, const struct block_s
 		CTB_CHECK(ctbd_event_record(e1));
 		CTB_CHECK(ctb_dot_exec(&h.p2, wd->d, h.t1->d, h.t2->d));
 		CTB_CHECK(ctbd_event_record(e2));
-		CTB_CHECK(ctb_dot_exec(&h.p3, h.k->d, h.t2->d, h.world > 1 ? h.send : bd->d));
+		CTB_CHECK(ctb_heff_step3(&h, bd->d));
 		CTB_CHECK(ctbd_event_record(e3));
 		CTB_CHECK(ctb_heff_exchange(&h, bd->d));
 		CTB_CHECK(ctbd_event_record(e4));

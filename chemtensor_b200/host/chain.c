@@ -302,6 +302,41 @@ struct ctb_tensor* ctb_env_step_left(const struct ctb_tensor* a, const struct ct
 /* effective Hamiltonian: plans built once per bond, three launches per matvec                     */
 /* ---------------------------------------------------------------------------------------------- */
 
+/* ---- peer-mapped landing buffers of the fused exchange (two, used alternately; see ctb_heff_finish) ---- */
+static void* g_land[2] = { NULL, NULL };
+static void** g_land_ptrs[2] = { NULL, NULL };
+static size_t g_land_bytes = 0;
+static int g_land_flip = 0, g_land_failed = 0;
+static long long g_fused_count = 0, g_allgather_count = 0;
+
+static void landing_release(void)
+{
+	for (int i = 0; i < 2; i++) {
+		if (g_land[i] != NULL) { ctbd_peer_buffer_destroy(g_land[i]); g_land[i] = NULL; }
+		free(g_land_ptrs[i]); g_land_ptrs[i] = NULL;
+	}
+	g_land_bytes = 0; g_land_flip = 0;
+}
+
+/* collective: every rank calls it with the same size; returns 1 when both landing buffers are available */
+static int landing_ensure(size_t bytes, int world)
+{
+	if (g_land_failed || getenv("CTB_NO_FUSED_EXCHANGE") != NULL) { return 0; }
+	if (g_land[0] != NULL && bytes <= g_land_bytes) { return 1; }
+	landing_release();
+	const size_t want = bytes + bytes / 4 + 4096;
+	for (int i = 0; i < 2; i++) {
+		if (ctbd_peer_buffer_create(want, &g_land[i]) < 0) { g_land_failed = 1; landing_release(); return 0; }
+		g_land_ptrs[i] = calloc((size_t)world, sizeof(void*));
+		ctbd_peer_buffer_ptrs(g_land[i], g_land_ptrs[i]);
+	}
+	g_land_bytes = want;
+	return 1;
+}
+
+void ctb_dist_release_buffers(void) { landing_release(); g_land_failed = 0; }
+void ctb_dist_counters(long long* fused, long long* allgather) { *fused = g_fused_count; *allgather = g_allgather_count; }
+
 /* Split of the bra bond of r among 'world' ranks.  Every sector is cut into ceil(m / grain) nearly equal contiguous chunks
  * (grain = one GEMM tile width, so a rank's blocks keep full tiles), each chunk is weighted by the step-1 flops of its
  * columns (computed from the block structures of a and r), and the chunks are handed out longest-processing-time first.
@@ -377,7 +412,7 @@ int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, str
 	if (ctb_dist_world > 1)
 	{
 		const int W = ctb_dist_world;
-		CTB_REQUIRE(W <= 255);
+		CTB_REQUIRE(W <= 8);
 		h->ind = ctb_calloc((size_t)W, sizeof(ct_long*));
 		h->nind = ctb_calloc((size_t)W, sizeof(ct_long));
 		if (split_bond(a, r, W, h->ind, h->nind))
@@ -462,7 +497,26 @@ int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, str
 	/* step 3: k . t2 over (Dl, Dw), k = transpose(l, [0,3,1,2]) once per bond (the reference redoes it every matvec) */
 	const int perm2[4] = { 0, 3, 1, 2 };
 	h->k = ctb_transpose(l, perm2, 0);
-	struct ctb_tensor* s = ctb_dot_prepare(h->k, TENSOR_AXIS_RANGE_TRAILING, 0, h->t2, TENSOR_AXIS_RANGE_LEADING, 0, 2, NULL, 0, &h->p3);
+	struct ctb_tensor* s = NULL;
+	if (h->world > 1 && landing_ensure((size_t)a->nstore * ctb_sizeof_dtype(a->dtype), h->world))
+	{
+		/* fused exchange: the step-3 GEMM stores its column slice straight into the packed layout of the FULL result, in the
+		 * peer-mapped landing buffer of every rank (NVLink stores from the epilogue); no all-gather, no scatter */
+		struct ctb_axis axes[5];
+		ctb_axis_copy(&axes[0], &h->k->ax[0]);
+		ctb_axis_copy(&axes[1], &h->k->ax[1]);
+		ctb_axis_copy(&axes[2], &h->t2->ax[2]);
+		ctb_axis_copy(&axes[3], &r->ax[2]);
+		ctb_axis_copy(&axes[4], &h->t2->ax[4]);
+		h->bfull5 = ctb_tensor_from_axes(a->dtype, 5, axes, 0);
+		CTB_REQUIRE(h->bfull5->nstore == a->nstore && h->bfull5->nblk == a->nblk);
+		const struct ctb_embed emb = { 3, h->bfull5, h->ind[h->rank] };
+		s = ctb_dot_prepare_embed(h->k, TENSOR_AXIS_RANGE_TRAILING, 0, h->t2, TENSOR_AXIS_RANGE_LEADING, 0, 2, &emb, &h->p3);
+		h->fused = 1;
+	}
+	else {
+		s = ctb_dot_prepare(h->k, TENSOR_AXIS_RANGE_TRAILING, 0, h->t2, TENSOR_AXIS_RANGE_LEADING, 0, 2, NULL, 0, &h->p3);
+	}
 	/* tracing out the two dummy bonds leaves the packed layout unchanged */
 	struct ctb_tensor* bs = ctb_drop_dummy_axes(s, 1);
 	ctb_tensor_free(s);
@@ -484,24 +538,48 @@ int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, str
 
 int ctb_heff_apply(struct ctb_heff* h, const void* a_data, void* b_data)
 {
-	void* out = (h->world > 1) ? h->send : b_data;
 	CTB_CHECK(ctb_dot_exec(&h->p1, a_data, h->r->d, h->t1->d));
 	CTB_CHECK(ctb_dot_exec(&h->p2, h->w->d, h->t1->d, h->t2->d));
-	CTB_CHECK(ctb_dot_exec(&h->p3, h->k->d, h->t2->d, out));
+	CTB_CHECK(ctb_heff_step3(h, b_data));
 	CTB_CHECK(ctb_heff_exchange(h, b_data));
 	ctb_global_stats.heff_flops += h->flops;
 	ctb_global_stats.heff_calls++;
 	return 0;
 }
 
+/* third contraction; sharded: into the own all-gather slot, or (fused) into the landing buffers of all ranks */
+int ctb_heff_step3(struct ctb_heff* h, void* b_data)
+{
+	if (h->world == 1) { return ctb_dot_exec(&h->p3, h->k->d, h->t2->d, b_data); }
+	if (!h->fused) { return ctb_dot_exec(&h->p3, h->k->d, h->t2->d, h->send); }
+	void* dst[8];
+	void** ptrs = g_land_ptrs[g_land_flip];
+	dst[0] = ptrs[h->rank];
+	int n = 1;
+	for (int p = 0; p < h->world; p++) { if (p != h->rank) { dst[n++] = ptrs[p]; } }
+	return ctb_dot_exec_multi(&h->p3, h->k->d, h->t2->d, n, dst);
+}
+
 int ctb_heff_exchange(struct ctb_heff* h, void* b_data)
 {
+	if (h->world > 1 && h->fused)
+	{
+		/* every rank's slice has been stored into every landing buffer by the step-3 epilogues: wait for all ranks, then hand the
+		 * full vector to the caller.  The two landing buffers alternate, so the next application may start writing at once. */
+		const size_t esize = ctb_sizeof_dtype(h->b->dtype);
+		CTB_CHECK(ctbd_barrier());
+		CTB_CHECK(ctbd_d2d(b_data, g_land_ptrs[g_land_flip][h->rank], (size_t)h->nstore * esize));
+		g_land_flip ^= 1;
+		g_fused_count++;
+		return 0;
+	}
 	if (h->world > 1)
 	{
 		/* exchange step: all-gather of the result slices over NVLink, then scatter into the packed layout of b */
 		const size_t esize = ctb_sizeof_dtype(h->b->dtype);
 		CTB_CHECK(ctbd_allgather(h->send, h->recv, (size_t)h->piece_cap * esize));
 		CTB_CHECK(ctbd_copy_plan_run(h->scatter, h->recv, b_data));
+		g_allgather_count++;
 	}
 	return 0;
 }
@@ -514,6 +592,7 @@ void ctb_heff_free(struct ctb_heff* h)
 	if (h->ind != NULL) { for (int p = 0; p < h->world; p++) { ctb_free(h->ind[p]); } ctb_free(h->ind); ctb_free(h->nind); }
 	ctb_tensor_free(h->r_own);
 	if (h->scatter != NULL) { ctbd_copy_plan_destroy(h->scatter); }
+	ctb_tensor_free(h->bfull5);
 	if (h->send != NULL) { ctbd_free(h->send); }
 	if (h->recv != NULL) { ctbd_free(h->recv); }
 	memset(h, 0, sizeof(*h));

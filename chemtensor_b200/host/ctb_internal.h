@@ -147,7 +147,14 @@ struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, in
 struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s, int conj_s,
 	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm,
 	int alloc_result, int flags, struct ctb_dot_plan* plan);
+/* the result (natural axis order, no buffer) is written into the packed layout of the larger tensor 'full', which has the same axes
+ * except 'axis', whose logical index j of the result corresponds to logical index ind[j] of 'full' */
+struct ctb_embed { int axis; const struct ctb_tensor* full; const ct_long* ind; };
+struct ctb_tensor* ctb_dot_prepare_embed(const struct ctb_tensor* s, int axrange_s, int conj_s,
+	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const struct ctb_embed* emb, struct ctb_dot_plan* plan);
 int  ctb_dot_exec(const struct ctb_dot_plan* plan, const void* s_data, const void* t_data, void* r_data);
+/* the same with the result stored to 'ndst' buffers (peer-mapped result buffers of all GPUs: GEMM fused with its all-gather) */
+int  ctb_dot_exec_multi(const struct ctb_dot_plan* plan, const void* s_data, const void* t_data, int ndst, void* const* r_datas);
 void ctb_dot_plan_free(struct ctb_dot_plan* plan);
 struct ctb_tensor* ctb_dot(const struct ctb_tensor* s, int axrange_s, int conj_s,
 	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm);
@@ -203,13 +210,18 @@ struct ctb_heff
 	ct_long piece_cap;            /* elements of one all-gather slot (largest piece) */
 	void* send; void* recv;       /* device: own piece; all pieces */
 	void* scatter;                /* device copy plan: gathered pieces -> packed layout of b */
+	int fused;                    /* 1: step 3 stores straight into the peer-mapped result buffers of all ranks (no all-gather) */
+	struct ctb_tensor* bfull5;    /* fused: 5-leg view of the full result the embedded step-3 plan writes into */
 	double flops_total;           /* algorithmic flops of the whole matvec (all ranks) */
 };
 /* rank / world of this process (ctb_dist_init); world == 1 means no sharding */
 extern int ctb_dist_rank, ctb_dist_world;
 int  ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h);
 int  ctb_heff_apply(struct ctb_heff* h, const void* a_data, void* b_data);
-/* sharded case: all-gather of the result slices (h->send) and scatter into b_data; no-op on one rank */
+int  ctb_heff_step3(struct ctb_heff* h, void* b_data);
+void ctb_dist_release_buffers(void);
+void ctb_dist_counters(long long* fused, long long* allgather);
+/* sharded case: all-gather of the result slices (h->send) and scatter into b_data, or (fused) barrier + local copy; no-op on one rank */
 int  ctb_heff_exchange(struct ctb_heff* h, void* b_data);
 void ctb_heff_free(struct ctb_heff* h);
 

@@ -28,6 +28,12 @@ static void i32vec_reserve(struct i32vec* t, size_t extra)
 
 /* element offsets of the rows (free axes of s, 'first' = 0) or columns (free axes of t, 'first' = nfs) of a natural
  * result block inside the permuted result block */
+/* optional embedding of the result into a larger tensor along one result axis (sharded effective Hamiltonian: the rank's column
+ * slice is written straight into the packed layout of the full tensor); set by ctb_dot_prepare_embed for the duration of one call */
+static const struct ctb_embed* g_embed = NULL;
+static int g_map_nat = -1;              /* natural axis the position map applies to, -1: none */
+static const int32_t* g_map_pos = NULL; /* position inside the piece sector -> position inside the full sector */
+
 static void append_offset_table(struct i32vec* tab, int first, int count, const struct ctb_axis* const* nat, const int* nat_sec,
 	const int* pos_of_nat, const ct_long* stride_r, ct_long base)
 {
@@ -38,7 +44,7 @@ static void append_offset_table(struct i32vec* tab, int first, int count, const 
 	for (ct_long i = 0; i < total; i++)
 	{
 		ct_long off = base;
-		for (int a = 0; a < count; a++) { off += dig[a] * stride_r[pos_of_nat[first + a]]; }
+		for (int a = 0; a < count; a++) { off += (first + a == g_map_nat ? (ct_long)g_map_pos[dig[a]] : (ct_long)dig[a]) * stride_r[pos_of_nat[first + a]]; }
 		CTB_REQUIRE(off < ((ct_long)1 << 31));
 		tab->v[tab->n++] = (int32_t)off;
 		for (int a = count - 1; a >= 0; a--) {
@@ -166,6 +172,28 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 			for (int i = 0; i < nfs; i++) { M *= nat[i]->secdim[nat_sec[i]]; }
 			o->c_off = r->blk_off[b];
 			o->m = (int32_t)M;
+			int idx_full[CTB_MAXDIM];
+			int32_t* posmap = NULL;
+			if (g_embed != NULL)
+			{
+				/* block of the full tensor this piece block lands in, and where the piece columns sit inside it */
+				const struct ctb_tensor* full = g_embed->full;
+				const int ea = g_embed->axis;
+				for (int i = 0; i < ndimr; i++) { idx_full[i] = idx_r[i]; }
+				idx_full[ea] = ctb_axis_find_sector(&full->ax[ea], r->ax[ea].qsec[idx_r[ea]]);
+				CTB_REQUIRE(idx_full[ea] >= 0);
+				const ct_long off_full = full->grid_off[ctb_grid_ravel(full, idx_full)];
+				CTB_REQUIRE(off_full >= 0);
+				o->c_off = off_full;
+				const int np = r->ax[ea].secdim[idx_r[ea]];
+				posmap = malloc((size_t)np * sizeof(int32_t));
+				for (int d = 0; d < np; d++) {
+					const ct_long lg = g_embed->ind[r->ax[ea].log_of[r->ax[ea].secstart[idx_r[ea]] + d]];
+					CTB_REQUIRE(full->ax[ea].sec_of[lg] == idx_full[ea]);
+					posmap[d] = full->ax[ea].pos_of[lg];
+				}
+				g_map_nat = p[ea]; g_map_pos = posmap;
+			}
 			/* enumerate contracted sector tuples in row-major order (reference :1951-1953) */
 			int idx_s[CTB_MAXDIM], idx_t[CTB_MAXDIM], kap[CTB_MAXDIM] = { 0 };
 			for (int i = 0; i < nfs; i++) { idx_s[offset_s + i] = nat_sec[i]; }
@@ -197,12 +225,16 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 			/* row/column offset tables: where element (i, j) of the natural block lands in the permuted block */
 			ct_long stride_r[CTB_MAXDIM];
 			ct_long st = 1;
-			for (int i = ndimr - 1; i >= 0; i--) { stride_r[i] = st; st *= r->ax[i].secdim[idx_r[i]]; }
+			for (int i = ndimr - 1; i >= 0; i--) {
+				stride_r[i] = st;
+				st *= (g_embed != NULL) ? g_embed->full->ax[i].secdim[idx_full[i]] : r->ax[i].secdim[idx_r[i]];
+			}
 			CTB_REQUIRE(st < ((ct_long)1 << 31));
 			o->row_tab = (int32_t)tab.n;
 			append_offset_table(&tab, 0, nfs, nat, nat_sec, pos_of_nat, stride_r, 0);
 			o->col_tab = (int32_t)tab.n;
 			append_offset_table(&tab, nfs, nft, nat, nat_sec, pos_of_nat, stride_r, 0);
+			if (posmap != NULL) { free(posmap); g_map_nat = -1; g_map_pos = NULL; }
 		}
 		else
 		{
@@ -400,6 +432,16 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	return r;
 }
 
+struct ctb_tensor* ctb_dot_prepare_embed(const struct ctb_tensor* s, int axrange_s, int conj_s,
+	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const struct ctb_embed* emb, struct ctb_dot_plan* plan)
+{
+	CTB_REQUIRE(emb != NULL && emb->full != NULL && emb->ind != NULL);
+	g_embed = emb;
+	struct ctb_tensor* r = ctb_dot_prepare_ex(s, axrange_s, conj_s, t, axrange_t, conj_t, ndim_mult, NULL, 0, 0, plan);
+	g_embed = NULL;
+	return r;
+}
+
 struct ctb_tensor* ctb_dot_prepare(const struct ctb_tensor* s, int axrange_s, int conj_s,
 	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm,
 	int alloc_result, struct ctb_dot_plan* plan)
@@ -411,6 +453,12 @@ int ctb_dot_exec(const struct ctb_dot_plan* plan, const void* s_data, const void
 {
 	if (plan->ntiles == 0) { return 0; }
 	return ctbd_gemm_run(plan->dev, s_data, t_data, r_data);
+}
+
+int ctb_dot_exec_multi(const struct ctb_dot_plan* plan, const void* s_data, const void* t_data, int ndst, void* const* r_datas)
+{
+	if (plan->ntiles == 0) { return 0; }
+	return ctbd_gemm_run_multi(plan->dev, s_data, t_data, ndst, r_datas);
 }
 
 void ctb_dot_plan_free(struct ctb_dot_plan* plan)

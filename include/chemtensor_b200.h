@@ -118,6 +118,8 @@ int ctb_dist_unique_id(void* id_out_128_bytes);
 int ctb_dist_init(int rank, int world, const void* unique_id);
 int ctb_dist_set_allgather(int (*fn)(void* ctx, const void* sendbuf, void* recvbuf, size_t bytes_per_rank, void* stream), void* ctx);
 int ctb_dist_finalize(void);
+/* out[0] = rank, out[1] = world, out[2] = exchanges done by the fused peer-store path, out[3] = exchanges done by all-gather + scatter */
+int ctb_dist_info(long long* out);
 /* 1 = CUDA kernels, 2 = host test double (tests/emu only) */
 int ctb_backend(void);
 /* kernels launched by the engine so far */

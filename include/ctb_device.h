@@ -95,6 +95,15 @@ int ctbd_dist_set_allgather(ctbd_allgather_fn fn, void* ctx);       /* optional 
 int ctbd_dist_finalize(void);
 /* recv[p * bytes_per_rank ...] = send of rank p, for all ranks p; device buffers; ordered on the layer's stream */
 int ctbd_allgather(const void* sendbuf, void* recvbuf, size_t bytes_per_rank);
+/* all ranks have completed (and made visible) everything enqueued before the barrier; ordered on the layer's stream */
+int ctbd_barrier(void);
+/* peer-mapped buffer: every rank allocates 'bytes' and maps the buffers of all other ranks of the box into its address space
+ * (CUDA IPC over NVLink peer access).  ptrs[p] is rank p's buffer as seen from this process (ptrs[rank] = the local one).  Collective
+ * call.  Returns < 0 when peer mapping is not available (no NCCL communicator, no P2P, test double): callers then fall back to the
+ * all-gather form of the exchange. */
+int ctbd_peer_buffer_create(size_t bytes, void** handle);
+int ctbd_peer_buffer_ptrs(void* handle, void** ptrs /* [world] */);
+int ctbd_peer_buffer_destroy(void* handle);
 
 /* ---- grouped block GEMM -------------------------------------------------------------------- */
 
@@ -174,6 +183,9 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan);
 int ctbd_gemm_plan_destroy(void* plan);
 /* C (every output block of the plan is overwritten) = sum over segments op(A) op(B); A, B, C device buffers */
 int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C);
+/* the same with the epilogue storing every output element to 'ndst' (<= 8) destination buffers: the GEMM fused with the all-gather
+ * of its result over NVLink peer memory (Cs[p] = peer-mapped buffer of rank p) */
+int ctbd_gemm_run_multi(void* plan, const void* A, const void* B, int ndst, void* const* Cs);
 /* number of tiles / kernel launches one run of the plan issues */
 int ctbd_gemm_plan_info(void* plan, int* ntiles, int* nlaunches);
 

@@ -34,6 +34,8 @@ def make_gloo_allgather(dist, torch, world):
 
 def main():
     kind, prefix = sys.argv[1], sys.argv[2]
+    if len(sys.argv) > 3 and sys.argv[3] == "allgather":
+        os.environ["CTB_NO_FUSED_EXCHANGE"] = "1"
     import torch
     import torch.distributed as dist
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -74,6 +76,9 @@ def main():
     out["dmrg_en"] = en
     out["dmrg_entropy"] = ent
     out["dmrg_site2"] = psi.site(2).serialize()
+    info = (C.c_longlong * 4)()
+    eng.ctb_dist_info(info)
+    out["exchange_counts"] = np.array([info[2], info[3]], dtype=np.int64)      # fused peer-store exchanges, all-gather exchanges
     np.savez(f"{prefix}_rank{rank}.npz", **out)
     eng.ctb_dist_finalize()
     dist.barrier()

@@ -16,6 +16,9 @@
 #include <string.h>
 #include <math.h>
 #include <complex.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/mman.h>
 #include "ctb_device.h"
 
 static char g_err[512] = "";
@@ -58,9 +61,9 @@ int ctbd_d2h_blocks(const void* dptr, int nblk, void* const* hptrs, const int64_
 	return 0;
 }
 /* exchange step: the test double only knows the host-callback form (gloo in the tests) */
-static ctbd_allgather_fn g_ag_fn = NULL; static void* g_ag_ctx = NULL; static int g_world = 1;
+static ctbd_allgather_fn g_ag_fn = NULL; static void* g_ag_ctx = NULL; static int g_world = 1, g_rank_emu = 0;
 int ctbd_dist_unique_id(void* id_out) { memset(id_out, 0, CTBD_UNIQUE_ID_BYTES); return 0; }
-int ctbd_dist_init(int rank, int world, const void* unique_id) { (void)rank; (void)unique_id; g_world = world; return 0; }
+int ctbd_dist_init(int rank, int world, const void* unique_id) { (void)unique_id; g_world = world; g_rank_emu = rank; return 0; }
 int ctbd_dist_set_allgather(ctbd_allgather_fn fn, void* ctx) { g_ag_fn = fn; g_ag_ctx = ctx; return 0; }
 int ctbd_dist_finalize(void) { g_world = 1; g_ag_fn = NULL; g_ag_ctx = NULL; return 0; }
 int ctbd_allgather(const void* sendbuf, void* recvbuf, size_t bytes_per_rank)
@@ -68,6 +71,58 @@ int ctbd_allgather(const void* sendbuf, void* recvbuf, size_t bytes_per_rank)
 	if (g_world == 1) { if (sendbuf != recvbuf) { memmove(recvbuf, sendbuf, bytes_per_rank); } return 0; }
 	if (g_ag_fn == NULL) { snprintf(g_err, sizeof(g_err), "dist: no all-gather callback registered"); return -1; }
 	return g_ag_fn(g_ag_ctx, sendbuf, recvbuf, bytes_per_rank, NULL);
+}
+int ctbd_barrier(void)
+{
+	if (g_world == 1) { return 0; }
+	static long long scratch[64];
+	return ctbd_allgather(scratch, scratch + 1, 8);
+}
+/* peer-mapped buffers of the test double: POSIX shared memory between the rank processes of one test run */
+struct emu_peer { int world; size_t bytes; void** ptrs; char (*names)[96]; };
+static int g_peer_counter = 0;
+int ctbd_peer_buffer_create(size_t bytes, void** handle)
+{
+	*handle = NULL;
+	if (g_world == 1 || g_ag_fn == NULL || getenv("CTB_NO_PEER") != NULL) { snprintf(g_err, sizeof(g_err), "peer buffers need a multi-rank run"); return -1; }
+	struct emu_peer* pb = calloc(1, sizeof(*pb));
+	pb->world = g_world; pb->bytes = bytes ? bytes : 64;
+	pb->ptrs = calloc((size_t)g_world, sizeof(void*));
+	pb->names = calloc((size_t)g_world, sizeof(*pb->names));
+	const char* port = getenv("MASTER_PORT");
+	const int id = g_peer_counter++;
+	for (int p = 0; p < g_world; p++) { snprintf(pb->names[p], sizeof(pb->names[p]), "/ctb_emu_%s_%d_%d", port ? port : "0", id, p); }
+	int fd = shm_open(pb->names[g_rank_emu], O_CREAT | O_RDWR, 0600);
+	if (fd < 0 || ftruncate(fd, (off_t)pb->bytes) != 0) { snprintf(g_err, sizeof(g_err), "shm_open failed"); return -1; }
+	pb->ptrs[g_rank_emu] = mmap(NULL, pb->bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	close(fd);
+	if (ctbd_barrier() < 0) { return -1; }
+	for (int p = 0; p < g_world; p++) {
+		if (p == g_rank_emu) { continue; }
+		fd = shm_open(pb->names[p], O_RDWR, 0600);
+		if (fd < 0) { snprintf(g_err, sizeof(g_err), "shm_open of a peer failed"); return -1; }
+		pb->ptrs[p] = mmap(NULL, pb->bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+		close(fd);
+	}
+	if (ctbd_barrier() < 0) { return -1; }
+	shm_unlink(pb->names[g_rank_emu]);      /* mappings stay valid; the name disappears */
+	*handle = pb;
+	return 0;
+}
+int ctbd_peer_buffer_ptrs(void* handle, void** ptrs) { struct emu_peer* pb = handle; for (int p = 0; p < pb->world; p++) { ptrs[p] = pb->ptrs[p]; } return 0; }
+int ctbd_peer_buffer_destroy(void* handle)
+{
+	struct emu_peer* pb = handle;
+	if (pb == NULL) { return 0; }
+	ctbd_barrier();
+	for (int p = 0; p < pb->world; p++) { if (pb->ptrs[p] != NULL) { munmap(pb->ptrs[p], pb->bytes); } }
+	free(pb->ptrs); free(pb->names); free(pb);
+	return 0;
+}
+int ctbd_gemm_run_multi(void* plan, const void* A, const void* B, int ndst, void* const* Cs)
+{
+	for (int d = 0; d < ndst; d++) { if (Cs[d] != NULL) { int rc = ctbd_gemm_run(plan, A, B, Cs[d]); if (rc < 0) { return rc; } } }
+	return 0;
 }
 int ctbd_d2d(void* dst, const void* src, size_t bytes) { memmove(dst, src, bytes); return 0; }
 int ctbd_sync(void) { return 0; }

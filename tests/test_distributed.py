@@ -23,13 +23,13 @@ def free_port():
         return s.getsockname()[1]
 
 
-def run_world(kind, world, tmp_path):
+def run_world(kind, world, tmp_path, mode="fused"):
     port = free_port()
     prefix = str(tmp_path / "dist")
     procs = []
     for rank in range(world):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
-        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "dist_worker.py"), kind, prefix], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "dist_worker.py"), kind, prefix, mode], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     outs = []
     for p in procs:
         try:
@@ -73,16 +73,25 @@ def check(results, single):
         assert np.array_equal(r["dmrg_site2"], results[0]["dmrg_site2"])
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_heff_and_dmrg_gloo(tmp_path, world):
-    results = run_world("emu", world, tmp_path)
+@pytest.mark.parametrize("world,mode", [(2, "fused"), (3, "fused"), (2, "allgather")])
+def test_sharded_heff_and_dmrg_gloo(tmp_path, world, mode):
+    """fused: step 3 stores into peer-mapped result buffers (shared memory between the rank processes here, NVLink peer memory on GPUs);
+    allgather: all-gather of the slices + scatter"""
+    results = run_world("emu", world, tmp_path, mode)
     check(results, single_rank_results(helpers.load("emu")))
+    for r in results:
+        fused, gathered = (int(x) for x in r["exchange_counts"])
+        assert (fused > 0 and gathered == 0) if mode == "fused" else (fused == 0 and gathered > 0)
 
 
 @pytest.mark.gpu
-def test_sharded_heff_and_dmrg_nccl(tmp_path):
+@pytest.mark.parametrize("mode", ["fused", "allgather"])
+def test_sharded_heff_and_dmrg_nccl(tmp_path, mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
-    results = run_world("cuda", 2, tmp_path)
+    results = run_world("cuda", 2, tmp_path, mode)
     check(results, single_rank_results(helpers.load("cuda")))
+    for r in results:
+        fused, gathered = (int(x) for x in r["exchange_counts"])
+        assert (fused > 0 and gathered == 0) if mode == "fused" else (fused == 0 and gathered > 0)

@@ -46,7 +46,7 @@ def main():
     layouts = [(cabi.AXIS_RANGE_TRAILING, cabi.AXIS_RANGE_LEADING, "NN")]
     if "--layouts" in sys.argv:
         layouts += [(cabi.AXIS_RANGE_LEADING, cabi.AXIS_RANGE_LEADING, "TN"), (cabi.AXIS_RANGE_TRAILING, cabi.AXIS_RANGE_TRAILING, "NT")]
-    for dtype, ncls in ((np.float64, 5), (np.complex128, 3)):
+    for dtype, ncls in ((np.float64, 7), (np.complex128, 3)):
         for (nb, m, n, k) in cases:
             if dtype == np.complex128 and nb * m * k > 2 ** 25:
                 continue
