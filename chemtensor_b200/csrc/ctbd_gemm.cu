@@ -727,8 +727,11 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 			occ_cache[cplx][c] = occ < 1 ? 1 : occ;
 		}
 		const int slots = rt().sm_count * occ_cache[cplx][c];
-		std::vector<double> tw;      /* tile weights in k-steps */
+		/* all tiles of one output block weigh the same: keep (weight, count) groups instead of one entry per tile */
+		std::vector<std::pair<double, int64_t>> grp;
+		grp.reserve((size_t)h->nouts);
 		double total = 0, wmax = 0;
+		int64_t ntl = 0;
 		for (int b = 0; b < h->nouts; b++) {
 			const ctbd_gemm_out& o = h->outs[b];
 			if (o.m <= 0 || o.n <= 0) { continue; }
@@ -736,21 +739,26 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 			for (int s = o.seg_begin; s < o.seg_end; s++) { steps += (double)ceil_div(h->segs[s].k, shapes[c].bk); }
 			const int64_t nt = ceil_div(o.m, shapes[c].bm) * ceil_div(o.n, shapes[c].bn);
 			const double w = steps + 32.0 / shapes[c].bk;
-			total += w * (double)nt; wmax = std::max(wmax, w);
-			if (tw.size() < 40000) { for (int64_t i = 0; i < nt && tw.size() < 40000; i++) { tw.push_back(w); } }
+			total += w * (double)nt; wmax = std::max(wmax, w); ntl += nt;
+			grp.push_back(std::make_pair(w, nt));
 		}
-		const int64_t ntl = (int64_t)tw.size();
 		if (ntl == 0) { continue; }
 		const int grid = (int)std::min<int64_t>(ntl, slots);
 		double makespan;
-		if (ntl < 40000) {
-			std::sort(tw.begin(), tw.end(), [](double a, double b) { return a > b; });
+		if (ntl <= 8 * (int64_t)slots) {
+			/* few tiles per slot: the exact longest-processing-time-first packing (wave quantisation matters here) */
+			std::sort(grp.begin(), grp.end(), [](const std::pair<double, int64_t>& a, const std::pair<double, int64_t>& b) { return a.first > b.first; });
 			std::vector<double> heap(grid, 0.0);     /* min-heap of slot loads */
 			auto cmpd = [](double a, double b) { return a > b; };
-			for (double w : tw) { std::pop_heap(heap.begin(), heap.end(), cmpd); heap.back() += w; std::push_heap(heap.begin(), heap.end(), cmpd); }
+			for (const auto& g : grp) {
+				for (int64_t i = 0; i < g.second; i++) { std::pop_heap(heap.begin(), heap.end(), cmpd); heap.back() += g.first; std::push_heap(heap.begin(), heap.end(), cmpd); }
+			}
 			makespan = *std::max_element(heap.begin(), heap.end());
 		}
-		else { makespan = std::max(total / grid, wmax); }
+		else {
+			/* many tiles per slot: the packing ends within about half a (mean) tile of the perfect split */
+			makespan = std::max(total / grid + 0.5 * total / (double)ntl, wmax);
+		}
 		const int per_sm = (int)ceil_div(grid, rt().sm_count);      /* CTAs sharing the tensor pipe of one SM */
 		const double cost = makespan * shapes[c].bk * shapes[c].bm * shapes[c].bn * shapes[c].eff * per_sm;
 		if (c == 0 || cost < best_cost) { best = c; best_cost = cost; }
@@ -760,19 +768,32 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 	p->cfg = best;
 	const int bm = shapes[best].bm, bn = shapes[best].bn, bk = shapes[best].bk;
 
+	/* tiles in longest-processing-time-first order: all tiles of an output block weigh the same, so the blocks are sorted (stable,
+	 * heaviest first) and their tiles listed block after block */
 	struct Item { GemmTile t; double w; };
 	std::vector<Item> items;
-	for (int b = 0; b < h->nouts; b++)
 	{
-		const ctbd_gemm_out& o = h->outs[b];
-		if (o.m <= 0 || o.n <= 0) { continue; }
-		int nsteps = 0;
-		for (int s = o.seg_begin; s < o.seg_end; s++) { nsteps += (int)ceil_div(h->segs[s].k, bk); }
-		for (int m0 = 0; m0 < o.m; m0 += bm) {
-			for (int n0 = 0; n0 < o.n; n0 += bn) {
-				Item it; it.t.out = b; it.t.m0 = m0; it.t.n0 = n0; it.t.nsteps = nsteps;
-				it.w = (double)nsteps + 2.0;
-				items.push_back(it);
+		std::vector<std::pair<int, int>> blk;      /* (k-steps, output block) */
+		blk.reserve((size_t)h->nouts);
+		int64_t ntot = 0;
+		for (int b = 0; b < h->nouts; b++) {
+			const ctbd_gemm_out& o = h->outs[b];
+			if (o.m <= 0 || o.n <= 0) { continue; }
+			int nsteps = 0;
+			for (int s = o.seg_begin; s < o.seg_end; s++) { nsteps += (int)ceil_div(h->segs[s].k, bk); }
+			blk.push_back(std::make_pair(nsteps, b));
+			ntot += ceil_div(o.m, bm) * ceil_div(o.n, bn);
+		}
+		std::stable_sort(blk.begin(), blk.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+		items.reserve((size_t)ntot);
+		for (const auto& pb : blk) {
+			const ctbd_gemm_out& o = h->outs[pb.second];
+			for (int m0 = 0; m0 < o.m; m0 += bm) {
+				for (int n0 = 0; n0 < o.n; n0 += bn) {
+					Item it; it.t.out = pb.second; it.t.m0 = m0; it.t.n0 = n0; it.t.nsteps = pb.first;
+					it.w = (double)pb.first + 2.0;
+					items.push_back(it);
+				}
 			}
 		}
 	}
@@ -792,20 +813,32 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 		if (occ < 1) { occ = 1; }
 		const int grid = std::min(p->ntiles, rt().sm_count * occ);
 		p->grid = grid;
-		/* longest-processing-time-first packing of the tiles into one queue per resident CTA */
-		std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.w > b.w; });
-		std::vector<double> load(grid, 0.0);
+		/* longest-processing-time-first packing into one queue per resident CTA.  The packing unit is a run of up to 'strip' tiles
+		 * that follow each other along n in the same row strip of a block (they share the A tile, so the run also helps L2 / shared
+		 * memory locality); 'strip' keeps about 16 units per queue, which is plenty for the balance and cuts the packing cost */
+		const int strip = (int)std::max<int64_t>(1, std::min<int64_t>(8, (int64_t)p->ntiles / (16 * (int64_t)grid)));
+		struct Unit { int first, count; double w; };
+		std::vector<Unit> units;
+		units.reserve((size_t)p->ntiles / strip + 16);
+		for (int i = 0; i < p->ntiles; ) {
+			int j = i + 1;
+			while (j < p->ntiles && j - i < strip && items[j].t.out == items[i].t.out && items[j].t.m0 == items[i].t.m0) { j++; }
+			Unit u; u.first = i; u.count = j - i; u.w = items[i].w * (j - i);
+			units.push_back(u);
+			i = j;
+		}
+		std::stable_sort(units.begin(), units.end(), [](const Unit& a, const Unit& b) { return a.w > b.w; });
 		std::vector<std::vector<int>> bins(grid);
 		/* binary heap of (load, bin) */
 		std::vector<std::pair<double, int>> heap(grid);
 		for (int g = 0; g < grid; g++) { heap[g] = std::make_pair(0.0, g); }
 		auto cmp = [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first || (a.first == b.first && a.second > b.second); };
 		std::make_heap(heap.begin(), heap.end(), cmp);
-		for (int i = 0; i < p->ntiles; i++) {
+		for (const Unit& u : units) {
 			std::pop_heap(heap.begin(), heap.end(), cmp);
 			std::pair<double, int>& top = heap.back();
-			bins[top.second].push_back(i);
-			top.first += items[i].w;
+			for (int i = 0; i < u.count; i++) { bins[top.second].push_back(u.first + i); }
+			top.first += u.w;
 			std::push_heap(heap.begin(), heap.end(), cmp);
 		}
 		std::vector<GemmTile> tl; tl.reserve(p->ntiles);

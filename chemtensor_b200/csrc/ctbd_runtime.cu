@@ -4,6 +4,7 @@
  */
 #include <stdlib.h>
 #include <dlfcn.h>
+#include <sys/mman.h>
 #include <omp.h>
 #include <unordered_map>
 #include <mutex>
@@ -50,19 +51,20 @@ using namespace ctbd;
 struct ncclUniqueIdBytes { char internal[CTBD_UNIQUE_ID_BYTES]; };   /* layout of ncclUniqueId (nccl.h), passed by value */
 
 namespace {
-constexpr size_t STAGE_CHUNK = (size_t)32 << 20;
+constexpr size_t STAGE_CHUNK = (size_t)8 << 20;      /* small chunks: the un-overlapped head (first pack) and tail (last DMA) stay short */
+constexpr int STAGE_SLOTS = 4;
 struct StageRing
 {
-	void* buf[2] = { nullptr, nullptr };
-	cudaEvent_t ev[2] = { nullptr, nullptr };
-	bool busy[2] = { false, false };
+	void* buf[STAGE_SLOTS] = { nullptr };
+	cudaEvent_t ev[STAGE_SLOTS] = { nullptr };
+	bool busy[STAGE_SLOTS] = { false };
 };
 StageRing g_ring;
 
 int ring_init()
 {
 	if (g_ring.buf[0] != nullptr) { return 0; }
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < STAGE_SLOTS; i++) {
 		CTBD_CUDA(cudaMallocHost(&g_ring.buf[i], STAGE_CHUNK));
 		CTBD_CUDA(cudaEventCreateWithFlags(&g_ring.ev[i], cudaEventDisableTiming));
 	}
@@ -126,7 +128,7 @@ int ctbd_shutdown(void)
 	Runtime& r = rt();
 	if (!r.ready) { return 0; }
 	cudaStreamSynchronize(r.stream);
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < STAGE_SLOTS; i++) {
 		if (g_ring.buf[i] != nullptr) { cudaFreeHost(g_ring.buf[i]); g_ring.buf[i] = nullptr; }
 		if (g_ring.ev[i] != nullptr) { cudaEventDestroy(g_ring.ev[i]); g_ring.ev[i] = nullptr; }
 		g_ring.busy[i] = false;
@@ -212,7 +214,7 @@ int ctbd_d2h(void* hptr, const void* dptr, size_t bytes)
 namespace {
 struct Piece { int b; int64_t boff, n; size_t pos; };          /* block, byte offset inside the block, bytes, position in the chunk */
 struct Chunk { int64_t dev, len; size_t p0, p1; };
-constexpr int64_t PIECE_MAX = (int64_t)1 << 20;                /* split large blocks so that the host copy parallelises */
+constexpr int64_t PIECE_MAX = (int64_t)256 << 10;               /* split large blocks so that the host copy parallelises */
 
 void plan_chunks(int nblk, const int64_t* dev_off, const int64_t* nbytes, std::vector<Piece>& pieces, std::vector<Chunk>& chunks)
 {
@@ -245,18 +247,19 @@ int host_copy_threads()
 int ctbd_h2d_blocks(void* dptr, int nblk, const void* const* hptrs, const int64_t* dst_off, const int64_t* nbytes)
 {
 	CTBD_REQUIRE_INIT();
+	CTBD_CUDA(cudaSetDevice(rt().device));      /* may run on a helper thread of the host side (the current device is per thread) */
 	if (ring_init() < 0) { return -1; }
 	std::vector<Piece> pieces; std::vector<Chunk> chunks;
 	plan_chunks(nblk, dst_off, nbytes, pieces, chunks);
 	const int nt = host_copy_threads();
 	for (size_t ci = 0; ci < chunks.size(); ci++)
 	{
-		const int slot = (int)(ci & 1);
+		const int slot = (int)(ci % STAGE_SLOTS);
 		if (ring_wait(slot) < 0) { return -1; }
 		char* stage = (char*)g_ring.buf[slot];
 		const long p0 = (long)chunks[ci].p0, p1 = (long)chunks[ci].p1;
 		/* pack: pageable host blocks -> pinned chunk, in parallel (the previous chunk is on the copy engine meanwhile) */
-		#pragma omp parallel for schedule(dynamic, 4) num_threads(nt) if (p1 - p0 > 8)
+		#pragma omp parallel for schedule(dynamic, 2) num_threads(nt) if (p1 - p0 > 2)
 		for (long q = p0; q < p1; q++) { memcpy(stage + pieces[q].pos, (const char*)hptrs[pieces[q].b] + pieces[q].boff, (size_t)pieces[q].n); }
 		CTBD_CUDA(cudaMemcpyAsync((char*)dptr + chunks[ci].dev, stage, (size_t)chunks[ci].len, cudaMemcpyHostToDevice, rt().stream));
 		CTBD_CUDA(cudaEventRecord(g_ring.ev[slot], rt().stream));
@@ -274,24 +277,57 @@ int ctbd_d2h_blocks(const void* dptr, int nblk, void* const* hptrs, const int64_
 	plan_chunks(nblk, src_off, nbytes, pieces, chunks);
 	const int nt = host_copy_threads();
 	auto issue = [&](size_t ci) -> int {
-		const int slot = (int)(ci & 1);
+		const int slot = (int)(ci % STAGE_SLOTS);
 		if (ring_wait(slot) < 0) { return -1; }
 		CTBD_CUDA(cudaMemcpyAsync(g_ring.buf[slot], (const char*)dptr + chunks[ci].dev, (size_t)chunks[ci].len, cudaMemcpyDeviceToHost, rt().stream));
 		CTBD_CUDA(cudaEventRecord(g_ring.ev[slot], rt().stream));
 		g_ring.busy[slot] = true;
 		return 0;
 	};
-	if (!chunks.empty() && issue(0) < 0) { return -1; }
+	/* the copy engine runs STAGE_SLOTS - 1 chunks ahead of the unpacking threads */
+	for (size_t ci = 0; ci + 1 < (size_t)STAGE_SLOTS && ci < chunks.size(); ci++) { if (issue(ci) < 0) { return -1; } }
 	for (size_t ci = 0; ci < chunks.size(); ci++)
 	{
-		const int slot = (int)(ci & 1);
-		if (ci + 1 < chunks.size() && issue(ci + 1) < 0) { return -1; }
+		const int slot = (int)(ci % STAGE_SLOTS);
+		if (ci + STAGE_SLOTS - 1 < chunks.size() && issue(ci + STAGE_SLOTS - 1) < 0) { return -1; }
 		if (ring_wait(slot) < 0) { return -1; }
 		const char* stage = (const char*)g_ring.buf[slot];
 		const long p0 = (long)chunks[ci].p0, p1 = (long)chunks[ci].p1;
 		/* unpack in parallel: the destination blocks are freshly allocated, so this is where their pages get faulted in */
-		#pragma omp parallel for schedule(dynamic, 4) num_threads(nt) if (p1 - p0 > 8)
+		#pragma omp parallel for schedule(dynamic, 2) num_threads(nt) if (p1 - p0 > 2)
 		for (long q = p0; q < p1; q++) { memcpy((char*)hptrs[pieces[q].b] + pieces[q].boff, stage + pieces[q].pos, (size_t)pieces[q].n); }
+	}
+	return 0;
+}
+
+/* Fault in the pages of freshly allocated host blocks with all copy threads (MADV_POPULATE_WRITE where the kernel has it, else one
+ * write per page).  Called while the device is still computing the result that will land in these blocks, so the page faults of
+ * the result download are off the critical path. */
+int ctbd_host_prefault(int nblk, void* const* hptrs, const int64_t* nbytes)
+{
+	std::vector<std::pair<char*, int64_t>> pieces;
+	const int64_t PIECE = (int64_t)2 << 20;
+	for (int b = 0; b < nblk; b++) {
+		for (int64_t off = 0; off < nbytes[b]; off += PIECE) { pieces.push_back(std::make_pair((char*)hptrs[b] + off, std::min<int64_t>(PIECE, nbytes[b] - off))); }
+	}
+	const long np = (long)pieces.size();
+	const int nt = host_copy_threads();
+	static int have_populate = 1;
+	#pragma omp parallel for schedule(dynamic, 4) num_threads(nt) if (np > 8)
+	for (long q = 0; q < np; q++) {
+		char* p0 = pieces[q].first; char* p1 = p0 + pieces[q].second;
+		bool done = false;
+#ifdef MADV_POPULATE_WRITE
+		if (have_populate) {
+			char* a0 = (char*)(((uintptr_t)p0 + 4095) & ~(uintptr_t)4095);
+			char* a1 = (char*)((uintptr_t)p1 & ~(uintptr_t)4095);
+			if (a1 > a0) {
+				if (madvise(a0, (size_t)(a1 - a0), MADV_POPULATE_WRITE) == 0) { done = true; p0[0] = 0; p1[-1] = 0; }
+				else { have_populate = 0; }
+			}
+		}
+#endif
+		if (!done) { for (char* p = p0; p < p1; p += 4096) { *(volatile char*)p = 0; } p1[-1] = 0; }
 	}
 	return 0;
 }

@@ -405,12 +405,20 @@ static int split_bond(const struct ctb_tensor* a, const struct ctb_tensor* r, in
 
 int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h)
 {
+	return ctb_heff_prepare_ex(a, w, l, r, h, NULL, NULL);
+}
+
+int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h,
+	void (*l_ready)(void*), void* ctx)
+{
 	CTB_REQUIRE(a->ndim == 3 && w->ndim == 4 && l->ndim == 4 && r->ndim == 4);
 	memset(h, 0, sizeof(*h));
 	h->w = w; h->r = r;
 	h->world = 1; h->rank = 0;
 	if (ctb_dist_world > 1)
 	{
+		/* the column slice of r is cut on the device right away: no overlap with in-flight payloads in the sharded case */
+		if (l_ready != NULL) { l_ready(ctx); l_ready = NULL; }
 		const int W = ctb_dist_world;
 		CTB_REQUIRE(W <= 8);
 		h->ind = ctb_calloc((size_t)W, sizeof(ct_long*));
@@ -488,15 +496,21 @@ int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, str
 		}
 	}
 	const struct ctb_tensor* ru = h->r;
+	const int trace = getenv("CTB_TRACE") != NULL;
+	const double tp0 = ctb_wall_ms();
 	/* step 1: a . r  -> t1 [dd, Dw', Dl, Dr', x'] */
 	const int perm0[5] = { 1, 2, 0, 3, 4 };
 	h->t1 = ctb_dot_prepare(a, TENSOR_AXIS_RANGE_TRAILING, 0, ru, TENSOR_AXIS_RANGE_LEADING, 0, 1, perm0, 1, &h->p1);
+	const double tp1 = ctb_wall_ms();
 	/* step 2: w . t1 over (dd_in, Dw') -> t2 [Dl, Dw, dd_out, Dr', x'] */
 	const int perm1[5] = { 2, 0, 1, 3, 4 };
 	h->t2 = ctb_dot_prepare_ex(w, TENSOR_AXIS_RANGE_TRAILING, 0, h->t1, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1, 1, CTB_DOT_MERGE_ROWS, &h->p2);
+	const double tp2 = ctb_wall_ms();
 	/* step 3: k . t2 over (Dl, Dw), k = transpose(l, [0,3,1,2]) once per bond (the reference redoes it every matvec) */
 	const int perm2[4] = { 0, 3, 1, 2 };
+	if (l_ready != NULL) { l_ready(ctx); }
 	h->k = ctb_transpose(l, perm2, 0);
+	const double tp3 = ctb_wall_ms();
 	struct ctb_tensor* s = NULL;
 	if (h->world > 1 && landing_ensure((size_t)a->nstore * ctb_sizeof_dtype(a->dtype), h->world))
 	{
@@ -517,6 +531,7 @@ int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, str
 	else {
 		s = ctb_dot_prepare(h->k, TENSOR_AXIS_RANGE_TRAILING, 0, h->t2, TENSOR_AXIS_RANGE_LEADING, 0, 2, NULL, 0, &h->p3);
 	}
+	if (trace) { fprintf(stderr, "ctb_heff_prepare: plan1 %.2f ms, plan2 %.2f ms, transpose(l) %.2f ms, plan3 %.2f ms\n", tp1 - tp0, tp2 - tp1, tp3 - tp2, ctb_wall_ms() - tp3); }
 	/* tracing out the two dummy bonds leaves the packed layout unchanged */
 	struct ctb_tensor* bs = ctb_drop_dummy_axes(s, 1);
 	ctb_tensor_free(s);

@@ -122,6 +122,11 @@ bool ctb_tensor_same_structure(const struct ctb_tensor* a, const struct ctb_tens
 /* host struct <-> device tensor */
 struct ctb_tensor* ctb_upload(const struct block_sparse_tensor* h);
 int  ctb_download(const struct ctb_tensor* t, struct block_sparse_tensor* h);   /* allocates the host payload */
+/* the two halves of ctb_upload / ctb_download, for callers that overlap the payload copies with other work */
+struct ctb_tensor* ctb_upload_begin(const struct block_sparse_tensor* h);
+int  ctb_upload_data(struct ctb_tensor* t, const struct block_sparse_tensor* h);
+void ctb_download_begin(const struct ctb_tensor* t, struct block_sparse_tensor* h, int prefault);
+int  ctb_download_data(const struct ctb_tensor* t, struct block_sparse_tensor* h);
 int  ctb_upload_entries(struct ctb_tensor* t, const void* entries);     /* packed entries, serialize order */
 int  ctb_download_entries(const struct ctb_tensor* t, void* entries);
 int  ctb_set_entry(struct ctb_tensor* t, ct_long offset, double re, double im);
@@ -217,6 +222,10 @@ struct ctb_heff
 /* rank / world of this process (ctb_dist_init); world == 1 means no sharding */
 extern int ctb_dist_rank, ctb_dist_world;
 int  ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h);
+/* the same; 'l_ready(ctx)' (may be NULL) is called right before the first device use of l's payload, so that a caller can build the
+ * plans of steps 1 and 2 (which need structure only, and the payload of w) while the payloads of a, l and r are still in flight */
+int  ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h,
+	void (*l_ready)(void*), void* ctx);
 int  ctb_heff_apply(struct ctb_heff* h, const void* a_data, void* b_data);
 int  ctb_heff_step3(struct ctb_heff* h, void* b_data);
 void ctb_dist_release_buffers(void);

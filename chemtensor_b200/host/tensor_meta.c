@@ -333,31 +333,51 @@ static void host_allocate_bst(int dtype, int ndim, const ct_long* dim, const enu
 	for (int i = 0; i < ndim; i++) { ctb_axis_free(&axes[i]); }
 }
 
-struct ctb_tensor* ctb_upload(const struct block_sparse_tensor* h)
+/* device tensor with the structure of the host tensor, buffer allocated, payload not yet copied */
+struct ctb_tensor* ctb_upload_begin(const struct block_sparse_tensor* h)
 {
 	int dirs[CTB_MAXDIM];
 	for (int i = 0; i < h->ndim; i++) { dirs[i] = (int)h->axis_dir[i]; }
-	struct ctb_tensor* t = ctb_tensor_create(h->dtype, h->ndim, h->dim_logical, dirs, (const qnumber* const*)h->qnums_logical, 1);
-	if (t->nstore == 0) { return t; }
+	return ctb_tensor_create(h->dtype, h->ndim, h->dim_logical, dirs, (const qnumber* const*)h->qnums_logical, 1);
+}
+
+/* host block pointers, byte offsets in the packed device buffer and byte lengths of the stored blocks */
+static void block_lists(const struct ctb_tensor* t, const struct block_sparse_tensor* h, void*** hptrs, int64_t** offs, int64_t** lens)
+{
 	const size_t esize = ctb_sizeof_dtype(t->dtype);
-	/* the separately allocated host blocks stream through the pinned staging ring of the device layer */
-	const void** hptrs = malloc((size_t)t->nblk * sizeof(void*));
-	int64_t* offs = malloc((size_t)t->nblk * sizeof(int64_t));
-	int64_t* lens = malloc((size_t)t->nblk * sizeof(int64_t));
+	*hptrs = malloc((size_t)t->nblk * sizeof(void*));
+	*offs = malloc((size_t)t->nblk * sizeof(int64_t));
+	*lens = malloc((size_t)t->nblk * sizeof(int64_t));
 	for (int b = 0; b < t->nblk; b++)
 	{
 		const struct dense_tensor* hb = h->blocks[t->blk_grid[b]];
 		CTB_REQUIRE(hb != NULL);
 		ct_long numel = 1;
 		for (int i = 0; i < hb->ndim; i++) { numel *= hb->dim[i]; }
-		hptrs[b] = hb->data; offs[b] = (int64_t)t->blk_off[b] * (int64_t)esize; lens[b] = (int64_t)numel * (int64_t)esize;
+		(*hptrs)[b] = hb->data; (*offs)[b] = (int64_t)t->blk_off[b] * (int64_t)esize; (*lens)[b] = (int64_t)numel * (int64_t)esize;
 	}
-	CTB_CHECK_ABORT(ctbd_h2d_blocks(t->d, t->nblk, hptrs, offs, lens));
+}
+
+/* payload copy of ctb_upload: the separately allocated host blocks stream through the pinned staging ring of the device layer */
+int ctb_upload_data(struct ctb_tensor* t, const struct block_sparse_tensor* h)
+{
+	if (t->nstore == 0) { return 0; }
+	void** hptrs; int64_t* offs; int64_t* lens;
+	block_lists(t, h, &hptrs, &offs, &lens);
+	const int rc = ctbd_h2d_blocks(t->d, t->nblk, (const void* const*)hptrs, offs, lens);
 	free(hptrs); free(offs); free(lens);
+	return rc;
+}
+
+struct ctb_tensor* ctb_upload(const struct block_sparse_tensor* h)
+{
+	struct ctb_tensor* t = ctb_upload_begin(h);
+	CTB_CHECK_ABORT(ctb_upload_data(t, h));
 	return t;
 }
 
-int ctb_download(const struct ctb_tensor* t, struct block_sparse_tensor* h)
+/* allocates the host payload of the result (uninitialised); with 'prefault' its pages are faulted in by the copy threads right away */
+void ctb_download_begin(const struct ctb_tensor* t, struct block_sparse_tensor* h, int prefault)
 {
 	ct_long dim[CTB_MAXDIM];
 	enum tensor_axis_direction dirs[CTB_MAXDIM];
@@ -368,22 +388,28 @@ int ctb_download(const struct ctb_tensor* t, struct block_sparse_tensor* h)
 		qn[i] = t->ax[i].qlog;
 	}
 	host_allocate_bst(t->dtype, t->ndim, dim, dirs, qn, h, 0);
-	if (t->nstore == 0) { return 0; }
-	const size_t esize = ctb_sizeof_dtype(t->dtype);
-	void** hptrs = malloc((size_t)t->nblk * sizeof(void*));
-	int64_t* offs = malloc((size_t)t->nblk * sizeof(int64_t));
-	int64_t* lens = malloc((size_t)t->nblk * sizeof(int64_t));
-	for (int b = 0; b < t->nblk; b++)
-	{
-		struct dense_tensor* hb = h->blocks[t->blk_grid[b]];
-		CTB_REQUIRE(hb != NULL);
-		ct_long numel = 1;
-		for (int i = 0; i < hb->ndim; i++) { numel *= hb->dim[i]; }
-		hptrs[b] = hb->data; offs[b] = (int64_t)t->blk_off[b] * (int64_t)esize; lens[b] = (int64_t)numel * (int64_t)esize;
+	if (prefault && t->nstore > 0) {
+		void** hptrs; int64_t* offs; int64_t* lens;
+		block_lists(t, h, &hptrs, &offs, &lens);
+		CTB_CHECK_ABORT(ctbd_host_prefault(t->nblk, hptrs, lens));
+		free(hptrs); free(offs); free(lens);
 	}
-	int rc = ctbd_d2h_blocks(t->d, t->nblk, hptrs, offs, lens);
+}
+
+int ctb_download_data(const struct ctb_tensor* t, struct block_sparse_tensor* h)
+{
+	if (t->nstore == 0) { return 0; }
+	void** hptrs; int64_t* offs; int64_t* lens;
+	block_lists(t, h, &hptrs, &offs, &lens);
+	const int rc = ctbd_d2h_blocks(t->d, t->nblk, hptrs, offs, lens);
 	free(hptrs); free(offs); free(lens);
 	return rc;
+}
+
+int ctb_download(const struct ctb_tensor* t, struct block_sparse_tensor* h)
+{
+	ctb_download_begin(t, h, 0);
+	return ctb_download_data(t, h);
 }
 
 int ctb_upload_entries(struct ctb_tensor* t, const void* entries)

@@ -40,18 +40,32 @@ static void append_offset_table(struct i32vec* tab, int first, int count, const 
 	ct_long total = 1;
 	for (int a = 0; a < count; a++) { total *= nat[first + a]->secdim[nat_sec[first + a]]; }
 	i32vec_reserve(tab, (size_t)total);
+	if (count == 0) { CTB_REQUIRE(base < ((ct_long)1 << 31)); tab->v[tab->n++] = (int32_t)base; return; }
+	/* the innermost axis is a plain strided run (or a lookup through the position map); the outer axes advance a digit counter */
+	const int last = count - 1;
+	const ct_long nlast = nat[first + last]->secdim[nat_sec[first + last]];
+	const ct_long slast = stride_r[pos_of_nat[first + last]];
+	const bool map_last = (first + last == g_map_nat);
 	int dig[CTB_MAXDIM] = { 0 };
-	for (ct_long i = 0; i < total; i++)
+	int32_t* out = tab->v + tab->n;
+	for (ct_long i = 0; i < total; i += nlast)
 	{
 		ct_long off = base;
-		for (int a = 0; a < count; a++) { off += (first + a == g_map_nat ? (ct_long)g_map_pos[dig[a]] : (ct_long)dig[a]) * stride_r[pos_of_nat[first + a]]; }
-		CTB_REQUIRE(off < ((ct_long)1 << 31));
-		tab->v[tab->n++] = (int32_t)off;
-		for (int a = count - 1; a >= 0; a--) {
+		for (int a = 0; a < last; a++) { off += (first + a == g_map_nat ? (ct_long)g_map_pos[dig[a]] : (ct_long)dig[a]) * stride_r[pos_of_nat[first + a]]; }
+		const ct_long hi = off + (map_last ? (nlast > 0 ? (ct_long)g_map_pos[nlast - 1] : 0) : nlast - 1) * slast;
+		CTB_REQUIRE(off < ((ct_long)1 << 31) && hi < ((ct_long)1 << 31));
+		if (map_last) {
+			for (ct_long j = 0; j < nlast; j++) { CTB_REQUIRE(g_map_pos[j] * slast + off < ((ct_long)1 << 31)); out[i + j] = (int32_t)(off + (ct_long)g_map_pos[j] * slast); }
+		}
+		else {
+			for (ct_long j = 0; j < nlast; j++) { out[i + j] = (int32_t)(off + j * slast); }
+		}
+		for (int a = last - 1; a >= 0; a--) {
 			if (++dig[a] < nat[first + a]->secdim[nat_sec[first + a]]) { break; }
 			dig[a] = 0;
 		}
 	}
+	tab->n += (size_t)total;
 }
 
 struct merge_key { ct_long key; int blk; };
@@ -75,6 +89,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 {
 	CTB_REQUIRE(s->dtype == t->dtype);
 	CTB_REQUIRE(ndim_mult >= 1 && s->ndim >= ndim_mult && t->ndim >= ndim_mult);
+	const double tp_begin = ctb_wall_ms();
 	const int nfs = s->ndim - ndim_mult;   /* free axes of s */
 	const int nft = t->ndim - ndim_mult;   /* free axes of t */
 	const int ndimr = nfs + nft;
@@ -422,7 +437,9 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	if (use_rowtab && nbrow > 0) { h.b_rowtab = browtab; h.n_b_rowtab = (int64_t)nbrow; }
 	if (mixmode && nmg > 0) { h.mix_groups = mgroups; h.n_mix_groups = (int32_t)nmg; h.mix_rows = mrows; h.n_mix_rows = (int32_t)nmr; }
 	plan->dev = NULL;
+	const double tpc = ctb_wall_ms();
 	CTB_CHECK_ABORT(ctbd_gemm_plan_create(&h, &plan->dev));
+	if (getenv("CTB_TRACE") != NULL) { fprintf(stderr, "  dot plan: host lists %.2f ms, device plan %.2f ms (%d blocks, %d segments, %d table entries)\n", tpc - tp_begin, ctb_wall_ms() - tpc, nouts, (int)nseg, (int)tab.n); }
 	plan->flops = flops;
 	plan->nouts = nouts; plan->nsegs = (int)nseg;
 	plan->ntiles = 0;

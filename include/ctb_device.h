@@ -77,6 +77,9 @@ int ctbd_d2d(void* dst, const void* src, size_t bytes);
  * streamed through the layer's persistent pinned staging ring; h2d returns once the host blocks have been consumed */
 int ctbd_h2d_blocks(void* dptr, int nblk, const void* const* hptrs, const int64_t* dst_off, const int64_t* nbytes);
 int ctbd_d2h_blocks(const void* dptr, int nblk, void* const* hptrs, const int64_t* src_off, const int64_t* nbytes);
+/* fault in the pages of freshly allocated (not yet written) host blocks in parallel; their contents are undefined afterwards.  Lets
+ * the caller take the page faults of a result download while the device is still computing that result */
+int ctbd_host_prefault(int nblk, void* const* hptrs, const int64_t* nbytes);
 int ctbd_sync(void);
 int ctbd_host_alloc(void** hptr, size_t bytes);      /* pinned host staging memory */
 int ctbd_host_free(void* hptr);

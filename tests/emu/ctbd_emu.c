@@ -125,6 +125,7 @@ int ctbd_gemm_run_multi(void* plan, const void* A, const void* B, int ndst, void
 	return 0;
 }
 int ctbd_d2d(void* dst, const void* src, size_t bytes) { memmove(dst, src, bytes); return 0; }
+int ctbd_host_prefault(int nblk, void* const* hptrs, const int64_t* nbytes) { (void)nblk; (void)hptrs; (void)nbytes; return 0; }
 int ctbd_sync(void) { return 0; }
 int ctbd_host_alloc(void** hptr, size_t bytes) { *hptr = malloc(bytes ? bytes : 1); return *hptr ? 0 : -1; }
 int ctbd_host_free(void* hptr) { free(hptr); return 0; }
@@ -156,6 +157,20 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan)
 		p->a_packed = calloc((size_t)h->n_a_gather, es);
 		for (int64_t i = 0; i < h->n_a_gather; i++) {
 			if (h->a_gather[i] >= 0) { memcpy((char*)p->a_packed + (size_t)i * es, (const char*)h->a_src + (size_t)h->a_gather[i] * es, es); }
+		}
+	}
+	/* analysis aid: CTB_EMU_PLAN_DUMP=<file> appends the block shapes of every plan (one line per output block: m n k1 k2 ...) */
+	const char* dump = getenv("CTB_EMU_PLAN_DUMP");
+	if (dump != NULL && h->n_mix_groups == 0) {
+		FILE* f = fopen(dump, "a");
+		if (f != NULL) {
+			fprintf(f, "plan %d %d %d %d\n", h->dtype, h->a_kcontig, h->b_ncontig, h->nouts);
+			for (int b = 0; b < h->nouts; b++) {
+				fprintf(f, "%d %d", h->outs[b].m, h->outs[b].n);
+				for (int sg = h->outs[b].seg_begin; sg < h->outs[b].seg_end; sg++) { fprintf(f, " %d", h->segs[sg].k); }
+				fprintf(f, "\n");
+			}
+			fclose(f);
 		}
 	}
 	*plan = p;
