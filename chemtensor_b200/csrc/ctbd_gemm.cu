@@ -283,6 +283,7 @@ struct GemmArgs
 	const void* A; const void* B; void* C;
 	int conj_a, conj_b;
 	int a_odd, b_odd;     /* operand base pointer is 8 (mod 16): shifts the parity test of the 16-byte copy path */
+	int c_odd;            /* multi-destination runs: some destination base is 8 (mod 16), 16-byte stores are then off */
 	const int64_t* b_rowtab;   /* optional: B rows gathered through a row table, seg.b_off indexes it (merged-row plans) */
 	int ndst;                  /* >= 1: additional destinations of the epilogue (peer-mapped buffers of the other GPUs) follow */
 	void* Cx[7];
@@ -460,15 +461,32 @@ __global__ void __launch_bounds__(Cfg::NT) grouped_gemm_kernel(const GemmArgs ar
 				if constexpr (!CPLX) { v0 = acc[i][j][0]; v1 = acc[i][j][1]; }
 				else { v0 = make_double2(acc[i][j][0], acc[i][j][2]); v1 = make_double2(acc[i][j][1], acc[i][j][3]); }
 				const int64_t o0 = out.c_off + ro + (gc < N ? coltab[gc] : 0), o1 = out.c_off + ro + (gc + 1 < N ? coltab[gc + 1] : 0);
-				if (gc < N)     { Cg[o0 - out.c_off] = v0; }
-				if (gc + 1 < N) { Cg[o1 - out.c_off] = v1; }
 				if (args.ndst > 1) {
-					/* fused all-gather: the same element goes to the peer-mapped result buffers of the other GPUs (posted NVLink stores) */
-					for (int d = 0; d < args.ndst - 1; d++) {
-						T* __restrict__ Cp = reinterpret_cast<T*>(args.Cx[d]);
-						if (gc < N)     { Cp[o0] = v0; }
-						if (gc + 1 < N) { Cp[o1] = v1; }
+					/* fused all-gather: the same element goes to the local result and to the peer-mapped result buffers of the other GPUs
+					 * (posted NVLink stores).  Two neighbouring columns travel as ONE 16-byte store where the layout allows it: full
+					 * sectors on the link instead of byte-masked halves. */
+					bool pair = false;
+					if constexpr (!CPLX) { pair = (args.c_odd == 0) && (gc + 1 < N) && (o1 == o0 + 1) && ((o0 & 1) == 0); }
+					if (pair) {
+						if constexpr (!CPLX) {
+							const double2 vv = make_double2(v0, v1);
+							*reinterpret_cast<double2*>(reinterpret_cast<T*>(args.C) + o0) = vv;
+							for (int d = 0; d < args.ndst - 1; d++) { *reinterpret_cast<double2*>(reinterpret_cast<T*>(args.Cx[d]) + o0) = vv; }
+						}
 					}
+					else {
+						if (gc < N)     { Cg[o0 - out.c_off] = v0; }
+						if (gc + 1 < N) { Cg[o1 - out.c_off] = v1; }
+						for (int d = 0; d < args.ndst - 1; d++) {
+							T* __restrict__ Cp = reinterpret_cast<T*>(args.Cx[d]);
+							if (gc < N)     { Cp[o0] = v0; }
+							if (gc + 1 < N) { Cp[o1] = v1; }
+						}
+					}
+				}
+				else {
+					if (gc < N)     { Cg[o0 - out.c_off] = v0; }
+					if (gc + 1 < N) { Cg[o1 - out.c_off] = v1; }
 				}
 			}
 		}
@@ -918,7 +936,7 @@ int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
 	args.conj_a = p->conj_a; args.conj_b = p->conj_b;
 	args.a_odd = (int)(((uintptr_t)args.A >> 3) & 1); args.b_odd = (int)(((uintptr_t)args.B >> 3) & 1);
 	args.b_rowtab = p->b_rowtab;
-	args.ndst = 1;
+	args.ndst = 1; args.c_odd = 0;
 	return CTBD_GEMM_DISPATCH(launch_cfg, p, args);
 }
 
@@ -936,6 +954,8 @@ int ctbd_gemm_run_multi(void* plan, const void* A, const void* B, int ndst, void
 	args.a_odd = (int)(((uintptr_t)args.A >> 3) & 1); args.b_odd = (int)(((uintptr_t)args.B >> 3) & 1);
 	args.b_rowtab = p->b_rowtab;
 	args.ndst = ndst;
+	args.c_odd = 0;
+	for (int d = 0; d < ndst; d++) { if ((((uintptr_t)Cs[d]) >> 3) & 1) { args.c_odd = 1; } }
 	for (int d = 1; d < ndst; d++) { args.Cx[d - 1] = Cs[d]; }
 	return CTBD_GEMM_DISPATCH(launch_cfg, p, args);
 }

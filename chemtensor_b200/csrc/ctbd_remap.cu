@@ -204,6 +204,35 @@ __global__ void __launch_bounds__(256) copy2d_kernel(int ntiles, const CopyTile*
 	}
 }
 
+struct CopySrcs { const void* p[8]; int64_t stride; int vec_ok; };
+
+/* source rows may live in peer memory: 16-byte loads where the run allows it, every lane keeps several loads in flight */
+template <typename T>
+__global__ void __launch_bounds__(256) copy2d_multi_kernel(int ntiles, const CopyTile* __restrict__ tiles, const ctbd_copy2d* __restrict__ descs,
+	const CopySrcs srcs, T* __restrict__ dst)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+	{
+		const CopyTile tl = tiles[t];
+		const ctbd_copy2d d = descs[tl.desc];
+		const int64_t q = d.src_off / srcs.stride, off = d.src_off - q * srcs.stride;
+		const T* __restrict__ sbase = reinterpret_cast<const T*>(srcs.p[q]) + off;
+		const int r1 = min(tl.row0 + COPY_ROWS, d.rows);
+		const bool vec = (sizeof(T) == 8) && srcs.vec_ok && ((d.cols & 1) == 0) && ((d.src_ld & 1) == 0) && ((d.dst_ld & 1) == 0) && ((off & 1) == 0) && ((d.dst_off & 1) == 0);
+		for (int i = tl.row0 + warp; i < r1; i += 8) {
+			const T* __restrict__ s = sbase + (int64_t)i * d.src_ld;
+			T* __restrict__ o = dst + d.dst_off + (int64_t)i * d.dst_ld;
+			if (vec) {
+				const double2* __restrict__ s2 = reinterpret_cast<const double2*>(s);
+				double2* __restrict__ o2 = reinterpret_cast<double2*>(o);
+				for (int j = lane; j < d.cols / 2; j += 32) { o2[j] = s2[j]; }
+			}
+			else { for (int j = lane; j < d.cols; j += 32) { o[j] = s[j]; } }
+		}
+	}
+}
+
 } // namespace ctbd
 
 using namespace ctbd;
@@ -294,6 +323,24 @@ int ctbd_copy_plan_run(void* plan, const void* src, void* dst)
 	const int grid = std::min(p->ntiles, rt().sm_count * 16);
 	if (p->dtype == CTBD_F64) { copy2d_kernel<double><<<grid, 256, 0, rt().stream>>>(p->ntiles, p->tiles, p->descs, (const double*)src, (double*)dst); }
 	else                      { copy2d_kernel<double2><<<grid, 256, 0, rt().stream>>>(p->ntiles, p->tiles, p->descs, (const double2*)src, (double2*)dst); }
+	CTBD_LAUNCH_CHECK();
+	return 0;
+}
+
+int ctbd_copy_plan_run_multi(void* plan, int nsrc, const void* const* srcs, int64_t src_stride, void* dst)
+{
+	CopyPlan* p = (CopyPlan*)plan;
+	if (p == nullptr || p->ntiles == 0) { return 0; }
+	if (nsrc < 1 || nsrc > 8 || src_stride <= 0) { return fail_msg("copy plan: between 1 and 8 sources"); }
+	CopySrcs cs;
+	for (int i = 0; i < 8; i++) { cs.p[i] = srcs[i < nsrc ? i : 0]; }
+	cs.stride = src_stride;
+	bool aligned = (((uintptr_t)dst) & 15) == 0;
+	for (int i = 0; i < nsrc; i++) { aligned = aligned && ((((uintptr_t)srcs[i]) & 15) == 0); }
+	cs.vec_ok = aligned ? 1 : 0;
+	const int grid = std::min(p->ntiles, rt().sm_count * 8);
+	if (p->dtype == CTBD_F64) { copy2d_multi_kernel<double><<<grid, 256, 0, rt().stream>>>(p->ntiles, p->tiles, p->descs, cs, (double*)dst); }
+	else                      { copy2d_multi_kernel<double2><<<grid, 256, 0, rt().stream>>>(p->ntiles, p->tiles, p->descs, cs, (double2*)dst); }
 	CTBD_LAUNCH_CHECK();
 	return 0;
 }

@@ -28,6 +28,8 @@ int ctb_dist_init(int rank, int world, const void* unique_id)
 int ctb_dist_set_allgather(ctbd_allgather_fn fn, void* ctx) { return ctbd_dist_set_allgather(fn, ctx); }
 /* out[0] = rank, out[1] = world, out[2] = exchanges done by the fused peer-store path, out[3] = by all-gather + scatter */
 int ctb_dist_info(long long* out) { out[0] = ctb_dist_rank; out[1] = ctb_dist_world; ctb_dist_counters(&out[2], &out[3]); return 0; }
+/* exchanges done by the pull path (peer-mapped send buffers read over NVLink) */
+long long ctb_dist_pull_exchanges(void) { return ctb_dist_pull_count(); }
 int ctb_dist_finalize(void) { ctb_dist_release_buffers(); ctb_dist_rank = 0; ctb_dist_world = 1; return ctbd_dist_finalize(); }
 int ctb_backend(void) { return ctbd_backend(); }
 long long ctb_launch_count(void) { return ctbd_launch_count(); }
@@ -585,7 +587,8 @@ void apply_local_hamiltonian(const struct block_sparse_tensor* a, const struct b
 	pthread_mutex_init(&job.mtx, NULL);
 	pthread_cond_init(&job.cv, NULL);
 	pthread_t th;
-	const bool threaded = (getenv("CTB_NO_OVERLAP") == NULL) && (pthread_create(&th, NULL, heff_upload_main, &job) == 0);
+	/* sharded: the plan builder cuts the column slice of r on the device right away, so all payloads go first */
+	const bool threaded = (ctb_dist_world == 1) && (getenv("CTB_NO_OVERLAP") == NULL) && (pthread_create(&th, NULL, heff_upload_main, &job) == 0);
 	if (!threaded) { heff_upload_main(&job); }
 	const double t1 = ctb_wall_ms();
 	struct ctb_heff h;
@@ -638,9 +641,10 @@ int ctb_heff_benchmark(const struct block_sparse_tensor* a, const struct block_s
 		CTB_CHECK(ctbd_event_record(e1));
 		CTB_CHECK(ctb_dot_exec(&h.p2, wd->d, h.t1->d, h.t2->d));
 		CTB_CHECK(ctbd_event_record(e2));
-		CTB_CHECK(ctb_heff_step3(&h, bd->d));
+		void* bl = ctb_heff_result_buffer(&h);      /* fused exchange: consume in place, as the Lanczos loop does */
+		CTB_CHECK(ctb_heff_step3(&h, bl != NULL ? bl : bd->d));
 		CTB_CHECK(ctbd_event_record(e3));
-		CTB_CHECK(ctb_heff_exchange(&h, bd->d));
+		CTB_CHECK(ctb_heff_exchange(&h, bl != NULL ? bl : bd->d));
 		CTB_CHECK(ctbd_event_record(e4));
 		float ms;
 		CTB_CHECK(ctbd_event_elapsed_ms(e0, e4, &ms)); tot += ms;

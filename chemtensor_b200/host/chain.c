@@ -334,7 +334,56 @@ static int landing_ensure(size_t bytes, int world)
 	return 1;
 }
 
-void ctb_dist_release_buffers(void) { landing_release(); g_land_failed = 0; }
+/* ---- peer-mapped send buffers of the pull exchange (two, used alternately): every rank writes its result slice locally, and after
+ * the barrier one kernel per rank reads the slices of all ranks over NVLink straight into the packed result ---- */
+static void* g_send[2] = { NULL, NULL };
+static void** g_send_ptrs[2] = { NULL, NULL };
+static size_t g_send_bytes = 0;
+static int g_send_flip = 0, g_send_failed = 0;
+static long long g_pull_count = 0;
+
+static void send_release(void)
+{
+	for (int i = 0; i < 2; i++) {
+		if (g_send[i] != NULL) { ctbd_peer_buffer_destroy(g_send[i]); g_send[i] = NULL; }
+		free(g_send_ptrs[i]); g_send_ptrs[i] = NULL;
+	}
+	g_send_bytes = 0; g_send_flip = 0;
+}
+
+/* collective: every rank calls it with the same size; returns 1 when both send buffers are available */
+static int send_ensure(size_t bytes, int world)
+{
+	if (g_send_failed) { return 0; }
+	if (g_send[0] != NULL && bytes <= g_send_bytes) { return 1; }
+	send_release();
+	const size_t want = bytes + bytes / 4 + 4096;
+	for (int i = 0; i < 2; i++) {
+		if (ctbd_peer_buffer_create(want, &g_send[i]) < 0) { g_send_failed = 1; send_release(); return 0; }
+		g_send_ptrs[i] = calloc((size_t)world, sizeof(void*));
+		ctbd_peer_buffer_ptrs(g_send[i], g_send_ptrs[i]);
+	}
+	g_send_bytes = want;
+	return 1;
+}
+
+/* exchange form of the sharded effective Hamiltonian: CTB_EXCHANGE = fused | pull | allgather (default: see exchange_mode) */
+enum { EXCH_ALLGATHER = 0, EXCH_FUSED = 1, EXCH_PULL = 2 };
+static int exchange_mode(int world)
+{
+	const char* env = getenv("CTB_EXCHANGE");
+	if (env != NULL) {
+		if (strcmp(env, "fused") == 0) { return EXCH_FUSED; }
+		if (strcmp(env, "pull") == 0) { return EXCH_PULL; }
+		if (strcmp(env, "allgather") == 0) { return EXCH_ALLGATHER; }
+	}
+	if (getenv("CTB_NO_FUSED_EXCHANGE") != NULL) { return EXCH_ALLGATHER; }
+	(void)world;
+	return EXCH_FUSED;
+}
+
+void ctb_dist_release_buffers(void) { landing_release(); g_land_failed = 0; send_release(); g_send_failed = 0; }
+long long ctb_dist_pull_count(void) { return g_pull_count; }
 void ctb_dist_counters(long long* fused, long long* allgather) { *fused = g_fused_count; *allgather = g_allgather_count; }
 
 /* Split of the bra bond of r among 'world' ranks.  Every sector is cut into ceil(m / grain) nearly equal contiguous chunks
@@ -353,7 +402,7 @@ static int cmp_chunk_desc(const void* x, const void* y)
 static int split_bond(const struct ctb_tensor* a, const struct ctb_tensor* r, int world, ct_long** ind, ct_long* nind)
 {
 	const struct ctb_axis* ax = &r->ax[2];
-	ct_long grain = 128;
+	ct_long grain = (world >= 8) ? 64 : 128;      /* one or two 64-column GEMM tiles */
 	const char* env = getenv("CTB_SHARD_GRAIN");
 	if (env != NULL && atol(env) > 0) { grain = atol(env); }
 	/* flops per column of each bra sector: sum over blocks r[Dr, w', Dr' = s] of (rows of a with that Dr sector) * nDr * mw' */
@@ -378,12 +427,18 @@ static int split_bond(const struct ctb_tensor* a, const struct ctb_tensor* r, in
 		const ct_long m = ax->secdim[s];
 		ct_long parts = (m + grain - 1) / grain;
 		/* never fewer chunks in total than ranks: small bonds are cut finer */
-		if (ax->dim < grain * world) { parts = (m * world + ax->dim - 1) / ax->dim; if (parts > m) { parts = m; } if (parts < 1) { parts = 1; } }
+		const bool fine = (ax->dim < grain * world);
+		if (fine) { parts = (m * world + ax->dim - 1) / ax->dim; if (parts > m) { parts = m; } if (parts < 1) { parts = 1; } }
 		for (ct_long c = 0; c < parts; c++) {
-			const ct_long p0 = (m * c) / parts, p1 = (m * (c + 1)) / parts;
+			/* chunk boundaries on multiples of the grain: whatever set of chunks a rank receives, its blocks are whole tiles plus at
+			 * most one remainder per sector */
+			const ct_long p0 = fine ? (m * c) / parts : c * grain;
+			const ct_long p1 = fine ? (m * (c + 1)) / parts : ((c + 1) * grain < m ? (c + 1) * grain : m);
 			if (p1 <= p0) { continue; }
 			if (nch == cap) { cap *= 2; ch = realloc(ch, cap * sizeof(*ch)); }
-			ch[nch].sec = s; ch[nch].pos0 = p0; ch[nch].len = p1 - p0; ch[nch].cost = (double)(p1 - p0) * (wcol[s] > 0 ? wcol[s] : 1.0);
+			ch[nch].sec = s; ch[nch].pos0 = p0; ch[nch].len = p1 - p0;
+			/* priced with the tile padding of a remainder chunk (64-column tiles) */
+			ch[nch].cost = (double)(fine ? (p1 - p0) : ((p1 - p0 + 63) / 64) * 64) * (wcol[s] > 0 ? wcol[s] : 1.0);
 			nch++;
 		}
 	}
@@ -512,7 +567,9 @@ int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, 
 	h->k = ctb_transpose(l, perm2, 0);
 	const double tp3 = ctb_wall_ms();
 	struct ctb_tensor* s = NULL;
-	if (h->world > 1 && landing_ensure((size_t)a->nstore * ctb_sizeof_dtype(a->dtype), h->world))
+	const int exch = (h->world > 1) ? exchange_mode(h->world) : EXCH_ALLGATHER;
+	if (h->world > 1 && exch == EXCH_PULL && send_ensure((size_t)h->piece_cap * ctb_sizeof_dtype(a->dtype), h->world)) { h->pull = 1; }
+	if (h->world > 1 && exch == EXCH_FUSED && landing_ensure((size_t)a->nstore * ctb_sizeof_dtype(a->dtype), h->world))
 	{
 		/* fused exchange: the step-3 GEMM stores its column slice straight into the packed layout of the FULL result, in the
 		 * peer-mapped landing buffer of every rank (NVLink stores from the epilogue); no all-gather, no scatter */
@@ -566,6 +623,7 @@ int ctb_heff_apply(struct ctb_heff* h, const void* a_data, void* b_data)
 int ctb_heff_step3(struct ctb_heff* h, void* b_data)
 {
 	if (h->world == 1) { return ctb_dot_exec(&h->p3, h->k->d, h->t2->d, b_data); }
+	if (h->pull) { return ctb_dot_exec(&h->p3, h->k->d, h->t2->d, g_send_ptrs[g_send_flip][h->rank]); }
 	if (!h->fused) { return ctb_dot_exec(&h->p3, h->k->d, h->t2->d, h->send); }
 	void* dst[8];
 	void** ptrs = g_land_ptrs[g_land_flip];
@@ -573,6 +631,13 @@ int ctb_heff_step3(struct ctb_heff* h, void* b_data)
 	int n = 1;
 	for (int p = 0; p < h->world; p++) { if (p != h->rank) { dst[n++] = ptrs[p]; } }
 	return ctb_dot_exec_multi(&h->p3, h->k->d, h->t2->d, n, dst);
+}
+
+/* Where the NEXT application can deliver its result without a copy: the local landing buffer of the fused exchange (valid, and
+ * free to be modified in place, until the application after next starts), or NULL when the caller must bring its own buffer. */
+void* ctb_heff_result_buffer(const struct ctb_heff* h)
+{
+	return (h->world > 1 && h->fused) ? g_land_ptrs[g_land_flip][h->rank] : NULL;
 }
 
 int ctb_heff_exchange(struct ctb_heff* h, void* b_data)
@@ -583,9 +648,21 @@ int ctb_heff_exchange(struct ctb_heff* h, void* b_data)
 		 * full vector to the caller.  The two landing buffers alternate, so the next application may start writing at once. */
 		const size_t esize = ctb_sizeof_dtype(h->b->dtype);
 		CTB_CHECK(ctbd_barrier());
-		CTB_CHECK(ctbd_d2d(b_data, g_land_ptrs[g_land_flip][h->rank], (size_t)h->nstore * esize));
+		/* a caller that asked for the landing buffer itself (ctb_heff_result_buffer) consumes the result in place */
+		if (b_data != g_land_ptrs[g_land_flip][h->rank]) { CTB_CHECK(ctbd_d2d(b_data, g_land_ptrs[g_land_flip][h->rank], (size_t)h->nstore * esize)); }
 		g_land_flip ^= 1;
 		g_fused_count++;
+		return 0;
+	}
+	if (h->world > 1 && h->pull)
+	{
+		/* all slices are complete after the barrier; one kernel reads them from the peer-mapped send buffers of all ranks (NVLink loads,
+		 * contiguous row runs) and writes the packed result.  The two send buffers alternate: a rank may run at most one application
+		 * ahead of the slowest reader (the next barrier), so the buffer being read is never the one being written. */
+		CTB_CHECK(ctbd_barrier());
+		CTB_CHECK(ctbd_copy_plan_run_multi(h->scatter, h->world, (const void* const*)g_send_ptrs[g_send_flip], (int64_t)h->piece_cap, b_data));
+		g_send_flip ^= 1;
+		g_pull_count++;
 		return 0;
 	}
 	if (h->world > 1)

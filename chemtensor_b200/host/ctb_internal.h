@@ -215,6 +215,7 @@ struct ctb_heff
 	ct_long piece_cap;            /* elements of one all-gather slot (largest piece) */
 	void* send; void* recv;       /* device: own piece; all pieces */
 	void* scatter;                /* device copy plan: gathered pieces -> packed layout of b */
+	int pull;                     /* 1: slices stay in peer-mapped send buffers, one kernel per rank pulls them over NVLink after the barrier */
 	int fused;                    /* 1: step 3 stores straight into the peer-mapped result buffers of all ranks (no all-gather) */
 	struct ctb_tensor* bfull5;    /* fused: 5-leg view of the full result the embedded step-3 plan writes into */
 	double flops_total;           /* algorithmic flops of the whole matvec (all ranks) */
@@ -228,8 +229,10 @@ int  ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w,
 	void (*l_ready)(void*), void* ctx);
 int  ctb_heff_apply(struct ctb_heff* h, const void* a_data, void* b_data);
 int  ctb_heff_step3(struct ctb_heff* h, void* b_data);
+void* ctb_heff_result_buffer(const struct ctb_heff* h);
 void ctb_dist_release_buffers(void);
 void ctb_dist_counters(long long* fused, long long* allgather);
+long long ctb_dist_pull_count(void);
 /* sharded case: all-gather of the result slices (h->send) and scatter into b_data, or (fused) barrier + local copy; no-op on one rank */
 int  ctb_heff_exchange(struct ctb_heff* h, void* b_data);
 void ctb_heff_free(struct ctb_heff* h);

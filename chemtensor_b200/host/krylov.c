@@ -102,9 +102,9 @@ int ctb_lanczos_min(struct ctb_heff* h, const struct ctb_tensor* a_start, int ma
 	const ct_long n  = a_start->nelem;      /* logical length (reference 'n') */
 	CTB_REQUIRE(ns > 0);
 
-	void* V = NULL; void* w = NULL; double* scal = NULL;
+	void* V = NULL; void* w_own = NULL; double* scal = NULL;
 	CTB_CHECK(ctbd_malloc(&V, (size_t)maxiter * (size_t)ns * esize));
-	CTB_CHECK(ctbd_malloc(&w, (size_t)ns * esize));
+	CTB_CHECK(ctbd_malloc(&w_own, (size_t)ns * esize));
 	/* scal: [0..maxiter) alpha (2 doubles each), [..] beta, then scratch */
 	CTB_CHECK(ctbd_malloc((void**)&scal, (size_t)(3 * maxiter + 4) * sizeof(double)));
 	double* d_alpha = scal;                 /* stride 2 (re, im) */
@@ -121,6 +121,9 @@ int ctb_lanczos_min(struct ctb_heff* h, const struct ctb_tensor* a_start, int ma
 	int numiter = maxiter;
 	for (int j = 0; j < maxiter - 1; j++)
 	{
+		/* sharded with the fused exchange: work in the landing buffer the peers have stored the result into (no copy) */
+		void* wl = ctb_heff_result_buffer(h);
+		void* w = (wl != NULL) ? wl : w_own;
 		CTB_CHECK(ctb_heff_apply(h, VJ(j), w));
 		CTB_CHECK(ctbd_dotc(dtype, ns, w, VJ(j), d_alpha + 2 * j));
 		CTB_CHECK(ctbd_lanczos_update(dtype, ns, w, VJ(j), j > 0 ? VJ(j - 1) : NULL, d_alpha + 2 * j, j > 0 ? d_beta + (j - 1) : NULL, d_beta + j));
@@ -133,6 +136,8 @@ int ctb_lanczos_min(struct ctb_heff* h, const struct ctb_tensor* a_start, int ma
 	if (numiter == maxiter)
 	{
 		const int j = maxiter - 1;
+		void* wl = ctb_heff_result_buffer(h);
+		void* w = (wl != NULL) ? wl : w_own;
 		CTB_CHECK(ctb_heff_apply(h, VJ(j), w));
 		CTB_CHECK(ctbd_dotc(dtype, ns, w, VJ(j), d_alpha + 2 * j));
 	}
@@ -174,7 +179,7 @@ int ctb_lanczos_min(struct ctb_heff* h, const struct ctb_tensor* a_start, int ma
 #undef VJ
 	ctb_free(alpha); ctb_free(beta);
 	CTB_CHECK(ctbd_free(scal));
-	CTB_CHECK(ctbd_free(w));
+	CTB_CHECK(ctbd_free(w_own));
 	CTB_CHECK(ctbd_free(V));
 	return rc;
 }

@@ -247,6 +247,10 @@ struct ctbd_copy2d
 };
 int ctbd_copy_plan_create(int dtype, int n, const struct ctbd_copy2d* descs_host, void** plan);
 int ctbd_copy_plan_run(void* plan, const void* src, void* dst);
+/* the same with the source split over 'nsrc' (<= 8) buffers: element offset o of the virtual source lives in srcs[o / src_stride] at
+ * o % src_stride.  With peer-mapped buffers (ctbd_peer_buffer_*) this is the "pull" form of the exchange: one kernel reads the result
+ * slices of all GPUs over NVLink (coalesced row runs) and writes the packed local result */
+int ctbd_copy_plan_run_multi(void* plan, int nsrc, const void* const* srcs, int64_t src_stride, void* dst);
 int ctbd_copy_plan_destroy(void* plan);
 
 /* ---- level-1 kernels for the Lanczos iteration (scalars stay on the device) ----------------- */

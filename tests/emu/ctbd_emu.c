@@ -310,6 +310,21 @@ int ctbd_copy_plan_run(void* plan, const void* src, void* dst)
 	}
 	return 0;
 }
+int ctbd_copy_plan_run_multi(void* plan, int nsrc, const void* const* srcs, int64_t src_stride, void* dst)
+{
+	const struct emu_copy_plan* p = plan;
+	g_launches++;
+	const size_t es = (p->dtype == CTBD_C128) ? 16 : 8;
+	for (int k = 0; k < p->n; k++) {
+		const struct ctbd_copy2d* d = &p->descs[k];
+		const int64_t q = d->src_off / src_stride, off = d->src_off % src_stride;
+		if (q < 0 || q >= nsrc) { return -1; }
+		for (int i = 0; i < d->rows; i++) {
+			memcpy((char*)dst + (size_t)(d->dst_off + (int64_t)i * d->dst_ld) * es, (const char*)srcs[q] + (size_t)(off + (int64_t)i * d->src_ld) * es, (size_t)d->cols * es);
+		}
+	}
+	return 0;
+}
 int ctbd_copy_plan_destroy(void* plan) { struct emu_copy_plan* p = plan; if (p) { free(p->descs); free(p); } return 0; }
 
 int ctbd_remap(const struct ctbd_remap_args* a)

@@ -73,19 +73,24 @@ def check(results, single):
         assert np.array_equal(r["dmrg_site2"], results[0]["dmrg_site2"])
 
 
-@pytest.mark.parametrize("world,mode", [(2, "fused"), (3, "fused"), (2, "allgather")])
+def assert_exchange_mode(r, mode):
+    fused, gathered, pulled = (int(x) for x in r["exchange_counts"])
+    want = {"fused": (True, False, False), "allgather": (False, True, False), "pull": (False, False, True)}[mode]
+    assert (fused > 0, gathered > 0, pulled > 0) == want, (mode, fused, gathered, pulled)
+
+
+@pytest.mark.parametrize("world,mode", [(2, "fused"), (3, "fused"), (2, "allgather"), (2, "pull"), (3, "pull")])
 def test_sharded_heff_and_dmrg_gloo(tmp_path, world, mode):
     """fused: step 3 stores into peer-mapped result buffers (shared memory between the rank processes here, NVLink peer memory on GPUs);
     allgather: all-gather of the slices + scatter"""
     results = run_world("emu", world, tmp_path, mode)
     check(results, single_rank_results(helpers.load("emu")))
     for r in results:
-        fused, gathered = (int(x) for x in r["exchange_counts"])
-        assert (fused > 0 and gathered == 0) if mode == "fused" else (fused == 0 and gathered > 0)
+        assert_exchange_mode(r, mode)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["fused", "allgather"])
+@pytest.mark.parametrize("mode", ["fused", "allgather", "pull"])
 def test_sharded_heff_and_dmrg_nccl(tmp_path, mode):
     import torch
     if torch.cuda.device_count() < 2:
@@ -93,5 +98,4 @@ def test_sharded_heff_and_dmrg_nccl(tmp_path, mode):
     results = run_world("cuda", 2, tmp_path, mode)
     check(results, single_rank_results(helpers.load("cuda")))
     for r in results:
-        fused, gathered = (int(x) for x in r["exchange_counts"])
-        assert (fused > 0 and gathered == 0) if mode == "fused" else (fused == 0 and gathered > 0)
+        assert_exchange_mode(r, mode)
