@@ -370,6 +370,32 @@ int nccl_fail(const char* what, int rc)
 }
 } // namespace
 
+namespace {
+struct PeerBuffer { void* local = nullptr; std::vector<void*> ptrs; };
+
+/* Barrier over peer-mapped arrival flags: rank r writes the epoch into slot r of every rank's flag array (posted NVLink stores, after a
+ * system-scope fence) and waits until all slots of its own array have reached the epoch.  One tiny kernel on the stream instead of a
+ * collective launch; the kernel boundary before it orders the peer stores of the preceding launch ahead of the arrival flag. */
+PeerBuffer* g_flags = nullptr;
+bool g_flags_failed = false;
+unsigned long long g_epoch = 0;
+struct FlagPtrs { unsigned long long* p[8]; };
+
+__global__ void flag_barrier_kernel(FlagPtrs peers, int rank, int world, unsigned long long epoch)
+{
+	const int p = threadIdx.x;
+	if (p < world) {
+		__threadfence_system();
+		volatile unsigned long long* arrive = peers.p[p] + rank;
+		*arrive = epoch;
+		volatile unsigned long long* seen = peers.p[rank] + p;
+		const long long t0 = clock64();
+		while (*seen < epoch) { if (clock64() - t0 > (1ll << 34)) { break; } }      /* a dead peer must not hang the device for ever */
+		__threadfence_system();
+	}
+}
+}
+
 int ctbd_dist_unique_id(void* id_out)
 {
 	if (nccl_load() < 0) { return -1; }
@@ -393,8 +419,11 @@ int ctbd_dist_init(int rank, int world, const void* unique_id)
 
 int ctbd_dist_set_allgather(ctbd_allgather_fn fn, void* ctx) { g_ag_fn = fn; g_ag_ctx = ctx; return 0; }
 
+int ctbd_peer_buffer_destroy(void* handle);
 int ctbd_dist_finalize(void)
 {
+	if (g_flags != nullptr) { PeerBuffer* f = g_flags; g_flags = nullptr; g_flags_failed = true; ctbd_peer_buffer_destroy(f); }
+	g_flags_failed = false; g_epoch = 0;
 	if (g_comm != nullptr) { cudaStreamSynchronize(rt().stream); g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
 	g_rank = 0; g_world = 1; g_ag_fn = nullptr; g_ag_ctx = nullptr;
 	return 0;
@@ -413,9 +442,27 @@ int ctbd_allgather(const void* sendbuf, void* recvbuf, size_t bytes_per_rank)
 	return rc == 0 ? 0 : nccl_fail("ncclAllGather", rc);
 }
 
+int ctbd_peer_buffer_create(size_t bytes, void** handle);
+
 int ctbd_barrier(void)
 {
 	if (g_world == 1) { return 0; }
+	if (g_comm != nullptr && g_ag_fn == nullptr && !g_flags_failed && g_world <= 8 && getenv("CTB_NCCL_BARRIER") == nullptr)
+	{
+		if (g_flags == nullptr) {
+			void* hnd = nullptr;
+			g_flags_failed = true;      /* the creation below runs barriers of its own (the NCCL form) */
+			if (ctbd_peer_buffer_create(sizeof(unsigned long long) * 8, &hnd) == 0) { g_flags = (PeerBuffer*)hnd; g_flags_failed = false; g_epoch = 0; }
+		}
+		if (g_flags != nullptr) {
+			FlagPtrs fp;
+			for (int p = 0; p < 8; p++) { fp.p[p] = (unsigned long long*)g_flags->ptrs[(size_t)(p < g_world ? p : 0)]; }
+			g_epoch++;
+			flag_barrier_kernel<<<1, 32, 0, rt().stream>>>(fp, g_rank, g_world, g_epoch);
+			CTBD_LAUNCH_CHECK();
+			return 0;
+		}
+	}
 	/* an 8-byte all-gather on the stream: completes on a rank only after every rank has reached it, and kernel boundaries make the
 	 * peer stores issued before it visible system-wide */
 	static void* scratch = nullptr;
@@ -423,9 +470,7 @@ int ctbd_barrier(void)
 	return ctbd_allgather(scratch, (char*)scratch + 8, 8);
 }
 
-namespace {
-struct PeerBuffer { void* local = nullptr; std::vector<void*> ptrs; };
-}
+
 
 int ctbd_peer_buffer_create(size_t bytes, void** handle)
 {
@@ -438,6 +483,7 @@ int ctbd_peer_buffer_create(size_t bytes, void** handle)
 	/* plain cudaMalloc: pool memory is not exportable through legacy CUDA IPC */
 	cudaError_t e = cudaMalloc(&pb->local, bytes > 0 ? bytes : 256);
 	if (e != cudaSuccess) { delete pb; return fail("cudaMalloc (peer buffer)", e, __FILE__, __LINE__); }
+	cudaMemset(pb->local, 0, bytes > 0 ? bytes : 256);      /* synchronous: done before any peer can learn the handle */
 	cudaIpcMemHandle_t mine;
 	e = cudaIpcGetMemHandle(&mine, pb->local);
 	int ok = (e == cudaSuccess) ? 1 : 0;

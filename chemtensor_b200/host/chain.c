@@ -399,26 +399,58 @@ static int cmp_chunk_desc(const void* x, const void* y)
 	return (a->pos0 > b->pos0) - (a->pos0 < b->pos0);
 }
 
-static int split_bond(const struct ctb_tensor* a, const struct ctb_tensor* r, int world, ct_long** ind, ct_long* nind)
+static int split_bond(const struct ctb_tensor* a, const struct ctb_tensor* l, const struct ctb_tensor* r, int world, ct_long** ind, ct_long* nind)
 {
 	const struct ctb_axis* ax = &r->ax[2];
 	ct_long grain = (world >= 8) ? 64 : 128;      /* one or two 64-column GEMM tiles */
 	const char* env = getenv("CTB_SHARD_GRAIN");
 	if (env != NULL && atol(env) > 0) { grain = atol(env); }
-	/* flops per column of each bra sector: sum over blocks r[Dr, w', Dr' = s] of (rows of a with that Dr sector) * nDr * mw' */
+	/* Padded GEMM work of a chunk of 'len' columns of bra sector s, in the 64 x 64 x 16 tiles of the kernel:
+	 *   step 1, every block r[Dr, w', s]:   sum over blocks a[l, sigma, Dr] of pad64(m_l m_sigma) pad16(m_Dr)   times pad64(m_w' len)
+	 *   step 3, every block b[l', sigma', s] (structure of a):  pad64(m_l') sum over blocks l[1, l, w, l'] of pad16(m_l m_w)   times pad64(m_sigma' len)
+	 * so per sector the weights are collected by the multiplier (m_w' or m_sigma') of the column count. */
+	enum { MULT_MAX = 64 };
+#define PAD_UP(x, g) ((((x) + (g) - 1) / (g)) * (g))
 	double* rows_a = ctb_calloc((size_t)a->ax[2].nsec, sizeof(double));
 	for (int b = 0; b < a->nblk; b++) {
 		int idx[CTB_MAXDIM];
 		ctb_grid_unravel(a, a->blk_grid[b], idx);
-		rows_a[idx[2]] += (double)a->ax[0].secdim[idx[0]] * (double)a->ax[1].secdim[idx[1]];
+		rows_a[idx[2]] += (double)PAD_UP((ct_long)a->ax[0].secdim[idx[0]] * a->ax[1].secdim[idx[1]], 64) * (double)PAD_UP((ct_long)a->ax[2].secdim[idx[2]], 16);
 	}
-	double* wcol = ctb_calloc((size_t)ax->nsec, sizeof(double));
+	double* wmul = ctb_calloc((size_t)ax->nsec * MULT_MAX, sizeof(double));     /* [sector][multiplier] */
+	double* wcol = ctb_calloc((size_t)ax->nsec, sizeof(double));                /* unpadded work per column (small-bond case) */
 	for (int b = 0; b < r->nblk; b++) {
 		int idx[CTB_MAXDIM];
 		ctb_grid_unravel(r, r->blk_grid[b], idx);
 		const int sa = ctb_axis_find_sector(&a->ax[2], r->ax[0].qsec[idx[0]]);
 		if (sa < 0) { continue; }
-		wcol[idx[2]] += rows_a[sa] * (double)r->ax[0].secdim[idx[0]] * (double)r->ax[1].secdim[idx[1]];
+		int mult = r->ax[1].secdim[idx[1]];
+		wcol[idx[2]] += rows_a[sa] * mult;
+		if (mult >= MULT_MAX) { mult = MULT_MAX - 1; }
+		wmul[(size_t)idx[2] * MULT_MAX + mult] += rows_a[sa];
+	}
+	{
+		double* kl = ctb_calloc((size_t)l->ax[3].nsec, sizeof(double));
+		for (int b = 0; b < l->nblk; b++) {
+			int idx[CTB_MAXDIM];
+			ctb_grid_unravel(l, l->blk_grid[b], idx);
+			kl[idx[3]] += (double)PAD_UP((ct_long)l->ax[1].secdim[idx[1]] * l->ax[2].secdim[idx[2]], 16);
+		}
+		for (int b = 0; b < a->nblk; b++) {
+			int idx[CTB_MAXDIM];
+			ctb_grid_unravel(a, a->blk_grid[b], idx);
+			/* the result has the structure of a; its first leg carries the quantum numbers of the bra leg of l */
+			const int sl = ctb_axis_find_sector(&l->ax[3], a->ax[0].qsec[idx[0]]);
+			if (sl < 0) { continue; }
+			const int sr = ctb_axis_find_sector(ax, a->ax[2].qsec[idx[2]]);
+			if (sr < 0) { continue; }
+			int mult = a->ax[1].secdim[idx[1]];
+			const double wgt = (double)PAD_UP((ct_long)a->ax[0].secdim[idx[0]], 64) * kl[sl];
+			wcol[sr] += wgt * mult;
+			if (mult >= MULT_MAX) { mult = MULT_MAX - 1; }
+			wmul[(size_t)sr * MULT_MAX + mult] += wgt;
+		}
+		ctb_free(kl);
 	}
 	/* the balanced chunks */
 	size_t nch = 0, cap = 64;
@@ -437,8 +469,12 @@ static int split_bond(const struct ctb_tensor* a, const struct ctb_tensor* r, in
 			if (p1 <= p0) { continue; }
 			if (nch == cap) { cap *= 2; ch = realloc(ch, cap * sizeof(*ch)); }
 			ch[nch].sec = s; ch[nch].pos0 = p0; ch[nch].len = p1 - p0;
-			/* priced with the tile padding of a remainder chunk (64-column tiles) */
-			ch[nch].cost = (double)(fine ? (p1 - p0) : ((p1 - p0 + 63) / 64) * 64) * (wcol[s] > 0 ? wcol[s] : 1.0);
+			if (fine) { ch[nch].cost = (double)(p1 - p0) * (wcol[s] > 0 ? wcol[s] : 1.0); }
+			else {
+				double cst = 0;
+				for (int mu = 1; mu < MULT_MAX; mu++) { cst += wmul[(size_t)s * MULT_MAX + mu] * (double)PAD_UP((ct_long)mu * (p1 - p0), 64); }
+				ch[nch].cost = cst > 0 ? cst : (double)(p1 - p0);
+			}
 			nch++;
 		}
 	}
@@ -453,7 +489,8 @@ static int split_bond(const struct ctb_tensor* a, const struct ctb_tensor* r, in
 	}
 	for (int p = 0; p < world; p++) { ind[p] = ctb_malloc((size_t)(ax->dim > 0 ? ax->dim : 1) * sizeof(ct_long)); nind[p] = 0; }
 	for (ct_long i = 0; i < ax->dim; i++) { const int p = owner[i]; ind[p][nind[p]++] = i; }
-	ctb_free(owner); ctb_free(load); ctb_free(wcol); ctb_free(rows_a); free(ch);
+	ctb_free(owner); ctb_free(load); ctb_free(wcol); ctb_free(wmul); ctb_free(rows_a); free(ch);
+#undef PAD_UP
 	for (int p = 0; p < world; p++) { if (nind[p] == 0) { return 0; } }
 	return 1;
 }
@@ -478,7 +515,7 @@ int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, 
 		CTB_REQUIRE(W <= 8);
 		h->ind = ctb_calloc((size_t)W, sizeof(ct_long*));
 		h->nind = ctb_calloc((size_t)W, sizeof(ct_long));
-		if (split_bond(a, r, W, h->ind, h->nind))
+		if (split_bond(a, l, r, W, h->ind, h->nind))
 		{
 			h->world = W; h->rank = ctb_dist_rank;
 			h->r_own = ctb_slice((struct ctb_tensor*)r, 2, h->ind[h->rank], h->nind[h->rank]);
