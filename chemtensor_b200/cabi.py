@@ -129,6 +129,7 @@ _EXT_SIGNATURES = {
     "ctb_dist_finalize": (C.c_int, []),
     "ctb_dist_info": (C.c_int, [C.POINTER(C.c_longlong)]),
     "ctb_dist_pull_exchanges": (C.c_longlong, []),
+    "ctb_dist_push_exchanges": (C.c_longlong, []),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES) + tuple(_EXT_SIGNATURES) + ("allocate_zero_dense_tensor", "allocate_block_sparse_tensor_like",

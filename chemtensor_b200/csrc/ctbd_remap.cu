@@ -233,6 +233,42 @@ __global__ void __launch_bounds__(256) copy2d_multi_kernel(int ntiles, const Cop
 	}
 }
 
+struct CopyDsts { void* p[8]; int n; int vec_ok; };
+
+/* one local read, the same strided block written to several (peer-mapped) destinations: 16 bytes per lane, whole row runs per warp */
+template <typename T>
+__global__ void __launch_bounds__(256) copy2d_push_kernel(int ntiles, const CopyTile* __restrict__ tiles, const ctbd_copy2d* __restrict__ descs,
+	const T* __restrict__ src, const CopyDsts dsts)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+	{
+		const CopyTile tl = tiles[t];
+		const ctbd_copy2d d = descs[tl.desc];
+		const int r1 = min(tl.row0 + COPY_ROWS, d.rows);
+		const bool vec = (sizeof(T) == 8) && dsts.vec_ok && ((d.cols & 1) == 0) && ((d.src_ld & 1) == 0) && ((d.dst_ld & 1) == 0) && ((d.src_off & 1) == 0) && ((d.dst_off & 1) == 0);
+		for (int i = tl.row0 + warp; i < r1; i += 8) {
+			const T* __restrict__ s = src + d.src_off + (int64_t)i * d.src_ld;
+			const int64_t doff = d.dst_off + (int64_t)i * d.dst_ld;
+			if (vec) {
+				const double2* __restrict__ s2 = reinterpret_cast<const double2*>(s);
+				for (int j = lane; j < d.cols / 2; j += 32) {
+					const double2 v = s2[j];
+					#pragma unroll
+					for (int q = 0; q < 8; q++) { if (q < dsts.n) { reinterpret_cast<double2*>(reinterpret_cast<T*>(dsts.p[q]) + doff)[j] = v; } }
+				}
+			}
+			else {
+				for (int j = lane; j < d.cols; j += 32) {
+					const T v = s[j];
+					#pragma unroll
+					for (int q = 0; q < 8; q++) { if (q < dsts.n) { (reinterpret_cast<T*>(dsts.p[q]) + doff)[j] = v; } }
+				}
+			}
+		}
+	}
+}
+
 } // namespace ctbd
 
 using namespace ctbd;
@@ -341,6 +377,23 @@ int ctbd_copy_plan_run_multi(void* plan, int nsrc, const void* const* srcs, int6
 	const int grid = std::min(p->ntiles, rt().sm_count * 8);
 	if (p->dtype == CTBD_F64) { copy2d_multi_kernel<double><<<grid, 256, 0, rt().stream>>>(p->ntiles, p->tiles, p->descs, cs, (double*)dst); }
 	else                      { copy2d_multi_kernel<double2><<<grid, 256, 0, rt().stream>>>(p->ntiles, p->tiles, p->descs, cs, (double2*)dst); }
+	CTBD_LAUNCH_CHECK();
+	return 0;
+}
+
+int ctbd_copy_plan_run_push(void* plan, const void* src, int ndst, void* const* dsts)
+{
+	CopyPlan* p = (CopyPlan*)plan;
+	if (p == nullptr || p->ntiles == 0) { return 0; }
+	if (ndst < 1 || ndst > 8) { return fail_msg("copy plan: between 1 and 8 destinations"); }
+	CopyDsts cd;
+	bool aligned = (((uintptr_t)src) & 15) == 0;
+	for (int i = 0; i < 8; i++) { cd.p[i] = dsts[i < ndst ? i : 0]; }
+	for (int i = 0; i < ndst; i++) { aligned = aligned && ((((uintptr_t)dsts[i]) & 15) == 0); }
+	cd.n = ndst; cd.vec_ok = aligned ? 1 : 0;
+	const int grid = std::min(p->ntiles, rt().sm_count * 8);
+	if (p->dtype == CTBD_F64) { copy2d_push_kernel<double><<<grid, 256, 0, rt().stream>>>(p->ntiles, p->tiles, p->descs, (const double*)src, cd); }
+	else                      { copy2d_push_kernel<double2><<<grid, 256, 0, rt().stream>>>(p->ntiles, p->tiles, p->descs, (const double2*)src, cd); }
 	CTBD_LAUNCH_CHECK();
 	return 0;
 }

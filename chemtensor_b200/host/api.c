@@ -30,6 +30,7 @@ int ctb_dist_set_allgather(ctbd_allgather_fn fn, void* ctx) { return ctbd_dist_s
 int ctb_dist_info(long long* out) { out[0] = ctb_dist_rank; out[1] = ctb_dist_world; ctb_dist_counters(&out[2], &out[3]); return 0; }
 /* exchanges done by the pull path (peer-mapped send buffers read over NVLink) */
 long long ctb_dist_pull_exchanges(void) { return ctb_dist_pull_count(); }
+long long ctb_dist_push_exchanges(void) { return ctb_dist_push_count(); }
 int ctb_dist_finalize(void) { ctb_dist_release_buffers(); ctb_dist_rank = 0; ctb_dist_world = 1; return ctbd_dist_finalize(); }
 int ctb_backend(void) { return ctbd_backend(); }
 long long ctb_launch_count(void) { return ctbd_launch_count(); }

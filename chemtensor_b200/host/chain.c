@@ -340,7 +340,7 @@ static void* g_send[2] = { NULL, NULL };
 static void** g_send_ptrs[2] = { NULL, NULL };
 static size_t g_send_bytes = 0;
 static int g_send_flip = 0, g_send_failed = 0;
-static long long g_pull_count = 0;
+static long long g_pull_count = 0, g_push_count = 0;
 
 static void send_release(void)
 {
@@ -368,13 +368,14 @@ static int send_ensure(size_t bytes, int world)
 }
 
 /* exchange form of the sharded effective Hamiltonian: CTB_EXCHANGE = fused | pull | allgather (default: see exchange_mode) */
-enum { EXCH_ALLGATHER = 0, EXCH_FUSED = 1, EXCH_PULL = 2 };
+enum { EXCH_ALLGATHER = 0, EXCH_FUSED = 1, EXCH_PULL = 2, EXCH_PUSH = 3 };
 static int exchange_mode(int world)
 {
 	const char* env = getenv("CTB_EXCHANGE");
 	if (env != NULL) {
 		if (strcmp(env, "fused") == 0) { return EXCH_FUSED; }
 		if (strcmp(env, "pull") == 0) { return EXCH_PULL; }
+		if (strcmp(env, "push") == 0) { return EXCH_PUSH; }
 		if (strcmp(env, "allgather") == 0) { return EXCH_ALLGATHER; }
 	}
 	if (getenv("CTB_NO_FUSED_EXCHANGE") != NULL) { return EXCH_ALLGATHER; }
@@ -384,6 +385,7 @@ static int exchange_mode(int world)
 
 void ctb_dist_release_buffers(void) { landing_release(); g_land_failed = 0; send_release(); g_send_failed = 0; }
 long long ctb_dist_pull_count(void) { return g_pull_count; }
+long long ctb_dist_push_count(void) { return g_push_count; }
 void ctb_dist_counters(long long* fused, long long* allgather) { *fused = g_fused_count; *allgather = g_allgather_count; }
 
 /* Split of the bra bond of r among 'world' ranks.  Every sector is cut into ceil(m / grain) nearly equal contiguous chunks
@@ -541,9 +543,11 @@ int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, 
 			{
 				size_t cap = 1024, nd = 0;
 				struct ctbd_copy2d* descs = malloc(cap * sizeof(*descs));
+				size_t nd_own0 = 0, nd_own1 = 0;      /* descriptors of this rank's own piece */
 				for (int p = 0; p < W; p++)
 				{
 					const struct ctb_tensor* pc = h->piece[p];
+					if (p == h->rank) { nd_own0 = nd; }
 					for (int blk = 0; blk < pc->nblk; blk++)
 					{
 						int idx[CTB_MAXDIM];
@@ -575,8 +579,12 @@ int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, 
 							j += len;
 						}
 					}
+					if (p == h->rank) { nd_own1 = nd; }
 				}
 				CTB_CHECK(ctbd_copy_plan_create(a->dtype, (int)nd, descs, &h->scatter));
+				/* push form of the exchange: the own piece, read from its local buffer (offsets relative to the piece) */
+				for (size_t q = nd_own0; q < nd_own1; q++) { descs[q].src_off -= (int64_t)h->rank * h->piece_cap; }
+				CTB_CHECK(ctbd_copy_plan_create(a->dtype, (int)(nd_own1 - nd_own0), descs + nd_own0, &h->push_plan));
 				free(descs);
 			}
 		}
@@ -606,6 +614,8 @@ int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, 
 	struct ctb_tensor* s = NULL;
 	const int exch = (h->world > 1) ? exchange_mode(h->world) : EXCH_ALLGATHER;
 	if (h->world > 1 && exch == EXCH_PULL && send_ensure((size_t)h->piece_cap * ctb_sizeof_dtype(a->dtype), h->world)) { h->pull = 1; }
+	/* push: step 3 writes the slice locally, one copy kernel then stores it into the landing buffers of all ranks (wide NVLink stores) */
+	if (h->world > 1 && exch == EXCH_PUSH && landing_ensure((size_t)a->nstore * ctb_sizeof_dtype(a->dtype), h->world)) { h->push = 1; }
 	if (h->world > 1 && exch == EXCH_FUSED && landing_ensure((size_t)a->nstore * ctb_sizeof_dtype(a->dtype), h->world))
 	{
 		/* fused exchange: the step-3 GEMM stores its column slice straight into the packed layout of the FULL result, in the
@@ -661,6 +671,10 @@ int ctb_heff_step3(struct ctb_heff* h, void* b_data)
 {
 	if (h->world == 1) { return ctb_dot_exec(&h->p3, h->k->d, h->t2->d, b_data); }
 	if (h->pull) { return ctb_dot_exec(&h->p3, h->k->d, h->t2->d, g_send_ptrs[g_send_flip][h->rank]); }
+	if (h->push) {
+		CTB_CHECK(ctb_dot_exec(&h->p3, h->k->d, h->t2->d, h->send));
+		return ctbd_copy_plan_run_push(h->push_plan, h->send, h->world, (void* const*)g_land_ptrs[g_land_flip]);
+	}
 	if (!h->fused) { return ctb_dot_exec(&h->p3, h->k->d, h->t2->d, h->send); }
 	void* dst[8];
 	void** ptrs = g_land_ptrs[g_land_flip];
@@ -674,12 +688,12 @@ int ctb_heff_step3(struct ctb_heff* h, void* b_data)
  * free to be modified in place, until the application after next starts), or NULL when the caller must bring its own buffer. */
 void* ctb_heff_result_buffer(const struct ctb_heff* h)
 {
-	return (h->world > 1 && h->fused) ? g_land_ptrs[g_land_flip][h->rank] : NULL;
+	return (h->world > 1 && (h->fused || h->push)) ? g_land_ptrs[g_land_flip][h->rank] : NULL;
 }
 
 int ctb_heff_exchange(struct ctb_heff* h, void* b_data)
 {
-	if (h->world > 1 && h->fused)
+	if (h->world > 1 && (h->fused || h->push))
 	{
 		/* every rank's slice has been stored into every landing buffer by the step-3 epilogues: wait for all ranks, then hand the
 		 * full vector to the caller.  The two landing buffers alternate, so the next application may start writing at once. */
@@ -688,7 +702,7 @@ int ctb_heff_exchange(struct ctb_heff* h, void* b_data)
 		/* a caller that asked for the landing buffer itself (ctb_heff_result_buffer) consumes the result in place */
 		if (b_data != g_land_ptrs[g_land_flip][h->rank]) { CTB_CHECK(ctbd_d2d(b_data, g_land_ptrs[g_land_flip][h->rank], (size_t)h->nstore * esize)); }
 		g_land_flip ^= 1;
-		g_fused_count++;
+		if (h->fused) { g_fused_count++; } else { g_push_count++; }
 		return 0;
 	}
 	if (h->world > 1 && h->pull)
@@ -721,6 +735,7 @@ void ctb_heff_free(struct ctb_heff* h)
 	if (h->ind != NULL) { for (int p = 0; p < h->world; p++) { ctb_free(h->ind[p]); } ctb_free(h->ind); ctb_free(h->nind); }
 	ctb_tensor_free(h->r_own);
 	if (h->scatter != NULL) { ctbd_copy_plan_destroy(h->scatter); }
+	if (h->push_plan != NULL) { ctbd_copy_plan_destroy(h->push_plan); }
 	ctb_tensor_free(h->bfull5);
 	if (h->send != NULL) { ctbd_free(h->send); }
 	if (h->recv != NULL) { ctbd_free(h->recv); }

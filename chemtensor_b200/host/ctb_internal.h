@@ -215,6 +215,8 @@ struct ctb_heff
 	ct_long piece_cap;            /* elements of one all-gather slot (largest piece) */
 	void* send; void* recv;       /* device: own piece; all pieces */
 	void* scatter;                /* device copy plan: gathered pieces -> packed layout of b */
+	int push;                     /* 1: local step 3, then one copy kernel stores the slice into the landing buffers of all ranks */
+	void* push_plan;              /* device copy plan: own piece -> packed layout of b */
 	int pull;                     /* 1: slices stay in peer-mapped send buffers, one kernel per rank pulls them over NVLink after the barrier */
 	int fused;                    /* 1: step 3 stores straight into the peer-mapped result buffers of all ranks (no all-gather) */
 	struct ctb_tensor* bfull5;    /* fused: 5-leg view of the full result the embedded step-3 plan writes into */
@@ -233,6 +235,7 @@ void* ctb_heff_result_buffer(const struct ctb_heff* h);
 void ctb_dist_release_buffers(void);
 void ctb_dist_counters(long long* fused, long long* allgather);
 long long ctb_dist_pull_count(void);
+long long ctb_dist_push_count(void);
 /* sharded case: all-gather of the result slices (h->send) and scatter into b_data, or (fused) barrier + local copy; no-op on one rank */
 int  ctb_heff_exchange(struct ctb_heff* h, void* b_data);
 void ctb_heff_free(struct ctb_heff* h);

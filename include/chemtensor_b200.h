@@ -121,6 +121,7 @@ int ctb_dist_finalize(void);
 /* out[0] = rank, out[1] = world, out[2] = exchanges done by the fused peer-store path, out[3] = exchanges done by all-gather + scatter */
 int ctb_dist_info(long long* out);
 long long ctb_dist_pull_exchanges(void);
+long long ctb_dist_push_exchanges(void);
 /* 1 = CUDA kernels, 2 = host test double (tests/emu only) */
 int ctb_backend(void);
 /* kernels launched by the engine so far */

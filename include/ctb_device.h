@@ -251,6 +251,9 @@ int ctbd_copy_plan_run(void* plan, const void* src, void* dst);
  * o % src_stride.  With peer-mapped buffers (ctbd_peer_buffer_*) this is the "pull" form of the exchange: one kernel reads the result
  * slices of all GPUs over NVLink (coalesced row runs) and writes the packed local result */
 int ctbd_copy_plan_run_multi(void* plan, int nsrc, const void* const* srcs, int64_t src_stride, void* dst);
+/* the "push" form: every copy is read once from the local 'src' and written to all 'ndst' (<= 8) destination buffers (peer-mapped
+ * result buffers of the GPUs of the box): wide posted NVLink stores, whole row runs per warp */
+int ctbd_copy_plan_run_push(void* plan, const void* src, int ndst, void* const* dsts);
 int ctbd_copy_plan_destroy(void* plan);
 
 /* ---- level-1 kernels for the Lanczos iteration (scalars stay on the device) ----------------- */

@@ -35,7 +35,7 @@ def make_gloo_allgather(dist, torch, world):
 def main():
     kind, prefix = sys.argv[1], sys.argv[2]
     if len(sys.argv) > 3:
-        os.environ["CTB_EXCHANGE"] = sys.argv[3]      # fused | pull | allgather
+        os.environ["CTB_EXCHANGE"] = sys.argv[3]      # fused | pull | push | allgather
     import torch
     import torch.distributed as dist
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -78,7 +78,7 @@ def main():
     out["dmrg_site2"] = psi.site(2).serialize()
     info = (C.c_longlong * 4)()
     eng.ctb_dist_info(info)
-    out["exchange_counts"] = np.array([info[2], info[3], eng.ctb_dist_pull_exchanges()], dtype=np.int64)      # fused peer-store, all-gather, pull exchanges
+    out["exchange_counts"] = np.array([info[2], info[3], eng.ctb_dist_pull_exchanges(), eng.ctb_dist_push_exchanges()], dtype=np.int64)      # fused peer-store, all-gather, pull, push exchanges
     np.savez(f"{prefix}_rank{rank}.npz", **out)
     eng.ctb_dist_finalize()
     dist.barrier()

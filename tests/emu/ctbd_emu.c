@@ -325,6 +325,11 @@ int ctbd_copy_plan_run_multi(void* plan, int nsrc, const void* const* srcs, int6
 	}
 	return 0;
 }
+int ctbd_copy_plan_run_push(void* plan, const void* src, int ndst, void* const* dsts)
+{
+	for (int q = 0; q < ndst; q++) { if (ctbd_copy_plan_run(plan, src, dsts[q]) < 0) { return -1; } }
+	return 0;
+}
 int ctbd_copy_plan_destroy(void* plan) { struct emu_copy_plan* p = plan; if (p) { free(p->descs); free(p); } return 0; }
 
 int ctbd_remap(const struct ctbd_remap_args* a)

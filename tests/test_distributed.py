@@ -74,12 +74,12 @@ def check(results, single):
 
 
 def assert_exchange_mode(r, mode):
-    fused, gathered, pulled = (int(x) for x in r["exchange_counts"])
-    want = {"fused": (True, False, False), "allgather": (False, True, False), "pull": (False, False, True)}[mode]
-    assert (fused > 0, gathered > 0, pulled > 0) == want, (mode, fused, gathered, pulled)
+    counts = tuple(int(x) > 0 for x in r["exchange_counts"])      # fused, all-gather, pull, push
+    want = {"fused": (True, False, False, False), "allgather": (False, True, False, False), "pull": (False, False, True, False), "push": (False, False, False, True)}[mode]
+    assert counts == want, (mode, r["exchange_counts"])
 
 
-@pytest.mark.parametrize("world,mode", [(2, "fused"), (3, "fused"), (2, "allgather"), (2, "pull"), (3, "pull")])
+@pytest.mark.parametrize("world,mode", [(2, "fused"), (3, "fused"), (2, "allgather"), (2, "pull"), (3, "pull"), (2, "push"), (3, "push")])
 def test_sharded_heff_and_dmrg_gloo(tmp_path, world, mode):
     """fused: step 3 stores into peer-mapped result buffers (shared memory between the rank processes here, NVLink peer memory on GPUs);
     allgather: all-gather of the slices + scatter"""
@@ -90,7 +90,7 @@ def test_sharded_heff_and_dmrg_gloo(tmp_path, world, mode):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["fused", "allgather", "pull"])
+@pytest.mark.parametrize("mode", ["fused", "allgather", "pull", "push"])
 def test_sharded_heff_and_dmrg_nccl(tmp_path, mode):
     import torch
     if torch.cuda.device_count() < 2:
