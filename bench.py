@@ -284,8 +284,9 @@ def main():
                    "what": "apply_local_hamiltonian(a, w, l, r, &b) on host structs: upload, per-bond plan build, 3 grouped GEMM launches, download"}
     launches = lib.ctb_launch_count() - launches0
 
-    # strong scaling: ONE matvec sharded over the ranks (bra bond of the right environment cut into balanced index sets, one
-    # NCCL all-gather per application); time = max over ranks of the device time, value = whole-job flops / that time
+    # strong scaling: ONE matvec sharded over the ranks (bra bond of the right environment cut into tile-aligned, work-balanced index
+    # sets; per application one exchange of the result slices over NVLink peer memory); time = max over ranks of the device time,
+    # value = whole-job flops / that time
     t_ms = ms.value
     if world > 1:
         tt = torch.tensor([t_ms], dtype=torch.float64, device="cuda")
@@ -325,8 +326,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": wl, "description": desc, "structure": args.structure, "vector_length": int(n_vec), "flops_per_matvec": flops_total,
                    "l2": "192 MiB buffer rewritten between timed matvecs", "setup_s": round(t_setup, 2),
-                   "multi_gpu": (f"one matvec sharded over {world} GPUs by balanced index sets of the bra bond of the right environment; "
-                                 "per application one NCCL all-gather of the result slices + scatter") if world > 1 else "single GPU"},
+                   "multi_gpu": (f"one matvec sharded over {world} GPUs by tile-aligned, work-balanced index sets of the bra bond of the right environment; "
+                                 f"exchange of the result slices per application: {exchange_name(lib)}") if world > 1 else "single GPU"},
         "roofline": roofline,
         "e2e": e2e,
         "gpu_launches": int(launches),
@@ -337,6 +338,18 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(wl, flops_total, args.structure)
     print(json.dumps(line), flush=True)
+
+
+def exchange_name(lib) -> str:
+    info = (C.c_longlong * 4)()
+    lib.ctb_dist_info(info)
+    if info[2] > 0:
+        return "fused (step-3 GEMM epilogue stores into the peer-mapped result buffers of all GPUs, peer-flag barrier)"
+    if lib.ctb_dist_push_exchanges() > 0:
+        return "push (local step 3, one copy kernel stores the slice into the peer-mapped result buffers, peer-flag barrier)"
+    if lib.ctb_dist_pull_exchanges() > 0:
+        return "pull (peer-mapped send buffers read over NVLink after the barrier)"
+    return "NCCL all-gather + scatter kernel"
 
 
 def sweep_seconds(lib, model, L, params, sector, D, sweeps=2, lanczos=10, tol=0.0):
