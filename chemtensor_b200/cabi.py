@@ -110,6 +110,17 @@ _SIGNATURES = {
     "lanczos_iteration_z": (None, [C.c_int64, LANCZOS_FUNC, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_int)]),
     "eigensystem_krylov_symmetric": (C.c_int, [C.c_int64, LANCZOS_FUNC, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
     "eigensystem_krylov_hermitian": (C.c_int, [C.c_int64, LANCZOS_FUNC, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
+    # other callers of the same primitives
+    "mps_vdot": (None, [C.POINTER(MPSStruct), C.POINTER(MPSStruct), C.c_void_p]),
+    "mps_norm": (C.c_double, [C.POINTER(MPSStruct)]),
+    "mpo_inner_product": (None, [C.POINTER(MPSStruct), C.POINTER(MPOStruct), C.POINTER(MPSStruct), C.c_void_p]),
+    "apply_mpo": (None, [C.POINTER(MPOStruct), C.POINTER(MPSStruct), C.POINTER(MPSStruct)]),
+    "compute_local_hamiltonian_environment": (None, [_P_BST, _P_BST, _P_BST, _P_BST, _P_BST]),
+    "split_block_sparse_matrix_svd_isometry": (C.c_int, [_P_BST, C.c_double, C.c_bool, C.c_int64, _P_BST, C.POINTER(TruncInfo)]),
+    "mps_local_orthonormalize_left_svd": (C.c_int, [C.c_double, C.c_int64, C.c_bool, _P_BST, _P_BST, C.POINTER(TruncInfo)]),
+    "mps_local_orthonormalize_right_svd": (C.c_int, [C.c_double, C.c_int64, C.c_bool, _P_BST, _P_BST, C.POINTER(TruncInfo)]),
+    "mps_compress": (C.c_int, [C.c_double, C.c_int64, C.c_int, C.POINTER(MPSStruct), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(TruncInfo)]),
+    "mps_compress_rescale": (C.c_int, [C.c_double, C.c_int64, C.c_int, C.POINTER(MPSStruct), C.POINTER(C.c_double), C.POINTER(TruncInfo)]),
     "dmrg_singlesite": (C.c_int, [C.POINTER(MPOStruct), C.c_int, C.c_int, C.POINTER(MPSStruct), C.POINTER(C.c_double)]),
     "dmrg_twosite": (C.c_int, [C.POINTER(MPOStruct), C.c_int, C.c_int, C.c_double, C.c_int64, C.POINTER(MPSStruct), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }

@@ -145,6 +145,15 @@ __global__ void __launch_bounds__(256) scale_kernel(int64_t nd, double* __restri
 	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += stride) { x[i] *= alpha; }
 }
 
+__global__ void __launch_bounds__(256) zscale_kernel(int64_t n, double2* __restrict__ x, double re, double im)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const double2 v = x[i];
+		x[i] = make_double2(v.x * re - v.y * im, v.x * im + v.y * re);
+	}
+}
+
 static constexpr int LINCOMB_MAX = 32;
 struct LincombCoef { double c[LINCOMB_MAX]; };
 
@@ -241,6 +250,15 @@ int ctbd_lincomb(int dtype, int64_t n, const void* V, int64_t ldv, int m, const 
 		lincomb_kernel<<<stream_blocks(nd, 256, 8), 256, 0, rt().stream>>>(nd, (const double*)V + (int64_t)j0 * ldd, ldd, mc, c, j0 > 0, (double*)out);
 		CTBD_LAUNCH_CHECK();
 	}
+	return 0;
+}
+
+int ctbd_zscale_host(int dtype, int64_t n, void* x, double re, double im)
+{
+	CTBD_REQUIRE_INIT();
+	if (dtype != CTBD_C128) { return ctbd_scale_host(dtype, n, x, re); }
+	zscale_kernel<<<stream_blocks(n, 256, 8), 256, 0, rt().stream>>>(n, (double2*)x, re, im);
+	CTBD_LAUNCH_CHECK();
 	return 0;
 }
 

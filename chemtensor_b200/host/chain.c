@@ -20,7 +20,7 @@ struct ctb_stats ctb_global_stats;
 int ctb_dist_rank = 0, ctb_dist_world = 1;
 
 /* metadata copy that shares the device buffer, with all axis directions reversed */
-static struct ctb_tensor* view_reversed_dirs(const struct ctb_tensor* t)
+struct ctb_tensor* ctb_view_reversed_dirs(const struct ctb_tensor* t)
 {
 	struct ctb_axis axes[CTB_MAXDIM];
 	for (int i = 0; i < t->ndim; i++) {
@@ -258,7 +258,7 @@ struct ctb_tensor* ctb_env_step_right(const struct ctb_tensor* a, const struct c
 	ctb_dot_plan_free(&pl);
 	ctb_tensor_free(s);
 	/* contract with conj(b) over (d_out, Dr'); conjugation fused into the operand load; result [Dl, Dw, Dl', x] */
-	struct ctb_tensor* br = view_reversed_dirs(b);
+	struct ctb_tensor* br = ctb_view_reversed_dirs(b);
 	const int perm2[4] = { 1, 2, 3, 0 };
 	struct ctb_tensor* r_next = ctb_dot_prepare(t, TENSOR_AXIS_RANGE_TRAILING, 0, br, TENSOR_AXIS_RANGE_TRAILING, ctb_is_complex(b->dtype), 2, perm2, 1, &pl);
 	CTB_CHECK_ABORT(ctb_dot_exec(&pl, t->d, br->d, r_next->d));
@@ -274,7 +274,7 @@ struct ctb_tensor* ctb_env_step_left(const struct ctb_tensor* a, const struct ct
 	CTB_REQUIRE(a->ndim == 3 && b->ndim == 3 && w->ndim == 4 && l->ndim == 4);
 	struct ctb_dot_plan pl;
 	/* l . conj(b), stored as [x, Dl, Dr', Dw, d'] */
-	struct ctb_tensor* br = view_reversed_dirs(b);
+	struct ctb_tensor* br = ctb_view_reversed_dirs(b);
 	const int perm0[5] = { 0, 1, 4, 2, 3 };
 	struct ctb_tensor* s = ctb_dot_prepare(l, TENSOR_AXIS_RANGE_TRAILING, 0, br, TENSOR_AXIS_RANGE_LEADING, ctb_is_complex(b->dtype), 1, perm0, 1, &pl);
 	CTB_CHECK_ABORT(ctb_dot_exec(&pl, l->d, br->d, s->d));

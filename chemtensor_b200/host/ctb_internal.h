@@ -186,6 +186,8 @@ int ctb_mps_split_svd(struct ctb_tensor* a, const ct_long d[2], const qnumber* c
 	bool renormalize, int svd_distr, struct ctb_tensor** a0, struct ctb_tensor** a1, struct trunc_info* info);
 int ctb_mps_local_qr(struct ctb_tensor** a, struct ctb_tensor** a_next);
 int ctb_mps_local_rq(struct ctb_tensor** a, struct ctb_tensor** a_prev);
+/* metadata copy that shares the device buffer, with all axis directions reversed (the bra side of a contraction) */
+struct ctb_tensor* ctb_view_reversed_dirs(const struct ctb_tensor* t);
 struct ctb_tensor* ctb_mpo_merge_pair(const struct ctb_tensor* w0, const struct ctb_tensor* w1);
 struct ctb_tensor* ctb_dummy_block_right(const struct ctb_tensor* a, const struct ctb_tensor* b, const struct ctb_tensor* w);
 struct ctb_tensor* ctb_dummy_block_left(const struct ctb_tensor* a, const struct ctb_tensor* b, const struct ctb_tensor* w);

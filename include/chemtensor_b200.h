@@ -105,6 +105,22 @@ int eigensystem_krylov_hermitian(const ct_long n, lanczos_linear_func_z afunc, c
 int dmrg_singlesite(const struct mpo* hamiltonian, const int num_sweeps, const int maxiter_lanczos, struct mps* psi, double* en_sweeps);
 int dmrg_twosite(const struct mpo* hamiltonian, const int num_sweeps, const int maxiter_lanczos, const double tol_split, const ct_long max_vdim, struct mps* psi, double* en_sweeps, double* entropy);
 
+/* ---- other callers of the same primitives ------------------------------------ */
+/* include/state/mps.h:73-75 (src/state/mps.c:314, :375) */
+void mps_vdot(const struct mps* chi, const struct mps* psi, void* ret);
+double mps_norm(const struct mps* psi);
+/* include/algorithm/chain_ops.h (src/algorithm/chain_ops.c:274, :485, :424) */
+void mpo_inner_product(const struct mps* chi, const struct mpo* op, const struct mps* psi, void* ret);
+void apply_mpo(const struct mpo* op, const struct mps* psi, struct mps* op_psi);
+void compute_local_hamiltonian_environment(const struct block_sparse_tensor* a, const struct block_sparse_tensor* b, const struct block_sparse_tensor* l, const struct block_sparse_tensor* r, struct block_sparse_tensor* dw);
+/* include/algorithm/bond_ops.h (src/algorithm/bond_ops.c:146) */
+int split_block_sparse_matrix_svd_isometry(const struct block_sparse_tensor* a, const double tol, const bool relative_thresh, const ct_long max_vdim, struct block_sparse_tensor* u, struct trunc_info* info);
+/* include/state/mps.h:93-103 (src/state/mps.c:764, :815, :868, :1071) */
+int mps_local_orthonormalize_left_svd(const double tol, const ct_long max_vdim, const bool renormalize, struct block_sparse_tensor* a, struct block_sparse_tensor* a_next, struct trunc_info* info);
+int mps_local_orthonormalize_right_svd(const double tol, const ct_long max_vdim, const bool renormalize, struct block_sparse_tensor* a, struct block_sparse_tensor* a_prev, struct trunc_info* info);
+int mps_compress(const double tol, const ct_long max_vdim, const enum mps_orthonormalization_mode mode, struct mps* mps, double* norm, double* trunc_scale, struct trunc_info* info);
+int mps_compress_rescale(const double tol, const ct_long max_vdim, const enum mps_orthonormalization_mode mode, struct mps* mps, double* trunc_scale, struct trunc_info* info);
+
 /* ---- engine extensions (no reference counterpart; measurement and lifecycle) -------------------------------- */
 /* explicit device selection / start-up; returns <0 when no CUDA device is usable */
 int ctb_init(int device);

@@ -271,6 +271,8 @@ int ctbd_lanczos_update(int dtype, int64_t n, void* w, const void* vj, const voi
 int ctbd_lincomb(int dtype, int64_t n, const void* V, int64_t ldv, int m, const double* coef_host, void* out);
 /* x *= alpha (host scalar, real) */
 int ctbd_scale_host(int dtype, int64_t n, void* x, double alpha);
+/* x *= (re + i im) for complex128 entries, x *= re for real ones (phase absorption of mps_compress, reference src/state/mps.c:938-977) */
+int ctbd_zscale_host(int dtype, int64_t n, void* x, double re, double im);
 
 /* ---- batched dense factorizations of the sector blocks -------------------------------------- */
 

@@ -472,6 +472,15 @@ int ctbd_lincomb(int dtype, int64_t n, const void* V, int64_t ldv, int m, const 
 	}
 	return 0;
 }
+int ctbd_zscale_host(int dtype, int64_t n, void* x, double re, double im)
+{
+	g_launches++;
+	const int cplx = (dtype == CTBD_C128);
+	const double complex f = cplx ? re + im * I : re;
+	for (int64_t i = 0; i < n; i++) { PUTC(x, i, f * GETC(x, i)); }
+	return 0;
+}
+
 int ctbd_scale_host(int dtype, int64_t n, void* x, double alpha)
 {
 	g_launches++;
