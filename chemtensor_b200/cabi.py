@@ -139,6 +139,7 @@ _EXT_SIGNATURES = {
     "ctb_dist_set_allgather": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ctb_dist_finalize": (C.c_int, []),
     "ctb_dist_info": (C.c_int, [C.POINTER(C.c_longlong)]),
+    "ctb_apply_local_hamiltonian_pair": (C.c_int, [_P_BST, _P_BST, _P_BST, _P_BST, _P_BST, _P_BST]),
     "ctb_dist_pull_exchanges": (C.c_longlong, []),
     "ctb_dist_push_exchanges": (C.c_longlong, []),
 }

@@ -616,6 +616,37 @@ void apply_local_hamiltonian(const struct block_sparse_tensor* a, const struct b
 	}
 }
 
+/* Extension: the effective Hamiltonian with the two single-site MPO tensors applied one after the other (no merged pair tensor,
+ * see ctb_heff_prepare_pair).  `a` and the result are the reference's two-site tensors [Dl, d0*d1, Dr]; equals
+ * apply_local_hamiltonian(a, mpo_merge_tensor_pair(w0, w1), l, r). */
+int ctb_apply_local_hamiltonian_pair(const struct block_sparse_tensor* a, const struct block_sparse_tensor* w0, const struct block_sparse_tensor* w1,
+	const struct block_sparse_tensor* l, const struct block_sparse_tensor* r, struct block_sparse_tensor* b)
+{
+	CTB_CHECK(ctbd_init(-1));
+	struct ctb_tensor* ad = ctb_upload(a); struct ctb_tensor* w0d = ctb_upload(w0); struct ctb_tensor* w1d = ctb_upload(w1);
+	struct ctb_tensor* ld = ctb_upload(l); struct ctb_tensor* rd = ctb_upload(r);
+	const ct_long dims[2] = { w0d->ax[1].dim, w1d->ax[1].dim };
+	const int dirs[2] = { TENSOR_AXIS_OUT, TENSOR_AXIS_OUT };
+	const qnumber* qn[2] = { w0d->ax[1].qlog, w1d->ax[1].qlog };
+	struct ctb_tensor* a4 = ctb_split_axis(ad, 1, dims, dirs, qn);
+	struct ctb_heff h;
+	int rc = ctb_heff_prepare_pair(a4, w0d, w1d, ld, rd, &h);
+	if (rc == 0) {
+		struct ctb_tensor* b4 = ctb_tensor_like(a4, 1);
+		rc = ctb_heff_apply(&h, a4->d, b4->d);
+		if (rc == 0) {
+			struct ctb_tensor* b3 = ctb_flatten_axes(b4, 1, TENSOR_AXIS_OUT);
+			rc = ctb_download(b3, b);
+			ctb_tensor_free(b3);
+		}
+		ctb_tensor_free(b4);
+		ctb_heff_free(&h);
+	}
+	ctb_tensor_free(a4);
+	ctb_tensor_free(ad); ctb_tensor_free(w0d); ctb_tensor_free(w1d); ctb_tensor_free(ld); ctb_tensor_free(rd);
+	return rc;
+}
+
 /* ---- measurement ---- */
 
 int ctb_heff_benchmark(const struct block_sparse_tensor* a, const struct block_sparse_tensor* w, const struct block_sparse_tensor* l, const struct block_sparse_tensor* r,

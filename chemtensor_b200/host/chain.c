@@ -413,18 +413,21 @@ static int split_bond(const struct ctb_tensor* a, const struct ctb_tensor* l, co
 	 * so per sector the weights are collected by the multiplier (m_w' or m_sigma') of the column count. */
 	enum { MULT_MAX = 64 };
 #define PAD_UP(x, g) ((((x) + (g) - 1) / (g)) * (g))
-	double* rows_a = ctb_calloc((size_t)a->ax[2].nsec, sizeof(double));
+	const int kb = a->ndim - 1;      /* ket bond of a: [Dl, d, Dr] or, with the physical legs kept apart, [Dl, d1, d2, Dr] */
+	double* rows_a = ctb_calloc((size_t)a->ax[kb].nsec, sizeof(double));
 	for (int b = 0; b < a->nblk; b++) {
 		int idx[CTB_MAXDIM];
 		ctb_grid_unravel(a, a->blk_grid[b], idx);
-		rows_a[idx[2]] += (double)PAD_UP((ct_long)a->ax[0].secdim[idx[0]] * a->ax[1].secdim[idx[1]], 64) * (double)PAD_UP((ct_long)a->ax[2].secdim[idx[2]], 16);
+		ct_long rows = 1;
+		for (int i = 0; i < kb; i++) { rows *= a->ax[i].secdim[idx[i]]; }
+		rows_a[idx[kb]] += (double)PAD_UP(rows, 64) * (double)PAD_UP((ct_long)a->ax[kb].secdim[idx[kb]], 16);
 	}
 	double* wmul = ctb_calloc((size_t)ax->nsec * MULT_MAX, sizeof(double));     /* [sector][multiplier] */
 	double* wcol = ctb_calloc((size_t)ax->nsec, sizeof(double));                /* unpadded work per column (small-bond case) */
 	for (int b = 0; b < r->nblk; b++) {
 		int idx[CTB_MAXDIM];
 		ctb_grid_unravel(r, r->blk_grid[b], idx);
-		const int sa = ctb_axis_find_sector(&a->ax[2], r->ax[0].qsec[idx[0]]);
+		const int sa = ctb_axis_find_sector(&a->ax[kb], r->ax[0].qsec[idx[0]]);
 		if (sa < 0) { continue; }
 		int mult = r->ax[1].secdim[idx[1]];
 		wcol[idx[2]] += rows_a[sa] * mult;
@@ -444,9 +447,10 @@ static int split_bond(const struct ctb_tensor* a, const struct ctb_tensor* l, co
 			/* the result has the structure of a; its first leg carries the quantum numbers of the bra leg of l */
 			const int sl = ctb_axis_find_sector(&l->ax[3], a->ax[0].qsec[idx[0]]);
 			if (sl < 0) { continue; }
-			const int sr = ctb_axis_find_sector(ax, a->ax[2].qsec[idx[2]]);
+			const int sr = ctb_axis_find_sector(ax, a->ax[kb].qsec[idx[kb]]);
 			if (sr < 0) { continue; }
-			int mult = a->ax[1].secdim[idx[1]];
+			int mult = 1;
+			for (int i = 1; i < kb; i++) { mult *= a->ax[i].secdim[idx[i]]; }
 			const double wgt = (double)PAD_UP((ct_long)a->ax[0].secdim[idx[0]], 64) * kl[sl];
 			wcol[sr] += wgt * mult;
 			if (mult >= MULT_MAX) { mult = MULT_MAX - 1; }
@@ -502,12 +506,34 @@ int ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, str
 	return ctb_heff_prepare_ex(a, w, l, r, h, NULL, NULL);
 }
 
+static int heff_prepare_any(const struct ctb_tensor* a, const struct ctb_tensor* w, const struct ctb_tensor* w_second, struct ctb_tensor* l, const struct ctb_tensor* r,
+	struct ctb_heff* h, void (*l_ready)(void*), void* ctx);
+
 int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h,
 	void (*l_ready)(void*), void* ctx)
 {
-	CTB_REQUIRE(a->ndim == 3 && w->ndim == 4 && l->ndim == 4 && r->ndim == 4);
+	CTB_REQUIRE(a->ndim == 3);
+	return heff_prepare_any(a, w, NULL, l, r, h, l_ready, ctx);
+}
+
+/* The two single-site MPO tensors applied one after the other instead of the merged pair tensor: `a` is the
+ * two-site tensor with its physical legs kept apart, [Dl, d1, d2, Dr], and so is the result.  The merged tensor of the reference
+ * (mpo_merge_tensor_pair, src/operator/mpo.c:255) grows with Dw^2 d^4 and is what makes large-bond MPOs infeasible there; the
+ * sequential form needs the two site tensors only and costs Dw d^2 (Dw' d) per (Dl, Dr') column instead of (Dw d^2)(d^2 Dw''). */
+int ctb_heff_prepare_pair(const struct ctb_tensor* a4, const struct ctb_tensor* w0, const struct ctb_tensor* w1, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h)
+{
+	CTB_REQUIRE(a4->ndim == 4 && w1 != NULL);
+	return heff_prepare_any(a4, w0, w1, l, r, h, NULL, NULL);
+}
+
+static int heff_prepare_any(const struct ctb_tensor* a, const struct ctb_tensor* w, const struct ctb_tensor* w_second, struct ctb_tensor* l, const struct ctb_tensor* r,
+	struct ctb_heff* h, void (*l_ready)(void*), void* ctx)
+{
+	const bool pair = (w_second != NULL);
+	const int kb = a->ndim - 1;      /* ket bond of a */
+	CTB_REQUIRE(a->ndim == (pair ? 4 : 3) && w->ndim == 4 && l->ndim == 4 && r->ndim == 4);
 	memset(h, 0, sizeof(*h));
-	h->w = w; h->r = r;
+	h->w = w; h->w_second = w_second; h->r = r;
 	h->world = 1; h->rank = 0;
 	if (ctb_dist_world > 1)
 	{
@@ -525,13 +551,12 @@ int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, 
 			h->piece = ctb_calloc((size_t)W, sizeof(struct ctb_tensor*));
 			for (int p = 0; p < W; p++) {
 				qnumber* q = ctb_malloc((size_t)h->nind[p] * sizeof(qnumber));
-				for (ct_long j = 0; j < h->nind[p]; j++) { q[j] = a->ax[2].qlog[h->ind[p][j]]; }
-				struct ctb_axis axes[3];
-				ctb_axis_copy(&axes[0], &a->ax[0]);
-				ctb_axis_copy(&axes[1], &a->ax[1]);
-				ctb_axis_init(&axes[2], h->nind[p], a->ax[2].dir, q);
+				for (ct_long j = 0; j < h->nind[p]; j++) { q[j] = a->ax[kb].qlog[h->ind[p][j]]; }
+				struct ctb_axis axes[4];
+				for (int i = 0; i < kb; i++) { ctb_axis_copy(&axes[i], &a->ax[i]); }
+				ctb_axis_init(&axes[kb], h->nind[p], a->ax[kb].dir, q);
 				ctb_free(q);
-				h->piece[p] = ctb_tensor_from_axes(a->dtype, 3, axes, 0);
+				h->piece[p] = ctb_tensor_from_axes(a->dtype, a->ndim, axes, 0);
 				if (h->piece[p]->nstore > h->piece_cap) { h->piece_cap = h->piece[p]->nstore; }
 			}
 			if (h->piece_cap == 0) { h->piece_cap = 1; }
@@ -552,23 +577,25 @@ int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, 
 					{
 						int idx[CTB_MAXDIM];
 						ctb_grid_unravel(pc, pc->blk_grid[blk], idx);
-						const int sfull = ctb_axis_find_sector(&a->ax[2], pc->ax[2].qsec[idx[2]]);
+						const int sfull = ctb_axis_find_sector(&a->ax[kb], pc->ax[kb].qsec[idx[kb]]);
 						CTB_REQUIRE(sfull >= 0);
-						const int ifull[3] = { idx[0], idx[1], sfull };
+						int ifull[CTB_MAXDIM];
+						int rows = 1;
+						for (int i = 0; i < kb; i++) { ifull[i] = idx[i]; rows *= pc->ax[i].secdim[idx[i]]; }
+						ifull[kb] = sfull;
 						const ct_long dst_blk = a->grid_off[ctb_grid_ravel(a, ifull)];
 						CTB_REQUIRE(dst_blk >= 0);
-						const int rows = pc->ax[0].secdim[idx[0]] * pc->ax[1].secdim[idx[1]];
-						const int np = pc->ax[2].secdim[idx[2]], nfull = a->ax[2].secdim[sfull];
+						const int np = pc->ax[kb].secdim[idx[kb]], nfull = a->ax[kb].secdim[sfull];
 						int j = 0;
 						while (j < np)
 						{
 							/* position inside the full sector of the j-th piece column of this sector */
-							const ct_long lg0 = h->ind[p][pc->ax[2].log_of[pc->ax[2].secstart[idx[2]] + j]];
-							const int pos0 = a->ax[2].pos_of[lg0];
+							const ct_long lg0 = h->ind[p][pc->ax[kb].log_of[pc->ax[kb].secstart[idx[kb]] + j]];
+							const int pos0 = a->ax[kb].pos_of[lg0];
 							int len = 1;
 							while (j + len < np) {
-								const ct_long lg = h->ind[p][pc->ax[2].log_of[pc->ax[2].secstart[idx[2]] + j + len]];
-								if (a->ax[2].pos_of[lg] != pos0 + len) { break; }
+								const ct_long lg = h->ind[p][pc->ax[kb].log_of[pc->ax[kb].secstart[idx[kb]] + j + len]];
+								if (a->ax[kb].pos_of[lg] != pos0 + len) { break; }
 								len++;
 							}
 							if (nd == cap) { cap *= 2; descs = realloc(descs, cap * sizeof(*descs)); }
@@ -598,13 +625,34 @@ int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, 
 	const struct ctb_tensor* ru = h->r;
 	const int trace = getenv("CTB_TRACE") != NULL;
 	const double tp0 = ctb_wall_ms();
-	/* step 1: a . r  -> t1 [dd, Dw', Dl, Dr', x'] */
-	const int perm0[5] = { 1, 2, 0, 3, 4 };
-	h->t1 = ctb_dot_prepare(a, TENSOR_AXIS_RANGE_TRAILING, 0, ru, TENSOR_AXIS_RANGE_LEADING, 0, 1, perm0, 1, &h->p1);
+	if (!pair)
+	{
+		/* step 1: a . r  -> t1 [dd, Dw', Dl, Dr', x'] */
+		const int perm0[5] = { 1, 2, 0, 3, 4 };
+		h->t1 = ctb_dot_prepare(a, TENSOR_AXIS_RANGE_TRAILING, 0, ru, TENSOR_AXIS_RANGE_LEADING, 0, 1, perm0, 1, &h->p1);
+	}
+	else
+	{
+		/* step 1: a . r  -> t1 [d2, Dw'', Dl, d1, Dr', x'] */
+		const int perm0[6] = { 2, 3, 0, 1, 4, 5 };
+		h->t1 = ctb_dot_prepare(a, TENSOR_AXIS_RANGE_TRAILING, 0, ru, TENSOR_AXIS_RANGE_LEADING, 0, 1, perm0, 1, &h->p1);
+	}
 	const double tp1 = ctb_wall_ms();
-	/* step 2: w . t1 over (dd_in, Dw') -> t2 [Dl, Dw, dd_out, Dr', x'] */
-	const int perm1[5] = { 2, 0, 1, 3, 4 };
-	h->t2 = ctb_dot_prepare_ex(w, TENSOR_AXIS_RANGE_TRAILING, 0, h->t1, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1, 1, CTB_DOT_MERGE_ROWS, &h->p2);
+	if (!pair)
+	{
+		/* step 2: w . t1 over (dd_in, Dw') -> t2 [Dl, Dw, dd_out, Dr', x'] */
+		const int perm1[5] = { 2, 0, 1, 3, 4 };
+		h->t2 = ctb_dot_prepare_ex(w, TENSOR_AXIS_RANGE_TRAILING, 0, h->t1, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1, 1, CTB_DOT_MERGE_ROWS, &h->p2);
+	}
+	else
+	{
+		/* step 2a: w(site i+1) . t1 over (d2_in, Dw'') -> tm [d1, Dw', Dl, d2_out, Dr', x'] */
+		const int perm1a[6] = { 3, 0, 2, 1, 4, 5 };
+		h->tm = ctb_dot_prepare_ex(w_second, TENSOR_AXIS_RANGE_TRAILING, 0, h->t1, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1a, 1, CTB_DOT_MERGE_ROWS, &h->p2a);
+		/* step 2b: w(site i) . tm over (d1_in, Dw') -> t2 [Dl, Dw, d1_out, d2_out, Dr', x'] */
+		const int perm1b[6] = { 2, 0, 1, 3, 4, 5 };
+		h->t2 = ctb_dot_prepare_ex(w, TENSOR_AXIS_RANGE_TRAILING, 0, h->tm, TENSOR_AXIS_RANGE_LEADING, 0, 2, perm1b, 1, CTB_DOT_MERGE_ROWS, &h->p2);
+	}
 	const double tp2 = ctb_wall_ms();
 	/* step 3: k . t2 over (Dl, Dw), k = transpose(l, [0,3,1,2]) once per bond (the reference redoes it every matvec) */
 	const int perm2[4] = { 0, 3, 1, 2 };
@@ -620,15 +668,16 @@ int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, 
 	{
 		/* fused exchange: the step-3 GEMM stores its column slice straight into the packed layout of the FULL result, in the
 		 * peer-mapped landing buffer of every rank (NVLink stores from the epilogue); no all-gather, no scatter */
-		struct ctb_axis axes[5];
+		struct ctb_axis axes[6];
+		const int nphys = a->ndim - 2;      /* one fused or two separate physical legs */
 		ctb_axis_copy(&axes[0], &h->k->ax[0]);
 		ctb_axis_copy(&axes[1], &h->k->ax[1]);
-		ctb_axis_copy(&axes[2], &h->t2->ax[2]);
-		ctb_axis_copy(&axes[3], &r->ax[2]);
-		ctb_axis_copy(&axes[4], &h->t2->ax[4]);
-		h->bfull5 = ctb_tensor_from_axes(a->dtype, 5, axes, 0);
+		for (int i = 0; i < nphys; i++) { ctb_axis_copy(&axes[2 + i], &h->t2->ax[2 + i]); }
+		ctb_axis_copy(&axes[2 + nphys], &r->ax[2]);
+		ctb_axis_copy(&axes[3 + nphys], &h->t2->ax[3 + nphys]);
+		h->bfull5 = ctb_tensor_from_axes(a->dtype, 4 + nphys, axes, 0);
 		CTB_REQUIRE(h->bfull5->nstore == a->nstore && h->bfull5->nblk == a->nblk);
-		const struct ctb_embed emb = { 3, h->bfull5, h->ind[h->rank] };
+		const struct ctb_embed emb = { 2 + nphys, h->bfull5, h->ind[h->rank] };
 		s = ctb_dot_prepare_embed(h->k, TENSOR_AXIS_RANGE_TRAILING, 0, h->t2, TENSOR_AXIS_RANGE_LEADING, 0, 2, &emb, &h->p3);
 		h->fused = 1;
 	}
@@ -648,7 +697,7 @@ int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, 
 		h->b = bs;
 		CTB_REQUIRE(ctb_tensor_same_structure(h->b, a));
 	}
-	h->flops = h->p1.flops + h->p2.flops + h->p3.flops;
+	h->flops = h->p1.flops + h->p2.flops + h->p3.flops + (pair ? h->p2a.flops : 0.0);
 	h->flops_total = h->flops * h->world;     /* the shards are balanced by construction; exact totals come from flops of world == 1 */
 	h->n = a->nelem;
 	h->nstore = a->nstore;
@@ -658,7 +707,11 @@ int ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, 
 int ctb_heff_apply(struct ctb_heff* h, const void* a_data, void* b_data)
 {
 	CTB_CHECK(ctb_dot_exec(&h->p1, a_data, h->r->d, h->t1->d));
-	CTB_CHECK(ctb_dot_exec(&h->p2, h->w->d, h->t1->d, h->t2->d));
+	if (h->w_second != NULL) {
+		CTB_CHECK(ctb_dot_exec(&h->p2a, h->w_second->d, h->t1->d, h->tm->d));
+		CTB_CHECK(ctb_dot_exec(&h->p2, h->w->d, h->tm->d, h->t2->d));
+	}
+	else { CTB_CHECK(ctb_dot_exec(&h->p2, h->w->d, h->t1->d, h->t2->d)); }
 	CTB_CHECK(ctb_heff_step3(h, b_data));
 	CTB_CHECK(ctb_heff_exchange(h, b_data));
 	ctb_global_stats.heff_flops += h->flops;
@@ -729,8 +782,8 @@ int ctb_heff_exchange(struct ctb_heff* h, void* b_data)
 
 void ctb_heff_free(struct ctb_heff* h)
 {
-	ctb_dot_plan_free(&h->p1); ctb_dot_plan_free(&h->p2); ctb_dot_plan_free(&h->p3);
-	ctb_tensor_free(h->t1); ctb_tensor_free(h->t2); ctb_tensor_free(h->k); ctb_tensor_free(h->b);
+	ctb_dot_plan_free(&h->p1); ctb_dot_plan_free(&h->p2); ctb_dot_plan_free(&h->p3); ctb_dot_plan_free(&h->p2a);
+	ctb_tensor_free(h->t1); ctb_tensor_free(h->t2); ctb_tensor_free(h->tm); ctb_tensor_free(h->k); ctb_tensor_free(h->b);
 	if (h->piece != NULL) { for (int p = 0; p < h->world; p++) { ctb_tensor_free(h->piece[p]); } ctb_free(h->piece); }
 	if (h->ind != NULL) { for (int p = 0; p < h->world; p++) { ctb_free(h->ind[p]); } ctb_free(h->ind); ctb_free(h->nind); }
 	ctb_tensor_free(h->r_own);

@@ -200,6 +200,11 @@ struct ctb_heff
 	struct ctb_dot_plan p1, p2, p3;
 	struct ctb_tensor* t1;   /* [dd, Dw', Dl, Dr', 1] */
 	struct ctb_tensor* t2;   /* [Dl, Dw, dd, Dr', 1]  */
+	/* pair form (ctb_heff_prepare_pair): the two site tensors w_second (site i+1) and w (site i) are applied one after the other,
+	 * a and the result keep the physical legs apart: t1 [d2, Dw'', Dl, d1, Dr', 1] -> tm [d1, Dw', Dl, d2, Dr', 1] -> t2 [Dl, Dw, d1, d2, Dr', 1] */
+	struct ctb_dot_plan p2a;
+	struct ctb_tensor* tm;
+	const struct ctb_tensor* w_second;
 	struct ctb_tensor* k;    /* transpose(l, [0,3,1,2]) computed once per bond */
 	struct ctb_tensor* b;    /* structure of the result (no buffer) */
 	const struct ctb_tensor* w;
@@ -231,6 +236,7 @@ int  ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, st
  * plans of steps 1 and 2 (which need structure only, and the payload of w) while the payloads of a, l and r are still in flight */
 int  ctb_heff_prepare_ex(const struct ctb_tensor* a, const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h,
 	void (*l_ready)(void*), void* ctx);
+int  ctb_heff_prepare_pair(const struct ctb_tensor* a4, const struct ctb_tensor* w0, const struct ctb_tensor* w1, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h);
 int  ctb_heff_apply(struct ctb_heff* h, const void* a_data, void* b_data);
 int  ctb_heff_step3(struct ctb_heff* h, void* b_data);
 void* ctb_heff_result_buffer(const struct ctb_heff* h);

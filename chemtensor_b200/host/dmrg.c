@@ -66,12 +66,25 @@ static int normalize_first_site(struct ctb_tensor** A0)
 	return rc;
 }
 
-static int minimize_local_energy(const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r,
+/* The merged pair tensor of the reference (dmrg.c:289-292) has up to Dw d^4 Dw'' entries.  Beyond this bound (dense count), or
+ * with CTB_HEFF_PAIR=1, the two site tensors are applied one after the other instead and no merged tensor is ever built. */
+#define CTB_PAIR_MERGE_LIMIT ((double)((ct_long)1 << 28))
+static bool use_pair_form(const struct ctb_tensor* w0, const struct ctb_tensor* w1)
+{
+	const char* env = getenv("CTB_HEFF_PAIR");
+	if (env != NULL) { return atoi(env) != 0; }
+	const double d0 = (double)w0->ax[1].dim, d1 = (double)w1->ax[1].dim;
+	return (double)w0->ax[0].dim * d0 * d0 * d1 * d1 * (double)w1->ax[3].dim > CTB_PAIR_MERGE_LIMIT;
+}
+
+/* w_second == NULL: w is the merged pair tensor and a_start [Dl, dd, Dr]; else w, w_second are the site tensors and a_start [Dl, d1, d2, Dr] */
+static int minimize_local_energy(const struct ctb_tensor* w, const struct ctb_tensor* w_second, struct ctb_tensor* l, const struct ctb_tensor* r,
 	const struct ctb_tensor* a_start, int maxiter, double* en, struct ctb_tensor** a_opt)
 {
 	struct ctb_heff h;
 	const double t0 = ctb_wall_ms();
-	CTB_CHECK(ctb_heff_prepare(a_start, w, l, r, &h));
+	if (w_second != NULL) { CTB_CHECK(ctb_heff_prepare_pair(a_start, w, w_second, l, r, &h)); }
+	else { CTB_CHECK(ctb_heff_prepare(a_start, w, l, r, &h)); }
 	int rc = ctb_lanczos_min(&h, a_start, maxiter, en, a_opt, NULL);
 	ctb_heff_free(&h);
 	if (a_start->nelem > ctb_global_stats.max_vector_len) { ctb_global_stats.max_vector_len = a_start->nelem; }
@@ -129,7 +142,7 @@ int dmrg_twosite(const struct mpo* hamiltonian, const int num_sweeps, const int 
 		}
 		Lb[0] = ctb_dummy_block_left(A[0], A[0], W[0]);
 		for (int i = 0; i < nsites - 1; i++) {
-			h2[i] = ctb_mpo_merge_pair(W[i], W[i + 1]);
+			if (!use_pair_form(W[i], W[i + 1])) { h2[i] = ctb_mpo_merge_pair(W[i], W[i + 1]); }
 		}
 		ctb_global_stats.env_ms += ctb_wall_ms() - t0;
 	}
@@ -148,12 +161,25 @@ int dmrg_twosite(const struct mpo* hamiltonian, const int num_sweeps, const int 
 			const int step    = (pass == 0 ? 1 : -1);
 			for (int i = i_begin; i != i_end; i += step)
 			{
-				struct ctb_tensor* a_cur = ctb_mps_merge_pair(A[i], A[i + 1]);
+				struct ctb_tensor* a_cur = NULL;
+				struct ctb_tensor* a_opt = NULL;
+				if (h2[i] != NULL)
+				{
+					a_cur = ctb_mps_merge_pair(A[i], A[i + 1]);
+					ret = minimize_local_energy(h2[i], NULL, Lb[i], Rb[i + 1], a_cur, maxiter_lanczos, &en, &a_opt);
+				}
+				else
+				{
+					/* pair form: the two-site tensor keeps its physical legs apart during the local solve (the Lanczos vector holds the
+					 * same entries in the packed order of the 4-leg tensor) and is fused afterwards for the split */
+					a_cur = ctb_dot(A[i], TENSOR_AXIS_RANGE_TRAILING, 0, A[i + 1], TENSOR_AXIS_RANGE_LEADING, 0, 1, NULL);
+					struct ctb_tensor* a_opt4 = NULL;
+					ret = minimize_local_energy(W[i], W[i + 1], Lb[i], Rb[i + 1], a_cur, maxiter_lanczos, &en, &a_opt4);
+					if (ret == 0) { a_opt = ctb_flatten_axes(a_opt4, 1, TENSOR_AXIS_OUT); }
+					ctb_tensor_free(a_opt4);
+				}
 				ctb_tensor_free(A[i]);     A[i] = NULL;
 				ctb_tensor_free(A[i + 1]); A[i + 1] = NULL;
-
-				struct ctb_tensor* a_opt = NULL;
-				ret = minimize_local_energy(h2[i], Lb[i], Rb[i + 1], a_cur, maxiter_lanczos, &en, &a_opt);
 				ctb_tensor_free(a_cur);
 				if (ret < 0) { break; }
 
@@ -236,7 +262,7 @@ int dmrg_singlesite(const struct mpo* hamiltonian, const int num_sweeps, const i
 		for (int i = 0; i < nsites - 1 && ret == 0; i++)
 		{
 			struct ctb_tensor* a_opt = NULL;
-			ret = minimize_local_energy(W[i], Lb[i], Rb[i], A[i], maxiter_lanczos, &en, &a_opt);
+			ret = minimize_local_energy(W[i], NULL, Lb[i], Rb[i], A[i], maxiter_lanczos, &en, &a_opt);
 			if (ret < 0) { break; }
 			ctb_tensor_free(A[i]);
 			A[i] = a_opt;
@@ -248,7 +274,7 @@ int dmrg_singlesite(const struct mpo* hamiltonian, const int num_sweeps, const i
 		for (int i = nsites - 1; i > 0 && ret == 0; i--)
 		{
 			struct ctb_tensor* a_opt = NULL;
-			ret = minimize_local_energy(W[i], Lb[i], Rb[i], A[i], maxiter_lanczos, &en, &a_opt);
+			ret = minimize_local_energy(W[i], NULL, Lb[i], Rb[i], A[i], maxiter_lanczos, &en, &a_opt);
 			if (ret < 0) { break; }
 			ctb_tensor_free(A[i]);
 			A[i] = a_opt;

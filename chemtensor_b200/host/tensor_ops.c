@@ -119,7 +119,14 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 
 	const int a_kcontig = (axrange_s == TENSOR_AXIS_RANGE_TRAILING);
 	const int b_ncontig = (axrange_t == TENSOR_AXIS_RANGE_LEADING);
-	const bool merge = (flags & CTB_DOT_MERGE_ROWS) != 0 && s->d != NULL && nft > 0 && r->nblk > 0;
+	bool merge = (flags & CTB_DOT_MERGE_ROWS) != 0 && s->d != NULL && nft > 0 && r->nblk > 0;
+	{
+		/* the merged (non-mixing) form addresses the whole result with 32-bit offsets: beyond that the plain per-block form is used */
+		ct_long kfull0 = 1;
+		for (int i = 0; i < ndim_mult; i++) { kfull0 *= s->ax[shift_s + i].dim; }
+		const bool mix_ok = b_ncontig && nft <= 4 && kfull0 <= CTB_MIX_KMAX;
+		if (merge && !mix_ok && r->nstore >= ((ct_long)1 << 31)) { merge = false; }
+	}
 
 	/* growable host arrays */
 	size_t cap_seg = 1024, nseg = 0;

@@ -177,7 +177,7 @@ def measured_bond_qnums(data_file: str, bond: int, scale: int = 1, shift_q: int 
 
 
 def heff_operands(lib: cabi.CLibrary, model: str, nsites: int, params, qnum_sector: int, max_vdim: int, site: int | None = None,
-                  dtype=np.float64, seed: int = 42, bonds=None):
+                  dtype=np.float64, seed: int = 42, bonds=None, with_sites: bool = False):
     """(a, w, l, r) for the pair (site, site+1): the merged two-site MPS tensor a[Dl, d^2, Dr], the merged MPO tensor
     w[Dw, d^2, d^2, Dw'] (real Hamiltonian entries), and environments l[1, Dl, Dw, Dl], r[Dr, Dw', Dr, 1] with the
     structure of the reference's contraction_operator_step_left/right outputs (chain_ops.c:116, :196) and random entries."""
@@ -207,4 +207,10 @@ def heff_operands(lib: cabi.CLibrary, model: str, nsites: int, params, qnum_sect
     r = cabi.bst_allocate(lib, dtype, (len(qr), len(qwb[site + 2]), len(qr), 1), [OUT, OUT, IN, IN], [qr, qwb[site + 2], qr, q0])
     fill_random(l, rng, 1.0 / np.sqrt(len(ql)))
     fill_random(r, rng, 1.0 / np.sqrt(len(qr)))
+    if with_sites:
+        # the two single-site MPO tensors the merged one was built from (pair form of the effective Hamiltonian)
+        qs = np.asarray(qsite, dtype=np.int32)
+        w0 = cabi.bst_from_dense(lib, np.ascontiguousarray(tensors[site]).astype(dtype), [OUT, OUT, IN, IN], [qwb[site], qs, qs, qwb[site + 1]])
+        w1 = cabi.bst_from_dense(lib, np.ascontiguousarray(tensors[site + 1]).astype(dtype), [OUT, OUT, IN, IN], [qwb[site + 1], qs, qs, qwb[site + 2]])
+        return a, w, l, r, w0, w1
     return a, w, l, r

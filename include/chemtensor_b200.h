@@ -137,6 +137,8 @@ int ctb_dist_finalize(void);
 /* out[0] = rank, out[1] = world, out[2] = exchanges done by the fused peer-store path, out[3] = exchanges done by all-gather + scatter */
 int ctb_dist_info(long long* out);
 long long ctb_dist_pull_exchanges(void);
+/* two-site effective Hamiltonian from the two single-site MPO tensors, no merged pair tensor */
+int ctb_apply_local_hamiltonian_pair(const struct block_sparse_tensor* a, const struct block_sparse_tensor* w0, const struct block_sparse_tensor* w1, const struct block_sparse_tensor* l, const struct block_sparse_tensor* r, struct block_sparse_tensor* b);
 long long ctb_dist_push_exchanges(void);
 /* 1 = CUDA kernels, 2 = host test double (tests/emu only) */
 int ctb_backend(void);

@@ -63,10 +63,14 @@ def main():
     # 1. one sharded two-site Heff application on seeded operands (Fermi-Hubbard and XXZ structures, real and complex)
     for tag, model, L, params, sector, D, dtype in (("fh", "fermi_hubbard", 8, (1.0, 4.0, 0.0), workloads.encode_qpair(8, 0), 40, np.float64),
                                                      ("xxz", "xxz", 12, (1.0, 0.8, 0.1), 0, 24, np.complex128)):
-        a, w, l, r = workloads.heff_operands(eng, model, L, params, sector, D, dtype=dtype, seed=7)
+        a, w, l, r, w0, w1 = workloads.heff_operands(eng, model, L, params, sector, D, dtype=dtype, seed=7, with_sites=True)
         b = cabi.BST(eng)
         eng.apply_local_hamiltonian(a.ptr, w.ptr, l.ptr, r.ptr, b.ptr)
         out[f"heff_{tag}"] = b.serialize()
+        # the same application in the pair form (two site tensors one after the other, no merged pair tensor), sharded as well
+        b2 = cabi.BST(eng)
+        assert eng.ctb_apply_local_hamiltonian_pair(a.ptr, w0.ptr, w1.ptr, l.ptr, r.ptr, b2.ptr) == 0
+        out[f"heff_{tag}_pair"] = b2.serialize()
     # 2. a short two-site DMRG with every local solve sharded
     mpo = workloads.mpo_chain(eng, "fermi_hubbard", 6, (1.0, 4.0, 0.0))
     psi = workloads.random_mps(eng, np.float64, 6, mpo.qsite, workloads.encode_qpair(6, 0), 32, seed=42)
@@ -75,6 +79,13 @@ def main():
     assert rc == 0
     out["dmrg_en"] = en
     out["dmrg_entropy"] = ent
+    # the same sweeps with every local solve in the pair form
+    os.environ["CTB_HEFF_PAIR"] = "1"
+    psi2 = workloads.random_mps(eng, np.float64, 6, mpo.qsite, workloads.encode_qpair(6, 0), 32, seed=42)
+    en2 = np.zeros(2); ent2 = np.zeros(5)
+    assert eng.dmrg_twosite(mpo.ptr, 2, 12, 1e-10, 32, psi2.ptr, en2.ctypes.data_as(C.POINTER(C.c_double)), ent2.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    del os.environ["CTB_HEFF_PAIR"]
+    out["dmrg_en_pair"] = en2
     out["dmrg_site2"] = psi.site(2).serialize()
     info = (C.c_longlong * 4)()
     eng.ctb_dist_info(info)

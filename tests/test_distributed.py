@@ -67,6 +67,11 @@ def check(results, single):
         for r in results[1:]:
             assert np.array_equal(r[key], results[0][key])      # every rank holds the same full vector, bit for bit
     for r in results:
+        # pair form (no merged MPO pair tensor), sharded: same vector as the merged form on one rank
+        for key in ("heff_fh", "heff_xxz"):
+            assert helpers.rel_err(r[key + "_pair"], single[key]) <= 1e-12
+        assert np.max(np.abs(r["dmrg_en_pair"] - single["dmrg_en"])) <= 1e-10
+    for r in results:
         assert np.max(np.abs(r["dmrg_en"] - single["dmrg_en"])) <= 1e-10
     for r in results[1:]:
         assert np.array_equal(r["dmrg_en"], results[0]["dmrg_en"])
