@@ -373,6 +373,43 @@ SWEEP_CASES = [
 ]
 
 
+def molecular_sweep_seconds(lib, n, D, pair_form, sweeps=2, lanczos=10, seed=5):
+    """BASELINE.json configs[3] in small: complex128 two-site DMRG on a synthetic molecular Hamiltonian (random complex integrals with
+    the Hermitian symmetrisation of the reference's perf/perf_dmrg_coeffs.py, spatial orbitals, d = 4).  The MPO comes from the
+    reference's own generator (oracle/_ref, input generator only).  pair_form: apply the two site MPO tensors one after the other
+    (no merged pair tensor) -- the form large MPO bonds need; None leaves the engine's automatic choice."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    ref = helpers.load("ref")
+    rng = np.random.default_rng(seed)
+    tkin = 0.5 * (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    vint = 0.1 * (rng.standard_normal((n, n, n, n)) + 1j * rng.standard_normal((n, n, n, n)))
+    tkin = 0.5 * (tkin + tkin.conj().T)
+    vint = 0.5 * (vint + vint.transpose((1, 0, 3, 2)))
+    vint = 0.5 * (vint + vint.transpose((2, 3, 0, 1)).conj())
+    mpo_r = helpers.ref_molecular_mpo(ref, tkin, vint, spin=True, optimize=False)
+    L = mpo_r.nsites
+    psi_r = helpers.ref_random_mps(ref, np.complex128, L, mpo_r.qsite, workloads.encode_qpair(n, 0), D, seed=42)
+    mpo, psi = helpers.clone_chain(lib, mpo_r), helpers.clone_chain(lib, psi_r)
+    if pair_form is not None:
+        os.environ["CTB_HEFF_PAIR"] = "1" if pair_form else "0"
+    en = np.zeros(sweeps); ent = np.zeros(L - 1)
+    t0 = time.perf_counter()
+    rc = lib.dmrg_twosite(mpo.ptr, sweeps, lanczos, 0.0, D, psi.ptr, en.ctypes.data_as(C.POINTER(C.c_double)), ent.ctypes.data_as(C.POINTER(C.c_double)))
+    dt = time.perf_counter() - t0
+    os.environ.pop("CTB_HEFF_PAIR", None)
+    if rc != 0:
+        return None
+    return {"s_per_sweep": dt / sweeps, "energies": [float(x) for x in en], "max_bond": int(max(psi.bond_dims())), "mpo_bond": int(max(mpo_r.bond_dims()))}
+
+
+MOLECULAR_SWEEP_CASES = [
+    # (name, spatial orbitals, bond dimension, time the reference too?)
+    ("mol_n8_D64_c128", 8, 64, True),
+    ("mol_n12_D256_c128", 12, 256, False),
+]
+
+
 def sweep_report(lib):
     """Two-site sweep seconds of the engine (and of the unmodified reference on the small case) -- reported, not the headline."""
     out = []
@@ -388,6 +425,27 @@ def sweep_report(lib):
                 "from chemtensor_b200 import cabi\n"
                 f"ref = cabi.CLibrary({REF_SO!r})\n"
                 f"print(json.dumps(bench.sweep_seconds(ref, {model!r}, {L}, {params!r}, {sector}, {D})))\n"
+            )
+            env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+            try:
+                r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
+                rec["reference_cpu"] = json.loads(r.stdout.strip().splitlines()[-1])
+                rec["reference_cpu"]["cores"] = os.cpu_count()
+            except Exception as exc:
+                rec["reference_cpu"] = {"failed": str(exc)}
+        out.append(rec)
+    for name, n, D, with_ref in MOLECULAR_SWEEP_CASES:
+        rec = {"config": name, "sweeps": 2, "lanczos_iterations": 10, "tol_split": 0.0, "dtype": "c128"}
+        rec["b200_merged_pair_tensor"] = molecular_sweep_seconds(lib, n, D, False)
+        rec["b200_pair_form"] = molecular_sweep_seconds(lib, n, D, True)
+        if with_ref and os.path.exists(REF_SO):
+            code = (
+                "import sys, json\n"
+                f"sys.path.insert(0, {ROOT!r})\n"
+                "import bench\n"
+                "from chemtensor_b200 import cabi\n"
+                f"ref = cabi.CLibrary({REF_SO!r})\n"
+                f"print(json.dumps(bench.molecular_sweep_seconds(ref, {n}, {D}, None)))\n"
             )
             env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
             try:

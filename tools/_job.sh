@@ -1,2 +1,7 @@
 cd $GRAFT_REPO_ROOT
-(timeout 900 python -m pytest tests/test_pair_form.py tests/test_dmrg.py tests/test_callers.py -m gpu -x -q 2>&1 | tail -15) > gpurun_out/pytest_pair_r1aa.log 2>&1; tail -n 6 gpurun_out/pytest_pair_r1aa.log
+(timeout 500 python bench.py --sweep --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_sweep_r1ac.json 2> gpurun_out/bench_sweep_r1ac.err); python -c "
+import json
+d=json.loads(open('gpurun_out/bench_sweep_r1ac.json').read().strip().splitlines()[-1])
+print(json.dumps(d['sweep'], indent=1))
+"
+tail -n 3 gpurun_out/bench_sweep_r1ac.err
