@@ -619,6 +619,7 @@ typedef TileCfg<double, 64, 128, 32, 32, 3>     CfgD3;
 typedef TileCfg<double, 32, 128, 32, 32, 4, 8>  CfgD4;
 typedef TileCfg<double, 64, 128, 32, 64, 3>     CfgD5;
 typedef TileCfg<double, 64, 64, 32, 32, 3>      CfgD6;
+typedef TileCfg<double, 64, 64, 32, 32, 3, 32>  CfgD7;   /* 64x64 with 32-deep k chunks: half the barriers per flop, two CTAs per SM */
 typedef TileCfg<double2, 64, 32, 32, 16, 3>     CfgZ0;
 typedef TileCfg<double2, 32, 32, 16, 16, 3>     CfgZ1;
 typedef TileCfg<double2, 32, 64, 32, 16, 4, 8>  CfgZ2;
@@ -626,7 +627,7 @@ typedef TileCfg<double2, 32, 64, 32, 16, 4, 8>  CfgZ2;
 /* eff: relative cost per padded multiply-add of the class */
 struct ClassShape { int bm, bn, bk; double eff; };
 /* eff from the measured large-block throughput of each class (tools/gemm_sweep.py, profiles/) */
-static const ClassShape g_shapes_d[7] = { { 64, 64, 16, 1.03 }, { 32, 32, 16, 1.22 }, { 128, 128, 16, 1.09 }, { 64, 128, 16, 1.075 }, { 32, 128, 8, 1.08 }, { 64, 128, 16, 1.0 }, { 64, 64, 16, 1.04 } };
+static const ClassShape g_shapes_d[8] = { { 64, 64, 16, 1.03 }, { 32, 32, 16, 1.22 }, { 128, 128, 16, 1.09 }, { 64, 128, 16, 1.075 }, { 32, 128, 8, 1.08 }, { 64, 128, 16, 1.0 }, { 64, 64, 16, 1.04 }, { 64, 64, 32, 1.5 } };
 static const ClassShape g_shapes_z[3] = { { 64, 32, 16, 1.0 }, { 32, 32, 16, 1.06 }, { 32, 64, 8, 1.03 } };
 
 template <typename T, typename Cfg>
@@ -658,7 +659,8 @@ static int launch_cfg(const GemmPlan* p, const GemmArgs& args)
 #define CTBD_GEMM_DISPATCH(FN, ...) \
 	(p->dtype == CTBD_F64 \
 		? (p->cfg == 0 ? FN<double, CfgD0>(__VA_ARGS__) : p->cfg == 1 ? FN<double, CfgD1>(__VA_ARGS__) : p->cfg == 2 ? FN<double, CfgD2>(__VA_ARGS__) \
-			: p->cfg == 3 ? FN<double, CfgD3>(__VA_ARGS__) : p->cfg == 4 ? FN<double, CfgD4>(__VA_ARGS__) : p->cfg == 5 ? FN<double, CfgD5>(__VA_ARGS__) : FN<double, CfgD6>(__VA_ARGS__)) \
+			: p->cfg == 3 ? FN<double, CfgD3>(__VA_ARGS__) : p->cfg == 4 ? FN<double, CfgD4>(__VA_ARGS__) : p->cfg == 5 ? FN<double, CfgD5>(__VA_ARGS__) \
+			: p->cfg == 6 ? FN<double, CfgD6>(__VA_ARGS__) : FN<double, CfgD7>(__VA_ARGS__)) \
 		: (p->cfg == 0 ? FN<double2, CfgZ0>(__VA_ARGS__) : p->cfg == 1 ? FN<double2, CfgZ1>(__VA_ARGS__) : FN<double2, CfgZ2>(__VA_ARGS__)))
 
 } // namespace ctbd
@@ -729,7 +731,7 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 		return 0;
 	}
 	const ClassShape* shapes = cplx ? g_shapes_z : g_shapes_d;
-	const int nshapes = cplx ? 3 : 7;
+	const int nshapes = cplx ? 3 : 8;
 
 	/* tile class with the shortest estimated launch: for every class the tiles are packed longest-processing-time-first into
 	 * the resident CTA slots (sm_count x occupancy) and the makespan is priced with the class' measured cost per multiply-add;

@@ -69,3 +69,25 @@ def test_flop_count_matches_engine_plans(eng):
         ms, fl = C.c_double(0), C.c_double(0)
         assert eng.ctb_heff_benchmark(a.ptr, w.ptr, l.ptr, r.ptr, 0, 1, 0, C.byref(ms), C.byref(fl), None, None) == 0
         assert fl.value == flops.heff_flops(a, w, l, r)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_shard_partition_is_exact_and_balanced(world):
+    """Plan-only view of the sharded matvec (no device work): the per-rank algorithmic flops of the three contractions add up to the
+    single-rank count EXACTLY (the shards partition the block GEMMs column-wise: a checksum of checksums), every rank's result slice
+    adds up to the full vector, and the partition (balanced in PADDED tile work, which is what a rank executes) keeps the algorithmic
+    flops of the ranks within 25 % of the mean even at D=1024 on 8 ranks."""
+    import bench
+    eng = helpers.load("emu")
+    a, w, l, r = bench.build_operands(eng, "fh_L32_D1024")
+    info = (C.c_double * 8)()
+    assert eng.ctb_heff_plan_info(a.ptr, w.ptr, l.ptr, r.ptr, 0, 1, info) == 0
+    total_flops, total_entries = info[0], info[4]
+    assert total_entries == a.num_elements()
+    flops_p, entries_p = [], []
+    for rank in range(world):
+        assert eng.ctb_heff_plan_info(a.ptr, w.ptr, l.ptr, r.ptr, rank, world, info) == 0
+        flops_p.append(info[0]); entries_p.append(info[4])
+    assert sum(flops_p) == total_flops
+    assert sum(entries_p) == total_entries
+    assert max(flops_p) <= 1.25 * total_flops / world

@@ -1,7 +1,5 @@
 cd $GRAFT_REPO_ROOT
-(timeout 500 python bench.py --sweep --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_sweep_r1ac.json 2> gpurun_out/bench_sweep_r1ac.err); python -c "
-import json
-d=json.loads(open('gpurun_out/bench_sweep_r1ac.json').read().strip().splitlines()[-1])
-print(json.dumps(d['sweep'], indent=1))
-"
-tail -n 3 gpurun_out/bench_sweep_r1ac.err
+for c in 7 0; do
+  echo "== class $c"; CTB_GEMM_CLASS=$c timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -n 1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['per_step_ms'], d['roofline']['per_step_tflops'])"
+done
+(timeout 300 python -m pytest tests/test_tensor_ops.py -m gpu -x -q 2>&1 | tail -2)
