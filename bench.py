@@ -363,7 +363,14 @@ def sweep_seconds(lib, model, L, params, sector, D, sweeps=2, lanczos=10, tol=0.
     dt = time.perf_counter() - t0
     if rc != 0:
         return None
-    return {"s_per_sweep": dt / sweeps, "energies": [float(x) for x in en], "max_bond": int(max(psi.bond_dims()))}
+    out = {"s_per_sweep": dt / sweeps, "energies": [float(x) for x in en], "max_bond": int(max(psi.bond_dims()))}
+    if lib.has("ctb_get_stats"):
+        st = (C.c_double * 9)()
+        lib.ctb_get_stats(st, 9)
+        # host wall-clock per phase of the whole call (each phase ends with a device sync)
+        out["phases_s"] = {"lanczos_incl_plans": st[3] / 1e3, "svd_split": st[4] / 1e3, "environments": st[5] / 1e3, "total": st[6] / 1e3,
+                           "heff_calls": int(st[1]), "heff_tflop": st[0] / 1e12, "max_vector_len": int(st[7])}
+    return out
 
 
 SWEEP_CASES = [

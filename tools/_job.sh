@@ -1,5 +1,11 @@
 cd $GRAFT_REPO_ROOT
-for c in 7 0; do
-  echo "== class $c"; CTB_GEMM_CLASS=$c timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -n 1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['per_step_ms'], d['roofline']['per_step_tflops'])"
-done
-(timeout 300 python -m pytest tests/test_tensor_ops.py -m gpu -x -q 2>&1 | tail -2)
+timeout 300 python - <<'PY'
+import sys, json
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import bench, helpers
+from chemtensor_b200 import workloads
+lib = helpers.load("cuda")
+for name, model, L, params, sector, D, _ in bench.SWEEP_CASES:
+    print(name, json.dumps(bench.sweep_seconds(lib, model, L, params, sector, D)), flush=True)
+PY
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4) > gpurun_out/pytest_gpu_r1ad.log 2>&1; tail -n 3 gpurun_out/pytest_gpu_r1ad.log
