@@ -542,86 +542,85 @@ __global__ void __launch_bounds__(SVD_SMEM_THREADS) svd_smem_kernel(const SvdMat
 	}
 }
 
+/* ---- blocks beyond shared memory: work matrices [G | W] in global memory, three phases ----
+ * setup (scaled copy of every block into its work matrix), iterate (block-Jacobi tournament until no rotation is left),
+ * finish (sort, normalise, write U, Vh, S).  The phases are separate so that a host-driven GEMM stage (ctbd_svdws_*) can work on
+ * the same work matrices between setup and iterate. */
 template <typename T>
-static int svd_batched_impl(int nmat_all, const ctbd_mat_desc* descs_all, const void* A, void* U, void* Vh, double* S)
+struct SvdBig
 {
-	if (nmat_all == 0) { return 0; }
-	/* blocks whose [G | W] fits into shared memory take the single-CTA path, the rest the global tournament below */
-	std::vector<SvdMat> small_mats;
-	std::vector<ctbd_mat_desc> big;
-	size_t smem_max = 0;
-	for (int b = 0; b < nmat_all; b++)
-	{
-		const int R = std::min(descs_all[b].m, descs_all[b].n), C = std::max(descs_all[b].m, descs_all[b].n);
-		const size_t need = (size_t)R * (C + R) * sizeof(T) + (size_t)R * (2 * sizeof(double) + sizeof(int)) + 16;
-		if (need <= SVD_SMEM_LIMIT && getenv("CTB_SVD_NO_SMEM") == nullptr) {
-			SvdMat mt; memset(&mt, 0, sizeof(mt));
-			mt.a_off = descs_all[b].a_off; mt.u_off = descs_all[b].o0_off; mt.vh_off = descs_all[b].o1_off; mt.s_off = descs_all[b].s_off;
-			mt.m = descs_all[b].m; mt.n = descs_all[b].n; mt.R = R; mt.C = C;
-			small_mats.push_back(mt);
-			smem_max = std::max(smem_max, need);
-		}
-		else { big.push_back(descs_all[b]); }
-	}
-	if (!small_mats.empty())
-	{
-		/* heaviest first */
-		std::stable_sort(small_mats.begin(), small_mats.end(), [](const SvdMat& x, const SvdMat& y) {
-			return (double)x.R * x.R * (x.C + x.R) > (double)y.R * y.R * (y.C + y.R); });
-		std::vector<int> sel(small_mats.size());
-		for (size_t i = 0; i < sel.size(); i++) { sel[i] = (int)i; }
-		void *d_small = nullptr, *d_sel = nullptr;
-		if (upload(small_mats.data(), small_mats.size() * sizeof(SvdMat), &d_small) < 0) { return -1; }
-		if (upload(sel.data(), sel.size() * sizeof(int), &d_sel) < 0) { return -1; }
-		static bool attr_done = false;
-		if (!attr_done) {
-			CTBD_CUDA(cudaFuncSetAttribute(svd_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVD_SMEM_LIMIT));
-			attr_done = true;
-		}
-		svd_smem_kernel<T><<<(int)small_mats.size(), SVD_SMEM_THREADS, smem_max, rt().stream>>>((const SvdMat*)d_small, (const int*)d_sel, DBL_EPSILON, 40,
-			(const T*)A, (T*)U, (T*)Vh, S);
-		CTBD_LAUNCH_CHECK();
-		ctbd_free(d_sel); ctbd_free(d_small);
-	}
-	const int nmat = (int)big.size();
-	const ctbd_mat_desc* descs = big.data();
-	if (nmat == 0) { return 0; }
-	std::vector<SvdMat> mats(nmat);
-	int64_t g_total = 0; int total_pairs = 0; int Rmax = 0; int64_t smax = 0;
+	int nmat = 0;
+	std::vector<SvdMat> mats;
+	void *d_mats = nullptr, *d_G = nullptr, *d_int = nullptr, *d_sig = nullptr, *d_scale = nullptr;
+	int64_t g_total = 0, smax = 0;
+	int total_pairs = 0, Rmax = 0;
+};
+
+template <typename T>
+static void svd_big_free(SvdBig<T>* st)
+{
+	if (st == nullptr) { return; }
+	ctbd_free(st->d_scale); ctbd_free(st->d_sig); ctbd_free(st->d_int); ctbd_free(st->d_G); ctbd_free(st->d_mats);
+	delete st;
+}
+
+template <typename T>
+static SvdBig<T>* svd_big_setup(int nmat, const ctbd_mat_desc* descs, const void* A)
+{
+	SvdBig<T>* st = new SvdBig<T>();
+	st->nmat = nmat;
+	st->mats.resize(nmat);
+	std::vector<SvdMat>& mats = st->mats;
 	for (int b = 0; b < nmat; b++)
 	{
 		SvdMat& mt = mats[b];
 		mt.a_off = descs[b].a_off; mt.u_off = descs[b].o0_off; mt.vh_off = descs[b].o1_off; mt.s_off = descs[b].s_off;
 		mt.m = descs[b].m; mt.n = descs[b].n;
 		mt.R = std::min(mt.m, mt.n); mt.C = std::max(mt.m, mt.n);
-		mt.g_off = g_total; g_total += (int64_t)mt.R * (mt.C + mt.R);
-		mt.pair_begin = total_pairs; mt.npair = (mt.R + 1) / 2; total_pairs += mt.npair;
-		Rmax = std::max(Rmax, mt.R);
-		smax = std::max(smax, mt.s_off + mt.R);
+		mt.g_off = st->g_total; st->g_total += (int64_t)mt.R * (mt.C + mt.R);
+		mt.pair_begin = st->total_pairs; mt.npair = (mt.R + 1) / 2; st->total_pairs += mt.npair;
+		st->Rmax = std::max(st->Rmax, mt.R);
+		st->smax = std::max(st->smax, mt.s_off + mt.R);
 	}
-	void *d_mats = nullptr, *d_G = nullptr, *d_int = nullptr, *d_sig = nullptr;
-	if (upload(mats.data(), (size_t)nmat * sizeof(SvdMat), &d_mats) < 0) { return -1; }
-	if (ctbd_malloc(&d_G, (size_t)g_total * sizeof(T)) < 0) { return -1; }
+	const int64_t smax = st->smax;
+	bool ok = upload(mats.data(), (size_t)nmat * sizeof(SvdMat), &st->d_mats) == 0;
+	ok = ok && ctbd_malloc(&st->d_G, (size_t)st->g_total * sizeof(T)) == 0;
 	/* ints: rot_count[nmat], done[nmat], pending[1], ord[smax] */
-	if (ctbd_malloc(&d_int, (size_t)(2 * nmat + 1 + smax) * sizeof(int)) < 0) { return -1; }
-	if (ctbd_malloc(&d_sig, (size_t)2 * smax * sizeof(double)) < 0) { return -1; }
-	int* rot_count = (int*)d_int; int* done = rot_count + nmat; int* pending = done + nmat; int* ord = pending + 1;
-
+	ok = ok && ctbd_malloc(&st->d_int, (size_t)(2 * nmat + 1 + smax) * sizeof(int)) == 0;
+	ok = ok && ctbd_malloc(&st->d_sig, (size_t)2 * smax * sizeof(double)) == 0;
+	ok = ok && ctbd_malloc(&st->d_scale, (size_t)nmat * sizeof(double)) == 0;
 	int64_t maxel = 0;
 	for (int b = 0; b < nmat; b++) { maxel = std::max(maxel, (int64_t)mats[b].R * (mats[b].C + mats[b].R)); }
-	void *d_aoff = nullptr, *d_numel = nullptr, *d_scale = nullptr;
+	void *d_aoff = nullptr, *d_numel = nullptr;
+	if (ok)
 	{
 		std::vector<int64_t> aoff(nmat), numel(nmat);
 		for (int b = 0; b < nmat; b++) { aoff[b] = mats[b].a_off; numel[b] = (int64_t)mats[b].m * mats[b].n; }
-		if (upload(aoff.data(), (size_t)nmat * sizeof(int64_t), &d_aoff) < 0) { return -1; }
-		if (upload(numel.data(), (size_t)nmat * sizeof(int64_t), &d_numel) < 0) { return -1; }
-		if (ctbd_malloc(&d_scale, (size_t)nmat * sizeof(double)) < 0) { return -1; }
-		absmax_scale_kernel<T><<<nmat, 256, 0, rt().stream>>>((const int64_t*)d_aoff, (const int64_t*)d_numel, (const T*)A, (double*)d_scale);
-		CTBD_LAUNCH_CHECK();
-		dim3 grid((unsigned)std::min<int64_t>(ceil_div(maxel, 256), 64), (unsigned)nmat);
-		svd_init_kernel<T><<<grid, 256, 0, rt().stream>>>(nmat, (const SvdMat*)d_mats, (const double*)d_scale, (const T*)A, (T*)d_G);
-		CTBD_LAUNCH_CHECK();
+		ok = ok && upload(aoff.data(), (size_t)nmat * sizeof(int64_t), &d_aoff) == 0;
+		ok = ok && upload(numel.data(), (size_t)nmat * sizeof(int64_t), &d_numel) == 0;
 	}
+	if (ok)
+	{
+		absmax_scale_kernel<T><<<nmat, 256, 0, rt().stream>>>((const int64_t*)d_aoff, (const int64_t*)d_numel, (const T*)A, (double*)st->d_scale);
+		rt().launches++;
+		dim3 grid((unsigned)std::min<int64_t>(ceil_div(maxel, 256), 64), (unsigned)nmat);
+		svd_init_kernel<T><<<grid, 256, 0, rt().stream>>>(nmat, (const SvdMat*)st->d_mats, (const double*)st->d_scale, (const T*)A, (T*)st->d_G);
+		rt().launches++;
+		if (cudaGetLastError() != cudaSuccess) { ok = false; }
+	}
+	ctbd_free(d_numel); ctbd_free(d_aoff);
+	if (!ok) { svd_big_free<T>(st); return nullptr; }
+	return st;
+}
+
+template <typename T>
+static int svd_big_iterate(SvdBig<T>* st)
+{
+	const int nmat = st->nmat;
+	const std::vector<SvdMat>& mats = st->mats;
+	void* d_mats = st->d_mats; void* d_G = st->d_G;
+	int* rot_count = (int*)st->d_int; int* done = rot_count + nmat; int* pending = done + nmat;
+	const int Rmax = st->Rmax, total_pairs = st->total_pairs;
 	int rc = 0;
 	/* rows per block such that two row blocks fit into shared memory */
 	const size_t blk_budget = 208 * 1024;
@@ -687,15 +686,68 @@ static int svd_batched_impl(int nmat_all, const ctbd_mat_desc* descs_all, const 
 			if (h_pending == 0) { break; }
 		}
 	}
-	if (rc == 0)
+	return rc;
+}
+
+template <typename T>
+static int svd_big_finish(SvdBig<T>* st, void* U, void* Vh, double* S)
+{
+	const int nmat = st->nmat;
+	int* ord = (int*)st->d_int + 2 * nmat + 1;
+	svd_finish_kernel<T><<<nmat, 256, 0, rt().stream>>>((const SvdMat*)st->d_mats, (const double*)st->d_scale, (const T*)st->d_G, (double*)st->d_sig, (double*)st->d_sig + st->smax, ord, (T*)U, (T*)Vh, S);
+	rt().launches++;
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { return fail("svd_finish_kernel", e, __FILE__, __LINE__); }
+	return 0;
+}
+
+template <typename T>
+static int svd_batched_impl(int nmat_all, const ctbd_mat_desc* descs_all, const void* A, void* U, void* Vh, double* S)
+{
+	if (nmat_all == 0) { return 0; }
+	/* blocks whose [G | W] fits into shared memory take the single-CTA path, the rest the global tournament below */
+	std::vector<SvdMat> small_mats;
+	std::vector<ctbd_mat_desc> big;
+	size_t smem_max = 0;
+	for (int b = 0; b < nmat_all; b++)
 	{
-		svd_finish_kernel<T><<<nmat, 256, 0, rt().stream>>>((const SvdMat*)d_mats, (const double*)d_scale, (const T*)d_G, (double*)d_sig, (double*)d_sig + smax, ord, (T*)U, (T*)Vh, S);
-		rt().launches++;
-		cudaError_t e = cudaGetLastError();
-		if (e != cudaSuccess) { rc = fail("svd_finish_kernel", e, __FILE__, __LINE__); }
+		const int R = std::min(descs_all[b].m, descs_all[b].n), C = std::max(descs_all[b].m, descs_all[b].n);
+		const size_t need = (size_t)R * (C + R) * sizeof(T) + (size_t)R * (2 * sizeof(double) + sizeof(int)) + 16;
+		if (need <= SVD_SMEM_LIMIT && getenv("CTB_SVD_NO_SMEM") == nullptr) {
+			SvdMat mt; memset(&mt, 0, sizeof(mt));
+			mt.a_off = descs_all[b].a_off; mt.u_off = descs_all[b].o0_off; mt.vh_off = descs_all[b].o1_off; mt.s_off = descs_all[b].s_off;
+			mt.m = descs_all[b].m; mt.n = descs_all[b].n; mt.R = R; mt.C = C;
+			small_mats.push_back(mt);
+			smem_max = std::max(smem_max, need);
+		}
+		else { big.push_back(descs_all[b]); }
 	}
-	ctbd_free(d_scale); ctbd_free(d_numel); ctbd_free(d_aoff);
-	ctbd_free(d_sig); ctbd_free(d_int); ctbd_free(d_G); ctbd_free(d_mats);
+	if (!small_mats.empty())
+	{
+		/* heaviest first */
+		std::stable_sort(small_mats.begin(), small_mats.end(), [](const SvdMat& x, const SvdMat& y) {
+			return (double)x.R * x.R * (x.C + x.R) > (double)y.R * y.R * (y.C + y.R); });
+		std::vector<int> sel(small_mats.size());
+		for (size_t i = 0; i < sel.size(); i++) { sel[i] = (int)i; }
+		void *d_small = nullptr, *d_sel = nullptr;
+		if (upload(small_mats.data(), small_mats.size() * sizeof(SvdMat), &d_small) < 0) { return -1; }
+		if (upload(sel.data(), sel.size() * sizeof(int), &d_sel) < 0) { return -1; }
+		static bool attr_done = false;
+		if (!attr_done) {
+			CTBD_CUDA(cudaFuncSetAttribute(svd_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVD_SMEM_LIMIT));
+			attr_done = true;
+		}
+		svd_smem_kernel<T><<<(int)small_mats.size(), SVD_SMEM_THREADS, smem_max, rt().stream>>>((const SvdMat*)d_small, (const int*)d_sel, DBL_EPSILON, 40,
+			(const T*)A, (T*)U, (T*)Vh, S);
+		CTBD_LAUNCH_CHECK();
+		ctbd_free(d_sel); ctbd_free(d_small);
+	}
+	if (big.empty()) { return 0; }
+	SvdBig<T>* st = svd_big_setup<T>((int)big.size(), big.data(), A);
+	if (st == nullptr) { return -1; }
+	int rc = svd_big_iterate<T>(st);
+	if (rc == 0) { rc = svd_big_finish<T>(st, U, Vh, S); }
+	svd_big_free<T>(st);
 	return rc;
 }
 
@@ -918,6 +970,62 @@ static int qr_batched_impl(int rq, int nmat, const ctbd_mat_desc* descs, const v
 	return rc;
 }
 
+/* ---- convergence measure of the GEMM-driven block-Jacobi stage (ctbd_svdws_*): over a list of small Gram matrices ----
+ * out[1] = max(out[1], max_i G_ii);  out[0] = max(out[0], max_{i != j} |G_ij|^2 / max(G_ii G_jj, (floor_rel out[1])^2)).
+ * Non-negative doubles order like their bit patterns, so the running maxima are atomicMax on the bits. */
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v)
+{
+	atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gram_diagmax_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ dim, const T* __restrict__ G, double* __restrict__ out)
+{
+	__shared__ double red[8];
+	const T* g = G + off[blockIdx.x];
+	const int n = dim[blockIdx.x];
+	double v = 0;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) { v = fmax(v, sqrt(abs2(g[(int64_t)i * n + i]))); }
+	const double m = block_max(v, red);
+	if (threadIdx.x == 0) { atomic_max_nonneg(out + 1, m); }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gram_offdiag_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ dim, const T* __restrict__ G, double floor_rel, double* __restrict__ out)
+{
+	__shared__ double red[8];
+	const T* g = G + off[blockIdx.x];
+	const int n = dim[blockIdx.x];
+	const double fl = floor_rel * out[1];
+	const double fl2 = fl * fl;
+	double v = 0;
+	for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+		const int i = e / n, j = e % n;
+		if (i == j) { continue; }
+		const double dii = sqrt(abs2(g[(int64_t)i * n + i])), djj = sqrt(abs2(g[(int64_t)j * n + j]));
+		const double den = fmax(dii * djj, fl2);
+		if (den > 0) { v = fmax(v, abs2(g[e]) / den); }
+	}
+	const double m = block_max(v, red);
+	if (threadIdx.x == 0) { atomic_max_nonneg(out, m); }
+}
+
+template <typename T>
+static int svdws_finish_impl(SvdBig<T>* st, const void* G_cur, int polish, void* U, void* Vh, double* S)
+{
+	int rc = 0;
+	if (G_cur != nullptr && G_cur != st->d_G) {
+		cudaError_t e = cudaMemcpyAsync(st->d_G, G_cur, (size_t)st->g_total * sizeof(T), cudaMemcpyDeviceToDevice, rt().stream);
+		if (e != cudaSuccess) { rc = fail("cudaMemcpyAsync (SVD workspace)", e, __FILE__, __LINE__); }
+	}
+	if (rc == 0 && polish) { rc = svd_big_iterate<T>(st); }
+	if (rc == 0) { rc = svd_big_finish<T>(st, U, Vh, S); }
+	svd_big_free<T>(st);
+	return rc;
+}
+
+struct SvdWs { int dtype; void* st; };
+
 } // namespace ctbd
 
 using namespace ctbd;
@@ -938,6 +1046,57 @@ int ctbd_qr_batched(int dtype, int rq, int nmat, const struct ctbd_mat_desc* des
 	if (dtype == CTBD_F64)  { return qr_batched_impl<double>(rq, nmat, descs_host, A, O0, O1); }
 	if (dtype == CTBD_C128) { return qr_batched_impl<double2>(rq, nmat, descs_host, A, O0, O1); }
 	return fail_msg("batched QR: unsupported dtype");
+}
+
+/* ---- work matrices of the big-block SVD exposed to a host-driven stage (see include/ctb_device.h) ---- */
+
+int ctbd_svdws_create(int dtype, int nmat, const struct ctbd_mat_desc* descs_host, const void* A, void** ws, void** G, int64_t* g_total)
+{
+	CTBD_REQUIRE_INIT();
+	if (nmat <= 0) { return fail_msg("SVD workspace: no blocks"); }
+	SvdWs* w = new SvdWs();
+	w->dtype = dtype; w->st = nullptr;
+	if (dtype == CTBD_F64) {
+		SvdBig<double>* st = svd_big_setup<double>(nmat, descs_host, A);
+		if (st != nullptr) { w->st = st; *G = st->d_G; *g_total = st->g_total; }
+	}
+	else if (dtype == CTBD_C128) {
+		SvdBig<double2>* st = svd_big_setup<double2>(nmat, descs_host, A);
+		if (st != nullptr) { w->st = st; *G = st->d_G; *g_total = st->g_total; }
+	}
+	if (w->st == nullptr) { delete w; return fail_msg("SVD workspace: setup failed"); }
+	*ws = w;
+	return 0;
+}
+
+int ctbd_svdws_finish(void* ws, const void* G_cur, int polish, void* U, void* Vh, double* S_dev)
+{
+	SvdWs* w = (SvdWs*)ws;
+	if (w == nullptr) { return 0; }
+	int rc;
+	if (w->dtype == CTBD_F64) { rc = svdws_finish_impl<double>((SvdBig<double>*)w->st, G_cur, polish, U, Vh, S_dev); }
+	else                      { rc = svdws_finish_impl<double2>((SvdBig<double2>*)w->st, G_cur, polish, U, Vh, S_dev); }
+	delete w;
+	return rc;
+}
+
+int ctbd_gram_offdiag(int dtype, int ngram, const int64_t* off_dev, const int32_t* dim_dev, const void* G, double floor_rel, double* out_dev)
+{
+	CTBD_REQUIRE_INIT();
+	if (ngram <= 0) { return 0; }
+	if (dtype == CTBD_F64) {
+		gram_diagmax_kernel<double><<<ngram, 256, 0, rt().stream>>>(off_dev, dim_dev, (const double*)G, out_dev);
+		gram_offdiag_kernel<double><<<ngram, 256, 0, rt().stream>>>(off_dev, dim_dev, (const double*)G, floor_rel, out_dev);
+	}
+	else if (dtype == CTBD_C128) {
+		gram_diagmax_kernel<double2><<<ngram, 256, 0, rt().stream>>>(off_dev, dim_dev, (const double2*)G, out_dev);
+		gram_offdiag_kernel<double2><<<ngram, 256, 0, rt().stream>>>(off_dev, dim_dev, (const double2*)G, floor_rel, out_dev);
+	}
+	else { return fail_msg("gram_offdiag: unsupported dtype"); }
+	rt().launches += 2;
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { return fail("gram_offdiag", e, __FILE__, __LINE__); }
+	return 0;
 }
 
 } // extern "C"

@@ -288,6 +288,18 @@ struct ctbd_mat_desc
 /* per block: A = U diag(S) Vh, singular values descending */
 int ctbd_svd_batched(int dtype, int nmat, const struct ctbd_mat_desc* descs_host,
 	const void* A, void* U, void* Vh, double* S_dev);
+/* The big-block SVD in pieces, for the GEMM-driven block-Jacobi stage of the host (host/svd_block.c):
+ *   create : every block gets a work matrix [G | W] (R x (C + R) row-major, R = min(m, n), C = max(m, n)): G = the block (its
+ *            conjugate transpose when m > n) normalised by a power of two, W = identity.  The work matrices are packed in
+ *            descriptor order into ONE device buffer (*G, *g_total elements); the host applies unitary row operations to them
+ *            (the same on G and W), possibly into a second buffer of the same size;
+ *   finish : takes the buffer that holds the current work matrices, optionally polishes them with the in-kernel block-Jacobi
+ *            tournament until no rotation is left, then sorts / normalises and writes U, Vh, S as ctbd_svd_batched does; releases ws.
+ *   gram_offdiag : convergence measure over a list of small square matrices G_k (element offsets / dimensions on the device):
+ *            out[1] = max(out[1], max_i |G_ii|), out[0] = max(out[0], max_{i != j} |G_ij|^2 / max(|G_ii| |G_jj|, (floor_rel out[1])^2)) */
+int ctbd_svdws_create(int dtype, int nmat, const struct ctbd_mat_desc* descs_host, const void* A, void** ws, void** G, int64_t* g_total);
+int ctbd_svdws_finish(void* ws, const void* G_cur, int polish, void* U, void* Vh, double* S_dev);
+int ctbd_gram_offdiag(int dtype, int ngram, const int64_t* off_dev, const int32_t* dim_dev, const void* G, double floor_rel, double* out_dev);
 /* rq == 0: A = Q R (Q: m x k isometry, R upper triangular);  rq != 0: A = R Q (Q: k x n) */
 int ctbd_qr_batched(int dtype, int rq, int nmat, const struct ctbd_mat_desc* descs_host,
 	const void* A, void* O0, void* O1);

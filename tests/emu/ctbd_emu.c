@@ -526,50 +526,135 @@ static int jacobi_rows(int R, int C, double complex* G /* R x (C+R): [G | W] */)
 	return 0;   /* best effort, as LAPACK's jacobi drivers */
 }
 
+/* work matrix [G | W] of one block in complex arithmetic (wide: G = A, tall: G = A^H; W = identity) */
+static double complex* svd_work_matrix(int cplx, const struct ctbd_mat_desc* d, const void* A)
+{
+	const int m = d->m, n = d->n;
+	const int wide = (m <= n);
+	const int R = wide ? m : n, C = wide ? n : m;
+	const int ld = C + R;
+	double complex* G = calloc((size_t)R * ld, sizeof(double complex));
+	for (int i = 0; i < R; i++) {
+		for (int k = 0; k < C; k++) {
+			G[i * ld + k] = wide ? GETC(A, d->a_off + (int64_t)i * n + k) : conj(GETC(A, d->a_off + (int64_t)k * n + i));
+		}
+		G[i * ld + C + i] = 1;
+	}
+	return G;
+}
+
+/* singular values = row norms of G (descending), vectors from the rows of [G | W] */
+static void svd_write_out(int cplx, const struct ctbd_mat_desc* d, const double complex* G, double unscale, void* U, void* Vh, double* S)
+{
+	const int m = d->m, n = d->n;
+	const int wide = (m <= n);
+	const int R = wide ? m : n, C = wide ? n : m;
+	const int ld = C + R;
+	double* sig = malloc((size_t)R * sizeof(double)); double* wn = malloc((size_t)R * sizeof(double)); int* ord = malloc((size_t)R * sizeof(int));
+	for (int i = 0; i < R; i++) {
+		double s = 0, w = 0;
+		for (int k = 0; k < C; k++) { const double complex x = G[i * ld + k]; s += creal(x) * creal(x) + cimag(x) * cimag(x); }
+		for (int k = 0; k < R; k++) { const double complex x = G[i * ld + C + k]; w += creal(x) * creal(x) + cimag(x) * cimag(x); }
+		sig[i] = sqrt(s); wn[i] = (w > 0) ? 1.0 / sqrt(w) : 1.0; ord[i] = i;
+	}
+	for (int i = 0; i < R; i++) { for (int j = i + 1; j < R; j++) { if (sig[ord[j]] > sig[ord[i]]) { int t = ord[i]; ord[i] = ord[j]; ord[j] = t; } } }
+	for (int r = 0; r < R; r++)
+	{
+		const int i = ord[r];
+		S[d->s_off + r] = unscale * sig[i];
+		const double inv = sig[i] > 0 ? 1.0 / sig[i] : 0.0;
+		if (wide) {
+			/* A = W^H G: Vh[r,:] = G[i,:]/sigma, U[:,r] = conj(W[i,:]) */
+			for (int k = 0; k < n; k++) { PUTC(Vh, d->o1_off + (int64_t)r * n + k, inv * G[i * ld + k]); }
+			for (int k = 0; k < m; k++) { PUTC(U, d->o0_off + (int64_t)k * R + r, wn[i] * conj(G[i * ld + C + k])); }
+		}
+		else {
+			/* A^H = W^H G  =>  A = G^H W: U[:,r] = conj(G[i,:])/sigma, Vh[r,:] = W[i,:] */
+			for (int k = 0; k < m; k++) { PUTC(U, d->o0_off + (int64_t)k * R + r, inv * conj(G[i * ld + k])); }
+			for (int k = 0; k < n; k++) { PUTC(Vh, d->o1_off + (int64_t)r * n + k, wn[i] * G[i * ld + C + k]); }
+		}
+	}
+	free(sig); free(wn); free(ord);
+}
+
 int ctbd_svd_batched(int dtype, int nmat, const struct ctbd_mat_desc* d, const void* A, void* U, void* Vh, double* S)
 {
 	g_launches++;
 	const int cplx = (dtype == CTBD_C128);
 	for (int b = 0; b < nmat; b++)
 	{
-		const int m = d[b].m, n = d[b].n;
-		const int wide = (m <= n);
-		const int R = wide ? m : n, C = wide ? n : m;
-		const int ld = C + R;
-		double complex* G = calloc((size_t)R * ld, sizeof(double complex));
-		for (int i = 0; i < R; i++) {
-			for (int k = 0; k < C; k++) {
-				/* wide: G = A;  tall: G = A^H */
-				G[i * ld + k] = wide ? GETC(A, d[b].a_off + (int64_t)i * n + k) : conj(GETC(A, d[b].a_off + (int64_t)k * n + i));
-			}
-			G[i * ld + C + i] = 1;
-		}
+		const int R = d[b].m <= d[b].n ? d[b].m : d[b].n, C = d[b].m <= d[b].n ? d[b].n : d[b].m;
+		double complex* G = svd_work_matrix(cplx, &d[b], A);
 		jacobi_rows(R, C, G);
-		/* singular values = row norms, sorted descending */
-		double* sig = malloc((size_t)R * sizeof(double)); int* ord = malloc((size_t)R * sizeof(int));
-		for (int i = 0; i < R; i++) {
-			double s = 0;
-			for (int k = 0; k < C; k++) { const double complex x = G[i * ld + k]; s += creal(x) * creal(x) + cimag(x) * cimag(x); }
-			sig[i] = sqrt(s); ord[i] = i;
-		}
-		for (int i = 0; i < R; i++) { for (int j = i + 1; j < R; j++) { if (sig[ord[j]] > sig[ord[i]]) { int t = ord[i]; ord[i] = ord[j]; ord[j] = t; } } }
-		for (int r = 0; r < R; r++)
-		{
-			const int i = ord[r];
-			S[d[b].s_off + r] = sig[i];
-			const double inv = sig[i] > 0 ? 1.0 / sig[i] : 0.0;
-			if (wide) {
-				/* A = W^H G: Vh[r,:] = G[i,:]/sigma, U[:,r] = conj(W[i,:]) */
-				for (int k = 0; k < n; k++) { PUTC(Vh, d[b].o1_off + (int64_t)r * n + k, inv * G[i * ld + k]); }
-				for (int k = 0; k < m; k++) { PUTC(U, d[b].o0_off + (int64_t)k * R + r, conj(G[i * ld + C + k])); }
-			}
-			else {
-				/* A^H = W^H G  =>  A = G^H W: U[:,r] = conj(G[i,:])/sigma, Vh[r,:] = W[i,:] */
-				for (int k = 0; k < m; k++) { PUTC(U, d[b].o0_off + (int64_t)k * R + r, inv * conj(G[i * ld + k])); }
-				for (int k = 0; k < n; k++) { PUTC(Vh, d[b].o1_off + (int64_t)r * n + k, G[i * ld + C + k]); }
-			}
-		}
-		free(sig); free(ord); free(G);
+		svd_write_out(cplx, &d[b], G, 1.0, U, Vh, S);
+		free(G);
+	}
+	return 0;
+}
+
+/* ---- the big-block SVD in pieces (see ctb_device.h): work matrices in the element type of the tensors, packed in one buffer ---- */
+struct emu_svdws { int dtype, nmat; struct ctbd_mat_desc* d; int64_t* g_off; int64_t g_total; void* G; };
+
+int ctbd_svdws_create(int dtype, int nmat, const struct ctbd_mat_desc* descs, const void* A, void** ws, void** Gout, int64_t* g_total)
+{
+	g_launches++;
+	const int cplx = (dtype == CTBD_C128);
+	struct emu_svdws* w = calloc(1, sizeof(*w));
+	w->dtype = dtype; w->nmat = nmat;
+	w->d = dup_mem(descs, (size_t)nmat * sizeof(*descs));
+	w->g_off = calloc((size_t)nmat, sizeof(int64_t));
+	for (int b = 0; b < nmat; b++) {
+		const int64_t R = descs[b].m <= descs[b].n ? descs[b].m : descs[b].n, C = descs[b].m <= descs[b].n ? descs[b].n : descs[b].m;
+		w->g_off[b] = w->g_total; w->g_total += R * (C + R);
+	}
+	w->G = calloc((size_t)w->g_total, cplx ? 16 : 8);
+	for (int b = 0; b < nmat; b++) {
+		const int64_t R = descs[b].m <= descs[b].n ? descs[b].m : descs[b].n, C = descs[b].m <= descs[b].n ? descs[b].n : descs[b].m;
+		double complex* G = svd_work_matrix(cplx, &descs[b], A);
+		for (int64_t e = 0; e < R * (C + R); e++) { PUTC(w->G, w->g_off[b] + e, G[e]); }
+		free(G);
+	}
+	*ws = w; *Gout = w->G; *g_total = w->g_total;
+	return 0;
+}
+
+int ctbd_svdws_finish(void* ws, const void* G_cur, int polish, void* U, void* Vh, double* S)
+{
+	struct emu_svdws* w = ws;
+	if (w == NULL) { return 0; }
+	g_launches++;
+	const int cplx = (w->dtype == CTBD_C128);
+	const void* src = (G_cur != NULL) ? G_cur : w->G;
+	for (int b = 0; b < w->nmat; b++) {
+		const int R = w->d[b].m <= w->d[b].n ? w->d[b].m : w->d[b].n, C = w->d[b].m <= w->d[b].n ? w->d[b].n : w->d[b].m;
+		double complex* G = malloc((size_t)R * (C + R) * sizeof(double complex));
+		for (int64_t e = 0; e < (int64_t)R * (C + R); e++) { G[e] = GETC(src, w->g_off[b] + e); }
+		if (polish) { jacobi_rows(R, C, G); }
+		svd_write_out(cplx, &w->d[b], G, 1.0, U, Vh, S);
+		free(G);
+	}
+	free(w->d); free(w->g_off); free(w->G); free(w);
+	return 0;
+}
+
+int ctbd_gram_offdiag(int dtype, int ngram, const int64_t* off, const int32_t* dim, const void* G, double floor_rel, double* out)
+{
+	g_launches++;
+	const int cplx = (dtype == CTBD_C128);
+	for (int k = 0; k < ngram; k++) {
+		for (int i = 0; i < dim[k]; i++) { const double v = cabs(GETC(G, off[k] + (int64_t)i * dim[k] + i)); if (v > out[1]) { out[1] = v; } }
+	}
+	const double fl2 = (floor_rel * out[1]) * (floor_rel * out[1]);
+	for (int k = 0; k < ngram; k++) {
+		const int n = dim[k];
+		for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) {
+			if (i == j) { continue; }
+			const double dii = cabs(GETC(G, off[k] + (int64_t)i * n + i)), djj = cabs(GETC(G, off[k] + (int64_t)j * n + j));
+			const double den = dii * djj > fl2 ? dii * djj : fl2;
+			const double complex g = GETC(G, off[k] + (int64_t)i * n + j);
+			const double v = creal(g) * creal(g) + cimag(g) * cimag(g);
+			if (den > 0 && v / den > out[0]) { out[0] = v / den; }
+		} }
 	}
 	return 0;
 }
