@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-(timeout 200 python -m pytest tests/test_factorizations.py tests/test_golden_engine.py tests/test_dmrg.py -m gpu -x -q 2>&1 | tail -4)
+(timeout 100 python -m pytest tests/test_zz_svd_workspace_gpu.py -m gpu -x -q 2>&1 | tail -12)
