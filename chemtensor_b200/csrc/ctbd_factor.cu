@@ -627,12 +627,27 @@ static int svd_big_iterate(SvdBig<T>* st)
 	bool use_block = (getenv("CTB_SVD_TOURNAMENT") == nullptr);
 	std::vector<SvdBlkMat> bm(nmat);
 	int items_intra = 0, items_round = 0, max_rounds = 0; size_t blk_smem = 0;
+	/* rows per block: at most 8 by default (and never more than fit into shared memory).  Smaller blocks mean more row-block pairs
+	 * per round (R / 2b per matrix -- with b = 32 a 500-row block keeps only 8 CTAs busy) at the price of more grid-wide rounds;
+	 * measured on the Fermi-Hubbard L=32 D=1024 sweep: SVD phase 5.66 s with a cap of 32, 4.07 s with 8 (profiles/r1_sweep_phases.json).
+	 * Tuning knob CTB_SVD_BLOCK_ROWS=<2..32>; "auto" picks the largest power of two that still gives every SM a pair. */
+	int rows_cap = 8;
+	{
+		const char* env = getenv("CTB_SVD_BLOCK_ROWS");
+		if (env != nullptr && strcmp(env, "auto") == 0) {
+			rows_cap = 32;
+			int64_t rows_total = 0;
+			for (int b = 0; b < nmat; b++) { rows_total += mats[b].R; }
+			while (rows_cap > 4 && rows_total / (2 * rows_cap) < rt().sm_count) { rows_cap /= 2; }
+		}
+		else if (env != nullptr && atoi(env) >= 2 && atoi(env) <= 32) { rows_cap = atoi(env); }
+	}
 	for (int b = 0; b < nmat && use_block; b++)
 	{
 		const size_t ld = (size_t)(mats[b].C + mats[b].R);
 		int rows_fit = (int)(blk_budget / (2 * ld * sizeof(T)));
 		if (rows_fit < 1) { use_block = false; break; }
-		if (rows_fit > 32) { rows_fit = 32; }
+		if (rows_fit > rows_cap) { rows_fit = rows_cap; }
 		SvdBlkMat& x = bm[b];
 		x.g_off = mats[b].g_off; x.R = mats[b].R; x.C = mats[b].C; x.b = rows_fit;
 		x.nb = (int)ceil_div(x.R, x.b);
