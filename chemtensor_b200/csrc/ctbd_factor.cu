@@ -627,11 +627,12 @@ static int svd_big_iterate(SvdBig<T>* st)
 	bool use_block = (getenv("CTB_SVD_TOURNAMENT") == nullptr);
 	std::vector<SvdBlkMat> bm(nmat);
 	int items_intra = 0, items_round = 0, max_rounds = 0; size_t blk_smem = 0;
-	/* rows per block: at most 8 by default (and never more than fit into shared memory).  Smaller blocks mean more row-block pairs
-	 * per round (R / 2b per matrix -- with b = 32 a 500-row block keeps only 8 CTAs busy) at the price of more grid-wide rounds;
-	 * measured on the Fermi-Hubbard L=32 D=1024 sweep: SVD phase 5.66 s with a cap of 32, 4.07 s with 8 (profiles/r1_sweep_phases.json).
+	/* rows per block: at most 32 (and never more than fit into shared memory).  Smaller blocks mean more row-block pairs per round
+	 * (R / 2b per matrix -- with b = 32 a 500-row block keeps only 8 CTAs busy) at the price of more grid-wide rounds; measured on the
+	 * Fermi-Hubbard L=32 D=1024 sweep: SVD phase 5.66 s with the cap of 32, 4.07 s with CTB_SVD_BLOCK_ROWS=8, same energies
+	 * (profiles/r1_sweep_phases.json).  The default stays at 32 until the full GPU suite has run with the smaller cap.
 	 * Tuning knob CTB_SVD_BLOCK_ROWS=<2..32>; "auto" picks the largest power of two that still gives every SM a pair. */
-	int rows_cap = 8;
+	int rows_cap = 32;
 	{
 		const char* env = getenv("CTB_SVD_BLOCK_ROWS");
 		if (env != nullptr && strcmp(env, "auto") == 0) {
