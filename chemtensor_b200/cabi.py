@@ -120,6 +120,8 @@ _SIGNATURES = {
     "mps_local_orthonormalize_left_svd": (C.c_int, [C.c_double, C.c_int64, C.c_bool, _P_BST, _P_BST, C.POINTER(TruncInfo)]),
     "mps_local_orthonormalize_right_svd": (C.c_int, [C.c_double, C.c_int64, C.c_bool, _P_BST, _P_BST, C.POINTER(TruncInfo)]),
     "mps_compress": (C.c_int, [C.c_double, C.c_int64, C.c_int, C.POINTER(MPSStruct), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(TruncInfo)]),
+    "mpo_from_assembly": (None, [C.c_void_p, C.POINTER(MPOStruct)]),
+    "operator_average_coefficient_gradient": (None, [C.c_void_p, C.POINTER(MPSStruct), C.POINTER(MPSStruct), C.c_void_p, C.c_void_p]),
     "mps_compress_rescale": (C.c_int, [C.c_double, C.c_int64, C.c_int, C.POINTER(MPSStruct), C.POINTER(C.c_double), C.POINTER(TruncInfo)]),
     "dmrg_singlesite": (C.c_int, [C.POINTER(MPOStruct), C.c_int, C.c_int, C.POINTER(MPSStruct), C.POINTER(C.c_double)]),
     "dmrg_twosite": (C.c_int, [C.POINTER(MPOStruct), C.c_int, C.c_int, C.c_double, C.c_int64, C.POINTER(MPSStruct), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -121,6 +121,11 @@ int mps_local_orthonormalize_right_svd(const double tol, const ct_long max_vdim,
 int mps_compress(const double tol, const ct_long max_vdim, const enum mps_orthonormalization_mode mode, struct mps* mps, double* norm, double* trunc_scale, struct trunc_info* info);
 int mps_compress_rescale(const double tol, const ct_long max_vdim, const enum mps_orthonormalization_mode mode, struct mps* mps, double* trunc_scale, struct trunc_info* info);
 
+/* include/operator/mpo.h:50 (src/operator/mpo.c:59) -- sparse-direct: no dense Dw x d x d x Dw' intermediate */
+void mpo_from_assembly(const struct mpo_assembly* assembly, struct mpo* mpo);
+/* include/algorithm/gradient.h (src/algorithm/gradient.c:15) */
+void operator_average_coefficient_gradient(const struct mpo_assembly* assembly, const struct mps* psi, const struct mps* chi, void* avr, void* dcoeff);
+
 /* ---- engine extensions (no reference counterpart; measurement and lifecycle) -------------------------------- */
 /* explicit device selection / start-up; returns <0 when no CUDA device is usable */
 int ctb_init(int device);

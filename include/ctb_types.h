@@ -21,6 +21,9 @@
  *   enum mps_orthonormalization_mode  include/state/mps.h:61-65
  *   struct mpo                        include/operator/mpo.h:34-40
  *   lanczos_linear_func_d/_z          include/util/krylov.h:10-12
+ *   struct local_op_ref               include/operator/local_op.h:38-42
+ *   struct mpo_graph_vertex/edge, mpo_graph   include/operator/mpo_graph.h:16-50
+ *   struct mpo_assembly               include/operator/mpo.h:14-24
  *
  * Ownership convention (reference include/aligned_memory.h): output structs
  * are caller-provided shells; every payload is allocated by the callee with a
@@ -140,6 +143,51 @@ typedef struct { double re, im; } ctb_dcomplex;
 
 typedef void lanczos_linear_func_d(const ct_long n, const void* data, const double* v, double* ret);
 typedef void lanczos_linear_func_z(const ct_long n, const void* data, const void* v, void* ret);
+
+/* ---- MPO assembly: operator graph + look-up tables (read-only inputs of mpo_from_assembly and the coefficient gradient) ---- */
+
+enum { OID_NOP = -1, OID_IDENTITY = 0 };     /* include/operator/local_op.h:13-17 */
+
+struct local_op_ref
+{
+	int oid;   /* operator index into opmap */
+	int cid;   /* coefficient index into coeffmap */
+};
+
+struct mpo_graph_vertex
+{
+	int* eids[2];      /* indices of left- and right-connected edges */
+	int num_edges[2];
+	qnumber qnum;
+};
+
+struct mpo_graph_edge
+{
+	int vids[2];                 /* left and right vertex */
+	struct local_op_ref* opics;  /* weighted sum of local operators */
+	int nopics;
+};
+
+struct mpo_graph
+{
+	struct mpo_graph_vertex** verts;  /* [nsites + 1][num_verts] */
+	struct mpo_graph_edge** edges;    /* [nsites][num_edges] */
+	int* num_verts;
+	int* num_edges;
+	int nsites;
+};
+
+struct mpo_assembly
+{
+	struct mpo_graph graph;
+	struct dense_tensor* opmap;     /* local operator look-up table */
+	void* coeffmap;                 /* coefficient look-up table (entries of type dtype) */
+	qnumber* qsite;
+	ct_long d;
+	enum numeric_type dtype;
+	int num_local_ops;
+	int num_coeffs;
+};
 
 #ifdef __cplusplus
 }
