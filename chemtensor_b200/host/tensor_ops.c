@@ -687,7 +687,7 @@ static int build_mat_descs(const struct ctb_tensor* a, const struct ctb_tensor* 
 	return n;
 }
 
-int ctb_svd(struct ctb_tensor* a, struct ctb_tensor** u, double** s_dev, ct_long* ns, struct ctb_tensor** vh)
+static int svd_direct(struct ctb_tensor* a, struct ctb_tensor** u, double** s_dev, ct_long* ns, struct ctb_tensor** vh)
 {
 	CTB_REQUIRE(a->ndim == 2);
 	const ct_long maxn = a->ax[0].dim > a->ax[1].dim ? a->ax[0].dim : a->ax[1].dim;
@@ -727,6 +727,55 @@ int ctb_svd(struct ctb_tensor* a, struct ctb_tensor** u, double** s_dev, ct_long
 	int rc = ctbd_svd_batched(a->dtype, nmat, descs, a->d, (*u)->d, (*vh)->d, *s_dev);
 	free(descs);
 	if (rc < 0) { fprintf(stderr, "chemtensor_b200: batched SVD failed: %s\n", ctbd_last_error()); return -1; }
+	return 0;
+}
+
+/* QR-preconditioned SVD (Drmac-Veselic flavour), built from the device primitives alone: a = q r per sector block (Householder),
+ * one-sided Jacobi on the ROWS of the triangular factor r, u = q u_r by the grouped GEMM.  On the graded spectra of two-site
+ * tensors the Jacobi iteration on r needs 3-4x fewer rotations than on a itself (tools/proto_block_jacobi.py and DESIGN.md
+ * section 6: 7-9 sweeps instead of 23-31 over 8-16 decades), and for tall blocks its rows are shorter.  Sector structure, bond
+ * quantum numbers and singular values are those of the direct path.  Opt-in (CTB_SVD_PRECONDITION=1) until it has been timed
+ * on the GPU against the Householder kernel's cost on large blocks. */
+static int svd_preconditioned_tall(struct ctb_tensor* a, struct ctb_tensor** u, double** s_dev, ct_long* ns, struct ctb_tensor** vh)
+{
+	struct ctb_tensor *q = NULL, *r = NULL, *u_r = NULL;
+	int rc = ctb_qr(a, &q, &r);
+	if (rc < 0) { return rc; }
+	rc = svd_direct(r, &u_r, s_dev, ns, vh);
+	ctb_tensor_free(r);
+	if (rc < 0) { ctb_tensor_free(q); return rc; }
+	*u = ctb_dot(q, TENSOR_AXIS_RANGE_TRAILING, 0, u_r, TENSOR_AXIS_RANGE_LEADING, 0, 1, NULL);
+	ctb_tensor_free(q);
+	ctb_tensor_free(u_r);
+	return 0;
+}
+
+int ctb_svd(struct ctb_tensor* a, struct ctb_tensor** u, double** s_dev, ct_long* ns, struct ctb_tensor** vh)
+{
+	CTB_REQUIRE(a->ndim == 2);
+	const char* env = getenv("CTB_SVD_PRECONDITION");
+	if (env == NULL || atoi(env) == 0 || a->nblk == 0) { return svd_direct(a, u, s_dev, ns, vh); }
+	/* orientation: the Householder step pays off on blocks with at least as many rows as columns */
+	double tall = 0, wide = 0;
+	for (int b = 0; b < a->nblk; b++) {
+		int idx[2];
+		ctb_grid_unravel(a, a->blk_grid[b], idx);
+		const double m = a->ax[0].secdim[idx[0]], n = a->ax[1].secdim[idx[1]];
+		if (m >= n) { tall += m * n * n; } else { wide += m * m * n; }
+	}
+	if (wide <= tall || a->ax[0].dir != -a->ax[1].dir) { return svd_preconditioned_tall(a, u, s_dev, ns, vh); }
+	/* mostly wide blocks: factorise the conjugate transpose and swap the factors back.  With opposite leg directions the bond of
+	 * the transposed problem carries the same quantum numbers in the same order (q_row = q_col for every conserving block). */
+	const int perm[2] = { 1, 0 };
+	const int cj = ctb_is_complex(a->dtype);
+	struct ctb_tensor* at = ctb_transpose(a, perm, cj);
+	struct ctb_tensor *ut = NULL, *vht = NULL;
+	int rc = svd_preconditioned_tall(at, &ut, s_dev, ns, &vht);
+	ctb_tensor_free(at);
+	if (rc < 0) { return rc; }
+	*u = ctb_transpose(vht, perm, cj);
+	*vh = ctb_transpose(ut, perm, cj);
+	ctb_tensor_free(ut); ctb_tensor_free(vht);
 	return 0;
 }
 
