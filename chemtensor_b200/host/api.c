@@ -261,7 +261,7 @@ void block_sparse_tensor_cyclic_partial_trace(const struct block_sparse_tensor* 
 {
 	ensure_init();
 	struct ctb_tensor* td = ctb_upload(t);
-	struct ctb_tensor* rd = ctb_drop_dummy_axes(td, ndim_trace);
+	struct ctb_tensor* rd = ctb_cyclic_partial_trace(td, ndim_trace);
 	ctb_tensor_free(td);
 	finish(rd, r);
 }

@@ -172,6 +172,7 @@ struct ctb_tensor* ctb_slice(struct ctb_tensor* t, int i_ax, const ct_long* ind,
 struct ctb_tensor* ctb_scale_axis(struct ctb_tensor* t, int i_ax, const double* scale_dev);
 /* drop 'ntrace' leading and trailing axes, all of logical dimension 1 (cyclic partial trace of dummy bonds) */
 struct ctb_tensor* ctb_drop_dummy_axes(const struct ctb_tensor* t, int ntrace);
+struct ctb_tensor* ctb_cyclic_partial_trace(struct ctb_tensor* t, int ntrace);
 
 /* block-wise factorizations of a block-sparse matrix */
 int ctb_svd(struct ctb_tensor* a, struct ctb_tensor** u, double** s_dev, ct_long* ns, struct ctb_tensor** vh);

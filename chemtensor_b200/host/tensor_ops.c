@@ -637,6 +637,66 @@ struct ctb_tensor* ctb_drop_dummy_axes(const struct ctb_tensor* t, int ntrace)
 	return r;
 }
 
+/* General cyclic partial trace (reference block_sparse_tensor.c:1560-1610): r[free] = sum_i t[i, free, i] over the 'ntrace' leading
+ * and trailing axes.  Composed of the device primitives: transpose to [free, lead, trail], then ONE grouped-GEMM contraction over
+ * (lead, trail) with the identity tensor delta[i, i'] of the traced legs (stored blocks: equal sectors only).  The pairs of unit
+ * legs of the hot path never get here (ctb_drop_dummy_axes is a plain copy). */
+struct ctb_tensor* ctb_cyclic_partial_trace(struct ctb_tensor* t, int ntrace)
+{
+	CTB_REQUIRE(ntrace >= 0 && t->ndim >= 2 * ntrace);
+	bool unit = true;
+	for (int i = 0; i < ntrace; i++) {
+		const struct ctb_axis* a = &t->ax[i]; const struct ctb_axis* b = &t->ax[t->ndim - ntrace + i];
+		CTB_REQUIRE(a->dim == b->dim && a->dir == -b->dir && ctb_axis_same_qnums(a, b));
+		if (a->dim != 1) { unit = false; }
+	}
+	if (ntrace == 0) { return ctb_tensor_clone(t); }
+	if (unit) { return ctb_drop_dummy_axes(t, ntrace); }
+	const int nfree = t->ndim - 2 * ntrace;
+	CTB_REQUIRE(2 * ntrace <= CTB_MAXDIM);
+	/* [free..., lead..., trail...] */
+	int perm[CTB_MAXDIM];
+	for (int i = 0; i < nfree; i++) { perm[i] = ntrace + i; }
+	for (int i = 0; i < ntrace; i++) { perm[nfree + i] = i; perm[nfree + ntrace + i] = t->ndim - ntrace + i; }
+	struct ctb_tensor* tp = ctb_transpose(t, perm, 0);
+	/* delta over the traced legs, directions opposite to those of tp's trailing legs */
+	struct ctb_axis axes[CTB_MAXDIM];
+	for (int i = 0; i < 2 * ntrace; i++) {
+		ctb_axis_copy(&axes[i], &tp->ax[nfree + i]);
+		axes[i].dir = -axes[i].dir;
+	}
+	struct ctb_tensor* delta = ctb_tensor_from_axes(t->dtype, 2 * ntrace, axes, 1);
+	{
+		/* host image of the packed entries: 1 where the leading multi-index equals the trailing one */
+		const size_t esize = ctb_sizeof_dtype(t->dtype);
+		void* ent = ctb_calloc((size_t)(delta->nstore > 0 ? delta->nstore : 1), esize);
+		ct_long total = 1;
+		for (int i = 0; i < ntrace; i++) { total *= delta->ax[i].dim; }
+		ct_long idx[CTB_MAXDIM] = { 0 };
+		for (ct_long k = 0; k < total; k++)
+		{
+			int sec[CTB_MAXDIM];
+			for (int i = 0; i < ntrace; i++) { idx[ntrace + i] = idx[i]; }
+			for (int i = 0; i < 2 * ntrace; i++) { sec[i] = delta->ax[i].sec_of[idx[i]]; }
+			const ct_long base = delta->grid_off[ctb_grid_ravel(delta, sec)];
+			CTB_REQUIRE(base >= 0);      /* equal quantum numbers with opposite directions always conserve */
+			ct_long off = 0;
+			for (int i = 0; i < 2 * ntrace; i++) { off = off * delta->ax[i].secdim[sec[i]] + delta->ax[i].pos_of[idx[i]]; }
+			((double*)ent)[(size_t)(base + off) * (esize / sizeof(double))] = 1.0;
+			for (int i = ntrace - 1; i >= 0; i--) {
+				if (++idx[i] < delta->ax[i].dim) { break; }
+				idx[i] = 0;
+			}
+		}
+		CTB_CHECK_ABORT(ctb_upload_entries(delta, ent));
+		ctb_free(ent);
+	}
+	struct ctb_tensor* r = ctb_dot(tp, TENSOR_AXIS_RANGE_TRAILING, 0, delta, TENSOR_AXIS_RANGE_LEADING, 0, 2 * ntrace, NULL);
+	ctb_tensor_free(delta);
+	ctb_tensor_free(tp);
+	return r;
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 /* block-wise SVD / QR / RQ                                                                        */
 /* ---------------------------------------------------------------------------------------------- */

@@ -73,3 +73,41 @@ def test_single_entry_tensor_through_the_split(eng, ref, rng, dtype):
     assert abs(out[0][2] - out[1][2]) <= 1e-15
     # u s vh reproduces the entry (the phase may sit in either factor)
     assert abs(out[0][0].serialize()[0] * out[0][1].serialize()[0] - a_e.serialize()[0]) <= 1e-15
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("ntrace", [1, 2])
+def test_cyclic_partial_trace_over_real_bonds(eng, ref, rng, dtype, ntrace):
+    """general form of block_sparse_tensor_cyclic_partial_trace (reference block_sparse_tensor.c:1560): traced legs of dimension > 1"""
+    lead_dims = [5, 3][:ntrace]
+    lead_q = [helpers.random_qnums(rng, d) for d in lead_dims]
+    lead_dir = [1, -1][:ntrace]
+    free_dims, free_dir = [4, 6], [1, -1]
+    free_q = [helpers.random_qnums(rng, d) for d in free_dims]
+    shape = tuple(lead_dims + free_dims + lead_dims)
+    dirs = tuple(lead_dir + free_dir + [-x for x in lead_dir])
+    qn = tuple(lead_q + free_q + lead_q)
+    t_e = helpers.random_bst(eng, rng, dtype, shape, dirs, qn)
+    t_r = cabi.bst_clone(ref, t_e)
+    r_e, r_r = cabi.BST(eng), cabi.BST(ref)
+    eng.block_sparse_tensor_cyclic_partial_trace(t_e.ptr, ntrace, r_e.ptr)
+    ref.block_sparse_tensor_cyclic_partial_trace(t_r.ptr, ntrace, r_r.ptr)
+    helpers.assert_bst_close(r_e, r_r, 1e-13)
+    dense = t_e.to_dense()
+    want = np.einsum("iabi->ab", dense) if ntrace == 1 else np.einsum("ijabij->ab", dense)
+    assert np.allclose(r_e.to_dense(), want, atol=1e-13)
+
+
+def test_cyclic_partial_trace_golden(eng):
+    """the reference's fixture test/tensor/data/test_block_sparse_tensor_cyclic_partial_trace.hdf5 (single complex data, computed here in
+    complex128; the reference test compares at 1e-6... of float32 accuracy)"""
+    from test_golden_engine import golden
+    ds, at = golden("block_sparse_tensor_cyclic_partial_trace")
+    dirs = [int(x) for x in at["axis_dir"]]
+    qn = [np.asarray(at[f"qnums{i}"], dtype=np.int32) for i in range(7)]
+    t = cabi.bst_from_dense(eng, np.ascontiguousarray(ds["t"].astype(np.complex128)), dirs, qn)
+    r = cabi.BST(eng)
+    eng.block_sparse_tensor_cyclic_partial_trace(t.ptr, 2, r.ptr)
+    want = ds["t_tr"].astype(np.complex128)
+    assert r.shape == want.shape
+    assert np.linalg.norm(r.to_dense() - want) <= 2e-6 * np.linalg.norm(want)
