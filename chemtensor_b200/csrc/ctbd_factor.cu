@@ -17,72 +17,11 @@
 #include <algorithm>
 #include <float.h>
 #include <cooperative_groups.h>
-#include "ctbd_common.cuh"
+#include "ctbd_factor.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace ctbd {
-
-/* ---- minimal complex helpers so that one template covers double and double2 ---- */
-__device__ __forceinline__ double  cj(double a)  { return a; }
-__device__ __forceinline__ double2 cj(double2 a) { return make_double2(a.x, -a.y); }
-__device__ __forceinline__ double  mul(double a, double b)   { return a * b; }
-__device__ __forceinline__ double2 mul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ double  smul(double s, double a)  { return s * a; }
-__device__ __forceinline__ double2 smul(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
-__device__ __forceinline__ double  add(double a, double b)   { return a + b; }
-__device__ __forceinline__ double2 add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double  sub(double a, double b)   { return a - b; }
-__device__ __forceinline__ double2 sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ double  abs2(double a)  { return a * a; }
-__device__ __forceinline__ double  abs2(double2 a) { return a.x * a.x + a.y * a.y; }
-__device__ __forceinline__ double  re(double a)  { return a; }
-__device__ __forceinline__ double  re(double2 a) { return a.x; }
-__device__ __forceinline__ double  im(double)  { return 0.0; }
-__device__ __forceinline__ double  im(double2 a) { return a.y; }
-template <typename T> __device__ __forceinline__ T from_real(double r);
-template <> __device__ __forceinline__ double  from_real<double>(double r)  { return r; }
-template <> __device__ __forceinline__ double2 from_real<double2>(double r) { return make_double2(r, 0.0); }
-__device__ __forceinline__ double  shfl_xor(double v, int o)  { return __shfl_xor_sync(0xffffffffu, v, o); }
-__device__ __forceinline__ double2 shfl_xor(double2 v, int o) { return make_double2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o)); }
-
-__device__ __forceinline__ double absmax_of(double a)  { return fabs(a); }
-__device__ __forceinline__ double absmax_of(double2 a) { return fmax(fabs(a.x), fabs(a.y)); }
-
-/* power-of-two factor that brings a block with largest entry 'amax' to O(1), as LAPACK's ?lascl-based drivers do:
- * the factorizations square entries (norms, Gram entries), which would under- or overflow for |a| ~ 1e+-160 */
-__device__ __forceinline__ double pow2_scale(double amax)
-{
-	if (!(amax > 0.0) || !isfinite(amax)) { return 1.0; }
-	int e; frexp(amax, &e);
-	return ldexp(1.0, -e);
-}
-
-/* block-wide maximum; result valid in all threads; 'red' has blockDim.x / 32 entries */
-__device__ __forceinline__ double block_max(double v, double* red)
-{
-	#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) { v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o)); }
-	__syncthreads();
-	if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = v; }
-	__syncthreads();
-	double r = red[0];
-	for (int w = 1; w < (int)(blockDim.x >> 5); w++) { r = fmax(r, red[w]); }
-	__syncthreads();
-	return r;
-}
-
-/* one CTA per matrix: scale[b] = power-of-two normalisation of block b (m x n entries at a_off) */
-template <typename T>
-__global__ void __launch_bounds__(256) absmax_scale_kernel(const int64_t* __restrict__ a_off, const int64_t* __restrict__ numel, const T* __restrict__ A, double* __restrict__ scale)
-{
-	__shared__ double red[8];
-	const T* a = A + a_off[blockIdx.x];
-	double v = 0;
-	for (int64_t e = threadIdx.x; e < numel[blockIdx.x]; e += blockDim.x) { v = fmax(v, absmax_of(a[e])); }
-	const double amax = block_max(v, red);
-	if (threadIdx.x == 0) { scale[blockIdx.x] = pow2_scale(amax); }
-}
 
 /* ============================================================================================== */
 /* SVD                                                                                              */
@@ -725,11 +664,15 @@ static int svd_batched_impl(int nmat_all, const ctbd_mat_desc* descs_all, const 
 	std::vector<SvdMat> small_mats;
 	std::vector<ctbd_mat_desc> big;
 	size_t smem_max = 0;
+	/* test knobs: CTB_SVD_NO_SMEM=1 / CTB_SVD_SMEM_LIMIT=<bytes> send smaller blocks down the big-block path */
+	size_t smem_limit = SVD_SMEM_LIMIT;
+	if (getenv("CTB_SVD_NO_SMEM") != nullptr) { smem_limit = 0; }
+	else if (getenv("CTB_SVD_SMEM_LIMIT") != nullptr) { smem_limit = std::min((size_t)atoll(getenv("CTB_SVD_SMEM_LIMIT")), SVD_SMEM_LIMIT); }
 	for (int b = 0; b < nmat_all; b++)
 	{
 		const int R = std::min(descs_all[b].m, descs_all[b].n), C = std::max(descs_all[b].m, descs_all[b].n);
 		const size_t need = (size_t)R * (C + R) * sizeof(T) + (size_t)R * (2 * sizeof(double) + sizeof(int)) + 16;
-		if (need <= SVD_SMEM_LIMIT && getenv("CTB_SVD_NO_SMEM") == nullptr) {
+		if (need <= smem_limit) {
 			SvdMat mt; memset(&mt, 0, sizeof(mt));
 			mt.a_off = descs_all[b].a_off; mt.u_off = descs_all[b].o0_off; mt.vh_off = descs_all[b].o1_off; mt.s_off = descs_all[b].s_off;
 			mt.m = descs_all[b].m; mt.n = descs_all[b].n; mt.R = R; mt.C = C;
@@ -759,6 +702,11 @@ static int svd_batched_impl(int nmat_all, const ctbd_mat_desc* descs_all, const 
 		ctbd_free(d_sel); ctbd_free(d_small);
 	}
 	if (big.empty()) { return 0; }
+	/* default: QR-preconditioned block Jacobi on the tensor pipe (ctbd_svd_bj.cu); CTB_SVD_BJ=0 keeps the scalar tournament below */
+	{
+		const char* env = getenv("CTB_SVD_BJ");
+		if (env == nullptr || atoi(env) != 0) { return svd_bj_impl<T>((int)big.size(), big.data(), A, U, Vh, S); }
+	}
 	SvdBig<T>* st = svd_big_setup<T>((int)big.size(), big.data(), A);
 	if (st == nullptr) { return -1; }
 	int rc = svd_big_iterate<T>(st);

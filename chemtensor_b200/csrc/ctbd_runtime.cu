@@ -162,17 +162,24 @@ int ctbd_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms)
 }
 int ctbd_event_destroy(void* ev) { CTBD_CUDA(cudaEventDestroy((cudaEvent_t)ev)); return 0; }
 
-int ctbd_malloc(void** dptr, size_t bytes)
+int ctbd_malloc_noinit(void** dptr, size_t bytes)
 {
 	CTBD_REQUIRE_INIT();
 	const size_t nb = bytes > 0 ? bytes : 16;
 	CTBD_CUDA(cudaMallocAsync(dptr, nb, rt().stream));
-	CTBD_CUDA(cudaMemsetAsync(*dptr, 0, nb, rt().stream));
 	{
 		std::lock_guard<std::mutex> lock(g_mutex);
 		g_allocs[*dptr] = nb;
 		rt().bytes_in_use += (long long)nb;
 	}
+	return 0;
+}
+
+int ctbd_malloc(void** dptr, size_t bytes)
+{
+	int rc = ctbd_malloc_noinit(dptr, bytes);
+	if (rc < 0) { return rc; }
+	CTBD_CUDA(cudaMemsetAsync(*dptr, 0, bytes > 0 ? bytes : 16, rt().stream));
 	return 0;
 }
 

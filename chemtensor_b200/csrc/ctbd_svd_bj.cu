@@ -1,0 +1,1077 @@
+/*
+ * ctbd_svd_bj.cu -- GEMM-rich batched SVD of the sector blocks that do not fit into shared memory.
+ *
+ * Replaces LAPACK ?gesvd per block (reference src/tensor/dense_tensor.c:3538-3671, called from block_sparse_tensor_svd,
+ * src/tensor/block_sparse_tensor.c:2686-2840) for the big blocks of a two-site split (bond_ops.c:15-138).
+ *
+ * Per block, with M = A (m <= n) or A^H (m > n), an R x C matrix, R <= C:
+ *   1. QR preconditioning (Drmac-Veselic):  M^H = Q Rf  by blocked Householder QR (panel kernel + compact-WY block reflector
+ *      kernels).  The rows of the triangular factor Rf are graded, which is what makes Jacobi converge in ~8 sweeps instead of
+ *      30-40 on the two-site matrices of a DMRG sweep (singular values over 16 decades; tools/proto_bj2.py).
+ *   2. One-sided BLOCK Jacobi on the rows of the work matrix X = [G | W] = [Rf | Q^H]  (R x (R + C), row-major): row blocks of 32
+ *      rows, round-robin tournament over the block pairs, all pairs of all blocks of the batch in the same three launches per round:
+ *        gram   : P = X_pair[:, :R] X_pair[:, :R]^H  (64 x 64, split-K partials)                 -- DMMA
+ *        eig    : P = Z^H diag Z by two-sided cyclic Jacobi ROTATIONS in shared memory (one CTA per pair; rotations keep the
+ *                 relative accuracy of graded Gram matrices and give a transformation close to the identity)
+ *        update : X_pair <- Z X_pair  (64 x (R + C))                                              -- DMMA
+ *      A pair whose rows are already orthogonal to working precision (|P_ij| <= eps sqrt(R) sqrt(P_ii P_jj)) is skipped; a block
+ *      is finished after a full cycle of its tournament without any active pair.
+ *   3. sigma = row norms of G (sorted descending as LAPACK does), Y = G / sigma;  M = Y^H diag(sigma) W:
+ *        m <= n:  U = Y^H, Vh = W;      m > n:  U = W^H, Vh = Y.
+ * The accumulated transformation is a product of plane rotations and Householder reflectors, so U and Vh are orthonormal to
+ * working precision whatever the conditioning of the block.
+ */
+#include <vector>
+#include <algorithm>
+#include <stdlib.h>
+#include <time.h>
+#include "ctbd_factor.cuh"
+
+namespace ctbd {
+
+static constexpr int BJ_B  = 32;           /* rows per row block */
+static constexpr int BJ_P  = 2 * BJ_B;     /* rows of a block pair */
+static constexpr int BJ_KC = 256;          /* columns per split-K part of the Gram kernel */
+static constexpr int BJ_KT = 32;           /* columns per pipeline stage */
+static constexpr int QR_NB = 32;           /* panel width of the blocked QR */
+static constexpr int QR_CB = 64;           /* columns per CTA of the block-reflector kernel */
+
+struct BjMat
+{
+	int64_t a_off, u_off, vh_off, s_off;
+	int64_t x_off;        /* work matrix X = [G | W], R x ld */
+	int64_t t_off;        /* QR work matrix (C x R, row-major, leading dimension R): M^H, afterwards Rf above and the reflectors below the diagonal */
+	int64_t tf_off;       /* T factors of the panels: npanel x 32 x 32 */
+	int32_t m, n, R, C, ld;
+	int32_t nb;           /* row blocks */
+	int32_t N1;           /* rounds of one tournament cycle */
+	int32_t item_begin;   /* first pair item of this block in a round */
+	int32_t nitem;        /* pair items per round */
+	int32_t npanel, ksplit;
+};
+
+template <typename T> struct BjCfg;
+template <> struct BjCfg<double>  { static constexpr int SG = 36, SZ = 68, NCU = 128, SXU = 132; };
+template <> struct BjCfg<double2> { static constexpr int SG = 36, SZ = 68, NCU = 64,  SXU = 66;  };
+
+__device__ __forceinline__ void bj_dmma(double& c0, double& c1, const double a, const double b)
+{
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+		: "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void bj_cp16(void* smem_dst, const void* gsrc, int src_bytes)
+{
+	const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void bj_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void bj_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
+
+__device__ __forceinline__ int bj_find(const BjMat* __restrict__ mats, int nmat, int item)
+{
+	int lo = 0, hi = nmat - 1;
+	while (lo < hi) {
+		const int mid = (lo + hi + 1) >> 1;
+		if (mats[mid].item_begin <= item) { lo = mid; } else { hi = mid - 1; }
+	}
+	return lo;
+}
+
+/* pair of players (I < J) of slot i in round r of the round-robin tournament over N (even) players */
+__device__ __forceinline__ void bj_pair(int N, int r, int i, int& I, int& J)
+{
+	if (N <= 2) { I = 0; J = 1; return; }
+	const int rr = r % (N - 1);
+	int p, q;
+	if (i == 0) { p = N - 1; q = rr; }
+	else { p = (rr + i) % (N - 1); q = (rr - i + (N - 1)) % (N - 1); }
+	I = min(p, q); J = max(p, q);
+}
+
+/* ============================================================================================== */
+/* stage 1: QR preconditioning                                                                      */
+/* ============================================================================================== */
+
+/* amax[b] = largest |entry| of block b (non-negative doubles order like their bit patterns) */
+template <typename T>
+__global__ void __launch_bounds__(256) bj_absmax_kernel(const BjMat* __restrict__ mats, const T* __restrict__ A, double* __restrict__ amax)
+{
+	__shared__ double red[8];
+	const BjMat mt = mats[blockIdx.y];
+	const T* a = A + mt.a_off;
+	const int64_t total = (int64_t)mt.m * mt.n;
+	double v = 0;
+	for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) { v = fmax(v, absmax_of(a[e])); }
+	const double m = block_max(v, red);
+	if (threadIdx.x == 0 && m > 0.0 && isfinite(m)) { atomicMax(reinterpret_cast<unsigned long long*>(amax + blockIdx.y), (unsigned long long)__double_as_longlong(m)); }
+}
+
+/* Tm = scale * M^H (C x R) */
+template <typename T>
+__global__ void __launch_bounds__(256) bj_load_kernel(const BjMat* __restrict__ mats, const double* __restrict__ amax, const T* __restrict__ A, T* __restrict__ Tm)
+{
+	const BjMat mt = mats[blockIdx.y];
+	const double sc = pow2_scale(amax[blockIdx.y]);
+	const T* a = A + mt.a_off;
+	T* t = Tm + mt.t_off;
+	const int64_t total = (int64_t)mt.R * mt.C;
+	const bool wide = (mt.m <= mt.n);
+	for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+	{
+		if (wide) {
+			/* A is R x C: M^H[i][j] = conj(A[j][i]); e runs over A */
+			const int j = (int)(e / mt.C), i = (int)(e % mt.C);
+			t[(int64_t)i * mt.R + j] = smul(sc, cj(a[e]));
+		}
+		else {
+			/* A is C x R = M^H */
+			t[e] = smul(sc, a[e]);
+		}
+	}
+}
+
+/* Householder QR of panel 'panel' (32 columns) of every block, one CTA of 32 x 32 threads per block.  LAPACK ?geqr2 / ?larfg
+ * conventions (beta = -sign(Re alpha) ||x||, H = I - tau v v^H, v_0 = 1, H^H applied to the trailing columns), followed by the
+ * triangular factor of the compact WY form (?larft, forward, columnwise): H_0 H_1 ... = I - V T V^H. */
+template <typename T>
+__global__ void __launch_bounds__(1024) bj_qr_panel_kernel(const BjMat* __restrict__ mats, int panel, T* __restrict__ Tm, T* __restrict__ Tf)
+{
+	const BjMat mt = mats[blockIdx.x];
+	if (panel >= mt.npanel) { return; }
+	const int R = mt.R;
+	const int j0 = panel * QR_NB;
+	const int nbw = min(QR_NB, R - j0);
+	const int rows = mt.C - j0;
+	T* P = Tm + mt.t_off + (int64_t)j0 * R + j0;
+	const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+
+	__shared__ T red[32][33];
+	__shared__ T s_e[32], s_w[32], s_tau[32];
+	__shared__ T s_ctau, s_scal;
+	__shared__ double s_beta;
+	__shared__ int s_skip;
+
+	for (int j = 0; j < nbw; j++)
+	{
+		/* e_c = sum_{i > j} conj(P[i][j]) P[i][c] for the columns c >= j of the panel */
+		T acc = from_real<T>(0.0);
+		if (tx >= j && tx < nbw) {
+			/* four rows in flight: the loop is bound by the latency of the L2 round trips */
+			int i = j + 1 + ty;
+			for (; i + 96 < rows; i += 128) {
+				const T x0 = P[(int64_t)i * R + j], x1 = P[(int64_t)(i + 32) * R + j], x2 = P[(int64_t)(i + 64) * R + j], x3 = P[(int64_t)(i + 96) * R + j];
+				const T p0 = P[(int64_t)i * R + tx], p1 = P[(int64_t)(i + 32) * R + tx], p2 = P[(int64_t)(i + 64) * R + tx], p3 = P[(int64_t)(i + 96) * R + tx];
+				acc = add(acc, mul(cj(x0), p0)); acc = add(acc, mul(cj(x1), p1)); acc = add(acc, mul(cj(x2), p2)); acc = add(acc, mul(cj(x3), p3));
+			}
+			for (; i < rows; i += 32) { acc = add(acc, mul(cj(P[(int64_t)i * R + j]), P[(int64_t)i * R + tx])); }
+		}
+		red[ty][tx] = acc;
+		__syncthreads();
+		if (ty == 0) {
+			T s = red[0][tx];
+			for (int r = 1; r < 32; r++) { s = add(s, red[r][tx]); }
+			s_e[tx] = s;
+		}
+		__syncthreads();
+		if (tid == 0)
+		{
+			const T alpha = P[(int64_t)j * R + j];
+			const double xn2 = re(s_e[j]);
+			if (xn2 == 0.0 && im(alpha) == 0.0) {
+				s_tau[j] = from_real<T>(0.0); s_ctau = from_real<T>(0.0); s_scal = from_real<T>(0.0);
+				s_beta = re(alpha); s_skip = 1;
+			}
+			else {
+				const double nrm = sqrt(abs2(alpha) + xn2);
+				const double beta = -(re(alpha) >= 0.0 ? 1.0 : -1.0) * nrm;
+				const T tau = smul(1.0 / beta, sub(from_real<T>(beta), alpha));
+				const T d = sub(alpha, from_real<T>(beta));
+				const double dmx = absmax_of(d);
+				const T ds = smul(1.0 / dmx, d);
+				s_scal = smul(1.0 / (abs2(ds) * dmx), cj(ds));      /* 1 / (alpha - beta) */
+				s_tau[j] = tau; s_ctau = cj(tau);
+				s_beta = beta; s_skip = 0;
+			}
+		}
+		__syncthreads();
+		if (s_skip) {
+			__syncthreads();
+			continue;
+		}
+		const T scal = s_scal, ctau = s_ctau;
+		if (ty == 0 && tx > j && tx < nbw) { s_w[tx] = add(P[(int64_t)j * R + tx], mul(cj(scal), s_e[tx])); }      /* w_c = v^H P[:, c] */
+		__syncthreads();
+		{
+			const bool upd = (tx > j && tx < nbw);
+			const T f = upd ? mul(ctau, s_w[tx]) : from_real<T>(0.0);
+			int i = j + ty;
+			if (i == j) {
+				if (upd) { P[(int64_t)j * R + tx] = sub(P[(int64_t)j * R + tx], f); }
+				if (tx == j) { P[(int64_t)j * R + j] = from_real<T>(s_beta); }
+				i += 32;
+			}
+			for (; i + 96 < rows; i += 128)
+			{
+				const T x0 = P[(int64_t)i * R + j], x1 = P[(int64_t)(i + 32) * R + j], x2 = P[(int64_t)(i + 64) * R + j], x3 = P[(int64_t)(i + 96) * R + j];
+				T p0 = from_real<T>(0.0), p1 = p0, p2 = p0, p3 = p0;
+				if (upd) { p0 = P[(int64_t)i * R + tx]; p1 = P[(int64_t)(i + 32) * R + tx]; p2 = P[(int64_t)(i + 64) * R + tx]; p3 = P[(int64_t)(i + 96) * R + tx]; }
+				const T v0 = mul(x0, scal), v1 = mul(x1, scal), v2 = mul(x2, scal), v3 = mul(x3, scal);
+				__syncwarp();
+				if (upd) {
+					P[(int64_t)i * R + tx] = sub(p0, mul(v0, f)); P[(int64_t)(i + 32) * R + tx] = sub(p1, mul(v1, f));
+					P[(int64_t)(i + 64) * R + tx] = sub(p2, mul(v2, f)); P[(int64_t)(i + 96) * R + tx] = sub(p3, mul(v3, f));
+				}
+				if (tx == j) { P[(int64_t)i * R + j] = v0; P[(int64_t)(i + 32) * R + j] = v1; P[(int64_t)(i + 64) * R + j] = v2; P[(int64_t)(i + 96) * R + j] = v3; }
+			}
+			for (; i < rows; i += 32)
+			{
+				{
+					const T v = mul(P[(int64_t)i * R + j], scal);
+					__syncwarp();
+					if (upd) { P[(int64_t)i * R + tx] = sub(P[(int64_t)i * R + tx], mul(v, f)); }
+					if (tx == j) { P[(int64_t)i * R + j] = v; }
+				}
+			}
+		}
+		__syncthreads();
+	}
+
+	/* S[a][b] = v_a^H v_b (a < b), through 32-row chunks of the masked panel (unit diagonal, zeros above) */
+	T (*chunk)[33] = red;          /* the reduction scratch is free now */
+	__shared__ T sT[32][33];       /* upper triangle: T;  strictly lower triangle: S transposed, S[b][i] at sT[i][b] */
+	T sacc = from_real<T>(0.0);
+	for (int i0 = 0; i0 < rows; i0 += 32)
+	{
+		const int i = i0 + ty;
+		T v = from_real<T>(0.0);
+		if (i < rows && tx < nbw) { v = (i > tx) ? P[(int64_t)i * R + tx] : from_real<T>(i == tx ? 1.0 : 0.0); }
+		chunk[ty][tx] = v;
+		__syncthreads();
+		#pragma unroll 8
+		for (int k = 0; k < 32; k++) { sacc = add(sacc, mul(cj(chunk[k][ty]), chunk[k][tx])); }
+		__syncthreads();
+	}
+	if (ty < tx) { sT[tx][ty] = sacc; }
+	if (ty <= tx) { sT[ty][tx] = from_real<T>(0.0); }
+	__syncthreads();
+	if (tid < 32)
+	{
+		/* row a = tid of T: T[a][i] = -tau_i sum_{b = a}^{i-1} T[a][b] S[b][i]  (a < i),  T[i][i] = tau_i */
+		const int a = tid;
+		for (int i = 0; i < nbw; i++)
+		{
+			const T ti = s_tau[i];
+			if (a == i) { sT[a][i] = ti; }
+			else if (a < i) {
+				T s = from_real<T>(0.0);
+				for (int b = a; b < i; b++) { s = add(s, mul(sT[a][b], sT[i][b])); }
+				sT[a][i] = mul(smul(-1.0, ti), s);
+			}
+		}
+	}
+	__syncthreads();
+	Tf[mt.tf_off + (int64_t)panel * 1024 + tid] = (ty <= tx) ? sT[ty][tx] : from_real<T>(0.0);
+}
+
+/* block reflector of panel 'panel' applied from the left to 64-column chunks of B (leading dimension R, rows j0 .. C-1):
+ *   mode 0: B = the QR work matrix itself, columns right of the panel, B <- (I - V T^H V^H) B   (trailing update)
+ *   mode 1: B = the Q work matrix, columns >= j0,                       B <- (I - V T V^H) B     (accumulation of Q, panels backwards) */
+template <typename T>
+__global__ void __launch_bounds__(256) bj_qr_apply_kernel(const BjMat* __restrict__ mats, int panel, int mode, const T* Tm, const T* __restrict__ Tf, T* Bm)
+{
+	const BjMat mt = mats[blockIdx.y];
+	if (panel >= mt.npanel) { return; }
+	const int R = mt.R;
+	const int j0 = panel * QR_NB;
+	const int nbw = min(QR_NB, R - j0);
+	const int rows = mt.C - j0;
+	const int col0 = (mode == 0 ? j0 + nbw : j0) + blockIdx.x * QR_CB;
+	if (col0 >= R) { return; }
+	const T* V = Tm + mt.t_off + (int64_t)j0 * R + j0;
+	T* B = Bm + mt.t_off + (int64_t)j0 * R;
+	const T* tf = Tf + mt.tf_off + (int64_t)panel * 1024;
+	const int tid = threadIdx.x;
+
+	extern __shared__ __align__(16) unsigned char bj_apply_raw[];
+	T* Vs  = reinterpret_cast<T*>(bj_apply_raw);     /* [64][33] */
+	T* Bs  = Vs + 64 * 33;                            /* [64][65] */
+	T* Ws  = Bs + 64 * 65;                            /* [32][65] */
+	T* Tfs = Ws + 32 * 65;                            /* [32][33] */
+
+	for (int e = tid; e < 1024; e += 256) { Tfs[(e >> 5) * 33 + (e & 31)] = tf[e]; }
+
+	auto load_chunk = [&](int i0) {
+		for (int e = tid; e < 64 * 32; e += 256) {
+			const int k = e >> 5, a = e & 31, i = i0 + k;
+			T v = from_real<T>(0.0);
+			if (i < rows && a < nbw) { v = (i > a) ? V[(int64_t)i * R + a] : from_real<T>(i == a ? 1.0 : 0.0); }
+			Vs[k * 33 + a] = v;
+		}
+		for (int e = tid; e < 64 * 64; e += 256) {
+			const int k = e >> 6, c = e & 63, i = i0 + k;
+			T v = from_real<T>(0.0);
+			if (i < rows && col0 + c < R) { v = B[(int64_t)i * R + col0 + c]; }
+			Bs[k * 65 + c] = v;
+		}
+	};
+
+	/* pass 1: W1 = V^H B (32 x 64); thread: rows a0 .. a0+3, columns c, c + 32 */
+	const int a0 = (tid >> 5) * 4, c = tid & 31;
+	T w[4][2];
+	#pragma unroll
+	for (int x = 0; x < 4; x++) { w[x][0] = from_real<T>(0.0); w[x][1] = from_real<T>(0.0); }
+	for (int i0 = 0; i0 < rows; i0 += 64)
+	{
+		__syncthreads();
+		load_chunk(i0);
+		__syncthreads();
+		#pragma unroll 4
+		for (int k = 0; k < 64; k++) {
+			const T b0 = Bs[k * 65 + c], b1 = Bs[k * 65 + c + 32];
+			#pragma unroll
+			for (int x = 0; x < 4; x++) {
+				const T va = cj(Vs[k * 33 + a0 + x]);
+				w[x][0] = add(w[x][0], mul(va, b0));
+				w[x][1] = add(w[x][1], mul(va, b1));
+			}
+		}
+	}
+	__syncthreads();
+	#pragma unroll
+	for (int x = 0; x < 4; x++) { Ws[(a0 + x) * 65 + c] = w[x][0]; Ws[(a0 + x) * 65 + c + 32] = w[x][1]; }
+	__syncthreads();
+	/* W2 = T^H W1 (mode 0) or T W1 (mode 1) */
+	#pragma unroll
+	for (int x = 0; x < 4; x++) {
+		T s0 = from_real<T>(0.0), s1 = from_real<T>(0.0);
+		for (int b = 0; b < 32; b++) {
+			const T t = (mode == 0) ? cj(Tfs[b * 33 + a0 + x]) : Tfs[(a0 + x) * 33 + b];
+			s0 = add(s0, mul(t, Ws[b * 65 + c]));
+			s1 = add(s1, mul(t, Ws[b * 65 + c + 32]));
+		}
+		w[x][0] = s0; w[x][1] = s1;
+	}
+	__syncthreads();
+	#pragma unroll
+	for (int x = 0; x < 4; x++) { Ws[(a0 + x) * 65 + c] = w[x][0]; Ws[(a0 + x) * 65 + c + 32] = w[x][1]; }
+
+	/* pass 2: B -= V W2; thread: rows k0 .. k0+7, columns c, c + 32 */
+	const int k0 = (tid >> 5) * 8;
+	for (int i0 = 0; i0 < rows; i0 += 64)
+	{
+		__syncthreads();
+		load_chunk(i0);
+		__syncthreads();
+		T d[8][2];
+		#pragma unroll
+		for (int x = 0; x < 8; x++) { d[x][0] = from_real<T>(0.0); d[x][1] = from_real<T>(0.0); }
+		#pragma unroll 4
+		for (int a = 0; a < 32; a++) {
+			const T w0 = Ws[a * 65 + c], w1 = Ws[a * 65 + c + 32];
+			#pragma unroll
+			for (int x = 0; x < 8; x++) {
+				const T v = Vs[(k0 + x) * 33 + a];
+				d[x][0] = add(d[x][0], mul(v, w0));
+				d[x][1] = add(d[x][1], mul(v, w1));
+			}
+		}
+		#pragma unroll
+		for (int x = 0; x < 8; x++) {
+			const int i = i0 + k0 + x;
+			if (i < rows) {
+				if (col0 + c < R)      { B[(int64_t)i * R + col0 + c]      = sub(Bs[(k0 + x) * 65 + c], d[x][0]); }
+				if (col0 + c + 32 < R) { B[(int64_t)i * R + col0 + c + 32] = sub(Bs[(k0 + x) * 65 + c + 32], d[x][1]); }
+			}
+		}
+	}
+}
+
+/* Qm = [I; 0] (C x R) */
+template <typename T>
+__global__ void __launch_bounds__(256) bj_qinit_kernel(const BjMat* __restrict__ mats, T* __restrict__ Qm)
+{
+	const BjMat mt = mats[blockIdx.y];
+	T* q = Qm + mt.t_off;
+	const int64_t total = (int64_t)mt.R * mt.C;
+	for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+		q[e] = from_real<T>((e / mt.R) == (e % mt.R) ? 1.0 : 0.0);
+	}
+}
+
+/* X = [triu(Rf) | Q^H] */
+template <typename T>
+__global__ void __launch_bounds__(256) bj_extract_kernel(const BjMat* __restrict__ mats, const T* __restrict__ Tm, const T* __restrict__ Qm, T* __restrict__ X)
+{
+	const BjMat mt = mats[blockIdx.y];
+	const T* t = Tm + mt.t_off;
+	const T* q = Qm + mt.t_off;
+	T* x = X + mt.x_off;
+	const int R = mt.R, C = mt.C, ld = mt.ld;
+	const int64_t total = (int64_t)R * ld;
+	for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+	{
+		const int r = (int)(e / ld), k = (int)(e % ld);
+		T v = from_real<T>(0.0);
+		if (k < R) { if (k >= r) { v = t[(int64_t)r * R + k]; } }
+		else if (k < R + C) { v = cj(q[(int64_t)(k - R) * R + r]); }
+		x[e] = v;
+	}
+}
+
+/* ============================================================================================== */
+/* stage 2: block Jacobi                                                                            */
+/* ============================================================================================== */
+
+/* partial Gram matrices of the block pairs of one round: Ppart[item][split] = X_pair[:, k-range] X_pair[:, k-range]^H */
+template <typename T>
+__global__ void __launch_bounds__(128) bj_gram_kernel(const BjMat* __restrict__ mats, int nmat, int round, const int* __restrict__ done,
+	const T* __restrict__ X, T* __restrict__ Ppart, int nsmax)
+{
+	constexpr int S = BjCfg<T>::SG;
+	constexpr int STAGES = 3;
+	constexpr bool CPLX = (sizeof(T) == 16);
+	constexpr int EPC = 16 / (int)sizeof(T);            /* elements per 16-byte chunk */
+	constexpr int CPR = BJ_KT / EPC;                    /* chunks per tile row */
+	constexpr int CPT = BJ_P * CPR / 128;               /* chunks per thread */
+	extern __shared__ __align__(16) unsigned char bj_gram_raw[];
+	T* tiles = reinterpret_cast<T*>(bj_gram_raw);
+
+	const int item = blockIdx.x;
+	const int mi = bj_find(mats, nmat, item);
+	if (done[mi]) { return; }
+	const BjMat mt = mats[mi];
+	const int split = blockIdx.y;
+	if (split >= mt.ksplit) { return; }
+	int I, J;
+	bj_pair(mt.nb + (mt.nb & 1), round, item - mt.item_begin, I, J);
+	const int R = mt.R, ld = mt.ld;
+	const int k_begin = split * BJ_KC, k_end = min(R, k_begin + BJ_KC);
+	const int ntile = (k_end - k_begin + BJ_KT - 1) / BJ_KT;
+	const T* Xm = X + mt.x_off;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int lr = lane >> 2, lc = lane & 3;
+
+	auto issue = [&](int stage, int kt) {
+		T* dst = tiles + (size_t)stage * BJ_P * S;
+		#pragma unroll
+		for (int t = 0; t < CPT; t++) {
+			const int idx = tid + 128 * t;
+			const int row = idx / CPR, ch = idx % CPR;
+			const int grow = (row < BJ_B) ? I * BJ_B + row : J * BJ_B + row - BJ_B;
+			const int k = k_begin + kt * BJ_KT + ch * EPC;
+			int bytes = 0;
+			const T* src = Xm;
+			if (grow < R && k < k_end) {
+				bytes = min(16, (k_end - k) * (int)sizeof(T));
+				src = Xm + (int64_t)grow * ld + k;
+			}
+			bj_cp16(dst + row * S + ch * EPC, src, bytes);
+		}
+	};
+
+	constexpr int NACC = CPLX ? 4 : 2;
+	double acc[4][4][NACC];
+	#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			#pragma unroll
+			for (int x = 0; x < NACC; x++) { acc[i][j][x] = 0.0; }
+		}
+	}
+	const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
+
+	#pragma unroll
+	for (int st = 0; st < STAGES - 1; st++) {
+		if (st < ntile) { issue(st, st); }
+		bj_commit();
+	}
+	for (int kt = 0; kt < ntile; kt++)
+	{
+		bj_wait<STAGES - 2>();
+		__syncthreads();
+		if (kt + STAGES - 1 < ntile) { issue((kt + STAGES - 1) % STAGES, kt + STAGES - 1); }
+		bj_commit();
+		const T* ts = tiles + (size_t)(kt % STAGES) * BJ_P * S;
+		#pragma unroll
+		for (int kk = 0; kk < BJ_KT; kk += 4)
+		{
+			T af[4], bf[4];
+			#pragma unroll
+			for (int i = 0; i < 4; i++) { af[i] = ts[(wr + 8 * i + lr) * S + kk + lc]; }
+			#pragma unroll
+			for (int j = 0; j < 4; j++) { bf[j] = ts[(wc + 8 * j + lr) * S + kk + lc]; }
+			if constexpr (!CPLX) {
+				#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					#pragma unroll
+					for (int j = 0; j < 4; j++) { bj_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]); }
+				}
+			}
+			else {
+				/* a conj(b): re += ar br + ai bi, im += ai br - ar bi */
+				#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					const double ar = af[i].x, ai = af[i].y, nar = -af[i].x;
+					#pragma unroll
+					for (int j = 0; j < 4; j++) {
+						bj_dmma(acc[i][j][0], acc[i][j][1], ar,  bf[j].x);
+						bj_dmma(acc[i][j][0], acc[i][j][1], ai,  bf[j].y);
+						bj_dmma(acc[i][j][2], acc[i][j][3], ai,  bf[j].x);
+						bj_dmma(acc[i][j][2], acc[i][j][3], nar, bf[j].y);
+					}
+				}
+			}
+		}
+	}
+	bj_wait<0>();
+
+	T* out = Ppart + ((size_t)item * nsmax + split) * (BJ_P * BJ_P);
+	#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const int row = wr + 8 * i + lr, col = wc + 8 * j + 2 * lc;
+			if constexpr (!CPLX) {
+				*reinterpret_cast<double2*>(out + row * BJ_P + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+			}
+			else {
+				out[row * BJ_P + col]     = make_double2(acc[i][j][0], acc[i][j][2]);
+				out[row * BJ_P + col + 1] = make_double2(acc[i][j][1], acc[i][j][3]);
+			}
+		}
+	}
+}
+
+/* ---- the pair eigen-problem ----
+ * One CTA of 1024 threads per block pair: sum the partial Gram matrices, test for convergence, then cyclic two-sided Jacobi as a
+ * systolic array (Brent-Luk): the 64 indices sit in 32 fixed slot pairs (2a, 2a+1), thread (a, b) owns the 2 x 2 block of slot pairs
+ * (a, b), computes the rotations of slot pairs a and b itself from the two diagonal blocks (no broadcast step), transforms its block
+ * and stores it where the round-robin permutation sends it; 63 steps bring every index pair together once and the slots back to
+ * their original order.  The same threads rotate and permute the rows of Z (Z P Z^H = diagonal).  Rotation angles are computed in
+ * single precision from exponent-normalised entries (the rotation itself is orthogonal to double precision: c = (1 + t^2)^(-1/2) by
+ * two Newton steps); an inexact angle only leaves a residual of 1e-7 of the entry, removed at the next visit.  At most
+ * 'max_inner' sweeps per visit -- the outer iteration does not converge faster with more (tools/proto_bj2.py).
+ * Z (64 x 64) goes to Zbuf, flag = 1 when the pair has to be updated. */
+static constexpr int BJ_EIG_THREADS = 1024;
+static constexpr int BJ_PS = BJ_P + 2;      /* shared-memory row stride of P and Z (even: 16-byte loads of column pairs) */
+
+/* x^(-1/2) for normal positive x: single-precision seed on the exponent-normalised argument, two Newton steps */
+__device__ __forceinline__ double bj_rsqrt(double x)
+{
+	const int hi = __double2hiint(x);
+	const int e = ((hi >> 20) & 0x7ff) - 1023;
+	const int e2 = e & ~1;                                    /* even part of the exponent */
+	const double xn = __hiloint2double(hi - e2 * (1 << 20), __double2loint(x));      /* x 2^-e2 in [1, 4) */
+	double y = (double)rsqrtf((float)xn);
+	y = y * (1.5 - 0.5 * xn * y * y);
+	y = y * (1.5 - 0.5 * xn * y * y);
+	return __hiloint2double(__double2hiint(y) - (e2 / 2) * (1 << 20), __double2loint(y));
+}
+
+/* plane rotation of an index pair with diagonal entries app, aqq and coupling g (phase removed: g = |g| ph):
+ * t = tan of the annihilating angle in single precision, c, s in double.  Returns false (identity) below the threshold. */
+template <typename T>
+__device__ __forceinline__ bool bj_rotation(double app, double aqq, T g, double tol2, double& c, double& s, T& ph)
+{
+	const double g2 = abs2(g);
+	c = 1.0; s = 0.0; ph = from_real<T>(1.0);
+	if (!(g2 > tol2 * fabs(app * aqq)) || g2 < 1e-290) { return false; }
+	double ag;
+	if constexpr (sizeof(T) == 8) { ag = g; }                 /* real: the sign stays in t */
+	else { const double r = bj_rsqrt(g2); ag = g2 * r; ph = smul(r, g); }
+	const double d = aqq - app, h = 2.0 * ag;
+	/* normalise by the exponent of the larger of |d|, |h| */
+	const double mx = fmax(fabs(d), fabs(h));
+	const int em = ((__double2hiint(mx) >> 20) & 0x7ff);
+	const double scl = __hiloint2double((2046 - em) << 20, 0);      /* 2^(1023 - em) */
+	const float df = (float)(d * scl), hf = (float)(h * scl);
+	const float rf = sqrtf(df * df + hf * hf);
+	const float tf = __fdividef(copysignf(hf, df >= 0.f ? hf : -hf), fabsf(df) + rf);
+	const double t = (double)tf;
+	const double w = 1.0 + t * t;
+	double y = (double)rsqrtf((float)w);
+	y = y * (1.5 - 0.5 * w * y * y);
+	y = y * (1.5 - 0.5 * w * y * y);
+	c = y; s = y * t;
+	return true;
+}
+
+/* round robin over 32 slot pairs (top row = even slots, bottom row = odd slots): per step slot 0 stays, the data of the other 63
+ * slots advance along the cycle 1, 2, 4, ..., 62, 63, 61, ..., 3.  bj_home = original index of the datum in slot s after k steps. */
+__device__ __forceinline__ int bj_cyc(int i) { return i == 0 ? 1 : (i <= 31 ? 2 * i : 127 - 2 * i); }
+__device__ __forceinline__ int bj_pos(int s) { return s == 1 ? 0 : ((s & 1) == 0 ? (s >> 1) : 63 - (s >> 1)); }
+__device__ __forceinline__ int bj_home(int s, int k) { return s == 0 ? 0 : bj_cyc((bj_pos(s) - k + 63) % 63); }
+
+__device__ __forceinline__ double  bj_shfl_up(double v)   { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double  bj_shfl_down(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double2 bj_shfl_up(double2 v)   { return make_double2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1)); }
+__device__ __forceinline__ double2 bj_shfl_down(double2 v) { return make_double2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1)); }
+
+/* two neighbouring entries of a shared-memory row (16-byte aligned for real entries) */
+__device__ __forceinline__ void bj_ld2(const double* p, double& a, double& b)  { const double2 v = *reinterpret_cast<const double2*>(p); a = v.x; b = v.y; }
+__device__ __forceinline__ void bj_st2(double* p, double a, double b)          { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+__device__ __forceinline__ void bj_ld2(const double2* p, double2& a, double2& b) { a = p[0]; b = p[1]; }
+__device__ __forceinline__ void bj_st2(double2* p, double2 a, double2 b)         { p[0] = a; p[1] = b; }
+
+/* y = ph x; for real entries the phase is 1 */
+__device__ __forceinline__ double  bj_phase(double, double x)    { return x; }
+__device__ __forceinline__ double2 bj_phase(double2 ph, double2 x) { return mul(ph, x); }
+
+/* Layout of the iteration: the ROWS of P and Z stay at their original index (the slot -> row map is the closed form bj_home), the
+ * COLUMNS of P are physically in slot order: thread (a, b) = (warp, lane) loads the two rows of slot pair a at the column pair of
+ * slot pair b as 16-byte accesses, applies the row rotation of a and the column rotation of b, passes the columns on to the
+ * neighbouring lanes by warp shuffles (the round-robin move) and stores in place -- no thread touches another thread's entries
+ * between the two barriers of a step.  Z only moves when its row pair is rotated. */
+template <typename T>
+__global__ void __launch_bounds__(BJ_EIG_THREADS, (sizeof(T) == 8 ? 2 : 1)) bj_eig_kernel(const BjMat* __restrict__ mats, int nmat, int round, const int* __restrict__ done,
+	const T* __restrict__ Ppart, int nsmax, int max_inner, T* __restrict__ Zbuf, int* __restrict__ flag, int* __restrict__ last_active)
+{
+	extern __shared__ __align__(16) unsigned char bj_eig_raw[];
+	T* Ps = reinterpret_cast<T*>(bj_eig_raw);
+	T* Zs = Ps + BJ_P * BJ_PS;
+	__shared__ double red[BJ_EIG_THREADS / 32];
+	__shared__ double s_c[32], s_s[32];
+	__shared__ T s_ph[32];
+	__shared__ int s_act[32], s_hp[32], s_hq[32];
+	__shared__ int s_nrot;
+
+	const int item = blockIdx.x, tid = threadIdx.x;
+	const int mi = bj_find(mats, nmat, item);
+	if (done[mi]) { if (tid == 0) { flag[item] = 0; } return; }
+	const BjMat mt = mats[mi];
+	const double tol = DBL_EPSILON * sqrt((double)max(mt.R, 256));
+	const double tol2 = tol * tol;
+
+	const T* pp = Ppart + (size_t)item * nsmax * (BJ_P * BJ_P);
+	for (int e = tid; e < BJ_P * BJ_P; e += BJ_EIG_THREADS) {
+		const int i = e >> 6, j = e & 63;
+		if (i <= j) {
+			T v = pp[e];
+			for (int sp = 1; sp < mt.ksplit; sp++) { v = add(v, pp[(size_t)sp * (BJ_P * BJ_P) + e]); }
+			if (i == j) { v = from_real<T>(re(v)); }
+			Ps[i * BJ_PS + j] = v;
+			if (i < j) { Ps[j * BJ_PS + i] = cj(v); }
+		}
+		Zs[i * BJ_PS + j] = from_real<T>(i == j ? 1.0 : 0.0);
+	}
+	if (tid == 0) { s_nrot = 0; }
+	__syncthreads();
+
+	/* largest relative overlap of two rows of the pair */
+	double v = 0;
+	for (int e = tid; e < BJ_P * BJ_P; e += BJ_EIG_THREADS) {
+		const int i = e >> 6, j = e & 63;
+		if (i < j) {
+			const double g2 = abs2(Ps[i * BJ_PS + j]);
+			const double d = re(Ps[i * BJ_PS + i]) * re(Ps[j * BJ_PS + j]);
+			if (g2 > 0.0 && d > 0.0) { v = fmax(v, g2 / d); }
+		}
+	}
+	const double vmax = block_max(v, red);
+	if (vmax <= tol2) { if (tid == 0) { flag[item] = 0; } return; }
+
+	const int al = tid >> 5, be = tid & 31;
+	const int cb2 = 2 * be;
+	int nrot_prev = 0, nrot_seen = 0;
+	for (int sweep = 0; sweep < max_inner; sweep++)
+	{
+		for (int step = 0; step < BJ_P - 1; step++)
+		{
+			if (tid < 32) {
+				const int r2 = 2 * tid;
+				const int hp = bj_home(r2, step), hq = bj_home(r2 + 1, step);
+				double c, sn; T ph;
+				const bool act = bj_rotation<T>(re(Ps[hp * BJ_PS + r2]), re(Ps[hq * BJ_PS + r2 + 1]), Ps[hp * BJ_PS + r2 + 1], tol2, c, sn, ph);
+				s_c[tid] = c; s_s[tid] = sn; s_ph[tid] = ph; s_act[tid] = act ? 1 : 0; s_hp[tid] = hp; s_hq[tid] = hq;
+				const unsigned bal = __ballot_sync(0xffffffffu, act);
+				if (tid == 0) { s_nrot += __popc(bal); }
+			}
+			__syncthreads();
+			nrot_seen = s_nrot;       /* stable until the next step's rotation phase, which follows this step's last barrier */
+			const bool acta = (s_act[al] != 0), actb = (s_act[be] != 0);
+			T* prow = Ps + s_hp[al] * BJ_PS + cb2;
+			T* qrow = Ps + s_hq[al] * BJ_PS + cb2;
+			T n00, n01, n10, n11;
+			bj_ld2(prow, n00, n01);
+			bj_ld2(qrow, n10, n11);
+			if (acta) {
+				/* rows: r0 = ca b0 - sa (pha b1), r1 = sa b0 + ca (pha b1); the same on the rows of Z */
+				const double ca = s_c[al], sa = s_s[al];
+				const T pha = s_ph[al];
+				const T y0 = bj_phase(pha, n10), y1 = bj_phase(pha, n11);
+				n10 = add(smul(sa, n00), smul(ca, y0)); n11 = add(smul(sa, n01), smul(ca, y1));
+				n00 = sub(smul(ca, n00), smul(sa, y0)); n01 = sub(smul(ca, n01), smul(sa, y1));
+				T* zp = Zs + s_hp[al] * BJ_PS + cb2;
+				T* zq = Zs + s_hq[al] * BJ_PS + cb2;
+				T z00, z01, z10, z11;
+				bj_ld2(zp, z00, z01);
+				bj_ld2(zq, z10, z11);
+				const T w0 = bj_phase(pha, z10), w1 = bj_phase(pha, z11);
+				bj_st2(zq, add(smul(sa, z00), smul(ca, w0)), add(smul(sa, z01), smul(ca, w1)));
+				bj_st2(zp, sub(smul(ca, z00), smul(sa, w0)), sub(smul(ca, z01), smul(sa, w1)));
+			}
+			if (actb) {
+				/* columns: c0' = cb c0 - sb conj(phb) c1, c1' = sb c0 + cb conj(phb) c1 */
+				const double cb = s_c[be], sb = s_s[be];
+				const T cphb = cj(s_ph[be]);
+				const T u0 = bj_phase(cphb, n01), u1 = bj_phase(cphb, n11);
+				n01 = add(smul(sb, n00), smul(cb, u0)); n11 = add(smul(sb, n10), smul(cb, u1));
+				n00 = sub(smul(cb, n00), smul(sb, u0)); n10 = sub(smul(cb, n10), smul(sb, u1));
+			}
+			if (al == be && acta) { n00 = from_real<T>(re(n00)); n11 = from_real<T>(re(n11)); n10 = cj(n01); }
+			/* round-robin move of the columns: lane g receives column 2g from lane g-1 and column 2g+1 from lane g+1 */
+			{
+				const T up0 = bj_shfl_up(be == 0 ? n01 : n00), dn0 = bj_shfl_down(n01);
+				const T up1 = bj_shfl_up(be == 0 ? n11 : n10), dn1 = bj_shfl_down(n11);
+				bj_st2(prow, be == 0 ? n00 : up0, be == 31 ? n00 : dn0);
+				bj_st2(qrow, be == 0 ? n10 : up1, be == 31 ? n10 : dn1);
+			}
+			__syncthreads();
+		}
+		if (nrot_seen == nrot_prev) { break; }
+		nrot_prev = nrot_seen;
+	}
+
+	T* z = Zbuf + (size_t)item * (BJ_P * BJ_P);
+	for (int e = tid; e < BJ_P * BJ_P; e += BJ_EIG_THREADS) { z[e] = Zs[(e >> 6) * BJ_PS + (e & 63)]; }
+	if (tid == 0) { flag[item] = 1; atomicMax(&last_active[mi], round + 1); }
+}
+
+/* X_pair[:, chunk] <- Z X_pair[:, chunk] for the active pairs of the round */
+template <typename T>
+__global__ void __launch_bounds__(128) bj_update_kernel(const BjMat* __restrict__ mats, int nmat, int round, const int* __restrict__ flag,
+	const T* __restrict__ Zbuf, T* __restrict__ X)
+{
+	constexpr int SZ = BjCfg<T>::SZ, NC = BjCfg<T>::NCU, SX = BjCfg<T>::SXU;
+	constexpr bool CPLX = (sizeof(T) == 16);
+	constexpr int EPC = 16 / (int)sizeof(T);
+	extern __shared__ __align__(16) unsigned char bj_upd_raw[];
+	T* Zs = reinterpret_cast<T*>(bj_upd_raw);      /* [64][SZ] */
+	T* Xs = Zs + BJ_P * SZ;                         /* [64][SX] */
+
+	const int item = blockIdx.x;
+	if (flag[item] == 0) { return; }
+	const int mi = bj_find(mats, nmat, item);
+	const BjMat mt = mats[mi];
+	const int ld = mt.ld, R = mt.R;
+	const int col0 = blockIdx.y * NC;
+	if (col0 >= ld) { return; }
+	int I, J;
+	bj_pair(mt.nb + (mt.nb & 1), round, item - mt.item_begin, I, J);
+	T* Xm = X + mt.x_off;
+	const T* z = Zbuf + (size_t)item * (BJ_P * BJ_P);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int lr = lane >> 2, lc = lane & 3;
+
+	{
+		constexpr int CPRZ = BJ_P / EPC;
+		for (int idx = tid; idx < BJ_P * CPRZ; idx += 128) {
+			const int row = idx / CPRZ, ch = idx % CPRZ;
+			bj_cp16(Zs + row * SZ + ch * EPC, z + row * BJ_P + ch * EPC, 16);
+		}
+		constexpr int CPRX = NC / EPC;
+		for (int idx = tid; idx < BJ_P * CPRX; idx += 128) {
+			const int row = idx / CPRX, ch = idx % CPRX;
+			const int grow = (row < BJ_B) ? I * BJ_B + row : J * BJ_B + row - BJ_B;
+			const int k = col0 + ch * EPC;
+			int bytes = 0;
+			const T* src = Xm;
+			if (grow < R && k < ld) { bytes = min(16, (ld - k) * (int)sizeof(T)); src = Xm + (int64_t)grow * ld + k; }
+			bj_cp16(Xs + row * SX + ch * EPC, src, bytes);
+		}
+		bj_commit();
+		bj_wait<0>();
+		__syncthreads();
+	}
+
+	/* warp tile: 32 rows x NC/2 columns */
+	constexpr int NJ = NC / 2 / 8;
+	constexpr int NACC = CPLX ? 4 : 2;
+	const int wr = (warp >> 1) * 32, wc = (warp & 1) * (NC / 2);
+	double acc[4][NJ][NACC];
+	#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		#pragma unroll
+		for (int j = 0; j < NJ; j++) {
+			#pragma unroll
+			for (int x = 0; x < NACC; x++) { acc[i][j][x] = 0.0; }
+		}
+	}
+	#pragma unroll 4
+	for (int kk = 0; kk < BJ_P; kk += 4)
+	{
+		T af[4], bf[NJ];
+		#pragma unroll
+		for (int i = 0; i < 4; i++) { af[i] = Zs[(wr + 8 * i + lr) * SZ + kk + lc]; }
+		#pragma unroll
+		for (int j = 0; j < NJ; j++) { bf[j] = Xs[(kk + lc) * SX + wc + 8 * j + lr]; }
+		if constexpr (!CPLX) {
+			#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				#pragma unroll
+				for (int j = 0; j < NJ; j++) { bj_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]); }
+			}
+		}
+		else {
+			#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const double ar = af[i].x, ai = af[i].y, nai = -af[i].y;
+				#pragma unroll
+				for (int j = 0; j < NJ; j++) {
+					bj_dmma(acc[i][j][0], acc[i][j][1], ar,  bf[j].x);
+					bj_dmma(acc[i][j][0], acc[i][j][1], nai, bf[j].y);
+					bj_dmma(acc[i][j][2], acc[i][j][3], ar,  bf[j].y);
+					bj_dmma(acc[i][j][2], acc[i][j][3], ai,  bf[j].x);
+				}
+			}
+		}
+	}
+	#pragma unroll
+	for (int i = 0; i < 4; i++)
+	{
+		const int row = wr + 8 * i + lr;
+		const int grow = (row < BJ_B) ? I * BJ_B + row : J * BJ_B + row - BJ_B;
+		if (grow >= R) { continue; }
+		T* dst = Xm + (int64_t)grow * ld;
+		#pragma unroll
+		for (int j = 0; j < NJ; j++)
+		{
+			const int k = col0 + wc + 8 * j + 2 * lc;
+			if constexpr (!CPLX) {
+				if (k + 1 < ld) { *reinterpret_cast<double2*>(dst + k) = make_double2(acc[i][j][0], acc[i][j][1]); }
+				else if (k < ld) { dst[k] = acc[i][j][0]; }
+			}
+			else {
+				if (k < ld)     { dst[k]     = make_double2(acc[i][j][0], acc[i][j][2]); }
+				if (k + 1 < ld) { dst[k + 1] = make_double2(acc[i][j][1], acc[i][j][3]); }
+			}
+		}
+	}
+}
+
+/* a block is finished when a full cycle of its tournament passed without an active pair; pending = number of unfinished blocks */
+static __global__ void bj_mark_kernel(const BjMat* __restrict__ mats, int nmat, int rounds_done, const int* __restrict__ last_active, int* __restrict__ done, int* __restrict__ pending)
+{
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nmat) { return; }
+	if (!done[b]) {
+		if (rounds_done - last_active[b] >= mats[b].N1) { done[b] = 1; }
+		else { atomicAdd(pending, 1); }
+	}
+}
+
+/* ============================================================================================== */
+/* stage 3: singular values and vectors                                                             */
+/* ============================================================================================== */
+
+/* sig[i] = norm of row i of G, wn[i] = 1 / norm of row i of W (removes the O(#transformations) eps drift of its length) */
+template <typename T>
+__global__ void __launch_bounds__(256) bj_norm_kernel(const BjMat* __restrict__ mats, const T* __restrict__ X, double* __restrict__ sig_work, double* __restrict__ wn_work)
+{
+	const BjMat mt = mats[blockIdx.y];
+	const int R = mt.R, C = mt.C, ld = mt.ld;
+	const T* x = X + mt.x_off;
+	double* sig = sig_work + mt.s_off;
+	double* wn = wn_work + mt.s_off;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+	for (int i = blockIdx.x * nwarp + warp; i < R; i += gridDim.x * nwarp) {
+		double s = 0, w = 0;
+		for (int k = lane; k < R; k += 32) { s += abs2(x[(int64_t)i * ld + k]); }
+		for (int k = lane; k < C; k += 32) { w += abs2(x[(int64_t)i * ld + R + k]); }
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); w += __shfl_xor_sync(0xffffffffu, w, o); }
+		if (lane == 0) { sig[i] = sqrt(s); wn[i] = (w > 0) ? 1.0 / sqrt(w) : 1.0; }
+	}
+}
+
+/* rank sort of the singular values of every block, descending, ties by index (LAPACK order); S = sorted values, unscaled */
+static __global__ void __launch_bounds__(256) bj_rank_kernel(const BjMat* __restrict__ mats, const double* __restrict__ amax, const double* __restrict__ sig_work,
+	int* __restrict__ ord_work, double* __restrict__ S)
+{
+	const BjMat mt = mats[blockIdx.y];
+	const int R = mt.R;
+	const double* sig = sig_work + mt.s_off;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R) { return; }
+	const double si = sig[i];
+	int rank = 0;
+	for (int j = 0; j < R; j++) { const double sj = sig[j]; rank += (sj > si || (sj == si && j < i)) ? 1 : 0; }
+	ord_work[mt.s_off + rank] = i;
+	S[mt.s_off + rank] = si / pow2_scale(amax[blockIdx.y]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bj_write_kernel(const BjMat* __restrict__ mats, const T* __restrict__ X,
+	const double* __restrict__ sig_work, const double* __restrict__ wn_work, const int* __restrict__ ord_work, T* __restrict__ U, T* __restrict__ Vh)
+{
+	const BjMat mt = mats[blockIdx.y];
+	const int R = mt.R, ld = mt.ld, m = mt.m, n = mt.n;
+	const T* x = X + mt.x_off;
+	const double* sig = sig_work + mt.s_off;
+	const double* wn = wn_work + mt.s_off;
+	const int* ord = ord_work + mt.s_off;
+	const bool wide = (m <= n);
+	T* u = U + mt.u_off;
+	T* vh = Vh + mt.vh_off;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	/* Vh: R x n */
+	for (int64_t e = first; e < (int64_t)R * n; e += stride) {
+		const int r = (int)(e / n), k = (int)(e % n);
+		const int i = ord[r];
+		if (wide) { vh[e] = smul(wn[i], x[(int64_t)i * ld + R + k]); }
+		else      { const double s = sig[i]; vh[e] = smul(s > 0 ? 1.0 / s : 0.0, x[(int64_t)i * ld + k]); }
+	}
+	/* U: m x R, U[k][r]; the index runs over (r, k) so that the reads are contiguous */
+	for (int64_t e = first; e < (int64_t)m * R; e += stride) {
+		const int r = (int)(e / m), k = (int)(e % m);
+		const int i = ord[r];
+		if (wide) { const double s = sig[i]; u[(int64_t)k * R + r] = smul(s > 0 ? 1.0 / s : 0.0, cj(x[(int64_t)i * ld + k])); }
+		else      { u[(int64_t)k * R + r] = smul(wn[i], cj(x[(int64_t)i * ld + R + k])); }
+	}
+}
+
+/* ============================================================================================== */
+/* host driver                                                                                      */
+/* ============================================================================================== */
+
+template <typename T>
+int svd_bj_impl(int nmat, const ctbd_mat_desc* descs, const void* A, void* U, void* Vh, double* S)
+{
+	if (nmat == 0) { return 0; }
+	std::vector<BjMat> mats(nmat);
+	int64_t x_total = 0, t_total = 0, tf_total = 0, smax = 0;
+	int items = 0, Rmax = 0, ldmax = 0, nsmax = 1, panels_max = 0;
+	for (int b = 0; b < nmat; b++)
+	{
+		BjMat& mt = mats[b];
+		mt.a_off = descs[b].a_off; mt.u_off = descs[b].o0_off; mt.vh_off = descs[b].o1_off; mt.s_off = descs[b].s_off;
+		mt.m = descs[b].m; mt.n = descs[b].n;
+		mt.R = std::min(mt.m, mt.n); mt.C = std::max(mt.m, mt.n);
+		mt.ld = (mt.R + mt.C + 1) & ~1;
+		mt.x_off = x_total; x_total += (int64_t)mt.R * mt.ld;
+		mt.t_off = t_total; t_total += (int64_t)mt.R * mt.C;
+		mt.npanel = (mt.R + QR_NB - 1) / QR_NB;
+		mt.tf_off = tf_total; tf_total += (int64_t)mt.npanel * 1024;
+		mt.nb = (mt.R + BJ_B - 1) / BJ_B;
+		const int N = mt.nb + (mt.nb & 1);
+		mt.N1 = std::max(1, N - 1);
+		mt.nitem = std::max(1, N / 2);
+		mt.item_begin = items; items += mt.nitem;
+		mt.ksplit = (mt.R + BJ_KC - 1) / BJ_KC;
+		Rmax = std::max(Rmax, mt.R); ldmax = std::max(ldmax, mt.ld);
+		nsmax = std::max(nsmax, mt.ksplit); panels_max = std::max(panels_max, mt.npanel);
+		smax = std::max(smax, mt.s_off + mt.R);
+	}
+	cudaStream_t st = rt().stream;
+	void *d_mats = nullptr, *d_X = nullptr, *d_T = nullptr, *d_Q = nullptr, *d_Tf = nullptr, *d_scale = nullptr, *d_P = nullptr, *d_Z = nullptr,
+		*d_int = nullptr, *d_sig = nullptr, *d_aoff = nullptr, *d_numel = nullptr;
+	auto cleanup = [&]() {
+		ctbd_free(d_numel); ctbd_free(d_aoff); ctbd_free(d_sig); ctbd_free(d_int); ctbd_free(d_Z); ctbd_free(d_P); ctbd_free(d_scale);
+		ctbd_free(d_Tf); ctbd_free(d_Q); ctbd_free(d_T); ctbd_free(d_X); ctbd_free(d_mats);
+	};
+	bool ok = upload(mats.data(), (size_t)nmat * sizeof(BjMat), &d_mats) == 0;
+	ok = ok && ctbd_malloc_noinit(&d_X, (size_t)x_total * sizeof(T)) == 0;
+	ok = ok && ctbd_malloc_noinit(&d_T, (size_t)t_total * sizeof(T)) == 0;
+	ok = ok && ctbd_malloc_noinit(&d_Q, (size_t)t_total * sizeof(T)) == 0;
+	ok = ok && ctbd_malloc_noinit(&d_Tf, (size_t)tf_total * sizeof(T)) == 0;
+	ok = ok && ctbd_malloc(&d_scale, (size_t)nmat * sizeof(double)) == 0;
+	ok = ok && ctbd_malloc_noinit(&d_P, (size_t)items * nsmax * BJ_P * BJ_P * sizeof(T)) == 0;
+	ok = ok && ctbd_malloc_noinit(&d_Z, (size_t)items * BJ_P * BJ_P * sizeof(T)) == 0;
+	/* ints: flag[items], last_active[nmat], done[nmat], pending[1], ord[smax] */
+	ok = ok && ctbd_malloc(&d_int, (size_t)(items + 2 * nmat + 1 + smax) * sizeof(int)) == 0;
+	ok = ok && ctbd_malloc(&d_sig, (size_t)2 * smax * sizeof(double)) == 0;
+	if (!ok) { cleanup(); return -1; }
+	int* flag = (int*)d_int; int* last_active = flag + items; int* done = last_active + nmat; int* pending = done + nmat; int* ord = pending + 1;
+	const BjMat* dm = (const BjMat*)d_mats;
+
+	static bool attr_done = false;
+	const int smem_apply = (int)((64 * 33 + 64 * 65 + 32 * 65 + 32 * 33) * sizeof(T));
+	const int smem_gram = (int)(3 * BJ_P * BjCfg<T>::SG * sizeof(T));
+	const int smem_eig = (int)(2 * BJ_P * BJ_PS * sizeof(T));
+	const int smem_upd = (int)((BJ_P * BjCfg<T>::SZ + BJ_P * BjCfg<T>::SXU) * sizeof(T));
+	if (!attr_done) {
+		cudaFuncSetAttribute(bj_qr_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_apply);
+		cudaFuncSetAttribute(bj_gram_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gram);
+		cudaFuncSetAttribute(bj_eig_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_eig);
+		cudaFuncSetAttribute(bj_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_upd);
+		attr_done = true;
+	}
+	int rc = 0;
+	auto check = [&](const char* what) {
+		rt().launches++;
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess && rc == 0) { rc = fail(what, e, __FILE__, __LINE__); }
+	};
+
+	/* CTB_SVD_PROFILE=1: wall time per stage (synchronising), printed to stderr */
+	const bool prof = (getenv("CTB_SVD_PROFILE") != nullptr);
+	auto now_ms = [&]() { cudaStreamSynchronize(st); struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+	double t_start = prof ? now_ms() : 0.0, t_qr = 0.0;
+
+	/* ---- stage 1 ---- */
+	const dim3 egrid(64, (unsigned)nmat);
+	bj_absmax_kernel<T><<<egrid, 256, 0, st>>>(dm, (const T*)A, (double*)d_scale); check("bj_absmax_kernel");
+	bj_load_kernel<T><<<egrid, 256, 0, st>>>(dm, (const double*)d_scale, (const T*)A, (T*)d_T); check("bj_load_kernel");
+	bj_qinit_kernel<T><<<egrid, 256, 0, st>>>(dm, (T*)d_Q); check("bj_qinit_kernel");
+	const dim3 agrid((unsigned)((Rmax + QR_CB - 1) / QR_CB), (unsigned)nmat);
+	for (int p = 0; p < panels_max && rc == 0; p++) {
+		bj_qr_panel_kernel<T><<<nmat, dim3(32, 32), 0, st>>>(dm, p, (T*)d_T, (T*)d_Tf); check("bj_qr_panel_kernel");
+		if ((p + 1) * QR_NB < Rmax) {
+			bj_qr_apply_kernel<T><<<agrid, 256, smem_apply, st>>>(dm, p, 0, (const T*)d_T, (const T*)d_Tf, (T*)d_T); check("bj_qr_apply_kernel");
+		}
+	}
+	for (int p = panels_max - 1; p >= 0 && rc == 0; p--) {
+		bj_qr_apply_kernel<T><<<agrid, 256, smem_apply, st>>>(dm, p, 1, (const T*)d_T, (const T*)d_Tf, (T*)d_Q); check("bj_qr_apply_kernel");
+	}
+	bj_extract_kernel<T><<<egrid, 256, 0, st>>>(dm, (const T*)d_T, (const T*)d_Q, (T*)d_X); check("bj_extract_kernel");
+
+	if (prof) { t_qr = now_ms(); fprintf(stderr, "[svd_bj] %d blocks, Rmax %d, sum R^2 C %.3e: QR stage %.2f ms (%d panels)\n", nmat, Rmax,
+		[&]() { double f = 0; for (int b = 0; b < nmat; b++) { f += (double)mats[b].R * mats[b].R * mats[b].C; } return f; }(), t_qr - t_start, panels_max); }
+
+	/* ---- stage 2 ---- */
+	const int max_cycles = 60;
+	int max_inner = 1;      /* knob: CTB_SVD_INNER_SWEEPS */
+	if (getenv("CTB_SVD_INNER_SWEEPS") != nullptr) { max_inner = std::max(1, atoi(getenv("CTB_SVD_INNER_SWEEPS"))); }
+	int round = 0;
+	bool converged = (Rmax < 2);
+	std::vector<int> h_done(nmat, 0);
+	for (int cyc = 0; cyc < max_cycles && rc == 0 && !converged; cyc++)
+	{
+		int nrounds = 1;
+		for (int b = 0; b < nmat; b++) { if (!h_done[b]) { nrounds = std::max(nrounds, mats[b].N1); } }
+		for (int r = 0; r < nrounds && rc == 0; r++, round++)
+		{
+			bj_gram_kernel<T><<<dim3((unsigned)items, (unsigned)nsmax), 128, smem_gram, st>>>(dm, nmat, round, done, (const T*)d_X, (T*)d_P, nsmax); check("bj_gram_kernel");
+			bj_eig_kernel<T><<<items, BJ_EIG_THREADS, smem_eig, st>>>(dm, nmat, round, done, (const T*)d_P, nsmax, max_inner, (T*)d_Z, flag, last_active);
+			check("bj_eig_kernel");
+			bj_update_kernel<T><<<dim3((unsigned)items, (unsigned)((ldmax + BjCfg<T>::NCU - 1) / BjCfg<T>::NCU)), 128, smem_upd, st>>>(dm, nmat, round, flag, (const T*)d_Z, (T*)d_X); check("bj_update_kernel");
+		}
+		if (rc < 0) { break; }
+		if (cudaMemsetAsync(pending, 0, sizeof(int), st) != cudaSuccess) { rc = fail_msg("block-Jacobi SVD: memset failed"); break; }
+		bj_mark_kernel<<<(nmat + 127) / 128, 128, 0, st>>>(dm, nmat, round, last_active, done, pending); check("bj_mark_kernel");
+		if (ctbd_d2h(h_done.data(), done, (size_t)nmat * sizeof(int)) < 0) { rc = -1; break; }
+		converged = true;
+		for (int b = 0; b < nmat; b++) { converged = converged && (h_done[b] != 0); }
+		if (prof) {
+			int nd = 0; for (int b = 0; b < nmat; b++) { nd += h_done[b]; }
+			fprintf(stderr, "[svd_bj]   cycle %d: %d rounds, %d / %d blocks finished, t = %.2f ms\n", cyc, nrounds, nd, nmat, now_ms() - t_qr);
+		}
+	}
+	if (rc == 0 && !converged) { rc = fail_msg("block-Jacobi SVD: not converged after 60 tournament cycles"); }
+
+	/* ---- stage 3 ---- */
+	if (rc == 0) {
+		bj_norm_kernel<T><<<egrid, 256, 0, st>>>(dm, (const T*)d_X, (double*)d_sig, (double*)d_sig + smax); check("bj_norm_kernel");
+		bj_rank_kernel<<<dim3((unsigned)((Rmax + 255) / 256), (unsigned)nmat), 256, 0, st>>>(dm, (const double*)d_scale, (const double*)d_sig, ord, S); check("bj_rank_kernel");
+		bj_write_kernel<T><<<dim3(32, (unsigned)nmat), 256, 0, st>>>(dm, (const T*)d_X, (const double*)d_sig, (const double*)d_sig + smax, ord, (T*)U, (T*)Vh); check("bj_write_kernel");
+	}
+	if (prof) { fprintf(stderr, "[svd_bj] total %.2f ms (%d rounds)\n", now_ms() - t_start, round); }
+	cleanup();
+	return rc;
+}
+
+template int svd_bj_impl<double>(int, const ctbd_mat_desc*, const void*, void*, void*, double*);
+template int svd_bj_impl<double2>(int, const ctbd_mat_desc*, const void*, void*, void*, double*);
+
+} // namespace ctbd

@@ -68,6 +68,7 @@ int ctbd_event_destroy(void* ev);
 /* ---- memory -------------------------------------------------------------------------------- */
 
 int ctbd_malloc(void** dptr, size_t bytes);          /* zero-initialised device memory */
+int ctbd_malloc_noinit(void** dptr, size_t bytes);   /* the same without the zero fill: for buffers the caller overwrites completely */
 int ctbd_free(void* dptr);
 int ctbd_memset_zero(void* dptr, size_t bytes);
 int ctbd_h2d(void* dptr, const void* hptr, size_t bytes);

@@ -46,6 +46,13 @@ int ctbd_malloc(void** dptr, size_t bytes)
 	*dptr = h + 1;
 	return 0;
 }
+/* the test double poisons un-initialised memory (all-ones bytes = NaN doubles) so that the CPU suite catches reads of it */
+int ctbd_malloc_noinit(void** dptr, size_t bytes)
+{
+	int rc = ctbd_malloc(dptr, bytes);
+	if (rc == 0) { memset(*dptr, 0xFF, bytes); }
+	return rc;
+}
 int ctbd_free(void* dptr) { if (dptr) { struct hdr* h = (struct hdr*)dptr - 1; g_bytes -= (long long)h->bytes; free(h); } return 0; }
 int ctbd_memset_zero(void* dptr, size_t bytes) { memset(dptr, 0, bytes); return 0; }
 int ctbd_h2d(void* d, const void* h, size_t bytes) { memcpy(d, h, bytes); return 0; }
