@@ -157,9 +157,13 @@ def run_reference(args):
     wl = args.workload
     if not os.path.exists(REF_SO):
         subprocess.run(["make", "-s", "-C", ROOT, "oracle"], check=False)
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the reference must get all host cores, so the variable is
+    # set BEFORE the library (and with it libgomp) is loaded, and the count the runtime really uses is what gets reported
+    want = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(want)
+    os.environ.pop("OMP_PROC_BIND", None)
     ref = cabi.CLibrary(REF_SO)
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = omp_threads(want)
     a, w, l, r = build_operands(ref, wl, structure=args.structure)
     flops = heff_flops_host(a, w, l, r)
     # bound the CPU work: cap the number of timed calls so that the arm ends within a few minutes
@@ -189,6 +193,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def omp_threads(want: int) -> int:
+    """Set and read back the OpenMP thread count of this process (libgomp is already mapped by the reference library)."""
+    try:
+        gomp = C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL)
+        gomp.omp_set_num_threads(C.c_int(want))
+        gomp.omp_get_max_threads.restype = C.c_int
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return int(os.environ.get("OMP_NUM_THREADS", "1"))
+
+
 def heff_flops_host(a, w, l, r) -> float:
     """Algorithmic flops of one matvec from sector metadata alone (integer exact): the three contractions of chain_ops.c:353-390."""
     from chemtensor_b200.flops import heff_flops
@@ -204,7 +219,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("CTB_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
     ap.add_argument("--structure", default="converged", choices=["converged", "random"],
                     help="sector structure of the synthetic operands: measured from converged sweeps (default) or the random-MPS rule")
-    ap.add_argument("--sweep", action="store_true", help="also report two-site DMRG sweep seconds (engine, and reference on the small case)")
+    ap.add_argument("--sweep", dest="sweep", action="store_true", default=True, help="report two-site DMRG sweep seconds as well (default; single GPU)")
+    ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the sweep block (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -264,6 +280,11 @@ def main():
             flops_total = float(tf_.item())
         # e2e through the reference-named C-ABI entry point with host structs
         e2e = None
+        b_sharded = None
+        if world > 1 and rank == 0 and not args.no_cpu_baseline:
+            b = cabi.BST(lib); lib.apply_local_hamiltonian(a.ptr, w.ptr, l.ptr, r.ptr, b.ptr); b_sharded = b.serialize(); del b
+        elif world > 1:
+            b = cabi.BST(lib); lib.apply_local_hamiltonian(a.ptr, w.ptr, l.ptr, r.ptr, b.ptr); del b      # the call is collective
         if not args.no_e2e:
             esize = np.dtype(dtype).itemsize
             h2d = sum(x.num_elements() for x in (a, w, l, r)) * esize
@@ -335,8 +356,19 @@ def main():
     }
     if args.sweep and world == 1:
         line["sweep"] = sweep_report(lib)
-    if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline(wl, flops_total, args.structure)
+    if not args.no_cpu_baseline:
+        base = cpu_baseline(wl, flops_total, args.structure, dump=b_dump_path(wl) if world > 1 else None)
+        line["cpu_baseline"] = base
+        if world > 1 and b_sharded is not None and base.get("value") is not None:
+            # the sharded result of this very run against the unmodified reference on the same operands (north_star: 1e-12 relative)
+            b_ref = np.load(b_dump_path(wl))
+            err = float(np.linalg.norm(b_sharded - b_ref) / np.linalg.norm(b_ref))
+            line["parity_checked"] = bool(err <= 1e-12)
+            line["parity_rel_err_vs_reference"] = err
+            os.remove(b_dump_path(wl))
+            if not line["parity_checked"]:
+                print(json.dumps(line), flush=True)
+                raise SystemExit(f"bench.py: sharded result differs from the reference by {err:.3e}")
     print(json.dumps(line), flush=True)
 
 
@@ -374,9 +406,10 @@ def sweep_seconds(lib, model, L, params, sector, D, sweeps=2, lanczos=10, tol=0.
 
 
 SWEEP_CASES = [
-    # (name, model, L, params, sector, D, time the reference too?)
-    ("fh_L16_D256", "fermi_hubbard", 16, (1.0, 4.0, 0.0), workloads.encode_qpair(16, 0), 256, True),
-    ("fh_L32_D1024", "fermi_hubbard", 32, (1.0, 4.0, 0.0), workloads.encode_qpair(32, 0), 1024, False),
+    # (name, model, L, params, sector, D, sweeps, time the reference too?)
+    ("fh_L64_D4096", "fermi_hubbard", 64, (1.0, 4.0, 0.0), workloads.encode_qpair(64, 0), 4096, 1, False),      # BASELINE.json configs[2], the north-star target
+    ("fh_L32_D1024", "fermi_hubbard", 32, (1.0, 4.0, 0.0), workloads.encode_qpair(32, 0), 1024, 2, False),
+    ("fh_L16_D256", "fermi_hubbard", 16, (1.0, 4.0, 0.0), workloads.encode_qpair(16, 0), 256, 2, True),
 ]
 
 
@@ -420,9 +453,9 @@ MOLECULAR_SWEEP_CASES = [
 def sweep_report(lib):
     """Two-site sweep seconds of the engine (and of the unmodified reference on the small case) -- reported, not the headline."""
     out = []
-    for name, model, L, params, sector, D, with_ref in SWEEP_CASES:
-        rec = {"config": name, "sweeps": 2, "lanczos_iterations": 10, "tol_split": 0.0}
-        ours = sweep_seconds(lib, model, L, params, sector, D)
+    for name, model, L, params, sector, D, nsw, with_ref in SWEEP_CASES:
+        rec = {"config": name, "sweeps": nsw, "lanczos_iterations": 10, "tol_split": 0.0, "start": "seeded random MPS (construct_random_mps rule), bonds saturate at max_vdim"}
+        ours = sweep_seconds(lib, model, L, params, sector, D, sweeps=nsw)
         rec["b200"] = ours
         if with_ref and os.path.exists(REF_SO):
             code = (
@@ -431,13 +464,16 @@ def sweep_report(lib):
                 "import bench\n"
                 "from chemtensor_b200 import cabi\n"
                 f"ref = cabi.CLibrary({REF_SO!r})\n"
-                f"print(json.dumps(bench.sweep_seconds(ref, {model!r}, {L}, {params!r}, {sector}, {D})))\n"
+                f"print(json.dumps(bench.sweep_seconds(ref, {model!r}, {L}, {params!r}, {sector}, {D}, sweeps={nsw})))\n"
             )
             env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
             try:
                 r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
                 rec["reference_cpu"] = json.loads(r.stdout.strip().splitlines()[-1])
                 rec["reference_cpu"]["cores"] = os.cpu_count()
+                if ours is not None:
+                    rec["max_energy_diff_vs_reference"] = float(np.max(np.abs(np.array(ours["energies"]) - np.array(rec["reference_cpu"]["energies"]))))
+                    rec["energy_parity_1e-10"] = bool(rec["max_energy_diff_vs_reference"] <= 1e-10)
             except Exception as exc:
                 rec["reference_cpu"] = {"failed": str(exc)}
         out.append(rec)
@@ -465,8 +501,13 @@ def sweep_report(lib):
     return out
 
 
-def cpu_baseline(wl: str, flops: float, structure: str = "converged"):
-    """The unmodified reference (oracle/_ref) on the host cores of this box, bounded sample, rank 0 only."""
+def b_dump_path(wl: str) -> str:
+    return f"/dev/shm/ctb_bench_ref_b_{wl}_{os.getpid()}.npy"
+
+
+def cpu_baseline(wl: str, flops: float, structure: str = "converged", dump=None):
+    """The unmodified reference (oracle/_ref) on the host cores of this box, bounded sample, rank 0 only.  dump: file the reference's
+    result vector goes to (parity check of the sharded runs)."""
     cores = os.cpu_count() or 1
     code = (
         "import os,sys,time,json\n"
@@ -479,14 +520,21 @@ def cpu_baseline(wl: str, flops: float, structure: str = "converged"):
         "t_all=time.perf_counter()\n"
         "while len(ts) < 5 and time.perf_counter()-t_all < 25:\n"
         "    t0=time.perf_counter(); b=cabi.BST(ref); ref.apply_local_hamiltonian(a.ptr,w.ptr,l.ptr,r.ptr,b.ptr); ts.append(time.perf_counter()-t0); del b\n"
-        "print(json.dumps({'ts': ts}))\n"
+        f"dump = {dump!r}\n"
+        "if dump:\n"
+        "    import numpy as np\n"
+        "    b=cabi.BST(ref); ref.apply_local_hamiltonian(a.ptr,w.ptr,l.ptr,r.ptr,b.ptr); np.save(dump, b.serialize())\n"
+        "gomp = __import__('ctypes').CDLL('libgomp.so.1'); gomp.omp_get_max_threads.restype = __import__('ctypes').c_int\n"
+        "print(json.dumps({'ts': ts, 'threads': int(gomp.omp_get_max_threads())}))\n"
     )
     env = dict(os.environ, OMP_NUM_THREADS=str(cores))
-    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_PROC_BIND"):
         env.pop(k, None)
     try:
         out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=1200)
-        ts = json.loads(out.stdout.strip().splitlines()[-1])["ts"]
+        rec = json.loads(out.stdout.strip().splitlines()[-1])
+        ts = rec["ts"]
+        cores = int(rec.get("threads", cores))
         best = min(ts)
         return {"value": flops / best / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "reference", "ms_per_step": best * 1e3,
                 "sample": f"best of {len(ts)} apply_local_hamiltonian calls of the unmodified reference (oracle/_ref, OpenMP {cores} threads) on the same operands"}

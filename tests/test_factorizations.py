@@ -90,8 +90,6 @@ def test_svd(eng, ref, rng, dtype, shape, precondition, monkeypatch):
     """precondition: the opt-in path a = q r, Jacobi on the triangular factor, u = q u_r (CTB_SVD_PRECONDITION=1); wide inputs go
     through the conjugate transpose.  Same sector structure, bond quantum numbers and singular values as the direct path."""
     if precondition:
-        if eng.ctb_backend() == 1:
-            pytest.skip("opt-in path, composed of GPU-validated primitives; its own GPU run (accuracy and timing) is scheduled for round 2")
         monkeypatch.setenv("CTB_SVD_PRECONDITION", "1")
     dense, dirs, qn = _matrix_inputs(rng, dtype, *shape)
     a, b = cabi.bst_from_dense(eng, dense, dirs, qn), cabi.bst_from_dense(ref, dense, dirs, qn)

@@ -51,7 +51,19 @@ INNER_CAP = 30
 FLOAT_T = False
 
 
-def jacobi_eig(P, tol, sort=False, max_sweeps=None):
+def cross_arrays(n):
+    """bipartite round robin between the first and second half of the indices: n/2 steps of n/2 disjoint cross pairs"""
+    key = ("cross", n)
+    if key not in _TOUR:
+        h = n // 2
+        _TOUR[key] = [(np.arange(h), h + (np.arange(h) + s) % h) for s in range(h)]
+    return _TOUR[key]
+
+
+CROSS_ONLY = False
+
+
+def jacobi_eig(P, tol, sort=False, max_sweeps=None, cross=False):
     """two-sided cyclic Jacobi (parallel ordering) on symmetric P; returns Q with Q^T P Q ~ diagonal"""
     n = P.shape[0]
     P = P.copy()
@@ -60,7 +72,7 @@ def jacobi_eig(P, tol, sort=False, max_sweeps=None):
         max_sweeps = INNER_CAP
     for sweep in range(max_sweeps):
         nrot = 0
-        for ps, qs in tour_arrays(n):
+        for ps, qs in (cross_arrays(n) if cross else tour_arrays(n)):
             g = P[ps, qs]
             a = P[ps, ps]
             b = P[qs, qs]
@@ -121,7 +133,7 @@ def block_jacobi(A, b, tol, sort=False, max_sweeps=40, verbose=True):
     for sweep in range(max_sweeps):
         active = 0
         inner = 0
-        for prs in (tournament(N) if nb > 1 else [[(0, 1)]]):
+        for rnd, prs in enumerate(tournament(N) if nb > 1 else [[(0, 1)]]):
             for p, q in prs:
                 if p > q:
                     p, q = q, p
@@ -136,7 +148,8 @@ def block_jacobi(A, b, tol, sort=False, max_sweeps=40, verbose=True):
                 if M.max() <= tol:
                     continue
                 active += 1
-                Q, ns = jacobi_eig(P, tol, sort=sort)
+                full_pair = (len(idx) == 2 * b)
+                Q, ns = jacobi_eig(P, tol, sort=sort, cross=(CROSS_ONLY and rnd > 0 and full_pair))
                 inner += ns
                 X[idx] = Q.T @ XP
         ro = rel_overlap(X[:, :C]).max()
@@ -169,6 +182,8 @@ if __name__ == "__main__":
         INNER_CAP = int(sys.argv[6])
     if len(sys.argv) > 7:
         FLOAT_T = bool(int(sys.argv[7]))
+    if len(sys.argv) > 8:
+        CROSS_ONLY = bool(int(sys.argv[8]))
     for decay in decays:
         A, s = make(R, C, decay)
         tol = np.finfo(float).eps * np.sqrt(C)
