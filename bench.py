@@ -375,6 +375,8 @@ def main():
 def exchange_name(lib) -> str:
     info = (C.c_longlong * 4)()
     lib.ctb_dist_info(info)
+    if info[2] > 0 and lib.ctb_dist_multicast_exchanges() > 0:
+        return "fused over NVSwitch multicast (step-3 GEMM epilogue stores every element ONCE to the multicast address with multimem.st, the switch replicates it into the result buffers of all GPUs; peer-flag barrier)"
     if info[2] > 0:
         return "fused (step-3 GEMM epilogue stores into the peer-mapped result buffers of all GPUs, peer-flag barrier)"
     if lib.ctb_dist_push_exchanges() > 0:

@@ -144,6 +144,7 @@ _EXT_SIGNATURES = {
     "ctb_apply_local_hamiltonian_pair": (C.c_int, [_P_BST, _P_BST, _P_BST, _P_BST, _P_BST, _P_BST]),
     "ctb_dist_pull_exchanges": (C.c_longlong, []),
     "ctb_dist_push_exchanges": (C.c_longlong, []),
+    "ctb_dist_multicast_exchanges": (C.c_longlong, []),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES) + tuple(_EXT_SIGNATURES) + ("allocate_zero_dense_tensor", "allocate_block_sparse_tensor_like",

@@ -286,8 +286,20 @@ struct GemmArgs
 	int c_odd;            /* multi-destination runs: some destination base is 8 (mod 16), 16-byte stores are then off */
 	const int64_t* b_rowtab;   /* optional: B rows gathered through a row table, seg.b_off indexes it (merged-row plans) */
 	int ndst;                  /* >= 1: additional destinations of the epilogue (peer-mapped buffers of the other GPUs) follow */
+	int mc;                    /* C is an NVSwitch multicast address: every element is stored once with multimem.st, the switch replicates it */
 	void* Cx[7];
 };
+
+/* stores to a multicast address (multimem.st; SASS: STG.E.{64,128}.STRONG.SYS on the multicast mapping) */
+__device__ __forceinline__ void mc_st8(double* p, double v)
+{
+	asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void mc_st16(void* p, double a, double b)
+{
+	asm volatile("{ .reg .b32 x0, x1, x2, x3;\n mov.b64 {x0, x1}, %1;\n mov.b64 {x2, x3}, %2;\n multimem.st.relaxed.sys.global.v4.f32 [%0], {x0, x1, x2, x3};\n }"
+		:: "l"(p), "d"(a), "d"(b) : "memory");
+}
 
 template <typename T, typename Cfg, bool A_KC, bool B_NC>
 __global__ void __launch_bounds__(Cfg::NT) grouped_gemm_kernel(const GemmArgs args)
@@ -461,7 +473,25 @@ __global__ void __launch_bounds__(Cfg::NT) grouped_gemm_kernel(const GemmArgs ar
 				if constexpr (!CPLX) { v0 = acc[i][j][0]; v1 = acc[i][j][1]; }
 				else { v0 = make_double2(acc[i][j][0], acc[i][j][2]); v1 = make_double2(acc[i][j][1], acc[i][j][3]); }
 				const int64_t o0 = out.c_off + ro + (gc < N ? coltab[gc] : 0), o1 = out.c_off + ro + (gc + 1 < N ? coltab[gc + 1] : 0);
-				if (args.ndst > 1) {
+				if (args.mc) {
+					/* fused all-gather over NVSwitch multicast: ONE store per element (16 bytes where two neighbouring columns are adjacent
+					 * in the packed layout), replicated into the result buffers of all GPUs by the switch */
+					if constexpr (!CPLX) {
+						double* Cm = reinterpret_cast<double*>(args.C);
+						const bool pair = (args.c_odd == 0) && (gc + 1 < N) && (o1 == o0 + 1) && ((o0 & 1) == 0);
+						if (pair) { mc_st16(Cm + o0, v0, v1); }
+						else {
+							if (gc < N)     { mc_st8(Cm + o0, v0); }
+							if (gc + 1 < N) { mc_st8(Cm + o1, v1); }
+						}
+					}
+					else {
+						double2* Cm = reinterpret_cast<double2*>(args.C);
+						if (gc < N)     { mc_st16(Cm + o0, v0.x, v0.y); }
+						if (gc + 1 < N) { mc_st16(Cm + o1, v1.x, v1.y); }
+					}
+				}
+				else if (args.ndst > 1) {
 					/* fused all-gather: the same element goes to the local result and to the peer-mapped result buffers of the other GPUs
 					 * (posted NVLink stores).  Two neighbouring columns travel as ONE 16-byte store where the layout allows it: full
 					 * sectors on the link instead of byte-masked halves. */
@@ -938,7 +968,7 @@ int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C)
 	args.conj_a = p->conj_a; args.conj_b = p->conj_b;
 	args.a_odd = (int)(((uintptr_t)args.A >> 3) & 1); args.b_odd = (int)(((uintptr_t)args.B >> 3) & 1);
 	args.b_rowtab = p->b_rowtab;
-	args.ndst = 1; args.c_odd = 0;
+	args.ndst = 1; args.mc = 0; args.c_odd = 0;
 	return CTBD_GEMM_DISPATCH(launch_cfg, p, args);
 }
 
@@ -955,10 +985,27 @@ int ctbd_gemm_run_multi(void* plan, const void* A, const void* B, int ndst, void
 	args.conj_a = p->conj_a; args.conj_b = p->conj_b;
 	args.a_odd = (int)(((uintptr_t)args.A >> 3) & 1); args.b_odd = (int)(((uintptr_t)args.B >> 3) & 1);
 	args.b_rowtab = p->b_rowtab;
-	args.ndst = ndst;
+	args.ndst = ndst; args.mc = 0;
 	args.c_odd = 0;
 	for (int d = 0; d < ndst; d++) { if ((((uintptr_t)Cs[d]) >> 3) & 1) { args.c_odd = 1; } }
 	for (int d = 1; d < ndst; d++) { args.Cx[d - 1] = Cs[d]; }
+	return CTBD_GEMM_DISPATCH(launch_cfg, p, args);
+}
+
+int ctbd_gemm_run_mc(void* plan, const void* A, const void* B, void* C_mc)
+{
+	GemmPlan* p = (GemmPlan*)plan;
+	if (p->n_mix_tiles > 0) { return fail_msg("grouped GEMM: the mixing form has no multicast epilogue"); }
+	if (p->ntiles == 0) { return 0; }
+	GemmArgs args;
+	args.tiles = p->tiles; args.queue = p->queue;
+	args.outs = p->outs; args.segs = p->segs; args.tab = p->tab;
+	args.A = (p->a_packed != nullptr) ? p->a_packed : A; args.B = B; args.C = C_mc;
+	args.conj_a = p->conj_a; args.conj_b = p->conj_b;
+	args.a_odd = (int)(((uintptr_t)args.A >> 3) & 1); args.b_odd = (int)(((uintptr_t)args.B >> 3) & 1);
+	args.b_rowtab = p->b_rowtab;
+	args.ndst = 1; args.mc = 1;
+	args.c_odd = (int)(((uintptr_t)C_mc >> 3) & 1);
 	return CTBD_GEMM_DISPATCH(launch_cfg, p, args);
 }
 

@@ -5,6 +5,10 @@
 #include <stdlib.h>
 #include <dlfcn.h>
 #include <sys/mman.h>
+#include <sys/socket.h>
+#include <sys/un.h>
+#include <unistd.h>
+#include <stddef.h>
 #include <omp.h>
 #include <unordered_map>
 #include <mutex>
@@ -239,14 +243,15 @@ void plan_chunks(int nblk, const int64_t* dev_off, const int64_t* nbytes, std::v
 	if (c.len > 0) { c.p1 = pieces.size(); chunks.push_back(c); }
 }
 
+int g_copy_world = 1;      /* ranks sharing the host cores (set by ctbd_dist_init) */
+
+/* host threads that pack / unpack the staging chunks: at most 8, and never more than this rank's share of the host cores -- with one
+ * process per GPU, 8 ranks x 8 spinning OpenMP threads on a 32-core box made every host-struct call 15x slower (round-1 record) */
 int host_copy_threads()
 {
-	static int nt = 0;
-	if (nt == 0) {
-		const char* env = getenv("CTB_COPY_THREADS");
-		nt = (env != nullptr) ? atoi(env) : std::min(8, omp_get_num_procs());
-		if (nt < 1) { nt = 1; }
-	}
+	const char* env = getenv("CTB_COPY_THREADS");
+	int nt = (env != nullptr) ? atoi(env) : std::min(8, std::max(1, omp_get_num_procs() / std::max(1, g_copy_world)));
+	if (nt < 1) { nt = 1; }
 	return nt;
 }
 } // namespace
@@ -397,7 +402,9 @@ __global__ void flag_barrier_kernel(FlagPtrs peers, int rank, int world, unsigne
 		*arrive = epoch;
 		volatile unsigned long long* seen = peers.p[rank] + p;
 		const long long t0 = clock64();
-		while (*seen < epoch) { if (clock64() - t0 > (1ll << 34)) { break; } }      /* a dead peer must not hang the device for ever */
+		/* a dead peer must not hang the device for ever, and the exchange must never continue with a partially filled buffer:
+		 * after about 9 s the kernel traps, the stream reports the error and every later call of the layer returns < 0 */
+		while (*seen < epoch) { if (clock64() - t0 > (1ll << 34)) { __trap(); } }
 		__threadfence_system();
 	}
 }
@@ -414,7 +421,7 @@ int ctbd_dist_init(int rank, int world, const void* unique_id)
 {
 	CTBD_REQUIRE_INIT();
 	if (world < 1 || rank < 0 || rank >= world) { return fail_msg("dist: bad rank / world"); }
-	g_rank = rank; g_world = world;
+	g_rank = rank; g_world = world; g_copy_world = world;
 	if (world == 1 || unique_id == nullptr) { return 0; }      /* single rank, or the host supplies the collective by callback */
 	if (nccl_load() < 0) { return -1; }
 	ncclUniqueIdBytes id;
@@ -432,7 +439,7 @@ int ctbd_dist_finalize(void)
 	if (g_flags != nullptr) { PeerBuffer* f = g_flags; g_flags = nullptr; g_flags_failed = true; ctbd_peer_buffer_destroy(f); }
 	g_flags_failed = false; g_epoch = 0;
 	if (g_comm != nullptr) { cudaStreamSynchronize(rt().stream); g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
-	g_rank = 0; g_world = 1; g_ag_fn = nullptr; g_ag_ctx = nullptr;
+	g_rank = 0; g_world = 1; g_copy_world = 1; g_ag_fn = nullptr; g_ag_ctx = nullptr;
 	return 0;
 }
 
@@ -472,8 +479,9 @@ int ctbd_barrier(void)
 	}
 	/* an 8-byte all-gather on the stream: completes on a rank only after every rank has reached it, and kernel boundaries make the
 	 * peer stores issued before it visible system-wide */
-	static void* scratch = nullptr;
-	if (scratch == nullptr) { if (ctbd_malloc(&scratch, (size_t)8 * (size_t)(g_world + 1)) < 0) { return -1; } }
+	static void* scratch = nullptr;      /* sized for the largest supported world (8 ranks + the send slot), so a re-init with more ranks stays in bounds */
+	if (scratch == nullptr) { if (ctbd_malloc(&scratch, (size_t)8 * 9) < 0) { return -1; } }
+	if (g_world > 8) { return fail_msg("dist: barrier supports at most 8 ranks"); }
 	return ctbd_allgather(scratch, (char*)scratch + 8, 8);
 }
 
@@ -558,6 +566,241 @@ int ctbd_peer_buffer_destroy(void* handle)
 	cudaStreamSynchronize(rt().stream);
 	cudaFree(pb->local);
 	delete pb;
+	return 0;
+}
+
+/* ---- NVSwitch multicast buffers ------------------------------------------------------------------------------------------
+ * One allocation per rank (cuMemCreate), all bound to ONE multicast object (cuMulticastCreate / BindMem): a store to the multicast
+ * address is replicated by the switch into the buffers of all ranks, so the all-gather of the sharded effective Hamiltonian costs
+ * every GPU one copy of its slice on the wire instead of world - 1 (17 MB instead of 120 MB per matvec at D = 4096 on 8 GPUs).
+ * The driver API is bound at run time (dlopen libcuda.so.1: the library must load on hosts without a driver); the multicast handle
+ * travels from rank 0 to the other processes as a POSIX file descriptor over a unix-domain socket (SCM_RIGHTS). */
+namespace {
+typedef int CUres;
+typedef unsigned long long CUhandle;      /* CUmemGenericAllocationHandle */
+typedef unsigned long long CUdptr;        /* CUdeviceptr */
+struct CuMcProp { unsigned int numDevices; size_t size; unsigned long long handleTypes; unsigned long long flags; };      /* CUmulticastObjectProp */
+struct CuLocation { int type; int id; };                                                                                   /* CUmemLocation */
+struct CuAllocProp { int type; int requestedHandleTypes; CuLocation location; void* win32HandleMetaData;                  /* CUmemAllocationProp */
+	struct { unsigned char compressionType, gpuDirectRDMACapable; unsigned short usage; unsigned char reserved[4]; } allocFlags; };
+struct CuAccessDesc { CuLocation location; int flags; };                                                                   /* CUmemAccessDesc */
+struct CudaDrv
+{
+	void* lib = nullptr;
+	CUres (*DeviceGet)(int*, int) = nullptr;
+	CUres (*DeviceGetAttribute)(int*, int, int) = nullptr;
+	CUres (*MulticastCreate)(CUhandle*, const CuMcProp*) = nullptr;
+	CUres (*MulticastAddDevice)(CUhandle, int) = nullptr;
+	CUres (*MulticastBindMem)(CUhandle, size_t, CUhandle, size_t, size_t, unsigned long long) = nullptr;
+	CUres (*MulticastUnbind)(CUhandle, int, size_t, size_t) = nullptr;
+	CUres (*MulticastGetGranularity)(size_t*, const CuMcProp*, int) = nullptr;
+	CUres (*MemCreate)(CUhandle*, size_t, const CuAllocProp*, unsigned long long) = nullptr;
+	CUres (*MemRelease)(CUhandle) = nullptr;
+	CUres (*MemGetAllocationGranularity)(size_t*, const CuAllocProp*, int) = nullptr;
+	CUres (*MemAddressReserve)(CUdptr*, size_t, size_t, CUdptr, unsigned long long) = nullptr;
+	CUres (*MemAddressFree)(CUdptr, size_t) = nullptr;
+	CUres (*MemMap)(CUdptr, size_t, size_t, CUhandle, unsigned long long) = nullptr;
+	CUres (*MemUnmap)(CUdptr, size_t) = nullptr;
+	CUres (*MemSetAccess)(CUdptr, size_t, const CuAccessDesc*, size_t) = nullptr;
+	CUres (*MemExportToShareableHandle)(void*, CUhandle, int, unsigned long long) = nullptr;
+	CUres (*MemImportFromShareableHandle)(CUhandle*, void*, int) = nullptr;
+};
+CudaDrv g_drv;
+int drv_load()
+{
+	if (g_drv.lib != nullptr) { return 0; }
+	g_drv.lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+	if (g_drv.lib == nullptr) { return fail_msg("multicast: libcuda.so.1 not found"); }
+	bool ok = true;
+	auto sym = [&](const char* n) { void* f = dlsym(g_drv.lib, n); if (f == nullptr) { ok = false; } return f; };
+	g_drv.DeviceGet = (decltype(g_drv.DeviceGet))sym("cuDeviceGet");
+	g_drv.DeviceGetAttribute = (decltype(g_drv.DeviceGetAttribute))sym("cuDeviceGetAttribute");
+	g_drv.MulticastCreate = (decltype(g_drv.MulticastCreate))sym("cuMulticastCreate");
+	g_drv.MulticastAddDevice = (decltype(g_drv.MulticastAddDevice))sym("cuMulticastAddDevice");
+	g_drv.MulticastBindMem = (decltype(g_drv.MulticastBindMem))sym("cuMulticastBindMem");
+	g_drv.MulticastUnbind = (decltype(g_drv.MulticastUnbind))sym("cuMulticastUnbind");
+	g_drv.MulticastGetGranularity = (decltype(g_drv.MulticastGetGranularity))sym("cuMulticastGetGranularity");
+	g_drv.MemCreate = (decltype(g_drv.MemCreate))sym("cuMemCreate");
+	g_drv.MemRelease = (decltype(g_drv.MemRelease))sym("cuMemRelease");
+	g_drv.MemGetAllocationGranularity = (decltype(g_drv.MemGetAllocationGranularity))sym("cuMemGetAllocationGranularity");
+	g_drv.MemAddressReserve = (decltype(g_drv.MemAddressReserve))sym("cuMemAddressReserve");
+	g_drv.MemAddressFree = (decltype(g_drv.MemAddressFree))sym("cuMemAddressFree");
+	g_drv.MemMap = (decltype(g_drv.MemMap))sym("cuMemMap");
+	g_drv.MemUnmap = (decltype(g_drv.MemUnmap))sym("cuMemUnmap");
+	g_drv.MemSetAccess = (decltype(g_drv.MemSetAccess))sym("cuMemSetAccess");
+	g_drv.MemExportToShareableHandle = (decltype(g_drv.MemExportToShareableHandle))sym("cuMemExportToShareableHandle");
+	g_drv.MemImportFromShareableHandle = (decltype(g_drv.MemImportFromShareableHandle))sym("cuMemImportFromShareableHandle");
+	if (!ok) { dlclose(g_drv.lib); g_drv.lib = nullptr; return fail_msg("multicast: the driver lacks the multicast / virtual memory entry points"); }
+	return 0;
+}
+
+/* every rank contributes 'slot' bytes; all[p * slot ...] = contribution of rank p */
+int small_allgather(const void* mine, size_t slot, std::vector<unsigned char>& all)
+{
+	all.assign(slot * (size_t)g_world, 0);
+	void* dbuf = nullptr;
+	if (ctbd_malloc(&dbuf, slot * (size_t)(g_world + 1)) < 0) { return -1; }
+	int rc = ctbd_h2d(dbuf, mine, slot);
+	if (rc == 0) { rc = ctbd_allgather(dbuf, (char*)dbuf + slot, slot); }
+	if (rc == 0) { rc = ctbd_d2h(all.data(), (char*)dbuf + slot, slot * (size_t)g_world); }
+	ctbd_free(dbuf);
+	return rc;
+}
+/* all ranks agree on success */
+bool all_agree(bool mine)
+{
+	long long f = mine ? 1 : 0;
+	std::vector<unsigned char> all;
+	if (small_allgather(&f, 8, all) < 0) { return false; }
+	bool ok = true;
+	for (int p = 0; p < g_world; p++) { long long v; memcpy(&v, all.data() + 8 * (size_t)p, 8); ok = ok && (v == 1); }
+	return ok;
+}
+
+int send_fd(int sock, int fd)
+{
+	struct msghdr msg; memset(&msg, 0, sizeof(msg));
+	char cbuf[CMSG_SPACE(sizeof(int))]; memset(cbuf, 0, sizeof(cbuf));
+	char data = 'f';
+	struct iovec io; io.iov_base = &data; io.iov_len = 1;
+	msg.msg_iov = &io; msg.msg_iovlen = 1; msg.msg_control = cbuf; msg.msg_controllen = sizeof(cbuf);
+	struct cmsghdr* cm = CMSG_FIRSTHDR(&msg);
+	cm->cmsg_level = SOL_SOCKET; cm->cmsg_type = SCM_RIGHTS; cm->cmsg_len = CMSG_LEN(sizeof(int));
+	memcpy(CMSG_DATA(cm), &fd, sizeof(int));
+	return sendmsg(sock, &msg, 0) == 1 ? 0 : -1;
+}
+int recv_fd(int sock)
+{
+	struct msghdr msg; memset(&msg, 0, sizeof(msg));
+	char cbuf[CMSG_SPACE(sizeof(int))]; memset(cbuf, 0, sizeof(cbuf));
+	char data = 0;
+	struct iovec io; io.iov_base = &data; io.iov_len = 1;
+	msg.msg_iov = &io; msg.msg_iovlen = 1; msg.msg_control = cbuf; msg.msg_controllen = sizeof(cbuf);
+	if (recvmsg(sock, &msg, 0) != 1) { return -1; }
+	struct cmsghdr* cm = CMSG_FIRSTHDR(&msg);
+	if (cm == nullptr || cm->cmsg_level != SOL_SOCKET || cm->cmsg_type != SCM_RIGHTS) { return -1; }
+	int fd = -1;
+	memcpy(&fd, CMSG_DATA(cm), sizeof(int));
+	return fd;
+}
+
+struct McBuffer
+{
+	CUhandle mc = 0, mem = 0;
+	CUdptr local = 0, mcva = 0;
+	size_t size = 0;
+	int dev = 0;
+	bool bound = false;
+};
+void mc_release(McBuffer* b)
+{
+	if (b == nullptr) { return; }
+	if (b->mcva != 0) { g_drv.MemUnmap(b->mcva, b->size); g_drv.MemAddressFree(b->mcva, b->size); }
+	if (b->bound) { g_drv.MulticastUnbind(b->mc, b->dev, 0, b->size); }
+	if (b->local != 0) { g_drv.MemUnmap(b->local, b->size); g_drv.MemAddressFree(b->local, b->size); }
+	if (b->mem != 0) { g_drv.MemRelease(b->mem); }
+	if (b->mc != 0) { g_drv.MemRelease(b->mc); }
+	delete b;
+}
+int g_mc_seq = 0;
+} // namespace
+
+/* collective; on success *local_ptr is this rank's buffer and *mc_ptr the multicast address (only multimem stores may touch it).
+ * Returns < 0 on every rank when any rank cannot take part (no NVSwitch multicast, no fabric manager, ...). */
+int ctbd_mc_buffer_create(size_t bytes, void** handle, void** local_ptr, void** mc_ptr)
+{
+	CTBD_REQUIRE_INIT();
+	*handle = nullptr; *local_ptr = nullptr; *mc_ptr = nullptr;
+	if (g_world == 1 || g_comm == nullptr) { return fail_msg("multicast buffer: needs the NCCL communicator of ctbd_dist_init"); }
+	if (getenv("CTB_NO_MULTICAST") != nullptr || getenv("CTB_NO_PEER") != nullptr) { return fail_msg("multicast buffer: disabled by the environment"); }
+	CTBD_CUDA(cudaSetDevice(rt().device));
+	CTBD_CUDA(cudaFree(nullptr));
+	bool ok = (drv_load() == 0);
+	McBuffer* b = new McBuffer();
+	int dev = 0, supported = 0;
+	if (ok) { ok = g_drv.DeviceGet(&dev, rt().device) == 0 && g_drv.DeviceGetAttribute(&supported, /* CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED */ 132, dev) == 0 && supported != 0; }
+	b->dev = dev;
+	ok = all_agree(ok);
+	if (!ok) { mc_release(b); return fail_msg("multicast buffer: multicast is not supported on every device of the team"); }
+
+	const int FD = 1;      /* CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR */
+	CuMcProp mp; memset(&mp, 0, sizeof(mp));
+	mp.numDevices = (unsigned)g_world; mp.handleTypes = FD; mp.size = bytes > 0 ? bytes : 1;
+	size_t gran = 0, mgran = 0;
+	CuAllocProp ap; memset(&ap, 0, sizeof(ap));
+	ap.type = 1 /* PINNED */; ap.requestedHandleTypes = FD; ap.location.type = 1 /* DEVICE */; ap.location.id = dev;
+	ok = g_drv.MulticastGetGranularity(&gran, &mp, /* RECOMMENDED */ 1) == 0 && g_drv.MemGetAllocationGranularity(&mgran, &ap, /* RECOMMENDED */ 1) == 0 && gran > 0 && mgran > 0;
+	if (ok) { if (mgran > gran) { gran = mgran; } b->size = ((mp.size + gran - 1) / gran) * gran; mp.size = b->size; }
+
+	/* rank 0 creates the multicast object and hands its descriptor to the other processes */
+	char sockname[64]; memset(sockname, 0, sizeof(sockname));
+	int lsock = -1, fd0 = -1;
+	if (g_rank == 0 && ok)
+	{
+		ok = g_drv.MulticastCreate(&b->mc, &mp) == 0 && g_drv.MemExportToShareableHandle(&fd0, b->mc, FD, 0) == 0;
+		if (ok) {
+			snprintf(sockname + 1, sizeof(sockname) - 2, "ctb_mc_%d_%d", (int)getpid(), g_mc_seq++);      /* abstract socket: leading NUL */
+			lsock = socket(AF_UNIX, SOCK_STREAM, 0);
+			struct sockaddr_un sa; memset(&sa, 0, sizeof(sa)); sa.sun_family = AF_UNIX;
+			memcpy(sa.sun_path, sockname, sizeof(sockname));
+			ok = lsock >= 0 && bind(lsock, (struct sockaddr*)&sa, (socklen_t)(offsetof(struct sockaddr_un, sun_path) + 1 + strlen(sockname + 1))) == 0 && listen(lsock, 16) == 0;
+		}
+	}
+	struct { char name[64]; long long ok; } slot; memset(&slot, 0, sizeof(slot));
+	memcpy(slot.name, sockname, sizeof(sockname)); slot.ok = ok ? 1 : 0;
+	std::vector<unsigned char> all;
+	if (small_allgather(&slot, sizeof(slot), all) < 0) { ok = false; }
+	for (int p = 0; p < g_world && ok; p++) { long long f; memcpy(&f, all.data() + sizeof(slot) * (size_t)p + 64, 8); ok = (f == 1); }
+	if (ok && g_rank == 0) {
+		for (int p = 1; p < g_world && ok; p++) {
+			const int c = accept(lsock, nullptr, nullptr);
+			ok = (c >= 0) && send_fd(c, fd0) == 0;
+			if (c >= 0) { close(c); }
+		}
+	}
+	else if (ok) {
+		struct sockaddr_un sa; memset(&sa, 0, sizeof(sa)); sa.sun_family = AF_UNIX;
+		memcpy(sa.sun_path, all.data(), 64);
+		const socklen_t len = (socklen_t)(offsetof(struct sockaddr_un, sun_path) + 1 + strlen((const char*)all.data() + 1));
+		const int c = socket(AF_UNIX, SOCK_STREAM, 0);
+		int fd = -1;
+		ok = (c >= 0);
+		for (int attempt = 0; ok && attempt < 2000; attempt++) {
+			if (connect(c, (struct sockaddr*)&sa, len) == 0) { fd = recv_fd(c); break; }
+			usleep(1000);
+		}
+		if (c >= 0) { close(c); }
+		ok = ok && fd >= 0 && g_drv.MemImportFromShareableHandle(&b->mc, (void*)(uintptr_t)fd, FD) == 0;
+		if (fd >= 0) { close(fd); }
+	}
+	if (lsock >= 0) { close(lsock); }
+	if (fd0 >= 0) { close(fd0); }
+	ok = all_agree(ok);
+	if (!ok) { mc_release(b); return fail_msg("multicast buffer: could not create / share the multicast object"); }
+
+	ok = g_drv.MulticastAddDevice(b->mc, dev) == 0;
+	ok = all_agree(ok);      /* every device has to be added before memory is bound */
+	if (ok) { ok = g_drv.MemCreate(&b->mem, b->size, &ap, 0) == 0; }
+	if (ok) { ok = g_drv.MulticastBindMem(b->mc, 0, b->mem, 0, b->size, 0) == 0; b->bound = ok; }
+	CuAccessDesc ad; ad.location.type = 1; ad.location.id = dev; ad.flags = 3 /* READWRITE */;
+	if (ok) { ok = g_drv.MemAddressReserve(&b->local, b->size, gran, 0, 0) == 0 && g_drv.MemMap(b->local, b->size, 0, b->mem, 0) == 0 && g_drv.MemSetAccess(b->local, b->size, &ad, 1) == 0; }
+	ok = all_agree(ok);      /* all ranks bound: the multicast address may be mapped */
+	if (ok) { ok = g_drv.MemAddressReserve(&b->mcva, b->size, gran, 0, 0) == 0 && g_drv.MemMap(b->mcva, b->size, 0, b->mc, 0) == 0 && g_drv.MemSetAccess(b->mcva, b->size, &ad, 1) == 0; }
+	if (ok) { ok = cudaMemset((void*)b->local, 0, b->size) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess; }
+	ok = all_agree(ok);
+	if (!ok) { (void)cudaGetLastError(); mc_release(b); return fail_msg("multicast buffer: binding / mapping failed"); }
+	*handle = b; *local_ptr = (void*)b->local; *mc_ptr = (void*)b->mcva;
+	return 0;
+}
+
+int ctbd_mc_buffer_destroy(void* handle)
+{
+	McBuffer* b = (McBuffer*)handle;
+	if (b == nullptr) { return 0; }
+	cudaStreamSynchronize(rt().stream);
+	ctbd_barrier();      /* nobody stores to the team any more */
+	cudaStreamSynchronize(rt().stream);
+	mc_release(b);
 	return 0;
 }
 

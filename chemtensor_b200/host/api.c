@@ -31,6 +31,7 @@ int ctb_dist_info(long long* out) { out[0] = ctb_dist_rank; out[1] = ctb_dist_wo
 /* exchanges done by the pull path (peer-mapped send buffers read over NVLink) */
 long long ctb_dist_pull_exchanges(void) { return ctb_dist_pull_count(); }
 long long ctb_dist_push_exchanges(void) { return ctb_dist_push_count(); }
+long long ctb_dist_multicast_exchanges(void) { return ctb_dist_multicast_count(); }
 int ctb_dist_finalize(void) { ctb_dist_release_buffers(); ctb_dist_rank = 0; ctb_dist_world = 1; return ctbd_dist_finalize(); }
 int ctb_backend(void) { return ctbd_backend(); }
 long long ctb_launch_count(void) { return ctbd_launch_count(); }

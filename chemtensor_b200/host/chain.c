@@ -305,26 +305,44 @@ struct ctb_tensor* ctb_env_step_left(const struct ctb_tensor* a, const struct ct
 /* ---- peer-mapped landing buffers of the fused exchange (two, used alternately; see ctb_heff_finish) ---- */
 static void* g_land[2] = { NULL, NULL };
 static void** g_land_ptrs[2] = { NULL, NULL };
+static void* g_land_mc[2] = { NULL, NULL };      /* != NULL: the landing buffers are bound to an NVSwitch multicast object; the address all ranks store to */
 static size_t g_land_bytes = 0;
-static int g_land_flip = 0, g_land_failed = 0;
-static long long g_fused_count = 0, g_allgather_count = 0;
+static int g_land_flip = 0, g_land_failed = 0, g_mc_failed = 0;
+static long long g_fused_count = 0, g_allgather_count = 0, g_mc_count = 0;
 
 static void landing_release(void)
 {
 	for (int i = 0; i < 2; i++) {
-		if (g_land[i] != NULL) { ctbd_peer_buffer_destroy(g_land[i]); g_land[i] = NULL; }
+		if (g_land[i] != NULL) { if (g_land_mc[i] != NULL) { ctbd_mc_buffer_destroy(g_land[i]); } else { ctbd_peer_buffer_destroy(g_land[i]); } g_land[i] = NULL; }
+		g_land_mc[i] = NULL;
 		free(g_land_ptrs[i]); g_land_ptrs[i] = NULL;
 	}
 	g_land_bytes = 0; g_land_flip = 0;
 }
 
-/* collective: every rank calls it with the same size; returns 1 when both landing buffers are available */
-static int landing_ensure(size_t bytes, int world)
+/* collective: every rank calls it with the same size; returns 1 when both landing buffers are available.  With multicast != 0 the
+ * buffers are first tried as NVSwitch multicast buffers (one store per element reaches all ranks), else (or when the box has no
+ * multicast) as CUDA-IPC peer-mapped buffers every rank stores into separately. */
+static int landing_ensure(size_t bytes, int world, int multicast)
 {
 	if (g_land_failed || getenv("CTB_NO_FUSED_EXCHANGE") != NULL) { return 0; }
-	if (g_land[0] != NULL && bytes <= g_land_bytes) { return 1; }
+	const int want_mc = multicast && !g_mc_failed && getenv("CTB_NO_MULTICAST") == NULL;
+	if (g_land[0] != NULL && bytes <= g_land_bytes && (g_land_mc[0] != NULL) == (want_mc != 0)) { return 1; }
 	landing_release();
 	const size_t want = bytes + bytes / 4 + 4096;
+	if (want_mc)
+	{
+		int ok = 1;
+		for (int i = 0; i < 2 && ok; i++) {
+			void* local = NULL;
+			if (ctbd_mc_buffer_create(want, &g_land[i], &local, &g_land_mc[i]) < 0) { ok = 0; break; }
+			g_land_ptrs[i] = calloc((size_t)world, sizeof(void*));
+			g_land_ptrs[i][ctb_dist_rank] = local;
+		}
+		if (ok) { g_land_bytes = want; return 1; }
+		landing_release();
+		g_mc_failed = 1;      /* the same decision on every rank: the creation is collective and agrees on failure */
+	}
 	for (int i = 0; i < 2; i++) {
 		if (ctbd_peer_buffer_create(want, &g_land[i]) < 0) { g_land_failed = 1; landing_release(); return 0; }
 		g_land_ptrs[i] = calloc((size_t)world, sizeof(void*));
@@ -383,7 +401,8 @@ static int exchange_mode(int world)
 	return EXCH_FUSED;
 }
 
-void ctb_dist_release_buffers(void) { landing_release(); g_land_failed = 0; send_release(); g_send_failed = 0; }
+void ctb_dist_release_buffers(void) { landing_release(); g_land_failed = 0; g_mc_failed = 0; send_release(); g_send_failed = 0; }
+long long ctb_dist_multicast_count(void) { return g_mc_count; }
 long long ctb_dist_pull_count(void) { return g_pull_count; }
 long long ctb_dist_push_count(void) { return g_push_count; }
 void ctb_dist_counters(long long* fused, long long* allgather) { *fused = g_fused_count; *allgather = g_allgather_count; }
@@ -663,8 +682,8 @@ static int heff_prepare_any(const struct ctb_tensor* a, const struct ctb_tensor*
 	const int exch = (h->world > 1) ? exchange_mode(h->world) : EXCH_ALLGATHER;
 	if (h->world > 1 && exch == EXCH_PULL && send_ensure((size_t)h->piece_cap * ctb_sizeof_dtype(a->dtype), h->world)) { h->pull = 1; }
 	/* push: step 3 writes the slice locally, one copy kernel then stores it into the landing buffers of all ranks (wide NVLink stores) */
-	if (h->world > 1 && exch == EXCH_PUSH && landing_ensure((size_t)a->nstore * ctb_sizeof_dtype(a->dtype), h->world)) { h->push = 1; }
-	if (h->world > 1 && exch == EXCH_FUSED && landing_ensure((size_t)a->nstore * ctb_sizeof_dtype(a->dtype), h->world))
+	if (h->world > 1 && exch == EXCH_PUSH && landing_ensure((size_t)a->nstore * ctb_sizeof_dtype(a->dtype), h->world, 0)) { h->push = 1; }
+	if (h->world > 1 && exch == EXCH_FUSED && landing_ensure((size_t)a->nstore * ctb_sizeof_dtype(a->dtype), h->world, 1))
 	{
 		/* fused exchange: the step-3 GEMM stores its column slice straight into the packed layout of the FULL result, in the
 		 * peer-mapped landing buffer of every rank (NVLink stores from the epilogue); no all-gather, no scatter */
@@ -729,6 +748,7 @@ int ctb_heff_step3(struct ctb_heff* h, void* b_data)
 		return ctbd_copy_plan_run_push(h->push_plan, h->send, h->world, (void* const*)g_land_ptrs[g_land_flip]);
 	}
 	if (!h->fused) { return ctb_dot_exec(&h->p3, h->k->d, h->t2->d, h->send); }
+	if (g_land_mc[g_land_flip] != NULL) { return ctb_dot_exec_mc(&h->p3, h->k->d, h->t2->d, g_land_mc[g_land_flip]); }
 	void* dst[8];
 	void** ptrs = g_land_ptrs[g_land_flip];
 	dst[0] = ptrs[h->rank];
@@ -755,7 +775,7 @@ int ctb_heff_exchange(struct ctb_heff* h, void* b_data)
 		/* a caller that asked for the landing buffer itself (ctb_heff_result_buffer) consumes the result in place */
 		if (b_data != g_land_ptrs[g_land_flip][h->rank]) { CTB_CHECK(ctbd_d2d(b_data, g_land_ptrs[g_land_flip][h->rank], (size_t)h->nstore * esize)); }
 		g_land_flip ^= 1;
-		if (h->fused) { g_fused_count++; } else { g_push_count++; }
+		if (h->fused) { g_fused_count++; if (g_land_mc[g_land_flip ^ 1] != NULL) { g_mc_count++; } } else { g_push_count++; }
 		return 0;
 	}
 	if (h->world > 1 && h->pull)

@@ -160,6 +160,8 @@ struct ctb_tensor* ctb_dot_prepare_embed(const struct ctb_tensor* s, int axrange
 int  ctb_dot_exec(const struct ctb_dot_plan* plan, const void* s_data, const void* t_data, void* r_data);
 /* the same with the result stored to 'ndst' buffers (peer-mapped result buffers of all GPUs: GEMM fused with its all-gather) */
 int  ctb_dot_exec_multi(const struct ctb_dot_plan* plan, const void* s_data, const void* t_data, int ndst, void* const* r_datas);
+/* the same with one multimem store per element to the NVSwitch multicast address r_mc (ctbd_mc_buffer_create) */
+int  ctb_dot_exec_mc(const struct ctb_dot_plan* plan, const void* s_data, const void* t_data, void* r_mc);
 void ctb_dot_plan_free(struct ctb_dot_plan* plan);
 struct ctb_tensor* ctb_dot(const struct ctb_tensor* s, int axrange_s, int conj_s,
 	const struct ctb_tensor* t, int axrange_t, int conj_t, int ndim_mult, const int* perm);
@@ -243,6 +245,7 @@ int  ctb_heff_step3(struct ctb_heff* h, void* b_data);
 void* ctb_heff_result_buffer(const struct ctb_heff* h);
 void ctb_dist_release_buffers(void);
 void ctb_dist_counters(long long* fused, long long* allgather);
+long long ctb_dist_multicast_count(void);
 long long ctb_dist_pull_count(void);
 long long ctb_dist_push_count(void);
 /* sharded case: all-gather of the result slices (h->send) and scatter into b_data, or (fused) barrier + local copy; no-op on one rank */

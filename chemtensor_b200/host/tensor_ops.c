@@ -485,6 +485,12 @@ int ctb_dot_exec_multi(const struct ctb_dot_plan* plan, const void* s_data, cons
 	return ctbd_gemm_run_multi(plan->dev, s_data, t_data, ndst, r_datas);
 }
 
+int ctb_dot_exec_mc(const struct ctb_dot_plan* plan, const void* s_data, const void* t_data, void* r_mc)
+{
+	if (plan->ntiles == 0) { return 0; }
+	return ctbd_gemm_run_mc(plan->dev, s_data, t_data, r_mc);
+}
+
 void ctb_dot_plan_free(struct ctb_dot_plan* plan)
 {
 	if (plan->dev != NULL) { ctbd_gemm_plan_destroy(plan->dev); plan->dev = NULL; }

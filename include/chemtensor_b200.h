@@ -145,6 +145,8 @@ long long ctb_dist_pull_exchanges(void);
 /* two-site effective Hamiltonian from the two single-site MPO tensors, no merged pair tensor */
 int ctb_apply_local_hamiltonian_pair(const struct block_sparse_tensor* a, const struct block_sparse_tensor* w0, const struct block_sparse_tensor* w1, const struct block_sparse_tensor* l, const struct block_sparse_tensor* r, struct block_sparse_tensor* b);
 long long ctb_dist_push_exchanges(void);
+/* exchanges of the fused form that went through NVSwitch multicast stores (one store per element instead of one per peer) */
+long long ctb_dist_multicast_exchanges(void);
 /* 1 = CUDA kernels, 2 = host test double (tests/emu only) */
 int ctb_backend(void);
 /* kernels launched by the engine so far */

@@ -109,6 +109,12 @@ int ctbd_peer_buffer_create(size_t bytes, void** handle);
 int ctbd_peer_buffer_ptrs(void* handle, void** ptrs /* [world] */);
 int ctbd_peer_buffer_destroy(void* handle);
 
+/* NVSwitch multicast buffer: every rank allocates 'bytes'; the buffers of all ranks are bound to one multicast object.  *local_ptr is
+ * this rank's buffer, *mc_ptr the multicast address: a (multimem) store to it lands in the buffers of ALL ranks, replicated by the
+ * switch.  Collective call; < 0 on every rank when multicast is not available (callers fall back to the peer-mapped form). */
+int ctbd_mc_buffer_create(size_t bytes, void** handle, void** local_ptr, void** mc_ptr);
+int ctbd_mc_buffer_destroy(void* handle);
+
 /* ---- grouped block GEMM -------------------------------------------------------------------- */
 
 /* one contracted sector tuple of one output block: C += op(A_seg) * op(B_seg), inner extent k */
@@ -190,6 +196,8 @@ int ctbd_gemm_run(void* plan, const void* A, const void* B, void* C);
 /* the same with the epilogue storing every output element to 'ndst' (<= 8) destination buffers: the GEMM fused with the all-gather
  * of its result over NVLink peer memory (Cs[p] = peer-mapped buffer of rank p) */
 int ctbd_gemm_run_multi(void* plan, const void* A, const void* B, int ndst, void* const* Cs);
+/* the same with every output element stored ONCE to a multicast address (ctbd_mc_buffer_create): the switch delivers it to all ranks */
+int ctbd_gemm_run_mc(void* plan, const void* A, const void* B, void* C_mc);
 /* number of tiles / kernel launches one run of the plan issues */
 int ctbd_gemm_plan_info(void* plan, int* ntiles, int* nlaunches);
 

@@ -35,7 +35,11 @@ def make_gloo_allgather(dist, torch, world):
 def main():
     kind, prefix = sys.argv[1], sys.argv[2]
     if len(sys.argv) > 3:
-        os.environ["CTB_EXCHANGE"] = sys.argv[3]      # fused | pull | push | allgather
+        mode = sys.argv[3]      # fused (NVSwitch multicast where available) | fused_uc (one store per peer) | pull | push | allgather
+        if mode == "fused_uc":
+            os.environ["CTB_NO_MULTICAST"] = "1"
+            mode = "fused"
+        os.environ["CTB_EXCHANGE"] = mode
     import torch
     import torch.distributed as dist
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -90,6 +94,7 @@ def main():
     info = (C.c_longlong * 4)()
     eng.ctb_dist_info(info)
     out["exchange_counts"] = np.array([info[2], info[3], eng.ctb_dist_pull_exchanges(), eng.ctb_dist_push_exchanges()], dtype=np.int64)      # fused peer-store, all-gather, pull, push exchanges
+    out["multicast_exchanges"] = np.array([eng.ctb_dist_multicast_exchanges()], dtype=np.int64)
     np.savez(f"{prefix}_rank{rank}.npz", **out)
     eng.ctb_dist_finalize()
     dist.barrier()

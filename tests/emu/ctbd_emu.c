@@ -126,6 +126,25 @@ int ctbd_peer_buffer_destroy(void* handle)
 	free(pb->ptrs); free(pb->names); free(pb);
 	return 0;
 }
+/* "multicast" buffers of the test double: the same shared-memory team; the multicast address is a token (the handle itself), and a
+ * store to it (ctbd_gemm_run_mc) is carried out as stores into the mappings of all ranks -- what the NVSwitch does in hardware */
+int ctbd_mc_buffer_create(size_t bytes, void** handle, void** local_ptr, void** mc_ptr)
+{
+	*local_ptr = NULL; *mc_ptr = NULL;
+	if (getenv("CTB_NO_MULTICAST") != NULL) { *handle = NULL; snprintf(g_err, sizeof(g_err), "multicast disabled"); return -1; }
+	if (ctbd_peer_buffer_create(bytes, handle) < 0) { return -1; }
+	struct emu_peer* pb = *handle;
+	*local_ptr = pb->ptrs[g_rank_emu];
+	*mc_ptr = pb;
+	return 0;
+}
+int ctbd_mc_buffer_destroy(void* handle) { return ctbd_peer_buffer_destroy(handle); }
+int ctbd_gemm_run_multi(void* plan, const void* A, const void* B, int ndst, void* const* Cs);
+int ctbd_gemm_run_mc(void* plan, const void* A, const void* B, void* C_mc)
+{
+	struct emu_peer* pb = C_mc;
+	return ctbd_gemm_run_multi(plan, A, B, pb->world, (void* const*)pb->ptrs);
+}
 int ctbd_gemm_run_multi(void* plan, const void* A, const void* B, int ndst, void* const* Cs)
 {
 	for (int d = 0; d < ndst; d++) { if (Cs[d] != NULL) { int rc = ctbd_gemm_run(plan, A, B, Cs[d]); if (rc < 0) { return rc; } } }

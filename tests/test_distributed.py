@@ -80,22 +80,26 @@ def check(results, single):
 
 def assert_exchange_mode(r, mode):
     counts = tuple(int(x) > 0 for x in r["exchange_counts"])      # fused, all-gather, pull, push
-    want = {"fused": (True, False, False, False), "allgather": (False, True, False, False), "pull": (False, False, True, False), "push": (False, False, False, True)}[mode]
+    want = {"fused": (True, False, False, False), "fused_uc": (True, False, False, False), "allgather": (False, True, False, False), "pull": (False, False, True, False), "push": (False, False, False, True)}[mode]
     assert counts == want, (mode, r["exchange_counts"])
+    if mode == "fused_uc":
+        assert int(r["multicast_exchanges"][0]) == 0
 
 
-@pytest.mark.parametrize("world,mode", [(2, "fused"), (3, "fused"), (2, "allgather"), (2, "pull"), (3, "pull"), (2, "push"), (3, "push")])
+@pytest.mark.parametrize("world,mode", [(2, "fused"), (3, "fused"), (2, "fused_uc"), (2, "allgather"), (2, "pull"), (3, "pull"), (2, "push"), (3, "push")])
 def test_sharded_heff_and_dmrg_gloo(tmp_path, world, mode):
-    """fused: step 3 stores into peer-mapped result buffers (shared memory between the rank processes here, NVLink peer memory on GPUs);
-    allgather: all-gather of the slices + scatter"""
+    """fused: step 3 stores into the result buffers of all ranks -- through one multicast store per element (NVSwitch multicast on GPUs,
+    its shared-memory double here) or, fused_uc, one store per peer-mapped buffer; allgather: all-gather of the slices + scatter"""
     results = run_world("emu", world, tmp_path, mode)
     check(results, single_rank_results(helpers.load("emu")))
     for r in results:
         assert_exchange_mode(r, mode)
+        if mode == "fused":
+            assert int(r["multicast_exchanges"][0]) > 0
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["fused", "allgather", "pull", "push"])
+@pytest.mark.parametrize("mode", ["fused", "fused_uc", "allgather", "pull", "push"])
 def test_sharded_heff_and_dmrg_nccl(tmp_path, mode):
     import torch
     if torch.cuda.device_count() < 2:
@@ -104,3 +108,4 @@ def test_sharded_heff_and_dmrg_nccl(tmp_path, mode):
     check(results, single_rank_results(helpers.load("cuda")))
     for r in results:
         assert_exchange_mode(r, mode)
+    print(f"mode {mode}: multicast exchanges per rank {[int(r['multicast_exchanges'][0]) for r in results]}")
