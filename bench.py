@@ -398,18 +398,26 @@ def sweep_seconds(lib, model, L, params, sector, D, sweeps=2, lanczos=10, tol=0.
     if rc != 0:
         return None
     out = {"s_per_sweep": dt / sweeps, "energies": [float(x) for x in en], "max_bond": int(max(psi.bond_dims()))}
-    if lib.has("ctb_get_stats"):
-        st = (C.c_double * 9)()
-        lib.ctb_get_stats(st, 9)
-        # host wall-clock per phase of the whole call (each phase ends with a device sync)
-        out["phases_s"] = {"lanczos_incl_plans": st[3] / 1e3, "svd_split": st[4] / 1e3, "environments": st[5] / 1e3, "total": st[6] / 1e3,
-                           "heff_calls": int(st[1]), "heff_tflop": st[0] / 1e12, "max_vector_len": int(st[7])}
+    ph = phases(lib)
+    if ph is not None:
+        out["phases_s"] = ph
     return out
+
+
+def phases(lib):
+    """Host wall-clock per phase of the last dmrg_* call of the engine (each phase ends with a device sync)."""
+    if not lib.has("ctb_get_stats"):
+        return None
+    st = (C.c_double * 19)()
+    lib.ctb_get_stats(st, 19)
+    return {"per_sweep_s": [st[11 + i] / 1e3 for i in range(8) if st[11 + i] > 0], "lanczos_incl_plans": st[3] / 1e3, "svd_or_qr_split": st[4] / 1e3, "environments": st[5] / 1e3, "total": st[6] / 1e3,
+            "host_plan_building_within_phases": st[9] / 1e3, "host_reblocking_calls_within_phases": st[10] / 1e3,
+            "heff_calls": int(st[1]), "heff_tflop": st[0] / 1e12, "max_vector_len": int(st[7])}
 
 
 SWEEP_CASES = [
     # (name, model, L, params, sector, D, sweeps, time the reference too?)
-    ("fh_L64_D4096", "fermi_hubbard", 64, (1.0, 4.0, 0.0), workloads.encode_qpair(64, 0), 4096, 1, False),      # BASELINE.json configs[2], the north-star target
+    ("fh_L64_D4096", "fermi_hubbard", 64, (1.0, 4.0, 0.0), workloads.encode_qpair(64, 0), 4096, 2, False),      # BASELINE.json configs[2], the north-star target
     ("fh_L32_D1024", "fermi_hubbard", 32, (1.0, 4.0, 0.0), workloads.encode_qpair(32, 0), 1024, 2, False),
     ("fh_L16_D256", "fermi_hubbard", 16, (1.0, 4.0, 0.0), workloads.encode_qpair(16, 0), 256, 2, True),
 ]
@@ -443,6 +451,54 @@ def molecular_sweep_seconds(lib, n, D, pair_form, sweeps=2, lanczos=10, seed=5):
     if rc != 0:
         return None
     return {"s_per_sweep": dt / sweeps, "energies": [float(x) for x in en], "max_bond": int(max(psi.bond_dims())), "mpo_bond": int(max(mpo_r.bond_dims()))}
+
+
+def perf_dmrg_c1(lib):
+    """BASELINE.json configs[0] = the reference's perf/perf_dmrg.c as shipped (:45-104): spin molecular Hamiltonian of 9 orbitals from
+    the integrals of perf/perf_dmrg_coeffs.py (bit-identical under numpy's default_rng(42)), d = 4, sector (N = 9, 2Sz = 1),
+    seed_rng_state(42) random MPS with max_vdim = 512, dmrg_twosite with 2 sweeps, 25 Lanczos iterations, tol_split = 1e-8.  The MPO
+    and the start state come from the reference's own generators (oracle/_ref, input generation only); the reference's energy on
+    every thread count is -51.2777797066802."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    ref = helpers.load("ref")
+    tkin, vint = helpers.perf_dmrg_coeffs()
+    mpo_r = helpers.ref_molecular_mpo(ref, tkin, vint, spin=True, optimize=False)
+    L = mpo_r.nsites
+    psi_r = helpers.ref_random_mps(ref, np.float64, L, mpo_r.qsite, workloads.encode_qpair(L, 1), 512, seed=42)
+    mpo, psi = (mpo_r, psi_r) if lib is ref else (helpers.clone_chain(lib, mpo_r), helpers.clone_chain(lib, psi_r))
+    en = np.zeros(2); ent = np.zeros(L - 1)
+    t0 = time.perf_counter()
+    rc = lib.dmrg_twosite(mpo.ptr, 2, 25, 1e-8, 512, psi.ptr, en.ctypes.data_as(C.POINTER(C.c_double)), ent.ctypes.data_as(C.POINTER(C.c_double)))
+    dt = time.perf_counter() - t0
+    if rc != 0:
+        return None
+    out = {"wall_s": dt, "energies": [float(x) for x in en], "bond_dims": [int(x) for x in psi.bond_dims()], "mpo_bond_dims": [int(x) for x in mpo_r.bond_dims()]}
+    ph = phases(lib) if lib is not ref else None
+    if ph is not None:
+        out["phases_s"] = ph
+    return out
+
+
+def xxz_c2(lib, single_site: bool, sweeps: int = 1, lanczos: int = 10):
+    """BASELINE.json configs[1]: Heisenberg XXZ chain L = 100 (J = 1, D = 0.8, h = 0.1), U(1) sector 2Sz = 0, max bond 1024,
+    tol_split = 0 (bonds saturate), from the seeded random MPS; two-site sweep or single-site sweep (dmrg_singlesite)."""
+    model, L, params, sector, D = "xxz", 100, (1.0, 0.8, 0.1), 0, 1024
+    if not single_site:
+        return sweep_seconds(lib, model, L, params, sector, D, sweeps=sweeps, lanczos=lanczos)
+    mpo = workloads.mpo_chain(lib, model, L, params)
+    psi = workloads.random_mps(lib, np.float64, L, mpo.qsite, sector, D, seed=42)
+    en = np.zeros(sweeps)
+    t0 = time.perf_counter()
+    rc = lib.dmrg_singlesite(mpo.ptr, sweeps, lanczos, psi.ptr, en.ctypes.data_as(C.POINTER(C.c_double)))
+    dt = time.perf_counter() - t0
+    if rc != 0:
+        return None
+    out = {"s_per_sweep": dt / sweeps, "energies": [float(x) for x in en], "max_bond": int(max(psi.bond_dims()))}
+    ph = phases(lib)
+    if ph is not None:
+        out["phases_s"] = ph
+    return out
 
 
 MOLECULAR_SWEEP_CASES = [
@@ -479,6 +535,35 @@ def sweep_report(lib):
             except Exception as exc:
                 rec["reference_cpu"] = {"failed": str(exc)}
         out.append(rec)
+    # BASELINE.json configs[0]: perf/perf_dmrg.c as shipped, engine and reference side by side
+    rec = {"config": "perf_dmrg_c1", "what": "perf/perf_dmrg.c as shipped: 9 orbitals, sector (9, 1), max_vdim 512, 2 sweeps x 25 Lanczos iterations, tol_split 1e-8",
+           "expected_energy": -51.2777797066802}
+    rec["b200"] = perf_dmrg_c1(lib)
+    if rec["b200"] is not None:
+        rec["b200_repeat_wall_s"] = (perf_dmrg_c1(lib) or {}).get("wall_s")      # second call: plans' device allocations come from the warm pool
+        rec["energy_error_vs_expected"] = abs(rec["b200"]["energies"][-1] - rec["expected_energy"])
+    if os.path.exists(REF_SO):
+        code = (
+            "import sys, json\n"
+            f"sys.path.insert(0, {ROOT!r})\n"
+            f"sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+            "import bench, helpers\n"
+            "print(json.dumps(bench.perf_dmrg_c1(helpers.load('ref'))))\n"
+        )
+        env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+        try:
+            r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
+            rec["reference_cpu"] = json.loads(r.stdout.strip().splitlines()[-1])
+            rec["reference_cpu"]["cores"] = os.cpu_count()
+            if rec["b200"] is not None:
+                rec["max_energy_diff_vs_reference"] = float(np.max(np.abs(np.array(rec["b200"]["energies"]) - np.array(rec["reference_cpu"]["energies"]))))
+                rec["energy_parity_1e-10"] = bool(rec["max_energy_diff_vs_reference"] <= 1e-10)
+        except Exception as exc:
+            rec["reference_cpu"] = {"failed": str(exc)}
+    out.append(rec)
+    # BASELINE.json configs[1]: XXZ L=100, D=1024, two-site and single-site
+    out.append({"config": "xxz_L100_D1024_twosite", "sweeps": 1, "lanczos_iterations": 10, "tol_split": 0.0, "b200": xxz_c2(lib, False)})
+    out.append({"config": "xxz_L100_D1024_singlesite", "sweeps": 1, "lanczos_iterations": 10, "b200": xxz_c2(lib, True)})
     for name, n, D, with_ref in MOLECULAR_SWEEP_CASES:
         rec = {"config": name, "sweeps": 2, "lanczos_iterations": 10, "tol_split": 0.0, "dtype": "c128"}
         rec["b200_merged_pair_tensor"] = molecular_sweep_seconds(lib, n, D, False)

@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(128) bj_gram_kernel(const BjMat* __restrict__ 
  * two Newton steps); an inexact angle only leaves a residual of 1e-7 of the entry, removed at the next visit.  At most
  * 'max_inner' sweeps per visit -- the outer iteration does not converge faster with more (tools/proto_bj2.py).
  * Z (64 x 64) goes to Zbuf, flag = 1 when the pair has to be updated. */
-static constexpr int BJ_EIG_THREADS = 1024;
+static constexpr int BJ_EIG_THREADS = 544;       /* warp 0 computes the rotations, worker warp w = 1 .. 16 owns the slot pairs w - 1 and w + 15 */
 static constexpr int BJ_PS = BJ_P + 2;      /* shared-memory row stride of P and Z (even: 16-byte loads of column pairs) */
 
 /* x^(-1/2) for normal positive x: single-precision seed on the exponent-normalised argument, two Newton steps */
@@ -625,15 +625,15 @@ __device__ __forceinline__ double2 bj_phase(double2 ph, double2 x) { return mul(
  * between the two barriers of a step.  Z only moves when its row pair is rotated. */
 template <typename T>
 __global__ void __launch_bounds__(BJ_EIG_THREADS, (sizeof(T) == 8 ? 2 : 1)) bj_eig_kernel(const BjMat* __restrict__ mats, int nmat, int round, const int* __restrict__ done,
-	const T* __restrict__ Ppart, int nsmax, int max_inner, T* __restrict__ Zbuf, int* __restrict__ flag, int* __restrict__ last_active)
+	const T* __restrict__ Ppart, int nsmax, int max_inner, T* __restrict__ Zbuf, int* __restrict__ flag, int* __restrict__ last_active, long long* __restrict__ dbg)
 {
 	extern __shared__ __align__(16) unsigned char bj_eig_raw[];
 	T* Ps = reinterpret_cast<T*>(bj_eig_raw);
 	T* Zs = Ps + BJ_P * BJ_PS;
 	__shared__ double red[BJ_EIG_THREADS / 32];
-	__shared__ double s_c[32], s_s[32];
-	__shared__ T s_ph[32];
-	__shared__ int s_act[32], s_hp[32], s_hq[32];
+	__shared__ double s_c[2][32], s_s[2][32];      /* rotations of two consecutive steps: Z is updated one step late */
+	__shared__ T s_ph[2][32];
+	__shared__ int s_act[2][32];
 	__shared__ int s_nrot;
 
 	const int item = blockIdx.x, tid = threadIdx.x;
@@ -671,67 +671,129 @@ __global__ void __launch_bounds__(BJ_EIG_THREADS, (sizeof(T) == 8 ? 2 : 1)) bj_e
 	const double vmax = block_max(v, red);
 	if (vmax <= tol2) { if (tid == 0) { flag[item] = 0; } return; }
 
-	const int al = tid >> 5, be = tid & 31;
+	/* Roles.  Warp 0, lane a: rotation of slot pair a from the three entries of its diagonal block.  Worker warp w, lane b: the 2 x 2
+	 * blocks (slot pairs w-1 and w+15) x (slot pair b) of P, and the column pair b of the corresponding rows of Z.  Per step:
+	 *   [warp 0: rotations of this step]  ||  [workers: load their entries of P; apply the PREVIOUS step's rotations to Z]
+	 *   barrier
+	 *   [workers: rotate rows and columns of P, store with the round-robin move of the columns]
+	 *   barrier
+	 * The row pairing is tracked incrementally (position on the 63-cycle), no division in the loop. */
+	const int wp = tid >> 5, be = tid & 31;
+	const bool worker = (wp > 0);
 	const int cb2 = 2 * be;
-	int nrot_prev = 0, nrot_seen = 0;
+	const int dc0 = (be == 0) ? 0 : (be == 31 ? 63 : cb2 + 2);      /* where the columns 2 be, 2 be + 1 move to */
+	const int dc1 = (be == 0) ? 2 : cb2 - 1;
+	int sl[2], qp[2], qq[2];      /* slot pairs of this thread; cycle positions of their two slots */
+	if (worker) { sl[0] = wp - 1; sl[1] = wp + 15; } else { sl[0] = be; sl[1] = be; }
+	#pragma unroll
+	for (int h = 0; h < 2; h++) { qp[h] = bj_pos(2 * sl[h]); qq[h] = bj_pos(2 * sl[h] + 1); }
+	int hp[2], hq[2], hp_prev[2] = { 0, 0 }, hq_prev[2] = { 0, 0 };
+	int nrot_prev = 0, nrot_seen = 0, g = 0;
+	bool have_prev = false;
+
+	auto z_update = [&](int par) {
+		#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const int al = sl[h];
+			if (s_act[par][al] == 0) { continue; }
+			const double ca = s_c[par][al], sa = s_s[par][al];
+			const T pha = s_ph[par][al];
+			T* zp = Zs + hp_prev[h] * BJ_PS + cb2;
+			T* zq = Zs + hq_prev[h] * BJ_PS + cb2;
+			T z00, z01, z10, z11;
+			bj_ld2(zp, z00, z01);
+			bj_ld2(zq, z10, z11);
+			const T w0 = bj_phase(pha, z10), w1 = bj_phase(pha, z11);
+			bj_st2(zq, add(smul(sa, z00), smul(ca, w0)), add(smul(sa, z01), smul(ca, w1)));
+			bj_st2(zp, sub(smul(ca, z00), smul(sa, w0)), sub(smul(ca, z01), smul(sa, w1)));
+		}
+	};
+
 	for (int sweep = 0; sweep < max_inner; sweep++)
 	{
-		for (int step = 0; step < BJ_P - 1; step++)
+		for (int step = 0; step < BJ_P - 1; step++, g++)
 		{
-			if (tid < 32) {
-				const int r2 = 2 * tid;
-				const int hp = bj_home(r2, step), hq = bj_home(r2 + 1, step);
+			const int par = g & 1;
+			const long long c0 = dbg ? clock64() : 0;
+			#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				hp[h] = (sl[h] == 0) ? 0 : bj_cyc(qp[h]);
+				hq[h] = bj_cyc(qq[h]);
+			}
+			T nv[2][4];
+			if (!worker) {
 				double c, sn; T ph;
-				const bool act = bj_rotation<T>(re(Ps[hp * BJ_PS + r2]), re(Ps[hq * BJ_PS + r2 + 1]), Ps[hp * BJ_PS + r2 + 1], tol2, c, sn, ph);
-				s_c[tid] = c; s_s[tid] = sn; s_ph[tid] = ph; s_act[tid] = act ? 1 : 0; s_hp[tid] = hp; s_hq[tid] = hq;
+				const int r2 = 2 * be;
+				const bool act = bj_rotation<T>(re(Ps[hp[0] * BJ_PS + r2]), re(Ps[hq[0] * BJ_PS + r2 + 1]), Ps[hp[0] * BJ_PS + r2 + 1], tol2, c, sn, ph);
+				s_c[par][be] = c; s_s[par][be] = sn; s_ph[par][be] = ph; s_act[par][be] = act ? 1 : 0;
 				const unsigned bal = __ballot_sync(0xffffffffu, act);
-				if (tid == 0) { s_nrot += __popc(bal); }
+				if (be == 0) { s_nrot += __popc(bal); }
 			}
+			else {
+				#pragma unroll
+				for (int h = 0; h < 2; h++) {
+					bj_ld2(Ps + hp[h] * BJ_PS + cb2, nv[h][0], nv[h][1]);
+					bj_ld2(Ps + hq[h] * BJ_PS + cb2, nv[h][2], nv[h][3]);
+				}
+				if (have_prev) { z_update(par ^ 1); }
+			}
+			const long long c1 = dbg ? clock64() : 0;
 			__syncthreads();
+			const long long c2 = dbg ? clock64() : 0;
 			nrot_seen = s_nrot;       /* stable until the next step's rotation phase, which follows this step's last barrier */
-			const bool acta = (s_act[al] != 0), actb = (s_act[be] != 0);
-			T* prow = Ps + s_hp[al] * BJ_PS + cb2;
-			T* qrow = Ps + s_hq[al] * BJ_PS + cb2;
-			T n00, n01, n10, n11;
-			bj_ld2(prow, n00, n01);
-			bj_ld2(qrow, n10, n11);
-			if (acta) {
-				/* rows: r0 = ca b0 - sa (pha b1), r1 = sa b0 + ca (pha b1); the same on the rows of Z */
-				const double ca = s_c[al], sa = s_s[al];
-				const T pha = s_ph[al];
-				const T y0 = bj_phase(pha, n10), y1 = bj_phase(pha, n11);
-				n10 = add(smul(sa, n00), smul(ca, y0)); n11 = add(smul(sa, n01), smul(ca, y1));
-				n00 = sub(smul(ca, n00), smul(sa, y0)); n01 = sub(smul(ca, n01), smul(sa, y1));
-				T* zp = Zs + s_hp[al] * BJ_PS + cb2;
-				T* zq = Zs + s_hq[al] * BJ_PS + cb2;
-				T z00, z01, z10, z11;
-				bj_ld2(zp, z00, z01);
-				bj_ld2(zq, z10, z11);
-				const T w0 = bj_phase(pha, z10), w1 = bj_phase(pha, z11);
-				bj_st2(zq, add(smul(sa, z00), smul(ca, w0)), add(smul(sa, z01), smul(ca, w1)));
-				bj_st2(zp, sub(smul(ca, z00), smul(sa, w0)), sub(smul(ca, z01), smul(sa, w1)));
-			}
-			if (actb) {
-				/* columns: c0' = cb c0 - sb conj(phb) c1, c1' = sb c0 + cb conj(phb) c1 */
-				const double cb = s_c[be], sb = s_s[be];
-				const T cphb = cj(s_ph[be]);
-				const T u0 = bj_phase(cphb, n01), u1 = bj_phase(cphb, n11);
-				n01 = add(smul(sb, n00), smul(cb, u0)); n11 = add(smul(sb, n10), smul(cb, u1));
-				n00 = sub(smul(cb, n00), smul(sb, u0)); n10 = sub(smul(cb, n10), smul(sb, u1));
-			}
-			if (al == be && acta) { n00 = from_real<T>(re(n00)); n11 = from_real<T>(re(n11)); n10 = cj(n01); }
-			/* round-robin move of the columns: lane g receives column 2g from lane g-1 and column 2g+1 from lane g+1 */
+			if (worker)
 			{
-				const T up0 = bj_shfl_up(be == 0 ? n01 : n00), dn0 = bj_shfl_down(n01);
-				const T up1 = bj_shfl_up(be == 0 ? n11 : n10), dn1 = bj_shfl_down(n11);
-				bj_st2(prow, be == 0 ? n00 : up0, be == 31 ? n00 : dn0);
-				bj_st2(qrow, be == 0 ? n10 : up1, be == 31 ? n10 : dn1);
+				const bool actb = (s_act[par][be] != 0);
+				const double cb = s_c[par][be], sb = s_s[par][be];
+				const T cphb = cj(s_ph[par][be]);
+				#pragma unroll
+				for (int h = 0; h < 2; h++)
+				{
+					const int al = sl[h];
+					T n00 = nv[h][0], n01 = nv[h][1], n10 = nv[h][2], n11 = nv[h][3];
+					const bool acta = (s_act[par][al] != 0);
+					if (acta) {
+						/* rows: r0 = ca b0 - sa (pha b1), r1 = sa b0 + ca (pha b1) */
+						const double ca = s_c[par][al], sa = s_s[par][al];
+						const T pha = s_ph[par][al];
+						const T y0 = bj_phase(pha, n10), y1 = bj_phase(pha, n11);
+						n10 = add(smul(sa, n00), smul(ca, y0)); n11 = add(smul(sa, n01), smul(ca, y1));
+						n00 = sub(smul(ca, n00), smul(sa, y0)); n01 = sub(smul(ca, n01), smul(sa, y1));
+					}
+					if (actb) {
+						/* columns: c0' = cb c0 - sb conj(phb) c1, c1' = sb c0 + cb conj(phb) c1 */
+						const T u0 = bj_phase(cphb, n01), u1 = bj_phase(cphb, n11);
+						n01 = add(smul(sb, n00), smul(cb, u0)); n11 = add(smul(sb, n10), smul(cb, u1));
+						n00 = sub(smul(cb, n00), smul(sb, u0)); n10 = sub(smul(cb, n10), smul(sb, u1));
+					}
+					if (al == be && acta) { n00 = from_real<T>(re(n00)); n11 = from_real<T>(re(n11)); n10 = cj(n01); }
+					/* every thread loaded its entries before the barrier, so the moved columns may be stored straight away */
+					T* prow = Ps + hp[h] * BJ_PS;
+					T* qrow = Ps + hq[h] * BJ_PS;
+					prow[dc0] = n00; prow[dc1] = n01; qrow[dc0] = n10; qrow[dc1] = n11;
+				}
 			}
+			const long long c3 = dbg ? clock64() : 0;
 			__syncthreads();
+			if (dbg != nullptr && blockIdx.x == 0 && be == 0 && wp < 2) {
+				/* per role (warp 0 = rotations, warp 1 = a worker): cycles before barrier 1, waiting in it, P update, waiting in barrier 2 */
+				long long* d = dbg + 8 * wp;
+				d[0] += c1 - c0; d[1] += c2 - c1; d[2] += c3 - c2; d[3] += clock64() - c3; d[4] += 1;
+			}
+			#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				hp_prev[h] = hp[h]; hq_prev[h] = hq[h];
+				qp[h] = (qp[h] == 0) ? 62 : qp[h] - 1;
+				qq[h] = (qq[h] == 0) ? 62 : qq[h] - 1;
+			}
+			have_prev = true;
 		}
 		if (nrot_seen == nrot_prev) { break; }
 		nrot_prev = nrot_seen;
 	}
+	/* the rotations of the last step are still owed to Z */
+	if (worker && have_prev) { z_update((g - 1) & 1); }
+	__syncthreads();
 
 	T* z = Zbuf + (size_t)item * (BJ_P * BJ_P);
 	for (int e = tid; e < BJ_P * BJ_P; e += BJ_EIG_THREADS) { z[e] = Zs[(e >> 6) * BJ_PS + (e & 63)]; }
@@ -1030,6 +1092,8 @@ int svd_bj_impl(int nmat, const ctbd_mat_desc* descs, const void* A, void* U, vo
 		[&]() { double f = 0; for (int b = 0; b < nmat; b++) { f += (double)mats[b].R * mats[b].R * mats[b].C; } return f; }(), t_qr - t_start, panels_max); }
 
 	/* ---- stage 2 ---- */
+	void* d_dbg = nullptr;      /* CTB_SVD_EIG_TIMING=1: in-kernel cycle counters of the pair eigen-solver (first pair of the batch) */
+	if (getenv("CTB_SVD_EIG_TIMING") != nullptr && ctbd_malloc(&d_dbg, 16 * sizeof(long long)) < 0) { d_dbg = nullptr; }
 	const int max_cycles = 60;
 	int max_inner = 1;      /* knob: CTB_SVD_INNER_SWEEPS */
 	if (getenv("CTB_SVD_INNER_SWEEPS") != nullptr) { max_inner = std::max(1, atoi(getenv("CTB_SVD_INNER_SWEEPS"))); }
@@ -1043,7 +1107,7 @@ int svd_bj_impl(int nmat, const ctbd_mat_desc* descs, const void* A, void* U, vo
 		for (int r = 0; r < nrounds && rc == 0; r++, round++)
 		{
 			bj_gram_kernel<T><<<dim3((unsigned)items, (unsigned)nsmax), 128, smem_gram, st>>>(dm, nmat, round, done, (const T*)d_X, (T*)d_P, nsmax); check("bj_gram_kernel");
-			bj_eig_kernel<T><<<items, BJ_EIG_THREADS, smem_eig, st>>>(dm, nmat, round, done, (const T*)d_P, nsmax, max_inner, (T*)d_Z, flag, last_active);
+			bj_eig_kernel<T><<<items, BJ_EIG_THREADS, smem_eig, st>>>(dm, nmat, round, done, (const T*)d_P, nsmax, max_inner, (T*)d_Z, flag, last_active, (long long*)d_dbg);
 			check("bj_eig_kernel");
 			bj_update_kernel<T><<<dim3((unsigned)items, (unsigned)((ldmax + BjCfg<T>::NCU - 1) / BjCfg<T>::NCU)), 128, smem_upd, st>>>(dm, nmat, round, flag, (const T*)d_Z, (T*)d_X); check("bj_update_kernel");
 		}
@@ -1067,6 +1131,17 @@ int svd_bj_impl(int nmat, const ctbd_mat_desc* descs, const void* A, void* U, vo
 		bj_write_kernel<T><<<dim3(32, (unsigned)nmat), 256, 0, st>>>(dm, (const T*)d_X, (const double*)d_sig, (const double*)d_sig + smax, ord, (T*)U, (T*)Vh); check("bj_write_kernel");
 	}
 	if (prof) { fprintf(stderr, "[svd_bj] total %.2f ms (%d rounds)\n", now_ms() - t_start, round); }
+	if (d_dbg != nullptr) {
+		long long h[16];
+		if (ctbd_d2h(h, d_dbg, sizeof(h)) == 0) {
+			for (int w = 0; w < 2; w++) {
+				const double n = (double)std::max(1ll, h[8 * w + 4]);
+				fprintf(stderr, "[svd_bj] eig %s: %.0f steps; cycles per step: before barrier 1 %.0f, in barrier 1 %.0f, P update %.0f, in barrier 2 %.0f\n",
+					w == 0 ? "rotation warp" : "worker warp  ", n, h[8 * w] / n, h[8 * w + 1] / n, h[8 * w + 2] / n, h[8 * w + 3] / n);
+			}
+		}
+		ctbd_free(d_dbg);
+	}
 	cleanup();
 	return rc;
 }

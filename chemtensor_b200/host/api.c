@@ -754,10 +754,11 @@ int ctb_heff_plan_info(const struct block_sparse_tensor* a, const struct block_s
 
 int ctb_get_stats(double* out, int n)
 {
-	const double v[9] = {
+	for (int i = 11; i < n && i < 19; i++) { out[i] = ctb_global_stats.sweep_ms[i - 11]; }
+	const double v[11] = {
 		ctb_global_stats.heff_flops, (double)ctb_global_stats.heff_calls, ctb_global_stats.env_flops,
 		ctb_global_stats.lanczos_ms, ctb_global_stats.svd_ms, ctb_global_stats.env_ms, ctb_global_stats.total_ms,
-		(double)ctb_global_stats.max_vector_len, (double)ctb_global_stats.max_bond_dim };
-	for (int i = 0; i < n && i < 9; i++) { out[i] = v[i]; }
+		(double)ctb_global_stats.max_vector_len, (double)ctb_global_stats.max_bond_dim, ctb_global_stats.plan_ms, ctb_global_stats.remap_ms };
+	for (int i = 0; i < n && i < 11; i++) { out[i] = v[i]; }
 	return 0;
 }

@@ -272,8 +272,12 @@ struct ctb_stats
 	double svd_ms, lanczos_ms, env_ms, total_ms;   /* host wall-clock per phase (includes device sync at phase end) */
 	long long max_vector_len;
 	long long max_bond_dim;
+	double plan_ms;          /* host time spent building contraction plans (work lists + their upload), part of the phases above */
+	double remap_ms;         /* host time spent in re-blocking calls (transpose / flatten / split / slice), part of the phases above */
+	double sweep_ms[8];      /* wall-clock of the first eight sweeps of the last dmrg_twosite / dmrg_singlesite call (device synchronised at the end of each) */
 };
 extern struct ctb_stats ctb_global_stats;
+extern double ctb_plan_profile[8];
 
 double ctb_wall_ms(void);
 

@@ -153,6 +153,7 @@ int dmrg_twosite(const struct mpo* hamiltonian, const int num_sweeps, const int 
 	for (int n = 0; n < num_sweeps && ret == 0; n++)
 	{
 		double en = 0;
+		const double t_sweep = ctb_wall_ms();
 		for (int pass = 0; pass < 2 && ret == 0; pass++)
 		{
 			/* pass 0: left to right over pairs 0..L-3; pass 1: right to left over pairs L-2..0 */
@@ -210,12 +211,17 @@ int dmrg_twosite(const struct mpo* hamiltonian, const int num_sweeps, const int 
 		if (ret < 0) { break; }
 		ret = normalize_first_site(&A[0]);
 		en_sweeps[n] = en;
+		if (n < 8) { CTB_CHECK(ctbd_sync()); ctb_global_stats.sweep_ms[n] = ctb_wall_ms() - t_sweep; }
 	}
 
 	if (ret == 0) {
 		CTB_CHECK(ctbd_sync());
 		ctb_global_stats.total_ms = ctb_wall_ms() - t_begin;
 		ret = download_mps(A, psi);
+	}
+	if (getenv("CTB_TRACE_PLAN") != NULL) {
+		fprintf(stderr, "contraction plans: %.0f plans, %.0f output blocks, %.0f table entries; result tensors %.1f ms, host lists (incl.) %.1f ms, device plans %.1f ms\n",
+			ctb_plan_profile[3], ctb_plan_profile[4], ctb_plan_profile[5], ctb_plan_profile[0], ctb_plan_profile[1], ctb_plan_profile[2]);
 	}
 
 	free_tensor_array(h2, nsites);

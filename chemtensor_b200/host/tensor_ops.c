@@ -68,7 +68,73 @@ static void append_offset_table(struct i32vec* tab, int first, int count, const 
 	tab->n += (size_t)total;
 }
 
+/* CTB_TRACE_PLAN: [0] result tensor, [1] host lists incl. [0], [2] device plan, [3] plans, [4] output blocks, [5] table entries */
+double ctb_plan_profile[8] = { 0 };
+
+/* Offset tables depend only on the extents and strides of their axes (and the base offset): blocks of one block row / column with
+ * equal sector dimensions share them.  The cache maps that key to the table already emitted into 'tab' -- on the 5-leg intermediates
+ * of a bond this removes most of the table volume (generation, upload and L2 footprint of the epilogue alike). */
+struct tab_key { int32_t count; int32_t ext[4]; int64_t stride[4]; int64_t base; };
+struct tab_cache { struct tab_key* key; int32_t* off; size_t cap, n; };
+static uint64_t tab_key_hash(const struct tab_key* k)
+{
+	uint64_t h = 1469598103934665603ull ^ (uint64_t)k->count;
+	for (int a = 0; a < 4; a++) { h = (h ^ (uint64_t)(uint32_t)k->ext[a]) * 1099511628211ull; h = (h ^ (uint64_t)k->stride[a]) * 1099511628211ull; }
+	h = (h ^ (uint64_t)k->base) * 1099511628211ull;
+	return h ^ (h >> 31);
+}
+static void tab_cache_init(struct tab_cache* c) { c->cap = 1 << 12; c->n = 0; c->key = calloc(c->cap, sizeof(*c->key)); c->off = malloc(c->cap * sizeof(int32_t)); for (size_t i = 0; i < c->cap; i++) { c->off[i] = -1; } }
+static void tab_cache_free(struct tab_cache* c) { free(c->key); free(c->off); }
+static void tab_cache_grow(struct tab_cache* c)
+{
+	struct tab_cache big; big.cap = c->cap * 2; big.n = c->n;
+	big.key = calloc(big.cap, sizeof(*big.key)); big.off = malloc(big.cap * sizeof(int32_t));
+	for (size_t i = 0; i < big.cap; i++) { big.off[i] = -1; }
+	for (size_t i = 0; i < c->cap; i++) {
+		if (c->off[i] < 0) { continue; }
+		size_t q = (size_t)tab_key_hash(&c->key[i]) & (big.cap - 1);
+		while (big.off[q] >= 0) { q = (q + 1) & (big.cap - 1); }
+		big.key[q] = c->key[i]; big.off[q] = c->off[i];
+	}
+	tab_cache_free(c);
+	*c = big;
+}
+/* start index in 'tab' of the offset table of the given axes: an existing identical table, or a freshly appended one */
+static int32_t cached_offset_table(struct tab_cache* c, struct i32vec* tab, int first, int count, const struct ctb_axis* const* nat, const int* nat_sec,
+	const int* pos_of_nat, const ct_long* stride_r, ct_long base)
+{
+	bool mapped = false;
+	for (int a = 0; a < count; a++) { mapped = mapped || (first + a == g_map_nat); }
+	if (mapped || count > 4) {
+		const int32_t at = (int32_t)tab->n;
+		append_offset_table(tab, first, count, nat, nat_sec, pos_of_nat, stride_r, base);
+		return at;
+	}
+	struct tab_key k;
+	memset(&k, 0, sizeof(k));
+	k.count = count; k.base = base;
+	for (int a = 0; a < count; a++) { k.ext[a] = nat[first + a]->secdim[nat_sec[first + a]]; k.stride[a] = stride_r[pos_of_nat[first + a]]; }
+	size_t q = (size_t)tab_key_hash(&k) & (c->cap - 1);
+	while (c->off[q] >= 0) {
+		if (memcmp(&c->key[q], &k, sizeof(k)) == 0) { return c->off[q]; }
+		q = (q + 1) & (c->cap - 1);
+	}
+	const int32_t at = (int32_t)tab->n;
+	append_offset_table(tab, first, count, nat, nat_sec, pos_of_nat, stride_r, base);
+	c->key[q] = k; c->off[q] = at;
+	if (++c->n * 2 > c->cap) { tab_cache_grow(c); }
+	return at;
+}
+
 struct merge_key { ct_long key; int blk; };
+/* sector of axis 'ax' of x that makes the block idx[] (all other axes given) charge-conserving, or -1 (reference rule, sum dir q = 0) */
+static int conserved_sector(const struct ctb_tensor* x, const int* idx, int ax)
+{
+	qnumber sum = 0;
+	for (int i = 0; i < x->ndim; i++) { if (i != ax) { sum += x->ax[i].dir * x->ax[i].qsec[idx[i]]; } }
+	return ctb_axis_find_sector(&x->ax[ax], -x->ax[ax].dir * sum);
+}
+
 static int cmp_merge_key(const void* a, const void* b)
 {
 	const struct merge_key* x = a; const struct merge_key* y = b;
@@ -116,6 +182,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	struct ctb_axis raxes[CTB_MAXDIM];
 	for (int i = 0; i < ndimr; i++) { ctb_axis_copy(&raxes[i], nat[p[i]]); }
 	struct ctb_tensor* r = ctb_tensor_from_axes(s->dtype, ndimr, raxes, alloc_result);
+	ctb_plan_profile[0] += ctb_wall_ms() - tp_begin;
 
 	const int a_kcontig = (axrange_s == TENSOR_AXIS_RANGE_TRAILING);
 	const int b_ncontig = (axrange_t == TENSOR_AXIS_RANGE_LEADING);
@@ -134,12 +201,15 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	struct ctbd_gemm_out* outs = malloc((r->nblk > 0 ? r->nblk : 1) * sizeof(*outs));
 	int nouts = 0;
 	struct i32vec tab = { NULL, 0, 0 };
+	struct tab_cache tcache;
+	tab_cache_init(&tcache);
 	double flops = 0;
 	const double flop_factor = ctb_is_complex(s->dtype) ? 8.0 : 2.0;
 
-	/* contracted sector grid */
-	ct_long ncontract = 1;
-	for (int i = 0; i < ndim_mult; i++) { ncontract *= s->ax[shift_s + i].nsec; }
+	/* contracted sector grid: the leading ndim_mult - 1 contracted axes are enumerated (row-major, the order in which the reference
+	 * accumulates, :1951-1953), the sector of the last one is fixed by charge conservation -- O(1) instead of a scan over its sectors */
+	ct_long nlead = 1;
+	for (int i = 0; i < ndim_mult - 1; i++) { nlead *= s->ax[shift_s + i].nsec; }
 
 	/* merged form: packed copy of the (small) s operand, one dense M' x K' matrix per distinct group content */
 	int64_t* gather = NULL; size_t ngather = 0, cap_gather = 0;
@@ -220,10 +290,14 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 			int idx_s[CTB_MAXDIM], idx_t[CTB_MAXDIM], kap[CTB_MAXDIM] = { 0 };
 			for (int i = 0; i < nfs; i++) { idx_s[offset_s + i] = nat_sec[i]; }
 			for (int i = 0; i < nft; i++) { idx_t[offset_t + i] = nat_sec[nfs + i]; }
-			for (ct_long c = 0; c < ncontract; c++)
+			/* the last contracted sector follows from charge conservation in s: only the leading contracted sectors are enumerated */
+			for (ct_long cl = 0; cl < nlead; cl++)
 			{
-				for (int i = 0; i < ndim_mult; i++) { idx_s[shift_s + i] = kap[i]; idx_t[shift_t + i] = kap[i]; }
-				const ct_long a_off = s->grid_off[ctb_grid_ravel(s, idx_s)];
+				for (int i = 0; i < ndim_mult - 1; i++) { idx_s[shift_s + i] = kap[i]; }
+				kap[ndim_mult - 1] = conserved_sector(s, idx_s, shift_s + ndim_mult - 1);
+				const bool present = (kap[ndim_mult - 1] >= 0);
+				if (present) { for (int i = 0; i < ndim_mult; i++) { idx_s[shift_s + i] = kap[i]; idx_t[shift_t + i] = kap[i]; } }
+				const ct_long a_off = present ? s->grid_off[ctb_grid_ravel(s, idx_s)] : -1;
 				if (a_off >= 0)
 				{
 					const ct_long b_off = t->grid_off[ctb_grid_ravel(t, idx_t)];
@@ -238,7 +312,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 					g->pad_ = 0;
 					flops += flop_factor * (double)M * (double)N * (double)K;
 				}
-				for (int i = ndim_mult - 1; i >= 0; i--) {
+				for (int i = ndim_mult - 2; i >= 0; i--) {
 					if (++kap[i] < s->ax[shift_s + i].nsec) { break; }
 					kap[i] = 0;
 				}
@@ -252,10 +326,8 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 				st *= (g_embed != NULL) ? g_embed->full->ax[i].secdim[idx_full[i]] : r->ax[i].secdim[idx_r[i]];
 			}
 			CTB_REQUIRE(st < ((ct_long)1 << 31));
-			o->row_tab = (int32_t)tab.n;
-			append_offset_table(&tab, 0, nfs, nat, nat_sec, pos_of_nat, stride_r, 0);
-			o->col_tab = (int32_t)tab.n;
-			append_offset_table(&tab, nfs, nft, nat, nat_sec, pos_of_nat, stride_r, 0);
+			o->row_tab = cached_offset_table(&tcache, &tab, 0, nfs, nat, nat_sec, pos_of_nat, stride_r, 0);
+			o->col_tab = cached_offset_table(&tcache, &tab, nfs, nft, nat, nat_sec, pos_of_nat, stride_r, 0);
 			if (posmap != NULL) { free(posmap); g_map_nat = -1; g_map_pos = NULL; }
 		}
 		else
@@ -265,10 +337,14 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 			for (int i = 0; i < nft; i++) { idx_t[offset_t + i] = nat_sec[nfs + i]; }
 			ct_long Ktot = 0;
 			const size_t seg_first = nseg;
-			for (ct_long c = 0; c < ncontract; c++)
+			for (ct_long cl = 0; cl < nlead; cl++)
 			{
-				for (int i = 0; i < ndim_mult; i++) { idx_t[shift_t + i] = kap[i]; }
-				const ct_long b_off = t->grid_off[ctb_grid_ravel(t, idx_t)];
+				for (int i = 0; i < ndim_mult - 1; i++) { idx_t[shift_t + i] = kap[i]; }
+				kap[ndim_mult - 1] = conserved_sector(t, idx_t, shift_t + ndim_mult - 1);
+				const bool present = (kap[ndim_mult - 1] >= 0);
+				if (present) { idx_t[shift_t + ndim_mult - 1] = kap[ndim_mult - 1]; }
+				const ct_long b_off = present ? t->grid_off[ctb_grid_ravel(t, idx_t)] : -1;
+				const ct_long c = cl * s->ax[shift_s + ndim_mult - 1].nsec + (present ? kap[ndim_mult - 1] : 0);      /* contracted grid cell */
 				if (b_off >= 0)
 				{
 					ct_long K = 1;
@@ -281,7 +357,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 					g->pad_ = (int32_t)c;     /* contracted grid cell, consumed below */
 					Ktot += K;
 				}
-				for (int i = ndim_mult - 1; i >= 0; i--) {
+				for (int i = ndim_mult - 2; i >= 0; i--) {
 					if (++kap[i] < s->ax[shift_s + i].nsec) { break; }
 					kap[i] = 0;
 				}
@@ -362,8 +438,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 					free(rows.v);
 				}
 				/* member column table */
-				const size_t ct0 = tab.n;
-				append_offset_table(&tab, nfs, nft, nat, ns, pos_of_nat, stride_r, 0);
+				const size_t ct0 = (size_t)cached_offset_table(&tcache, &tab, nfs, nft, nat, ns, pos_of_nat, stride_r, 0);
 				for (ct_long i = 0; i < M; i++) { tab.v[rowcol0 + (size_t)(row0 + i)] = (int32_t)ct0; }
 				}
 				/* packed entries of this member's rows */
@@ -446,12 +521,15 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	plan->dev = NULL;
 	const double tpc = ctb_wall_ms();
 	CTB_CHECK_ABORT(ctbd_gemm_plan_create(&h, &plan->dev));
+	ctb_plan_profile[1] += tpc - tp_begin; ctb_plan_profile[2] += ctb_wall_ms() - tpc; ctb_plan_profile[3] += 1; ctb_plan_profile[4] += nouts; ctb_plan_profile[5] += (double)tab.n;
+	ctb_global_stats.plan_ms += ctb_wall_ms() - tp_begin;
 	if (getenv("CTB_TRACE") != NULL) { fprintf(stderr, "  dot plan: host lists %.2f ms, device plan %.2f ms (%d blocks, %d segments, %d table entries)\n", tpc - tp_begin, ctb_wall_ms() - tpc, nouts, (int)nseg, (int)tab.n); }
 	plan->flops = flops;
 	plan->nouts = nouts; plan->nsegs = (int)nseg;
 	plan->ntiles = 0;
 	CTB_CHECK_ABORT(ctbd_gemm_plan_info(plan->dev, &plan->ntiles, NULL));
 
+	tab_cache_free(&tcache);
 	free(tab.v); free(outs); free(segs); free(gather); free(mk); free(packed); free(browtab); free(mgroups); free(mrows);
 	return r;
 }
@@ -513,9 +591,11 @@ struct ctb_tensor* ctb_dot(const struct ctb_tensor* s, int axrange_s, int conj_s
 static void run_remap(struct ctbd_remap_args* args, struct ctb_tensor* dst, struct ctb_tensor* src)
 {
 	if (dst->nstore == 0) { return; }
+	const double t0 = ctb_wall_ms();
 	args->dst_layout = ctb_tensor_layout(dst); args->dst = dst->d;
 	args->src_layout = ctb_tensor_layout(src); args->src = src->d;
 	CTB_CHECK_ABORT(ctbd_remap(args));
+	ctb_global_stats.remap_ms += ctb_wall_ms() - t0;
 }
 
 struct ctb_tensor* ctb_transpose(struct ctb_tensor* t, const int* perm, int conj)

@@ -26,6 +26,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 REF = os.environ.get("CTB_REFERENCE_TREE", "/root/reference")
 
 FIXTURES = {
+    "perf_dmrg_coeffs": "perf/perf_dmrg_coeffs.hdf5",      # integrals of BASELINE.json configs[0] (perf/perf_dmrg.c)
     "dmrg_twosite": "test/algorithm/data/test_dmrg_twosite.hdf5",
     "dmrg_singlesite": "test/algorithm/data/test_dmrg_singlesite.hdf5",
     "retained_bond_indices": "test/algorithm/data/test_retained_bond_indices.hdf5",

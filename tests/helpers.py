@@ -157,13 +157,13 @@ def ref_mpo(ref: cabi.CLibrary, model: str, nsites: int, *params) -> RefChain:
 
 
 def perf_dmrg_coeffs(nsites: int = 9, seed: int = 42):
-    """The integrals of the reference's perf/perf_dmrg_coeffs.py:8-17 (bit-identical under numpy's default_rng)."""
+    """The integrals of the reference's perf/perf_dmrg_coeffs.py:6-17, in the same order of random draws (bit-identical to the
+    datasets of perf/perf_dmrg_coeffs.hdf5 under numpy's default_rng; checked in tests/test_oracle_golden.py)."""
     rng = np.random.default_rng(seed)
-    tkin = 0.5 * rng.standard_normal((nsites, nsites))
-    vint = 0.1 * rng.standard_normal((nsites, nsites, nsites, nsites))
-    tkin = 0.5 * (tkin + tkin.T)
-    vint = 0.5 * (vint + vint.transpose((1, 0, 3, 2)))
-    vint = 0.5 * (vint + vint.transpose((2, 3, 0, 1)))
+    tkin = rng.standard_normal(2 * (nsites,))
+    vint = rng.standard_normal(4 * (nsites,))
+    tkin = 0.5 * (tkin + tkin.conj().T)
+    vint = 0.5 * (vint + vint.conj().transpose(2, 3, 0, 1))
     return tkin, vint
 
 

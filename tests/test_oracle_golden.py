@@ -143,3 +143,13 @@ def test_heff_and_env_known_answers():
     a2, w2, rn = dense("env_d/a_right"), dense("env_d/w_right"), dense("env_d/r_next")
     got = orc.contraction_operator_step_right(a2, a2, w2, r[..., 0])
     assert np.linalg.norm(got - rn[..., 0]) <= 1e-13 * np.linalg.norm(rn)
+
+
+def test_perf_dmrg_coefficients_bit_identical():
+    """BASELINE.json configs[0]: helpers.perf_dmrg_coeffs() reproduces the datasets of the reference's perf/perf_dmrg_coeffs.hdf5
+    (generator perf/perf_dmrg_coeffs.py, numpy default_rng(42)) bit for bit, so the benchmark needs no HDF5 reader at run time."""
+    import helpers
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_perf_dmrg_coeffs.npz"))
+    tkin, vint = helpers.perf_dmrg_coeffs()
+    assert np.array_equal(g["ds/tkin"], tkin)
+    assert np.array_equal(g["ds/vint"], vint)
