@@ -103,8 +103,11 @@ static int download_mps(struct ctb_tensor** A, struct mps* psi)
 {
 	for (int i = 0; i < psi->nsites; i++)
 	{
+		/* into a temporary first: a failed copy must not leave psi holding a released tensor */
+		struct block_sparse_tensor tmp;
+		CTB_CHECK(ctb_download(A[i], &tmp));
 		delete_block_sparse_tensor(&psi->a[i]);
-		CTB_CHECK(ctb_download(A[i], &psi->a[i]));
+		psi->a[i] = tmp;
 	}
 	return 0;
 }

@@ -103,53 +103,49 @@ int ctb_lanczos_min(struct ctb_heff* h, const struct ctb_tensor* a_start, int ma
 	CTB_REQUIRE(ns > 0);
 
 	void* V = NULL; void* w_own = NULL; double* scal = NULL;
-	CTB_CHECK(ctbd_malloc(&V, (size_t)maxiter * (size_t)ns * esize));
-	CTB_CHECK(ctbd_malloc(&w_own, (size_t)ns * esize));
+	double *alpha = NULL, *beta = NULL, *host_scal = NULL;
+	int rc = 0, numiter = maxiter;
+#define LZ(call) do { rc = (call); if (rc < 0) { goto done; } } while (0)
+	/* zero-filled: the alignment padding between the blocks of a packed vector takes part in the level-1 kernels */
+	LZ(ctbd_malloc(&V, (size_t)maxiter * (size_t)ns * esize));
+	LZ(ctbd_malloc(&w_own, (size_t)ns * esize));
 	/* scal: [0..maxiter) alpha (2 doubles each), [..] beta, then scratch */
-	CTB_CHECK(ctbd_malloc((void**)&scal, (size_t)(3 * maxiter + 4) * sizeof(double)));
+	LZ(ctbd_malloc((void**)&scal, (size_t)(3 * maxiter + 4) * sizeof(double)));
 	double* d_alpha = scal;                 /* stride 2 (re, im) */
 	double* d_beta  = scal + 2 * maxiter;
 	double* d_tmp   = scal + 3 * maxiter;
-	double* alpha = ctb_calloc((size_t)maxiter, sizeof(double));
-	double* beta  = ctb_calloc((size_t)maxiter, sizeof(double));
+	alpha = ctb_calloc((size_t)maxiter, sizeof(double));
+	beta  = ctb_calloc((size_t)maxiter, sizeof(double));
+	host_scal = ctb_calloc((size_t)(3 * maxiter + 4), sizeof(double));
 #define VJ(j) ((void*)((char*)V + (size_t)(j) * (size_t)ns * esize))
 
 	/* v_0 = vstart / ||vstart|| */
-	CTB_CHECK(ctbd_nrm2(dtype, ns, a_start->d, d_tmp));
-	CTB_CHECK(ctbd_rscale(dtype, ns, a_start->d, d_tmp, 1, VJ(0)));
+	LZ(ctbd_nrm2(dtype, ns, a_start->d, d_tmp));
+	LZ(ctbd_rscale(dtype, ns, a_start->d, d_tmp, 1, VJ(0)));
 
-	int numiter = maxiter;
-	for (int j = 0; j < maxiter - 1; j++)
+	/* All iterations are enqueued without waiting for the device: the breakdown test of the reference (beta_j < 100 n eps ends the
+	 * iteration with numiter = j + 1, krylov.c:58) is evaluated afterwards on the coefficients -- whatever was computed past a
+	 * breakdown is never read.  One synchronising copy per local solve instead of one per iteration (the small-bond regime is
+	 * launch-bound: a matvec there takes tens of microseconds). */
+	for (int j = 0; j < maxiter; j++)
 	{
 		/* sharded with the fused exchange: work in the landing buffer the peers have stored the result into (no copy) */
 		void* wl = ctb_heff_result_buffer(h);
 		void* w = (wl != NULL) ? wl : w_own;
-		CTB_CHECK(ctb_heff_apply(h, VJ(j), w));
-		CTB_CHECK(ctbd_dotc(dtype, ns, w, VJ(j), d_alpha + 2 * j));
-		CTB_CHECK(ctbd_lanczos_update(dtype, ns, w, VJ(j), j > 0 ? VJ(j - 1) : NULL, d_alpha + 2 * j, j > 0 ? d_beta + (j - 1) : NULL, d_beta + j));
-		double ab[1];
-		CTB_CHECK(ctbd_d2h(ab, d_beta + j, sizeof(double)));
-		beta[j] = ab[0];
-		if (beta[j] < 100 * (double)n * DBL_EPSILON) { numiter = j + 1; break; }
-		CTB_CHECK(ctbd_rscale(dtype, ns, w, d_beta + j, 1, VJ(j + 1)));
+		LZ(ctb_heff_apply(h, VJ(j), w));
+		LZ(ctbd_dotc(dtype, ns, w, VJ(j), d_alpha + 2 * j));
+		if (j == maxiter - 1) { break; }      /* the last iteration only contributes alpha */
+		LZ(ctbd_lanczos_update(dtype, ns, w, VJ(j), j > 0 ? VJ(j - 1) : NULL, d_alpha + 2 * j, j > 0 ? d_beta + (j - 1) : NULL, d_beta + j));
+		LZ(ctbd_rscale(dtype, ns, w, d_beta + j, 1, VJ(j + 1)));
 	}
-	if (numiter == maxiter)
-	{
-		const int j = maxiter - 1;
-		void* wl = ctb_heff_result_buffer(h);
-		void* w = (wl != NULL) ? wl : w_own;
-		CTB_CHECK(ctb_heff_apply(h, VJ(j), w));
-		CTB_CHECK(ctbd_dotc(dtype, ns, w, VJ(j), d_alpha + 2 * j));
-	}
-	{
-		double* atmp = ctb_malloc((size_t)(2 * maxiter) * sizeof(double));
-		CTB_CHECK(ctbd_d2h(atmp, d_alpha, (size_t)(2 * numiter) * sizeof(double)));
-		for (int j = 0; j < numiter; j++) { alpha[j] = atmp[2 * j]; }
-		ctb_free(atmp);
+	LZ(ctbd_d2h(host_scal, scal, (size_t)(3 * maxiter) * sizeof(double)));
+	for (int j = 0; j < maxiter; j++) { alpha[j] = host_scal[2 * j]; }
+	for (int j = 0; j < maxiter - 1; j++) {
+		beta[j] = host_scal[2 * maxiter + j];
+		if (!(beta[j] >= 100 * (double)n * DBL_EPSILON)) { numiter = j + 1; break; }      /* also catches a NaN */
 	}
 	if (numiter_out != NULL) { *numiter_out = numiter; }
 
-	int rc = 0;
 	if (numiter < 1) { rc = -1; }
 	for (int j = 0; j < numiter && rc == 0; j++) {
 		if (!isfinite(alpha[j]) || (j + 1 < numiter && !isfinite(beta[j]))) {
@@ -176,11 +172,13 @@ int ctb_lanczos_min(struct ctb_heff* h, const struct ctb_tensor* a_start, int ma
 		}
 		ctb_free(z);
 	}
+done:
 #undef VJ
-	ctb_free(alpha); ctb_free(beta);
-	CTB_CHECK(ctbd_free(scal));
-	CTB_CHECK(ctbd_free(w_own));
-	CTB_CHECK(ctbd_free(V));
+#undef LZ
+	ctb_free(alpha); ctb_free(beta); ctb_free(host_scal);
+	ctbd_free(scal);
+	ctbd_free(w_own);
+	ctbd_free(V);
 	return rc;
 }
 
