@@ -145,6 +145,7 @@ _EXT_SIGNATURES = {
     "ctb_dist_pull_exchanges": (C.c_longlong, []),
     "ctb_dist_push_exchanges": (C.c_longlong, []),
     "ctb_dist_multicast_exchanges": (C.c_longlong, []),
+    "ctb_retained_bond_indices_device": (C.c_int, [C.POINTER(C.c_double), C.c_int64, C.c_double, C.c_bool, C.c_int64, C.POINTER(IndexList), C.POINTER(TruncInfo)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES) + tuple(_EXT_SIGNATURES) + ("allocate_zero_dense_tensor", "allocate_block_sparse_tensor_like",

@@ -345,6 +345,30 @@ int block_sparse_tensor_svd(const struct block_sparse_tensor* a, struct block_sp
 
 double von_neumann_entropy(const double* sigma, const ct_long n) { return ctb_von_neumann_entropy(sigma, n); }
 
+/* Extension: the same selection through the DEVICE kernels the split uses (ctbd_truncate_select): sigma goes up, the index list and the
+ * three scalars come back.  Exists so that the device rule can be tested against the reference's retained_bond_indices directly. */
+int ctb_retained_bond_indices_device(const double* sigma, const ct_long n, const double tol, const bool relative_thresh, const ct_long max_vdim, struct index_list* list, struct trunc_info* info)
+{
+	CTB_CHECK(ctbd_init(-1));
+	list->ind = NULL; list->num = 0;
+	info->norm_sigma = 0; info->entropy = 0; info->tol_eff = tol;
+	if (n <= 0) { return 0; }
+	double *d_s = NULL, *d_ret = NULL;
+	CTB_CHECK(ctbd_malloc((void**)&d_s, (size_t)n * sizeof(double)));
+	CTB_CHECK(ctbd_malloc((void**)&d_ret, (size_t)n * sizeof(double)));
+	CTB_CHECK(ctbd_h2d(d_s, sigma, (size_t)n * sizeof(double)));
+	ct_long* ind = ctb_malloc((size_t)n * sizeof(ct_long));
+	int64_t nret = 0;
+	double info3[3];
+	int rc = ctbd_truncate_select((int64_t)n, d_s, tol, relative_thresh ? 1 : 0, (int64_t)max_vdim, 0, &nret, (int64_t*)ind, info3, d_ret);
+	ctbd_free(d_ret); ctbd_free(d_s);
+	if (rc < 0) { ctb_free(ind); return rc; }
+	info->norm_sigma = info3[0]; info->entropy = info3[1]; info->tol_eff = info3[2];
+	if (nret == 0) { ctb_free(ind); return 0; }
+	list->ind = ind; list->num = (ct_long)nret;
+	return 0;
+}
+
 void retained_bond_indices(const double* sigma, const ct_long n, const double tol, const bool relative_thresh, const ct_long max_vdim, struct index_list* list, struct trunc_info* info)
 {
 	ctb_retained_bond_indices(sigma, n, tol, relative_thresh, max_vdim, list, info);

@@ -46,35 +46,24 @@ int ctb_split_matrix_svd(struct ctb_tensor* a, double tol, bool relative_thresh,
 	int rc = ctb_svd(a, &u, &s_dev, &ns, &vh);
 	if (rc < 0) { return rc; }
 
-	/* only the singular values cross to the host; the selection rule is integer/ordering logic */
-	double* sigma = ctb_malloc((size_t)ns * sizeof(double));
-	CTB_CHECK(ctbd_d2h(sigma, s_dev, (size_t)ns * sizeof(double)));
-	struct index_list retained;
-	ctb_retained_bond_indices(sigma, ns, tol, relative_thresh, max_vdim, &retained, info);
+	/* the selection rule runs on the device (ctbd_truncate_select); the host receives what its metadata needs -- the ascending list of
+	 * retained indices and three scalars -- and the retained (possibly renormalised) values stay on the device for the scaling */
+	ct_long* ind_buf = ctb_malloc((size_t)(ns > 0 ? ns : 1) * sizeof(ct_long));
+	double* s_ret_dev = NULL;
+	CTB_CHECK(ctbd_malloc((void**)&s_ret_dev, (size_t)(ns > 0 ? ns : 1) * sizeof(double)));
+	int64_t nret64 = 0;
+	double info3[3] = { 0, 0, tol };
+	CTB_CHECK(ctbd_truncate_select((int64_t)ns, s_dev, tol, relative_thresh ? 1 : 0, (int64_t)max_vdim, renormalize ? 1 : 0, &nret64, (int64_t*)ind_buf, info3, s_ret_dev));
+	info->norm_sigma = info3[0]; info->entropy = info3[1]; info->tol_eff = info3[2];
 
-	ct_long nret = retained.num;
-	double* s_ret = NULL;
+	ct_long nret = (ct_long)nret64;
 	const ct_long ind0[1] = { 0 };
-	const ct_long* ind = retained.ind;
+	const ct_long* ind = ind_buf;
 	if (nret == 0)
 	{
-		/* dummy bond of dimension 1 carrying a zero singular value (reference bond_ops.c:50-84) */
+		/* dummy bond of dimension 1 carrying a zero singular value (reference bond_ops.c:50-84); s_ret_dev[0] = 0 */
 		nret = 1;
 		ind = ind0;
-		s_ret = ctb_calloc(1, sizeof(double));
-	}
-	else
-	{
-		s_ret = ctb_malloc((size_t)nret * sizeof(double));
-		for (ct_long i = 0; i < nret; i++) { s_ret[i] = sigma[ind[i]]; }
-		if (renormalize)
-		{
-			double nrm_all = 0;
-			for (ct_long i = 0; i < ns; i++) { nrm_all += sigma[i] * sigma[i]; }
-			nrm_all = sqrt(nrm_all);
-			const double scale = nrm_all / info->norm_sigma;
-			for (ct_long i = 0; i < nret; i++) { s_ret[i] *= scale; }
-		}
 	}
 	struct ctb_tensor* us  = ctb_slice(u, 1, ind, nret);
 	struct ctb_tensor* vhs = ctb_slice(vh, 0, ind, nret);
@@ -82,9 +71,6 @@ int ctb_split_matrix_svd(struct ctb_tensor* a, double tol, bool relative_thresh,
 	ctb_tensor_free(vh);
 	CTB_CHECK(ctbd_free(s_dev));
 
-	double* s_ret_dev = NULL;
-	CTB_CHECK(ctbd_malloc((void**)&s_ret_dev, (size_t)nret * sizeof(double)));
-	CTB_CHECK(ctbd_h2d(s_ret_dev, s_ret, (size_t)nret * sizeof(double)));
 	if (svd_distr == SVD_DISTR_LEFT) {
 		*a0 = ctb_scale_axis(us, 1, s_ret_dev);
 		ctb_tensor_free(us);
@@ -96,9 +82,7 @@ int ctb_split_matrix_svd(struct ctb_tensor* a, double tol, bool relative_thresh,
 		*a0 = us;
 	}
 	CTB_CHECK(ctbd_free(s_ret_dev));
-	ctb_free(s_ret);
-	ctb_free(sigma);
-	ctb_free(retained.ind);
+	ctb_free(ind_buf);
 	return 0;
 }
 

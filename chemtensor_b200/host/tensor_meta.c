@@ -362,13 +362,49 @@ static void block_lists(const struct ctb_tensor* t, const struct block_sparse_te
 	}
 }
 
-/* payload copy of ctb_upload: the separately allocated host blocks stream through the pinned staging ring of the device layer */
+/* payload copy of ctb_upload: the separately allocated host blocks stream through the pinned staging ring of the device layer.
+ * One process per GPU (ctb_dist_world > 1): every rank holds the same host tensor, so each uploads only ITS 1/world byte range of the
+ * packed layout over its own PCIe link and the ranges are all-gathered over NVLink -- the host-to-device traffic of a call shrinks
+ * with the number of ranks instead of being repeated by every one of them (collective: all ranks upload the same tensors in the
+ * same order, which the one-process-per-GPU contract already demands). */
+#define CTB_SHARDED_UPLOAD_MIN ((int64_t)8 << 20)
 int ctb_upload_data(struct ctb_tensor* t, const struct block_sparse_tensor* h)
 {
 	if (t->nstore == 0) { return 0; }
 	void** hptrs; int64_t* offs; int64_t* lens;
 	block_lists(t, h, &hptrs, &offs, &lens);
-	const int rc = ctbd_h2d_blocks(t->d, t->nblk, (const void* const*)hptrs, offs, lens);
+	const int64_t total = (int64_t)t->nstore * (int64_t)ctb_sizeof_dtype(t->dtype);
+	int rc = 0;
+	const char* env_min = getenv("CTB_SHARDED_UPLOAD_MIN");      /* bytes; the tests lower it to exercise the path on small tensors */
+	const int64_t min_bytes = (env_min != NULL) ? (int64_t)atoll(env_min) : CTB_SHARDED_UPLOAD_MIN;
+	if (ctb_dist_world > 1 && total >= min_bytes && getenv("CTB_NO_SHARDED_UPLOAD") == NULL)
+	{
+		const int W = ctb_dist_world, me = ctb_dist_rank;
+		int64_t chunk = (total + W - 1) / W;
+		chunk = (chunk + 255) / 256 * 256;
+		const int64_t lo = (int64_t)me * chunk, hi = (lo + chunk < total) ? lo + chunk : total;
+		void* tmp = NULL;
+		rc = ctbd_malloc(&tmp, (size_t)chunk * (size_t)W);      /* zero-filled: the alignment padding between blocks stays zero */
+		if (rc == 0)
+		{
+			/* the pieces of the host blocks that fall into [lo, hi) */
+			int nb = 0;
+			for (int b = 0; b < t->nblk; b++)
+			{
+				const int64_t b0 = offs[b], b1 = offs[b] + lens[b];
+				const int64_t c0 = b0 > lo ? b0 : lo, c1 = b1 < hi ? b1 : hi;
+				if (c1 <= c0) { continue; }
+				hptrs[nb] = (char*)hptrs[b] + (c0 - b0); offs[nb] = c0; lens[nb] = c1 - c0; nb++;
+			}
+			rc = ctbd_h2d_blocks(tmp, nb, (const void* const*)hptrs, offs, lens);
+			if (rc == 0) { rc = ctbd_allgather((char*)tmp + lo, tmp, (size_t)chunk); }      /* in place: the own range already sits in its slot */
+			if (rc == 0) { rc = ctbd_d2d(t->d, tmp, (size_t)total); }
+			ctbd_free(tmp);
+		}
+	}
+	else {
+		rc = ctbd_h2d_blocks(t->d, t->nblk, (const void* const*)hptrs, offs, lens);
+	}
 	free(hptrs); free(offs); free(lens);
 	return rc;
 }

@@ -69,6 +69,8 @@ int block_sparse_tensor_svd(const struct block_sparse_tensor* a, struct block_sp
 /* include/algorithm/truncation.h:10, :40; src/algorithm/truncation.c:13, :110 */
 double von_neumann_entropy(const double* sigma, const ct_long n);
 void retained_bond_indices(const double* sigma, const ct_long n, const double tol, const bool relative_thresh, const ct_long max_vdim, struct index_list* list, struct trunc_info* info);
+/* extension: the same rule evaluated by the device kernels the SVD split uses (rank sort + sequential sums on the GPU) */
+int ctb_retained_bond_indices_device(const double* sigma, const ct_long n, const double tol, const bool relative_thresh, const ct_long max_vdim, struct index_list* list, struct trunc_info* info);
 /* include/algorithm/bond_ops.h:22; src/algorithm/bond_ops.c:15 */
 int split_block_sparse_matrix_svd(const struct block_sparse_tensor* a, const double tol, const bool relative_thresh, const ct_long max_vdim, const bool renormalize, const enum singular_value_distr svd_distr, struct block_sparse_tensor* a0, struct block_sparse_tensor* a1, struct trunc_info* info);
 

@@ -309,6 +309,13 @@ int ctbd_svd_batched(int dtype, int nmat, const struct ctbd_mat_desc* descs_host
 int ctbd_svdws_create(int dtype, int nmat, const struct ctbd_mat_desc* descs_host, const void* A, void** ws, void** G, int64_t* g_total);
 int ctbd_svdws_finish(void* ws, const void* G_cur, int polish, void* U, void* Vh, double* S_dev);
 int ctbd_gram_offdiag(int dtype, int ngram, const int64_t* off_dev, const int32_t* dim_dev, const void* G, double floor_rel, double* out_dev);
+/* Singular-value selection of a split on the device (reference src/algorithm/truncation.c:110-223, same integer / ordering and
+ * floating-point semantics, equal values ordered by index): S_dev holds n singular values.  Returns on the HOST what the tensor
+ * metadata needs -- the ascending list of retained indices (ind_host, capacity n), their number, and info3 = { norm_sigma, entropy,
+ * tol_eff } -- and on the DEVICE the retained values, rescaled to the norm of all values when renormalize != 0 (s_ret_dev,
+ * capacity n).  The singular values themselves do not cross to the host. */
+int ctbd_truncate_select(int64_t n, const double* S_dev, double tol, int relative, int64_t max_vdim, int renormalize,
+	int64_t* nret, int64_t* ind_host, double* info3_host, double* s_ret_dev);
 /* rq == 0: A = Q R (Q: m x k isometry, R upper triangular);  rq != 0: A = R Q (Q: k x n) */
 int ctbd_qr_batched(int dtype, int rq, int nmat, const struct ctbd_mat_desc* descs_host,
 	const void* A, void* O0, void* O1);

@@ -40,6 +40,8 @@ def main():
             os.environ["CTB_NO_MULTICAST"] = "1"
             mode = "fused"
         os.environ["CTB_EXCHANGE"] = mode
+        if mode in ("fused", "allgather"):
+            os.environ["CTB_SHARDED_UPLOAD_MIN"] = "1"      # every host tensor goes up as 1/world per rank + all-gather
     import torch
     import torch.distributed as dist
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])

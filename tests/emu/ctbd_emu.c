@@ -761,3 +761,58 @@ int ctbd_qr_batched(int dtype, int rq, int nmat, const struct ctbd_mat_desc* d, 
 	}
 	return 0;
 }
+
+/* ---- singular-value selection (see ctb_device.h): plain loops with the reference's rule, equal values ordered by index ---- */
+struct emu_sv { double v; int64_t i; };
+static int emu_cmp_sv(const void* a, const void* b)
+{
+	const struct emu_sv* x = a; const struct emu_sv* y = b;
+	if (x->v < y->v) { return -1; }
+	if (x->v > y->v) { return 1; }
+	return (x->i > y->i) - (x->i < y->i);
+}
+int ctbd_truncate_select(int64_t n, const double* S, double tol, int relative, int64_t max_vdim, int renormalize,
+	int64_t* nret, int64_t* ind_host, double* info3, double* s_ret)
+{
+	*nret = 0; info3[0] = 0; info3[1] = 0; info3[2] = tol;
+	if (n <= 0) { return 0; }
+	struct emu_sv* srt = malloc((size_t)n * sizeof(*srt));
+	for (int64_t i = 0; i < n; i++) { srt[i].v = S[i]; srt[i].i = i; }
+	qsort(srt, (size_t)n, sizeof(*srt), emu_cmp_sv);
+	double sqsum = 0;
+	for (int64_t i = 0; i < n; i++) { srt[i].v = srt[i].v * srt[i].v; sqsum += srt[i].v; }
+	if (sqsum == 0) { free(srt); s_ret[0] = 0; return 0; }
+	if (relative) { for (int64_t i = 0; i < n; i++) { srt[i].v /= sqsum; } }
+	for (int64_t i = 1; i < n; i++) { srt[i].v += srt[i - 1].v; }
+	if (max_vdim < n) {
+		info3[2] = fmax(tol, srt[n - max_vdim - 1].v);
+		for (int64_t i = 0; i < n - max_vdim; i++) { srt[i].v = 0; }
+	}
+	double* accum = malloc((size_t)n * sizeof(double));
+	for (int64_t i = 0; i < n; i++) { accum[srt[i].i] = srt[i].v; }
+	free(srt);
+	int64_t num = 0;
+	double scale = 0, ssq = 1, nrm_all = 0;
+	for (int64_t i = 0; i < n; i++) {
+		nrm_all += S[i] * S[i];
+		if (!(accum[i] > tol)) { continue; }
+		ind_host[num++] = i;
+		const double a = fabs(S[i]);
+		if (a > 0) {
+			if (scale < a) { ssq = 1 + ssq * (scale / a) * (scale / a); scale = a; }
+			else { ssq += (a / scale) * (a / scale); }
+		}
+	}
+	free(accum);
+	if (num == 0) { s_ret[0] = 0; return 0; }
+	const double norm_sigma = scale * sqrt(ssq);
+	const double resc = renormalize ? sqrt(nrm_all) / norm_sigma : 1.0;
+	double entropy = 0;
+	for (int64_t k = 0; k < num; k++) {
+		const double p = S[ind_host[k]] / norm_sigma;
+		if (p > 0) { const double sq = p * p; entropy -= sq * log(sq); }
+		s_ret[k] = renormalize ? S[ind_host[k]] * resc : S[ind_host[k]];
+	}
+	*nret = num; info3[0] = norm_sigma; info3[1] = entropy;
+	return 0;
+}

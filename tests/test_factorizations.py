@@ -308,3 +308,43 @@ def test_factorizations_of_tiny_magnitudes(ref, rng):
     sv = np.ctypeslib.as_array(C.cast(s.data, C.POINTER(C.c_double)), shape=(ns,)).copy()
     assert helpers.rel_err((u.to_dense() * sv) @ vh.to_dense(), dense) <= 1e-13
     eng.delete_dense_tensor(C.byref(s))
+
+
+@pytest.mark.parametrize("case", ["random", "ties", "all_equal", "zeros", "max_vdim_cut", "absolute"])
+def test_retained_bond_indices_device_rule(eng, ref, rng, case):
+    """The selection kernels of the split (rank sort with index tie-break, sequential round-to-nearest sums) against the reference's
+    retained_bond_indices (truncation.c:110-223): index list exact -- also with exactly equal singular values at the cut, where the
+    order of equal values decides -- norm and entropy to 1e-13, tol_eff exact."""
+    n = 517
+    sigma = np.abs(rng.standard_normal(n)) * np.exp(-0.02 * np.arange(n))
+    tol, relative, max_vdim = 1e-4, True, 10 ** 6
+    if case == "ties":
+        sigma = np.round(sigma, 2)                # many exactly equal values, some of them zero
+        rng.shuffle(sigma)
+        tol = 0.02
+    elif case == "all_equal":
+        sigma[:] = 0.25
+        tol = 0.3
+    elif case == "zeros":
+        sigma[:] = 0.0
+    elif case == "max_vdim_cut":
+        sigma = np.round(sigma, 2)
+        rng.shuffle(sigma)
+        tol, max_vdim = 0.0, 97
+    elif case == "absolute":
+        tol, relative = 0.37, False
+    sigma = np.ascontiguousarray(sigma)
+    out = []
+    for lib, fn in ((eng, "ctb_retained_bond_indices_device"), (ref, "retained_bond_indices")):
+        lst, info = cabi.IndexList(), cabi.TruncInfo()
+        getattr(lib, fn)(sigma.ctypes.data_as(C.POINTER(C.c_double)), n, tol, relative, max_vdim, C.byref(lst), C.byref(info))
+        out.append(([int(lst.ind[i]) for i in range(lst.num)], info.norm_sigma, info.entropy, info.tol_eff))
+    if case in ("ties", "max_vdim_cut", "all_equal"):
+        # equal values: the reference's qsort leaves their order open; the number retained and the retained VALUES are defined
+        assert len(out[0][0]) == len(out[1][0])
+        assert np.array_equal(np.sort(sigma[out[0][0]]), np.sort(sigma[out[1][0]]))
+    else:
+        assert out[0][0] == out[1][0]
+    assert abs(out[0][1] - out[1][1]) <= 1e-13 * max(1.0, abs(out[1][1]))
+    assert abs(out[0][2] - out[1][2]) <= 1e-12
+    assert out[0][3] == out[1][3]
