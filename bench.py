@@ -315,6 +315,16 @@ def main():
         t_ms = float(tt.item())
     value = flops_total / (t_ms * 1e-3) / 1e12
 
+    # strong scaling of whole two-site sweeps: every rank runs the same dmrg_twosite call (sharded matvec, sector-sharded SVD)
+    sweep_dist = None
+    if args.sweep and world > 1:
+        sweep_dist = []
+        for name, model, L_, params_, sector_, D_, nsw, _ in SWEEP_CASES[:2]:
+            nsw = 1 if D_ >= 4096 else nsw
+            rec = {"config": name, "sweeps": nsw, "lanczos_iterations": 10, "tol_split": 0.0, "n_gpus": world,
+                   "sharded": "effective-Hamiltonian applications by bra-bond column slices (exchange as in config.multi_gpu); SVD split by sector blocks dealt to the ranks by cost, one all-gather of the factors; environments, plans and level-1 work replicated"}
+            rec["b200"] = sweep_seconds(lib, model, L_, params_, sector_, D_, sweeps=nsw)
+            sweep_dist.append(rec)
     if rank != 0:
         return
     kdom = int(np.argmax([step_ms[i] for i in range(3)]))
@@ -356,6 +366,8 @@ def main():
     }
     if args.sweep and world == 1:
         line["sweep"] = sweep_report(lib)
+    elif sweep_dist is not None:
+        line["sweep"] = sweep_dist
     if not args.no_cpu_baseline:
         base = cpu_baseline(wl, flops_total, args.structure, dump=b_dump_path(wl) if world > 1 else None)
         line["cpu_baseline"] = base

@@ -145,6 +145,7 @@ _EXT_SIGNATURES = {
     "ctb_dist_pull_exchanges": (C.c_longlong, []),
     "ctb_dist_push_exchanges": (C.c_longlong, []),
     "ctb_dist_multicast_exchanges": (C.c_longlong, []),
+    "ctb_remap_benchmark": (C.c_int, [_P_BST, C.POINTER(C.c_double)]),
     "ctb_retained_bond_indices_device": (C.c_int, [C.POINTER(C.c_double), C.c_int64, C.c_double, C.c_bool, C.c_int64, C.POINTER(IndexList), C.POINTER(TruncInfo)]),
 }
 

@@ -776,6 +776,59 @@ int ctb_heff_plan_info(const struct block_sparse_tensor* a, const struct block_s
 	return rc;
 }
 
+/* device time (CUDA events, 192 MiB L2 flush between repetitions) of the re-blocking kernel on a device-resident tensor:
+ * out[0], out[1] = ms and algorithmic bytes (2 x stored entries x element size) of transposing the axes to reverse order;
+ * out[2], out[3] = the same for fusing axes (0, 1) -- the HBM-bound kernels of merge / split (reference block_sparse_tensor.c:785, :950) */
+int ctb_remap_benchmark(const struct block_sparse_tensor* t, double* out)
+{
+	CTB_CHECK(ctbd_init(-1));
+	struct ctb_tensor* td = ctb_upload(t);
+	const size_t flush_bytes = (size_t)192 << 20;
+	void* flush = NULL;
+	CTB_CHECK(ctbd_malloc(&flush, flush_bytes));
+	void *e0 = NULL, *e1 = NULL;
+	CTB_CHECK(ctbd_event_create(&e0)); CTB_CHECK(ctbd_event_create(&e1));
+	const double bytes = 2.0 * (double)td->nelem * (double)ctb_sizeof_dtype(td->dtype);
+	int perm[CTB_MAXDIM];
+	for (int i = 0; i < td->ndim; i++) { perm[i] = td->ndim - 1 - i; }
+	for (int which = 0; which < 2; which++)
+	{
+		double best = 1e30;
+		for (int rep = 0; rep < 5; rep++)
+		{
+			/* the first call also uploads the sector tables of both layouts; it is not the one that counts */
+			CTB_CHECK(ctbd_memset_zero(flush, flush_bytes));
+			struct ctb_tensor* r = NULL;
+			if (which == 0) {
+				/* destination allocated outside the timed region */
+				struct ctb_tensor* warm = ctb_transpose(td, perm, 0);
+				CTB_CHECK(ctbd_memset_zero(flush, flush_bytes));
+				CTB_CHECK(ctbd_event_record(e0));
+				r = ctb_transpose(td, perm, 0);
+				CTB_CHECK(ctbd_event_record(e1));
+				ctb_tensor_free(warm);
+			}
+			else {
+				struct ctb_tensor* warm = ctb_flatten_axes(td, 0, td->ax[0].dir);
+				CTB_CHECK(ctbd_memset_zero(flush, flush_bytes));
+				CTB_CHECK(ctbd_event_record(e0));
+				r = ctb_flatten_axes(td, 0, td->ax[0].dir);
+				CTB_CHECK(ctbd_event_record(e1));
+				ctb_tensor_free(warm);
+			}
+			float ms = 0;
+			CTB_CHECK(ctbd_event_elapsed_ms(e0, e1, &ms));
+			if (rep > 0 && ms < best) { best = ms; }
+			ctb_tensor_free(r);
+		}
+		out[2 * which] = best; out[2 * which + 1] = bytes;
+	}
+	ctbd_event_destroy(e0); ctbd_event_destroy(e1);
+	CTB_CHECK(ctbd_free(flush));
+	ctb_tensor_free(td);
+	return 0;
+}
+
 int ctb_get_stats(double* out, int n)
 {
 	for (int i = 11; i < n && i < 19; i++) { out[i] = ctb_global_stats.sweep_ms[i - 11]; }

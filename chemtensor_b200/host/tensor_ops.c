@@ -518,6 +518,15 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	if (merge) { h.a_gather = gather; h.n_a_gather = (int64_t)ngather; h.a_src = s->d; }
 	if (use_rowtab && nbrow > 0) { h.b_rowtab = browtab; h.n_b_rowtab = (int64_t)nbrow; }
 	if (mixmode && nmg > 0) { h.mix_groups = mgroups; h.n_mix_groups = (int32_t)nmg; h.mix_rows = mrows; h.n_mix_rows = (int32_t)nmr; }
+	if (getenv("CTB_DUMP_PLAN") != NULL) {
+		/* tuning aid: (m, n, total k) of every output block, appended as text */
+		FILE* f = fopen(getenv("CTB_DUMP_PLAN"), "a");
+		if (f != NULL) {
+			fprintf(f, "plan %d\n", nouts);
+			for (int b = 0; b < nouts; b++) { long long kt = 0; for (int q = outs[b].seg_begin; q < outs[b].seg_end; q++) { kt += segs[q].k; } fprintf(f, "%d %d %lld %d\n", outs[b].m, outs[b].n, kt, outs[b].seg_end - outs[b].seg_begin); }
+			fclose(f);
+		}
+	}
 	plan->dev = NULL;
 	const double tpc = ctb_wall_ms();
 	CTB_CHECK_ABORT(ctbd_gemm_plan_create(&h, &plan->dev));
@@ -833,6 +842,83 @@ static int build_mat_descs(const struct ctb_tensor* a, const struct ctb_tensor* 
 	return n;
 }
 
+/* One process per GPU ("SVD/QR: sectors are independent -> distribute sector blocks by cost m n min(m, n)"): the
+ * sector blocks are dealt to the ranks longest-processing-time first, every rank factorises its own blocks, packs U, Vh and the
+ * singular values of those blocks into one buffer, and ONE all-gather hands every rank the factors of all blocks (each block is
+ * computed by exactly one rank, so all ranks end up with bit-identical tensors, as the replicated form gave them). */
+struct svd_owner { double cost; int blk; };
+static int cmp_svd_owner(const void* x, const void* y)
+{
+	const struct svd_owner* a = x; const struct svd_owner* b = y;
+	if (a->cost != b->cost) { return a->cost > b->cost ? -1 : 1; }
+	return (a->blk > b->blk) - (a->blk < b->blk);
+}
+static int svd_sharded(struct ctb_tensor* a, struct ctb_tensor* u, struct ctb_tensor* vh, double* s_dev, int nmat, const struct ctbd_mat_desc* descs)
+{
+	const int W = ctb_dist_world, me = ctb_dist_rank;
+	const size_t es = ctb_sizeof_dtype(a->dtype);
+	struct svd_owner* ord = malloc((size_t)nmat * sizeof(*ord));
+	for (int b = 0; b < nmat; b++) {
+		const double r = descs[b].m < descs[b].n ? descs[b].m : descs[b].n, c = descs[b].m < descs[b].n ? descs[b].n : descs[b].m;
+		ord[b].cost = r * r * c; ord[b].blk = b;
+	}
+	qsort(ord, (size_t)nmat, sizeof(*ord), cmp_svd_owner);
+	int* owner = malloc((size_t)nmat * sizeof(int));
+	double* load = calloc((size_t)W, sizeof(double));
+	int64_t* bytes = calloc((size_t)W, sizeof(int64_t));      /* packed size of every rank's results */
+	int64_t* pos = malloc((size_t)nmat * sizeof(int64_t));    /* byte offset of a block inside its owner's packed buffer */
+	for (int q = 0; q < nmat; q++) {
+		int best = 0;
+		for (int p = 1; p < W; p++) { if (load[p] < load[best]) { best = p; } }
+		const int b = ord[q].blk;
+		owner[b] = best; load[best] += ord[q].cost;
+	}
+	for (int b = 0; b < nmat; b++) {
+		const int64_t k = descs[b].m < descs[b].n ? descs[b].m : descs[b].n;
+		pos[b] = bytes[owner[b]];
+		int64_t sz = ((int64_t)descs[b].m * k + k * (int64_t)descs[b].n) * (int64_t)es + k * (int64_t)sizeof(double);
+		bytes[owner[b]] += (sz + 15) / 16 * 16;
+	}
+	int64_t slot = 16;
+	for (int p = 0; p < W; p++) { if (bytes[p] > slot) { slot = bytes[p]; } }
+	slot = (slot + 255) / 256 * 256;
+
+	/* own blocks */
+	struct ctbd_mat_desc* mine = malloc((size_t)nmat * sizeof(*mine));
+	int nmine = 0;
+	for (int b = 0; b < nmat; b++) { if (owner[b] == me) { mine[nmine++] = descs[b]; } }
+	int rc = (nmine > 0) ? ctbd_svd_batched(a->dtype, nmine, mine, a->d, u->d, vh->d, s_dev) : 0;
+	free(mine);
+
+	void* pack = NULL;
+	if (rc == 0) { rc = ctbd_malloc_noinit(&pack, (size_t)slot * (size_t)W); }
+	if (rc == 0)
+	{
+		char* my = (char*)pack + (size_t)me * (size_t)slot;
+		for (int b = 0; b < nmat && rc == 0; b++) {
+			if (owner[b] != me) { continue; }
+			const int64_t k = descs[b].m < descs[b].n ? descs[b].m : descs[b].n;
+			const size_t nu = (size_t)descs[b].m * (size_t)k * es, nv = (size_t)k * (size_t)descs[b].n * es;
+			rc = ctbd_d2d(my + pos[b], (const char*)u->d + (size_t)descs[b].o0_off * es, nu);
+			if (rc == 0) { rc = ctbd_d2d(my + pos[b] + nu, (const char*)vh->d + (size_t)descs[b].o1_off * es, nv); }
+			if (rc == 0) { rc = ctbd_d2d(my + pos[b] + nu + nv, (const char*)s_dev + (size_t)descs[b].s_off * sizeof(double), (size_t)k * sizeof(double)); }
+		}
+		if (rc == 0) { rc = ctbd_allgather(my, pack, (size_t)slot); }
+		for (int b = 0; b < nmat && rc == 0; b++) {
+			if (owner[b] == me) { continue; }
+			const char* src = (const char*)pack + (size_t)owner[b] * (size_t)slot + pos[b];
+			const int64_t k = descs[b].m < descs[b].n ? descs[b].m : descs[b].n;
+			const size_t nu = (size_t)descs[b].m * (size_t)k * es, nv = (size_t)k * (size_t)descs[b].n * es;
+			rc = ctbd_d2d((char*)u->d + (size_t)descs[b].o0_off * es, src, nu);
+			if (rc == 0) { rc = ctbd_d2d((char*)vh->d + (size_t)descs[b].o1_off * es, src + nu, nv); }
+			if (rc == 0) { rc = ctbd_d2d((char*)s_dev + (size_t)descs[b].s_off * sizeof(double), src + nu + nv, (size_t)k * sizeof(double)); }
+		}
+	}
+	if (pack != NULL) { ctbd_free(pack); }
+	free(pos); free(bytes); free(load); free(owner); free(ord);
+	return rc;
+}
+
 static int svd_direct(struct ctb_tensor* a, struct ctb_tensor** u, double** s_dev, ct_long* ns, struct ctb_tensor** vh)
 {
 	CTB_REQUIRE(a->ndim == 2);
@@ -870,7 +956,9 @@ static int svd_direct(struct ctb_tensor* a, struct ctb_tensor** u, double** s_de
 	}
 	struct ctbd_mat_desc* descs = malloc((size_t)a->nblk * sizeof(*descs));
 	const int nmat = build_mat_descs(a, *u, *vh, 0, descs);
-	int rc = ctbd_svd_batched(a->dtype, nmat, descs, a->d, (*u)->d, (*vh)->d, *s_dev);
+	int rc;
+	if (ctb_dist_world > 1 && nmat > 1 && getenv("CTB_NO_SHARDED_SVD") == NULL) { rc = svd_sharded(a, *u, *vh, *s_dev, nmat, descs); }
+	else { rc = ctbd_svd_batched(a->dtype, nmat, descs, a->d, (*u)->d, (*vh)->d, *s_dev); }
 	free(descs);
 	if (rc < 0) { fprintf(stderr, "chemtensor_b200: batched SVD failed: %s\n", ctbd_last_error()); return -1; }
 	return 0;

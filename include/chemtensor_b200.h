@@ -170,6 +170,8 @@ int ctb_heff_plan_info(const struct block_sparse_tensor* a, const struct block_s
  * [0] heff flops, [1] heff calls, [2] env flops, [3] lanczos ms, [4] svd ms, [5] env ms, [6] total ms,
  * [7] longest Lanczos vector, [8] largest bond dimension */
 int ctb_get_stats(double* out, int n);
+/* device time and algorithmic bytes of the re-blocking kernel on t: out = { ms transpose, bytes, ms flatten(0,1), bytes } */
+int ctb_remap_benchmark(const struct block_sparse_tensor* t, double* out);
 
 #ifdef __cplusplus
 }

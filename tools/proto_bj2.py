@@ -207,6 +207,14 @@ if __name__ == "__main__":
                 Vho = (Qf @ W.T).T
                 print("  sigma rel err max %.2e" % np.max(np.abs(np.sort(sig)[::-1] - sv) / sv), " U orth %.2e" % np.abs(Uo.T @ Uo - np.eye(R)).max(),
                       " Vh orth %.2e" % np.abs(Vho @ Vho.T - np.eye(R)).max(), " recon %.2e" % (np.abs((Uo * sig) @ Vho - A).max() / np.abs(A).max()))
+            elif var in ("qrlq", "qrlqqr"):
+                # two (three) preconditioning steps: A^T = Q1 R1, R1^T = Q2 R2, (R2^T = Q3 R3); Jacobi on the rows of the last factor
+                Q1, R1 = np.linalg.qr(A.T)
+                Q2, R2 = np.linalg.qr(R1.T)
+                Rl = R2
+                if var == "qrlqqr":
+                    Q3, Rl = np.linalg.qr(R2.T)
+                X, hist = block_jacobi(Rl, b, tol)
             elif var == "qrp":
                 Qf, Rf, piv = scipy.linalg.qr(A.T, mode="economic", pivoting=True)
                 X, hist = block_jacobi(Rf, b, tol)
