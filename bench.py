@@ -231,6 +231,10 @@ def main():
         return
 
     rank, world, local = dist_setup(args.gpus)
+    if world > 1:
+        # a rank that is terminated from outside (launcher timeout) says where it was
+        import faulthandler, signal
+        faulthandler.register(signal.SIGTERM, all_threads=True, chain=True)
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
@@ -323,7 +327,11 @@ def main():
             nsw = 1 if D_ >= 4096 else nsw
             rec = {"config": name, "sweeps": nsw, "lanczos_iterations": 10, "tol_split": 0.0, "n_gpus": world,
                    "sharded": "effective-Hamiltonian applications by bra-bond column slices (exchange as in config.multi_gpu); SVD split by sector blocks dealt to the ranks by cost, one all-gather of the factors; environments, plans and level-1 work replicated"}
+            if os.environ.get("CTB_BENCH_VERBOSE"):
+                print(f"[bench rank {rank}] sweep case {name} starts", file=sys.stderr, flush=True)
             rec["b200"] = sweep_seconds(lib, model, L_, params_, sector_, D_, sweeps=nsw)
+            if os.environ.get("CTB_BENCH_VERBOSE"):
+                print(f"[bench rank {rank}] sweep case {name} done: {rec['b200'] and rec['b200']['s_per_sweep']}", file=sys.stderr, flush=True)
             sweep_dist.append(rec)
     if rank != 0:
         return

@@ -615,7 +615,7 @@ void apply_local_hamiltonian(const struct block_sparse_tensor* a, const struct b
 	pthread_t th;
 	/* sharded: the plan builder cuts the column slice of r on the device right away, so all payloads go first */
 	const bool threaded = (ctb_dist_world == 1) && (getenv("CTB_NO_OVERLAP") == NULL) && (pthread_create(&th, NULL, heff_upload_main, &job) == 0);
-	if (!threaded) { heff_upload_main(&job); }
+	if (!threaded) { ctb_collective_upload++; heff_upload_main(&job); ctb_collective_upload--; }
 	const double t1 = ctb_wall_ms();
 	struct ctb_heff h;
 	CTB_CHECK_ABORT(ctb_heff_prepare_ex(ad, wd, ld, rd, &h, heff_wait_first, &job));

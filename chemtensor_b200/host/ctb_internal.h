@@ -234,6 +234,7 @@ struct ctb_heff
 };
 /* rank / world of this process (ctb_dist_init); world == 1 means no sharding */
 extern int ctb_dist_rank, ctb_dist_world;
+extern int ctb_collective_upload;      /* see ctb_upload_data */
 int  ctb_heff_prepare(const struct ctb_tensor* a, const struct ctb_tensor* w, struct ctb_tensor* l, const struct ctb_tensor* r, struct ctb_heff* h);
 /* the same; 'l_ready(ctx)' (may be NULL) is called right before the first device use of l's payload, so that a caller can build the
  * plans of steps 1 and 2 (which need structure only, and the payload of w) while the payloads of a, l and r are still in flight */

@@ -95,7 +95,9 @@ static int minimize_local_energy(const struct ctb_tensor* w, const struct ctb_te
 static int upload_chain(const struct block_sparse_tensor* host, int n, struct ctb_tensor*** dev)
 {
 	*dev = calloc((size_t)n, sizeof(struct ctb_tensor*));
+	ctb_collective_upload++;      /* dmrg_* is called by all ranks together */
 	for (int i = 0; i < n; i++) { (*dev)[i] = ctb_upload(&host[i]); }
+	ctb_collective_upload--;
 	return 0;
 }
 

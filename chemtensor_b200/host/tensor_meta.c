@@ -368,6 +368,9 @@ static void block_lists(const struct ctb_tensor* t, const struct block_sparse_te
  * with the number of ranks instead of being repeated by every one of them (collective: all ranks upload the same tensors in the
  * same order, which the one-process-per-GPU contract already demands). */
 #define CTB_SHARDED_UPLOAD_MIN ((int64_t)8 << 20)
+/* > 0 only inside the entry points every rank calls together (apply_local_hamiltonian, dmrg_*): the sharded upload is a collective,
+ * and a query a host makes on one rank only (ctb_heff_plan_info, block_sparse_tensor_dot, ...) must never wait for the others */
+int ctb_collective_upload = 0;
 int ctb_upload_data(struct ctb_tensor* t, const struct block_sparse_tensor* h)
 {
 	if (t->nstore == 0) { return 0; }
@@ -377,7 +380,7 @@ int ctb_upload_data(struct ctb_tensor* t, const struct block_sparse_tensor* h)
 	int rc = 0;
 	const char* env_min = getenv("CTB_SHARDED_UPLOAD_MIN");      /* bytes; the tests lower it to exercise the path on small tensors */
 	const int64_t min_bytes = (env_min != NULL) ? (int64_t)atoll(env_min) : CTB_SHARDED_UPLOAD_MIN;
-	if (ctb_dist_world > 1 && total >= min_bytes && getenv("CTB_NO_SHARDED_UPLOAD") == NULL)
+	if (ctb_dist_world > 1 && ctb_collective_upload > 0 && total >= min_bytes && getenv("CTB_NO_SHARDED_UPLOAD") == NULL)
 	{
 		const int W = ctb_dist_world, me = ctb_dist_rank;
 		int64_t chunk = (total + W - 1) / W;
