@@ -768,6 +768,15 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 	 * this accounts for padding, the per-tile overhead AND wave quantisation (few huge tiles leave SMs idle) */
 	int best = 0; double best_cost = 0;
 	static int occ_cache[2][8] = { { 0 } };
+	/* k-steps of every output block for the three chunk depths the classes use (one pass over the segments instead of one per class) */
+	std::vector<double> steps_bk[3];      /* 8, 16, 32 */
+	for (int q = 0; q < 3; q++) { steps_bk[q].assign((size_t)h->nouts, 0.0); }
+	for (int b = 0; b < h->nouts; b++) {
+		const ctbd_gemm_out& o = h->outs[b];
+		double s8 = 0, s16 = 0, s32 = 0;
+		for (int s = o.seg_begin; s < o.seg_end; s++) { const int k = h->segs[s].k; s8 += (double)((k + 7) >> 3); s16 += (double)((k + 15) >> 4); s32 += (double)((k + 31) >> 5); }
+		steps_bk[0][b] = s8; steps_bk[1][b] = s16; steps_bk[2][b] = s32;
+	}
 	for (int c = 0; c < nshapes; c++)
 	{
 		if (occ_cache[cplx][c] == 0) {
@@ -785,8 +794,7 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 		for (int b = 0; b < h->nouts; b++) {
 			const ctbd_gemm_out& o = h->outs[b];
 			if (o.m <= 0 || o.n <= 0) { continue; }
-			double steps = 0;
-			for (int s = o.seg_begin; s < o.seg_end; s++) { steps += (double)ceil_div(h->segs[s].k, shapes[c].bk); }
+			const double steps = steps_bk[shapes[c].bk == 8 ? 0 : (shapes[c].bk == 16 ? 1 : 2)][b];
 			const int64_t nt = ceil_div(o.m, shapes[c].bm) * ceil_div(o.n, shapes[c].bn);
 			const double w = steps + 32.0 / shapes[c].bk;
 			total += w * (double)nt; wmax = std::max(wmax, w); ntl += nt;
@@ -829,8 +837,7 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 		for (int b = 0; b < h->nouts; b++) {
 			const ctbd_gemm_out& o = h->outs[b];
 			if (o.m <= 0 || o.n <= 0) { continue; }
-			int nsteps = 0;
-			for (int s = o.seg_begin; s < o.seg_end; s++) { nsteps += (int)ceil_div(h->segs[s].k, bk); }
+			const int nsteps = (int)steps_bk[bk == 8 ? 0 : (bk == 16 ? 1 : 2)][b];
 			blk.push_back(std::make_pair(nsteps, b));
 			ntot += ceil_div(o.m, bm) * ceil_div(o.n, bn);
 		}

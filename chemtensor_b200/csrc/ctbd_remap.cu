@@ -11,6 +11,7 @@
  */
 #include <vector>
 #include <algorithm>
+#include <stdlib.h>
 #include "ctbd_common.cuh"
 
 namespace ctbd {
@@ -36,6 +37,8 @@ struct Layout
 {
 	LayoutDev d;
 	void* arena;    /* one device allocation holding all tables */
+	int64_t max_block;   /* entries of the largest stored block, largest logical dimension: the fast kernel works in 32 bits */
+	int64_t max_dim;
 };
 
 struct RemapParams
@@ -133,6 +136,456 @@ __global__ void __launch_bounds__(256) remap_kernel(const LayoutDev D, const Lay
 		v = conj_if<T>(v, p.conj);
 		if (p.scale_ax >= 0) { v = scale_by(v, p.scale[ld[p.scale_ax]]); }
 		dst[e] = v;
+	}
+}
+
+template <int ND> __device__ __forceinline__ int pick(const int (&a)[ND], int idx)
+{
+	int v = a[0];
+	#pragma unroll
+	for (int i = 1; i < ND; i++) { if (i == idx) { v = a[i]; } }
+	return v;
+}
+
+/* Fast gather form of the same remap (round 2): the per-element work of remap_kernel above (binary search over the block list, 64-bit
+ * div/mod chains, ~5 dependent table loads per axis) is amortised.
+ *   - one block search per WARP chunk of 32 x K consecutive destination entries (uniform loads), afterwards the block index only moves
+ *     forward; all in-block arithmetic is 32-bit (the host checks that no block exceeds 2^31 entries, else the kernel above runs);
+ *   - the decode of the outer destination axes is cached per destination ROW (fixed outer positions, innermost axis running);
+ *   - the sector tables of a source axis are consulted only when the logical index on that axis changed, the block-grid lookup only
+ *     when the source cell changed: along a row that is one load of log_of, one of sec_of / pos_of and the entry itself;
+ *   - writes are coalesced (lane = consecutive destination entry), reads along every innermost source run; the K loads of a thread
+ *     are issued back to back before the K stores.
+ * ND = compile-time bound on the number of axes of both layouts (4 or 8): keeps the per-axis caches in registers. */
+template <typename T, int ND, int K>
+__global__ void __launch_bounds__(256) remap_fast_kernel(const LayoutDev D, const LayoutDev S, const RemapParams p, T* __restrict__ dst, const T* __restrict__ src)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	constexpr int64_t CH = 256 * K;
+	const int dn = D.ndim, sn = S.ndim;
+	const int last = dn - 1;
+	for (int64_t cbase = (int64_t)blockIdx.x * CH; cbase < D.nstore; cbase += (int64_t)gridDim.x * CH)
+	{
+		const int64_t wbase = cbase + (int64_t)warp * (32 * K);
+		if (wbase >= D.nstore) { continue; }
+		int b;
+		{
+			int lo = 0, hi = D.nblk - 1;
+			while (lo < hi) {
+				const int mid = (lo + hi + 1) >> 1;
+				if (D.blk_off[mid] <= wbase) { lo = mid; } else { hi = mid - 1; }
+			}
+			b = lo;
+		}
+		int cur_b = -1;
+		int64_t boff = 0, bend = D.blk_off[b + 1];
+		int d_s0[ND], d_bd[ND], d_ld[ND];      /* destination block: first slot of the sector in log_of, block extent; logical index of the row */
+		uint32_t cur_row = 0xFFFFFFFFu;
+		int64_t ind_c = 0;                       /* SLICE: ind[ld[i_ax]] of the row (or of the entry when i_ax is the innermost axis) */
+		int s_ls[ND], s_sec[ND], s_pos[ND], s_bd[ND];
+		#pragma unroll
+		for (int j = 0; j < ND; j++) { s_ls[j] = -1; s_sec[j] = -1; s_pos[j] = 0; s_bd[j] = 1; d_s0[j] = 0; d_bd[j] = 1; d_ld[j] = 0; }
+		int64_t cur_cell = -1, sbase = -1;
+		int64_t addr[K];
+		int sidx[K];
+		#pragma unroll
+		for (int k = 0; k < K; k++)
+		{
+			const int64_t e = wbase + k * 32 + lane;
+			addr[k] = -2;
+			sidx[k] = 0;
+			if (e >= D.nstore) { continue; }
+			while (e >= bend) { b++; bend = D.blk_off[b + 1]; }
+			if (b != cur_b)
+			{
+				cur_b = b;
+				boff = D.blk_off[b];
+				int64_t cell = D.blk_grid[b];
+				#pragma unroll
+				for (int i = ND - 1; i >= 0; i--) {
+					if (i < dn) {
+						const int ns = D.nsec[i];
+						const int sc = (int)(cell % ns); cell /= ns;
+						const int s0 = D.secstart[i][sc];
+						d_s0[i] = s0; d_bd[i] = D.secstart[i][sc + 1] - s0;
+					}
+				}
+				cur_row = 0xFFFFFFFFu;
+			}
+			const uint32_t r = (uint32_t)(e - boff);
+			const uint32_t bl = (uint32_t)pick<ND>(d_bd, last);
+			const uint32_t row = r / bl;
+			const int pos = (int)(r - row * bl);
+			if (row != cur_row)
+			{
+				cur_row = row;
+				uint32_t q = row;
+				#pragma unroll
+				for (int i = ND - 2; i >= 0; i--) {
+					if (i < last) {
+						const uint32_t bd = (uint32_t)d_bd[i];
+						const uint32_t qq = q / bd;
+						d_ld[i] = D.log_of[i][d_s0[i] + (int)(q - qq * bd)];
+						q = qq;
+					}
+				}
+				if (p.op == CTBD_REMAP_SLICE && p.i_ax != last) { ind_c = p.ind[pick<ND>(d_ld, p.i_ax)]; }
+			}
+			const int ll = D.log_of[last][pick<ND>(d_s0, last) + pos];
+			#pragma unroll
+			for (int i = 0; i < ND; i++) { if (i == last) { d_ld[i] = ll; } }
+			if (p.op == CTBD_REMAP_SLICE && p.i_ax == last) { ind_c = p.ind[ll]; }
+			/* source logical multi-index */
+			int ls[ND];
+			#pragma unroll
+			for (int j = 0; j < ND; j++) { ls[j] = 0; }
+			switch (p.op)
+			{
+				case CTBD_REMAP_TRANSPOSE:
+					#pragma unroll
+					for (int i = 0; i < ND; i++) { if (i < dn) {
+						#pragma unroll
+						for (int j = 0; j < ND; j++) { if (p.perm[i] == j) { ls[j] = d_ld[i]; } }
+					} }
+					break;
+				case CTBD_REMAP_FLATTEN:
+				{
+					const int sd1 = (int)S.dim[p.i_ax + 1];
+					#pragma unroll
+					for (int i = 0; i < ND; i++) { if (i < dn) {
+						if (i < p.i_ax) { ls[i] = d_ld[i]; }
+						else if (i == p.i_ax) {
+							const int hi = d_ld[i] / sd1;
+							#pragma unroll
+							for (int j = 0; j < ND - 1; j++) { if (j == i) { ls[j] = hi; ls[j + 1] = d_ld[i] - hi * sd1; } }
+						}
+						else { if (i + 1 < ND) { ls[i + 1] = d_ld[i]; } }
+					} }
+					break;
+				}
+				case CTBD_REMAP_SPLIT:
+				{
+					const int dd1 = (int)D.dim[p.i_ax + 1];
+					#pragma unroll
+					for (int i = 0; i < ND; i++) { if (i < dn) {
+						if (i < p.i_ax) { ls[i] = d_ld[i]; }
+						else if (i == p.i_ax) { ls[i] = d_ld[i] * dd1; }
+						else if (i == p.i_ax + 1) { if (i >= 1) { ls[i - 1] += d_ld[i]; } }
+						else { if (i >= 1) { ls[i - 1] = d_ld[i]; } }
+					} }
+					break;
+				}
+				case CTBD_REMAP_SLICE:
+					#pragma unroll
+					for (int i = 0; i < ND; i++) { if (i < dn) { ls[i] = (i == p.i_ax) ? (int)ind_c : d_ld[i]; } }
+					break;
+				default:
+					#pragma unroll
+					for (int i = 0; i < ND; i++) { if (i < dn) { ls[i] = d_ld[i]; } }
+					break;
+			}
+			int64_t scell = 0;
+			uint32_t soff = 0;
+			#pragma unroll
+			for (int j = 0; j < ND; j++) {
+				if (j < sn) {
+					if (ls[j] != s_ls[j]) {
+						s_ls[j] = ls[j];
+						const int sc = S.sec_of[j][ls[j]];
+						s_pos[j] = S.pos_of[j][ls[j]];
+						if (sc != s_sec[j]) { s_bd[j] = S.secstart[j][sc + 1] - S.secstart[j][sc]; }
+						s_sec[j] = sc;
+					}
+					scell = scell * S.nsec[j] + s_sec[j];
+					soff = soff * (uint32_t)s_bd[j] + (uint32_t)s_pos[j];
+				}
+			}
+			if (scell != cur_cell) { cur_cell = scell; sbase = S.grid_off[scell]; }
+			addr[k] = (sbase >= 0) ? sbase + (int64_t)soff : -1;
+			if (p.scale_ax >= 0) { sidx[k] = pick<ND>(d_ld, p.scale_ax); }
+		}
+		T vals[K];
+		double scl[K];
+		#pragma unroll
+		for (int k = 0; k < K; k++) {
+			vals[k] = (addr[k] >= 0) ? src[addr[k]] : zero_of<T>();
+			scl[k] = (p.scale_ax >= 0 && addr[k] != -2) ? p.scale[sidx[k]] : 1.0;
+		}
+		#pragma unroll
+		for (int k = 0; k < K; k++) {
+			if (addr[k] != -2) {
+				T v = conj_if<T>(vals[k], p.conj);
+				if (p.scale_ax >= 0) { v = scale_by(v, scl[k]); }
+				dst[wbase + k * 32 + lane] = v;
+			}
+		}
+	}
+}
+
+/* ---- run form of the gather (round 2, second step) -------------------------------------------------------------------------------
+ * ncu of remap_fast_kernel above: 340 warp instructions per 32 entries, issue-bound at 0.7 - 0.9 TB/s.  Almost all entries of the
+ * tensors of a sweep lie in long runs: consecutive destination entries of one destination row whose source entries are equally
+ * spaced in ONE source block.  This kernel finds the runs instead of decoding every entry:
+ *   - a warp owns 1024 consecutive destination entries = 16 sub-chunks of 64; lane l decodes ONE probe entry -- the first (l even) or
+ *     last (l odd) entry of sub-chunk l / 2 -- with the complete decode (block search, sector tables, source block lookup);
+ *   - a sub-chunk is a run iff both probes lie in the same destination row, their innermost logical indices differ by the entry
+ *     distance n - 1, they map into the same source block, agree in every source position except on the one source axis the
+ *     innermost destination axis drives (jstar), and differ there by n - 1.  Logical indices ascend along a destination row and
+ *     positions ascend with the logical index inside a sector, so the entries in between are then equally spaced as well
+ *     (a SLICE of the innermost axis needs an ascending index list for this; the host checks it);
+ *   - a run is copied with two coalesced loads / stores per lane (address = first + i * stride); sub-chunks that are not runs are
+ *     decoded entry by entry with the same decode function.
+ * About 1 warp instruction per destination entry instead of 10. */
+struct Probe
+{
+	int b;              /* destination block */
+	uint32_t row;       /* destination row inside the block (outer positions) */
+	int ll;             /* logical index on the innermost destination axis */
+	int sidx;           /* index into the scale vector */
+	int64_t scell;      /* source grid cell */
+	int64_t sbase;      /* element offset of the source block, < 0: not stored */
+	uint32_t soff;      /* offset inside the source block */
+	uint32_t srest;     /* soff without the contribution of source axis jstar */
+	int spos;           /* position on source axis jstar */
+	uint32_t sstr;      /* stride of source axis jstar inside the source block */
+};
+
+template <int ND>
+__device__ __forceinline__ void remap_decode(const LayoutDev& D, const LayoutDev& S, const RemapParams& p, const int jstar, const int64_t e, int b, Probe& o)
+{
+	const int dn = D.ndim, sn = S.ndim;
+	while (e >= D.blk_off[b + 1]) { b++; }
+	o.b = b; o.row = 0; o.ll = 0;
+	uint32_t r = (uint32_t)(e - D.blk_off[b]);
+	int64_t cell = D.blk_grid[b];
+	int ld[ND];
+	uint32_t bd_last = 1;
+	/* sectors of the block (innermost first), then the positions of the entry */
+	int s0[ND], bd[ND];
+	#pragma unroll
+	for (int i = ND - 1; i >= 0; i--) {
+		s0[i] = 0; bd[i] = 1;
+		if (i < dn) {
+			const int ns = D.nsec[i];
+			const int sc = (int)(cell % ns); cell /= ns;
+			s0[i] = D.secstart[i][sc];
+			bd[i] = D.secstart[i][sc + 1] - s0[i];
+		}
+	}
+	#pragma unroll
+	for (int i = ND - 1; i >= 0; i--) {
+		ld[i] = 0;
+		if (i < dn) {
+			const uint32_t q = r / (uint32_t)bd[i];
+			ld[i] = D.log_of[i][s0[i] + (int)(r - q * (uint32_t)bd[i])];
+			if (i == dn - 1) { bd_last = (uint32_t)bd[i]; o.row = q; o.ll = ld[i]; }
+			r = q;
+		}
+	}
+	(void)bd_last;
+	o.sidx = 0;
+	if (p.scale_ax >= 0) {
+		#pragma unroll
+		for (int i = 0; i < ND; i++) { if (i == p.scale_ax) { o.sidx = ld[i]; } }
+	}
+	int ls[ND];
+	#pragma unroll
+	for (int j = 0; j < ND; j++) { ls[j] = 0; }
+	if (p.op == CTBD_REMAP_TRANSPOSE) {
+		#pragma unroll
+		for (int i = 0; i < ND; i++) { if (i < dn) {
+			#pragma unroll
+			for (int j = 0; j < ND; j++) { if (p.perm[i] == j) { ls[j] = ld[i]; } }
+		} }
+	}
+	else if (p.op == CTBD_REMAP_FLATTEN) {
+		const int sd1 = (int)S.dim[p.i_ax + 1];
+		#pragma unroll
+		for (int i = 0; i < ND; i++) { if (i < dn) {
+			if (i < p.i_ax) { ls[i] = ld[i]; }
+			else if (i == p.i_ax) {
+				const int hi = ld[i] / sd1;
+				#pragma unroll
+				for (int j = 0; j < ND - 1; j++) { if (j == i) { ls[j] = hi; ls[j + 1] = ld[i] - hi * sd1; } }
+			}
+			else { if (i + 1 < ND) { ls[i + 1] = ld[i]; } }
+		} }
+	}
+	else if (p.op == CTBD_REMAP_SPLIT) {
+		const int dd1 = (int)D.dim[p.i_ax + 1];
+		#pragma unroll
+		for (int i = 0; i < ND; i++) { if (i < dn) {
+			if (i < p.i_ax) { ls[i] = ld[i]; }
+			else if (i == p.i_ax) { ls[i] = ld[i] * dd1; }
+			else if (i == p.i_ax + 1) { if (i >= 1) { ls[i - 1] += ld[i]; } }
+			else { if (i >= 1) { ls[i - 1] = ld[i]; } }
+		} }
+	}
+	else if (p.op == CTBD_REMAP_SLICE) {
+		#pragma unroll
+		for (int i = 0; i < ND; i++) { if (i < dn) { ls[i] = (i == p.i_ax) ? (int)p.ind[ld[i]] : ld[i]; } }
+	}
+	else {
+		#pragma unroll
+		for (int i = 0; i < ND; i++) { if (i < dn) { ls[i] = ld[i]; } }
+	}
+	int64_t scell = 0;
+	uint32_t soff = 0, srest = 0, sstr = 1;
+	int spos = 0;
+	#pragma unroll
+	for (int j = 0; j < ND; j++) {
+		if (j < sn) {
+			const int sc = S.sec_of[j][ls[j]];
+			const int ps = S.pos_of[j][ls[j]];
+			const uint32_t sb = (uint32_t)(S.secstart[j][sc + 1] - S.secstart[j][sc]);
+			scell = scell * S.nsec[j] + sc;
+			soff = soff * sb + (uint32_t)ps;
+			srest = srest * sb + (j == jstar ? 0u : (uint32_t)ps);
+			sstr = (j == jstar) ? 1u : sstr * sb;
+			if (j == jstar) { spos = ps; }
+		}
+	}
+	/* sstr so far = product of the block extents of the axes behind jstar (reset to 1 at jstar, multiplied afterwards) */
+	o.scell = scell; o.soff = soff; o.srest = srest; o.spos = spos; o.sstr = sstr;
+	o.sbase = S.grid_off[scell];
+}
+
+template <typename T, int ND>
+__global__ void __launch_bounds__(256) remap_run_kernel(const LayoutDev D, const LayoutDev S, const RemapParams p, const int jstar, const int lin_ok,
+	T* __restrict__ dst, const T* __restrict__ src)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	constexpr int SUB = 64, NSUB = 16;
+	constexpr int64_t WCH = SUB * NSUB;           /* entries per warp chunk */
+	constexpr int64_t CH = 8 * WCH;
+	const unsigned FULL = 0xFFFFFFFFu;
+	for (int64_t cbase = (int64_t)blockIdx.x * CH; cbase < D.nstore; cbase += (int64_t)gridDim.x * CH)
+	{
+		const int64_t wbase = cbase + (int64_t)warp * WCH;
+		if (wbase >= D.nstore) { continue; }
+		/* probe of this lane */
+		const int64_t sub0 = wbase + (int64_t)(lane >> 1) * SUB;
+		int64_t pe = sub0 + ((lane & 1) ? (SUB - 1) : 0);
+		if (pe > D.nstore - 1) { pe = D.nstore - 1; }
+		const bool sub_valid = (sub0 < D.nstore);
+		Probe pr;
+		pr.b = 0; pr.row = 0; pr.ll = 0; pr.sidx = 0; pr.scell = -1; pr.sbase = -1; pr.soff = 0; pr.srest = 0; pr.spos = 0; pr.sstr = 1;
+		if (sub_valid)
+		{
+			int lo = 0, hi = D.nblk - 1;
+			while (lo < hi) {
+				const int mid = (lo + hi + 1) >> 1;
+				if (D.blk_off[mid] <= pe) { lo = mid; } else { hi = mid - 1; }
+			}
+			remap_decode<ND>(D, S, p, jstar, pe, lo, pr);
+		}
+		/* exchange with the partner probe: even lanes judge their sub-chunk */
+		const int     o_b     = __shfl_xor_sync(FULL, pr.b, 1);
+		const uint32_t o_row  = __shfl_xor_sync(FULL, pr.row, 1);
+		const int     o_ll    = __shfl_xor_sync(FULL, pr.ll, 1);
+		const int64_t o_scell = __shfl_xor_sync(FULL, pr.scell, 1);
+		const uint32_t o_rest = __shfl_xor_sync(FULL, pr.srest, 1);
+		const int     o_spos  = __shfl_xor_sync(FULL, pr.spos, 1);
+		const int64_t o_pe    = __shfl_xor_sync(FULL, pe, 1);
+		const int nn = (int)(o_pe - pe);          /* even lanes: entries of the sub-chunk - 1 */
+		int is_run = 0;
+		if (sub_valid && (lane & 1) == 0) {
+			is_run = (lin_ok != 0) && (o_b == pr.b) && (o_row == pr.row) && (o_ll - pr.ll == nn) && (o_scell == pr.scell) && (pr.sbase >= 0)
+				&& (o_rest == pr.srest) && (o_spos - pr.spos == nn);
+			if (nn == 0 && pr.sbase >= 0) { is_run = 1; }
+		}
+		/* four sub-chunks per pass: when all four are runs their eight loads per lane are in flight together */
+		#pragma unroll 1
+		for (int q4 = 0; q4 < NSUB; q4 += 4)
+		{
+			if (wbase + (int64_t)q4 * SUB >= D.nstore) { break; }
+			int run[4], n[4];
+			bool all_runs = true;
+			#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				run[u] = __shfl_sync(FULL, is_run, 2 * (q4 + u));
+				n[u] = __shfl_sync(FULL, nn, 2 * (q4 + u)) + 1;
+				const bool present = (wbase + (int64_t)(q4 + u) * SUB < D.nstore);
+				if (!present) { n[u] = 0; run[u] = 1; }
+				all_runs = all_runs && (run[u] != 0);
+			}
+			if (all_runs)
+			{
+				T v[4][2];
+				double sc[4][2];
+				#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const int64_t a0 = __shfl_sync(FULL, pr.sbase, 2 * (q4 + u)) + (int64_t)__shfl_sync(FULL, pr.soff, 2 * (q4 + u));
+					const int64_t st = (int64_t)__shfl_sync(FULL, pr.sstr, 2 * (q4 + u));
+					const int si = __shfl_sync(FULL, pr.sidx, 2 * (q4 + u));
+					const int inner = (p.scale_ax == D.ndim - 1);
+					#pragma unroll
+					for (int t = 0; t < 2; t++) {
+						const int i = lane + 32 * t;
+						v[u][t] = zero_of<T>(); sc[u][t] = 1.0;
+						if (i < n[u]) {
+							v[u][t] = src[a0 + (int64_t)i * st];
+							if (p.scale_ax >= 0) { sc[u][t] = p.scale[si + (inner ? i : 0)]; }
+						}
+					}
+				}
+				#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const int64_t first = wbase + (int64_t)(q4 + u) * SUB;
+					#pragma unroll
+					for (int t = 0; t < 2; t++) {
+						const int i = lane + 32 * t;
+						if (i < n[u]) {
+							T x = conj_if<T>(v[u][t], p.conj);
+							if (p.scale_ax >= 0) { x = scale_by(x, sc[u][t]); }
+							dst[first + i] = x;
+						}
+					}
+				}
+				continue;
+			}
+			#pragma unroll 1
+			for (int u = 0; u < 4; u++)
+			{
+				const int q = q4 + u;
+				const int64_t first = wbase + (int64_t)q * SUB;
+				if (first >= D.nstore) { break; }
+				const int nq = __shfl_sync(FULL, nn, 2 * q) + 1;
+				if (__shfl_sync(FULL, is_run, 2 * q))
+				{
+					const int64_t a0 = __shfl_sync(FULL, pr.sbase, 2 * q) + (int64_t)__shfl_sync(FULL, pr.soff, 2 * q);
+					const int64_t st = (int64_t)__shfl_sync(FULL, pr.sstr, 2 * q);
+					const int si = __shfl_sync(FULL, pr.sidx, 2 * q);
+					const int inner = (p.scale_ax == D.ndim - 1);
+					#pragma unroll
+					for (int t = 0; t < 2; t++) {
+						const int i = lane + 32 * t;
+						if (i < nq) {
+							T x = conj_if<T>(src[a0 + (int64_t)i * st], p.conj);
+							if (p.scale_ax >= 0) { x = scale_by(x, p.scale[si + (inner ? i : 0)]); }
+							dst[first + i] = x;
+						}
+					}
+				}
+				else
+				{
+					/* entry by entry */
+					const int bh = __shfl_sync(FULL, pr.b, 2 * q);
+					#pragma unroll 1
+					for (int t = 0; t < 2; t++) {
+						const int i = lane + 32 * t;
+						if (i < nq) {
+							Probe z;
+							remap_decode<ND>(D, S, p, jstar, first + i, bh, z);
+							T x = (z.sbase >= 0) ? src[z.sbase + (int64_t)z.soff] : zero_of<T>();
+							x = conj_if<T>(x, p.conj);
+							if (p.scale_ax >= 0) { x = scale_by(x, p.scale[z.sidx]); }
+							dst[first + i] = x;
+						}
+					}
+				}
+			}
+		}
 	}
 }
 
@@ -320,6 +773,9 @@ int ctbd_layout_create(const struct ctbd_layout_host* h, void** layout)
 	d.grid_off = (const int64_t*)(base + o_grid);
 	d.blk_grid = (const int64_t*)(base + o_bg);
 	d.blk_off  = (const int64_t*)(base + o_bo);
+	L->max_block = 0; L->max_dim = 0;
+	for (int b = 0; b < h->nblk; b++) { L->max_block = std::max<int64_t>(L->max_block, h->blk_off[b + 1] - h->blk_off[b]); }
+	for (int i = 0; i < h->ndim; i++) { L->max_dim = std::max<int64_t>(L->max_dim, h->dim[i]); }
 	*layout = L;
 	return 0;
 }
@@ -441,16 +897,63 @@ int ctbd_remap(const struct ctbd_remap_args* a)
 		p.ind = (const int64_t*)ind_dev;
 	}
 	const int threads = 256;
-	int64_t blocks = ceil_div(D->d.nstore, threads);
-	const int64_t maxb = (int64_t)rt().sm_count * 16;
-	if (blocks > maxb) { blocks = maxb; }
-	if (D->d.dtype == CTBD_F64) {
-		remap_kernel<double><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, (double*)a->dst, (const double*)a->src);
+	static const int use_old = (getenv("CTB_REMAP_OLD") != nullptr) ? 1 : 0;
+	if (D->d.dtype != CTBD_F64 && D->d.dtype != CTBD_C128) { return fail_msg("remap: unsupported dtype"); }
+	if (!use_old && D->max_block < ((int64_t)1 << 31) && S->max_block < ((int64_t)1 << 31) && D->max_dim < ((int64_t)1 << 31) && S->max_dim < ((int64_t)1 << 31))
+	{
+		/* run form (probe decode + equally spaced copies); CTB_REMAP_FAST=1 selects the per-entry row-cached kernel */
+		static const int use_fast = (getenv("CTB_REMAP_FAST") != nullptr) ? 1 : 0;
+		const bool small = (D->d.ndim <= 4 && S->d.ndim <= 4);
+		if (!use_fast)
+		{
+			const int dn = D->d.ndim, sn = S->d.ndim;
+			int jstar = sn - 1;
+			if (a->op == CTBD_REMAP_TRANSPOSE) { jstar = a->perm[dn - 1]; }
+			int lin_ok = 1;
+			if (a->op == CTBD_REMAP_SLICE && a->i_ax == dn - 1) {
+				/* a run needs the index list of the innermost axis to ascend */
+				for (int64_t j = 1; j < D->d.dim[dn - 1]; j++) { if (a->ind[j] <= a->ind[j - 1]) { lin_ok = 0; break; } }
+			}
+			int64_t blocks = ceil_div(D->d.nstore, (int64_t)8 * 1024);
+			const int64_t maxb = (int64_t)rt().sm_count * 8;
+			if (blocks > maxb) { blocks = maxb; }
+			if (D->d.dtype == CTBD_F64) {
+				if (small) { remap_run_kernel<double, 4><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, jstar, lin_ok, (double*)a->dst, (const double*)a->src); }
+				else       { remap_run_kernel<double, 8><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, jstar, lin_ok, (double*)a->dst, (const double*)a->src); }
+			}
+			else {
+				if (small) { remap_run_kernel<double2, 4><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, jstar, lin_ok, (double2*)a->dst, (const double2*)a->src); }
+				else       { remap_run_kernel<double2, 8><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, jstar, lin_ok, (double2*)a->dst, (const double2*)a->src); }
+			}
+		}
+		else
+		{
+		constexpr int K = 4;
+		int64_t blocks = ceil_div(D->d.nstore, (int64_t)threads * K);
+		const int64_t maxb = (int64_t)rt().sm_count * 8;
+		if (blocks > maxb) { blocks = maxb; }
+		if (D->d.dtype == CTBD_F64) {
+			if (small) { remap_fast_kernel<double, 4, K><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, (double*)a->dst, (const double*)a->src); }
+			else       { remap_fast_kernel<double, 8, K><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, (double*)a->dst, (const double*)a->src); }
+		}
+		else {
+			if (small) { remap_fast_kernel<double2, 4, K><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, (double2*)a->dst, (const double2*)a->src); }
+			else       { remap_fast_kernel<double2, 8, K><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, (double2*)a->dst, (const double2*)a->src); }
+		}
+		}
 	}
-	else if (D->d.dtype == CTBD_C128) {
-		remap_kernel<double2><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, (double2*)a->dst, (const double2*)a->src);
+	else
+	{
+		int64_t blocks = ceil_div(D->d.nstore, threads);
+		const int64_t maxb = (int64_t)rt().sm_count * 16;
+		if (blocks > maxb) { blocks = maxb; }
+		if (D->d.dtype == CTBD_F64) {
+			remap_kernel<double><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, (double*)a->dst, (const double*)a->src);
+		}
+		else {
+			remap_kernel<double2><<<(int)blocks, threads, 0, rt().stream>>>(D->d, S->d, p, (double2*)a->dst, (const double2*)a->src);
+		}
 	}
-	else { return fail_msg("remap: unsupported dtype"); }
 	CTBD_LAUNCH_CHECK();
 	if (ind_dev != nullptr) { ctbd_free(ind_dev); }
 	return 0;

@@ -38,7 +38,7 @@ int fail_msg(const char* msg)
 int upload(const void* host, size_t bytes, void** dev)
 {
 	*dev = nullptr;
-	int rc = ctbd_malloc(dev, bytes);
+	int rc = ctbd_malloc_noinit(dev, bytes);      /* fully overwritten by the copy */
 	if (rc < 0) { return rc; }
 	if (bytes > 0) { CTBD_CUDA(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, rt().stream)); }
 	return 0;

@@ -776,9 +776,11 @@ int ctb_heff_plan_info(const struct block_sparse_tensor* a, const struct block_s
 	return rc;
 }
 
-/* device time (CUDA events, 192 MiB L2 flush between repetitions) of the re-blocking kernel on a device-resident tensor:
- * out[0], out[1] = ms and algorithmic bytes (2 x stored entries x element size) of transposing the axes to reverse order;
- * out[2], out[3] = the same for fusing axes (0, 1) -- the HBM-bound kernels of merge / split (reference block_sparse_tensor.c:785, :950) */
+/* device time (CUDA events around the kernel launch alone, 192 MiB L2 flush between repetitions) of the re-blocking kernel on a
+ * device-resident tensor: out[2c], out[2c+1] = ms and algorithmic bytes (2 x stored entries x element size) of
+ *   c = 0: transposing the axes to reverse order, c = 1: fusing axes (0, 1), c = 2: fusing the last two axes
+ * -- the HBM-bound kernels of merge / split (reference block_sparse_tensor.c:785, :950).  The destination tensor, its sector tables
+ * and their upload are prepared outside the timed region (round 1 timed them with the kernel). */
 int ctb_remap_benchmark(const struct block_sparse_tensor* t, double* out)
 {
 	CTB_CHECK(ctbd_init(-1));
@@ -791,36 +793,37 @@ int ctb_remap_benchmark(const struct block_sparse_tensor* t, double* out)
 	const double bytes = 2.0 * (double)td->nelem * (double)ctb_sizeof_dtype(td->dtype);
 	int perm[CTB_MAXDIM];
 	for (int i = 0; i < td->ndim; i++) { perm[i] = td->ndim - 1 - i; }
-	for (int which = 0; which < 2; which++)
+	for (int which = 0; which < 3; which++)
 	{
+		struct ctbd_remap_args args;
+		memset(&args, 0, sizeof(args));
+		args.scale_ax = -1;
+		struct ctb_tensor* r = NULL;
+		if (which == 0) {
+			r = ctb_transpose(td, perm, 0);
+			args.op = CTBD_REMAP_TRANSPOSE;
+			for (int i = 0; i < td->ndim; i++) { args.perm[i] = perm[i]; }
+		}
+		else {
+			const int i_ax = (which == 1) ? 0 : td->ndim - 2;
+			r = ctb_flatten_axes(td, i_ax, td->ax[i_ax].dir);
+			args.op = CTBD_REMAP_FLATTEN;
+			args.i_ax = i_ax;
+		}
+		args.dst_layout = ctb_tensor_layout(r);  args.dst = r->d;
+		args.src_layout = ctb_tensor_layout(td); args.src = td->d;
 		double best = 1e30;
 		for (int rep = 0; rep < 5; rep++)
 		{
-			/* the first call also uploads the sector tables of both layouts; it is not the one that counts */
 			CTB_CHECK(ctbd_memset_zero(flush, flush_bytes));
-			struct ctb_tensor* r = NULL;
-			if (which == 0) {
-				/* destination allocated outside the timed region */
-				struct ctb_tensor* warm = ctb_transpose(td, perm, 0);
-				CTB_CHECK(ctbd_memset_zero(flush, flush_bytes));
-				CTB_CHECK(ctbd_event_record(e0));
-				r = ctb_transpose(td, perm, 0);
-				CTB_CHECK(ctbd_event_record(e1));
-				ctb_tensor_free(warm);
-			}
-			else {
-				struct ctb_tensor* warm = ctb_flatten_axes(td, 0, td->ax[0].dir);
-				CTB_CHECK(ctbd_memset_zero(flush, flush_bytes));
-				CTB_CHECK(ctbd_event_record(e0));
-				r = ctb_flatten_axes(td, 0, td->ax[0].dir);
-				CTB_CHECK(ctbd_event_record(e1));
-				ctb_tensor_free(warm);
-			}
+			CTB_CHECK(ctbd_event_record(e0));
+			CTB_CHECK(ctbd_remap(&args));
+			CTB_CHECK(ctbd_event_record(e1));
 			float ms = 0;
 			CTB_CHECK(ctbd_event_elapsed_ms(e0, e1, &ms));
 			if (rep > 0 && ms < best) { best = ms; }
-			ctb_tensor_free(r);
 		}
+		ctb_tensor_free(r);
 		out[2 * which] = best; out[2 * which + 1] = bytes;
 	}
 	ctbd_event_destroy(e0); ctbd_event_destroy(e1);

@@ -278,7 +278,7 @@ struct ctb_stats
 	double sweep_ms[8];      /* wall-clock of the first eight sweeps of the last dmrg_twosite / dmrg_singlesite call (device synchronised at the end of each) */
 };
 extern struct ctb_stats ctb_global_stats;
-extern double ctb_plan_profile[8];
+extern double ctb_plan_profile[16];
 
 double ctb_wall_ms(void);
 

@@ -227,6 +227,9 @@ int dmrg_twosite(const struct mpo* hamiltonian, const int num_sweeps, const int 
 	if (getenv("CTB_TRACE_PLAN") != NULL) {
 		fprintf(stderr, "contraction plans: %.0f plans, %.0f output blocks, %.0f table entries; result tensors %.1f ms, host lists (incl.) %.1f ms, device plans %.1f ms\n",
 			ctb_plan_profile[3], ctb_plan_profile[4], ctb_plan_profile[5], ctb_plan_profile[0], ctb_plan_profile[1], ctb_plan_profile[2]);
+		fprintf(stderr, "  of the host lists: enumeration of the contracted sector tuples %.1f ms (plain) + %.1f ms (merged rows)\n", ctb_plan_profile[6], ctb_plan_profile[7]);
+		fprintf(stderr, "  merged rows: row descriptors / tables %.1f ms, gather lists %.1f ms, packed-matrix reuse search %.1f ms; plain: offset tables %.1f ms\n",
+			ctb_plan_profile[8], ctb_plan_profile[9], ctb_plan_profile[10], ctb_plan_profile[11]);
 	}
 
 	free_tensor_array(h2, nsites);

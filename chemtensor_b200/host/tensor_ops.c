@@ -69,7 +69,10 @@ static void append_offset_table(struct i32vec* tab, int first, int count, const 
 }
 
 /* CTB_TRACE_PLAN: [0] result tensor, [1] host lists incl. [0], [2] device plan, [3] plans, [4] output blocks, [5] table entries */
-double ctb_plan_profile[8] = { 0 };
+double ctb_plan_profile[16] = { 0 };
+/* fine-grained timers only when tracing (they sit inside the per-output-block loop) */
+static int plan_trace_on(void) { static int on = -1; if (on < 0) { on = (getenv("CTB_TRACE_PLAN") != NULL) ? 1 : 0; } return on; }
+#define TP_NOW() (plan_trace_on() ? ctb_wall_ms() : 0.0)
 
 /* Offset tables depend only on the extents and strides of their axes (and the base offset): blocks of one block row / column with
  * equal sector dimensions share them.  The cache maps that key to the table already emitted into 'tab' -- on the 5-leg intermediates
@@ -225,7 +228,9 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	struct ctbd_mix_group* mgroups = NULL; size_t nmg = 0, cap_mg = 0;
 	struct ctbd_mix_row* mrows = NULL; size_t nmr = 0, cap_mr = 0;
 	struct merge_key* mk = NULL;
-	struct { uint64_t h; size_t base, len; }* packed = NULL; size_t npacked = 0, cap_packed = 0;
+	struct { uint64_t h; size_t base, len, sig, slen; }* packed = NULL; size_t npacked = 0, cap_packed = 0;
+	int64_t* sig = NULL; size_t nsig = 0, cap_sig = 0;      /* signatures of the packed matrices */
+	int32_t* pidx = NULL; size_t pidx_cap = 0;      /* hash index into packed[] */
 	if (merge)
 	{
 		CTB_REQUIRE(mixmode || r->nstore < ((ct_long)1 << 31));
@@ -291,6 +296,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 			for (int i = 0; i < nfs; i++) { idx_s[offset_s + i] = nat_sec[i]; }
 			for (int i = 0; i < nft; i++) { idx_t[offset_t + i] = nat_sec[nfs + i]; }
 			/* the last contracted sector follows from charge conservation in s: only the leading contracted sectors are enumerated */
+			const double tq0 = TP_NOW();
 			for (ct_long cl = 0; cl < nlead; cl++)
 			{
 				for (int i = 0; i < ndim_mult - 1; i++) { idx_s[shift_s + i] = kap[i]; }
@@ -318,6 +324,8 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 				}
 			}
 			o->seg_end = (int32_t)nseg;
+			ctb_plan_profile[6] += TP_NOW() - tq0;
+			const double tq5 = TP_NOW();
 			/* row/column offset tables: where element (i, j) of the natural block lands in the permuted block */
 			ct_long stride_r[CTB_MAXDIM];
 			ct_long st = 1;
@@ -329,6 +337,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 			o->row_tab = cached_offset_table(&tcache, &tab, 0, nfs, nat, nat_sec, pos_of_nat, stride_r, 0);
 			o->col_tab = cached_offset_table(&tcache, &tab, nfs, nft, nat, nat_sec, pos_of_nat, stride_r, 0);
 			if (posmap != NULL) { free(posmap); g_map_nat = -1; g_map_pos = NULL; }
+			ctb_plan_profile[11] += TP_NOW() - tq5;
 		}
 		else
 		{
@@ -337,6 +346,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 			for (int i = 0; i < nft; i++) { idx_t[offset_t + i] = nat_sec[nfs + i]; }
 			ct_long Ktot = 0;
 			const size_t seg_first = nseg;
+			const double tq1 = TP_NOW();
 			for (ct_long cl = 0; cl < nlead; cl++)
 			{
 				for (int i = 0; i < ndim_mult - 1; i++) { idx_t[shift_t + i] = kap[i]; }
@@ -363,6 +373,9 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 				}
 			}
 			o->seg_end = (int32_t)nseg;
+			ctb_plan_profile[7] += TP_NOW() - tq1;
+			const double tq2 = TP_NOW();
+			double tq_pack = 0;
 			/* stacked rows of all members */
 			ct_long Mtot = 0;
 			for (int q = b0; q < b1; q++) {
@@ -386,10 +399,9 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 			if (mixmode) {
 				while (nmr + (size_t)Mtot > cap_mr) { cap_mr = cap_mr ? 2 * cap_mr : 4096; mrows = realloc(mrows, cap_mr * sizeof(*mrows)); }
 			}
-			/* gather list of the packed Mtot x Ktot matrix (k contiguous) */
+			/* the packed Mtot x Ktot matrix (k contiguous): its gather list is generated further down, for a new matrix only */
 			const size_t glen = (size_t)(Mtot * Ktot);
-			while (ngather + glen > cap_gather) { cap_gather = cap_gather ? 2 * cap_gather : 65536; gather = realloc(gather, cap_gather * sizeof(int64_t)); }
-			int64_t* gl = gather + ngather;
+			const size_t sig_first = nsig;
 			ct_long row0 = 0;
 			for (int q = b0; q < b1; q++)
 			{
@@ -441,34 +453,76 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 				const size_t ct0 = (size_t)cached_offset_table(&tcache, &tab, nfs, nft, nat, ns, pos_of_nat, stride_r, 0);
 				for (ct_long i = 0; i < M; i++) { tab.v[rowcol0 + (size_t)(row0 + i)] = (int32_t)ct0; }
 				}
-				/* packed entries of this member's rows */
+				/* signature of this member's part of the packed matrix: (rows, offset of the s block of every contracted tuple) */
+				const double tq3 = TP_NOW();
+				while (nsig + 1 + (nseg - seg_first) > cap_sig) { cap_sig = cap_sig ? 2 * cap_sig : 4096; sig = realloc(sig, cap_sig * sizeof(int64_t)); }
+				sig[nsig++] = M;
 				for (size_t sg = seg_first; sg < nseg; sg++)
 				{
 					ct_long cell = segs[sg].pad_;
 					for (int i = ndim_mult - 1; i >= 0; i--) { idx_s[shift_s + i] = (int)(cell % s->ax[shift_s + i].nsec); cell /= s->ax[shift_s + i].nsec; }
 					const ct_long a_off = s->grid_off[ctb_grid_ravel(s, idx_s)];
 					CTB_REQUIRE(a_off >= 0);   /* conservation in s follows from r and t */
-					const ct_long K = segs[sg].k, kcol = segs[sg].a_off;
-					for (ct_long i = 0; i < M; i++) {
-						for (ct_long kk = 0; kk < K; kk++) {
-							gl[(row0 + i) * Ktot + kcol + kk] = a_kcontig ? a_off + i * K + kk : a_off + kk * M + i;
-						}
-					}
+					sig[nsig++] = a_off;
 				}
+				tq_pack += TP_NOW() - tq3;
 				row0 += M;
 			}
-			/* reuse an identical packed matrix if one exists */
-			const uint64_t hsh = hash_i64(gl, glen) ^ (uint64_t)glen;
+			ctb_plan_profile[8] += TP_NOW() - tq2 - tq_pack; ctb_plan_profile[9] += tq_pack;
+			const double tq4 = TP_NOW();
+			/* reuse an identical packed matrix if one exists.  The packed Mtot x Ktot matrix is a function of its signature -- the
+			 * rows of every member, the extents of the contracted tuples and the offsets of the s blocks -- so identical matrices are
+			 * recognised from a few numbers per (member, tuple) and the gather list is generated only for a new one (generating and
+			 * hashing every list first was more than half of the plan-building time of a molecular bond) */
+			while (nsig + (nseg - seg_first) > cap_sig) { cap_sig = cap_sig ? 2 * cap_sig : 4096; sig = realloc(sig, cap_sig * sizeof(int64_t)); }
+			for (size_t sg = seg_first; sg < nseg; sg++) { sig[nsig++] = segs[sg].k; }
+			const size_t slen = nsig - sig_first;
+			const uint64_t hsh = hash_i64(sig + sig_first, slen) ^ (uint64_t)glen;
 			size_t base = ngather;
 			bool found = false;
-			for (size_t q = 0; q < npacked; q++) {
-				if (packed[q].h == hsh && packed[q].len == glen && memcmp(gather + packed[q].base, gl, glen * sizeof(int64_t)) == 0) { base = packed[q].base; found = true; break; }
+			if (2 * (npacked + 1) > pidx_cap) {
+				pidx_cap = pidx_cap ? 2 * pidx_cap : 1024;
+				free(pidx); pidx = malloc(pidx_cap * sizeof(int32_t));
+				for (size_t q = 0; q < pidx_cap; q++) { pidx[q] = -1; }
+				for (size_t q = 0; q < npacked; q++) {
+					size_t sl = (size_t)packed[q].h & (pidx_cap - 1);
+					while (pidx[sl] >= 0) { sl = (sl + 1) & (pidx_cap - 1); }
+					pidx[sl] = (int32_t)q;
+				}
+			}
+			size_t slot = (size_t)hsh & (pidx_cap - 1);
+			while (pidx[slot] >= 0) {
+				const size_t q = (size_t)pidx[slot];
+				if (packed[q].h == hsh && packed[q].len == glen && packed[q].slen == slen && memcmp(sig + packed[q].sig, sig + sig_first, slen * sizeof(int64_t)) == 0) { base = packed[q].base; found = true; break; }
+				slot = (slot + 1) & (pidx_cap - 1);
 			}
 			if (!found) {
 				if (npacked == cap_packed) { cap_packed = cap_packed ? 2 * cap_packed : 256; packed = realloc(packed, cap_packed * sizeof(*packed)); }
-				packed[npacked].h = hsh; packed[npacked].base = base; packed[npacked].len = glen; npacked++;
+				packed[npacked].h = hsh; packed[npacked].base = base; packed[npacked].len = glen; packed[npacked].sig = sig_first; packed[npacked].slen = slen;
+				pidx[slot] = (int32_t)npacked;
+				npacked++;
+				/* gather list of the new packed matrix (k contiguous) */
+				while (ngather + glen > cap_gather) { cap_gather = cap_gather ? 2 * cap_gather : 65536; gather = realloc(gather, cap_gather * sizeof(int64_t)); }
+				int64_t* gl = gather + ngather;
+				const int64_t* sp = sig + sig_first;
+				ct_long r0 = 0;
+				for (int q = b0; q < b1; q++) {
+					const ct_long M = *sp++;
+					for (size_t sg = seg_first; sg < nseg; sg++) {
+						const ct_long a_off = *sp++;
+						const ct_long K = segs[sg].k, kcol = segs[sg].a_off;
+						for (ct_long i = 0; i < M; i++) {
+							int64_t* row = gl + (r0 + i) * Ktot + kcol;
+							if (a_kcontig) { const ct_long a0 = a_off + i * K; for (ct_long kk = 0; kk < K; kk++) { row[kk] = a0 + kk; } }
+							else { for (ct_long kk = 0; kk < K; kk++) { row[kk] = a_off + kk * M + i; } }
+						}
+					}
+					r0 += M;
+				}
 				ngather += glen;
 			}
+			else { nsig = sig_first; }      /* the signature of a reused matrix is not kept */
+			ctb_plan_profile[10] += TP_NOW() - tq4;
 			for (size_t sg = seg_first; sg < nseg; sg++) {
 				segs[sg].a_off += (int64_t)base;
 				segs[sg].lda = (int32_t)Ktot;
@@ -539,7 +593,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 	CTB_CHECK_ABORT(ctbd_gemm_plan_info(plan->dev, &plan->ntiles, NULL));
 
 	tab_cache_free(&tcache);
-	free(tab.v); free(outs); free(segs); free(gather); free(mk); free(packed); free(browtab); free(mgroups); free(mrows);
+	free(tab.v); free(outs); free(segs); free(gather); free(mk); free(packed); free(pidx); free(sig); free(browtab); free(mgroups); free(mrows);
 	return r;
 }
 

@@ -89,9 +89,9 @@ def main():
     for name, call in (("block_sparse_tensor_transpose of a[Dl, dd, Dr] (host structs in and out)", None),):
         pass
     if lib.has("ctb_remap_benchmark"):
-        res = (C.c_double * 4)()
+        res = (C.c_double * 6)()
         if lib.ctb_remap_benchmark(a.ptr, res) == 0:
-            for k, label in enumerate(("transpose [2, 1, 0]", "flatten axes (0, 1)")):
+            for k, label in enumerate(("transpose [2, 1, 0]", "flatten axes (0, 1)", "flatten axes (1, 2)")):
                 t = res[2 * k]; nbytes = res[2 * k + 1]
                 print(json.dumps({"kernel": f"remap_kernel: {label} of the two-site tensor", "stored_entries": int(nel), "algorithmic_bytes": nbytes, "ms": t, "GB_per_s": nbytes / t / 1e6,
                                   "frac_of_measured_copy_peak": nbytes / t / 1e6 / peak, "peak_GB_per_s": peak, "peak_source": kind}), flush=True)
