@@ -521,6 +521,11 @@ def xxz_c2(lib, single_site: bool, sweeps: int = 1, lanczos: int = 10):
     return out
 
 
+MOLECULAR_LARGE_CASES = [
+    # (name, spatial orbitals, bond dimension)
+    ("mol_n24_D1024_c128", 24, 1024),
+]
+
 MOLECULAR_SWEEP_CASES = [
     # (name, spatial orbitals, bond dimension, time the reference too?)
     ("mol_n8_D64_c128", 8, 64, True),
@@ -604,6 +609,18 @@ def sweep_report(lib):
                 rec["reference_cpu"]["cores"] = os.cpu_count()
             except Exception as exc:
                 rec["reference_cpu"] = {"failed": str(exc)}
+        out.append(rec)
+    # BASELINE.json configs[3] at the largest size this round runs: 24 spatial orbitals (MPO bond 2 n^2 + 3 n + 2 = 1226), complex128,
+    # D = 1024, ONE sweep from the seeded random MPS.  The merged pair tensor of the reference would have 1226 x 256 x 1226 entries
+    # per bond; the engine switches to the pair form (two site MPO tensors applied one after the other) by itself.
+    for name, n, D in MOLECULAR_LARGE_CASES:
+        rec = {"config": name, "sweeps": 1, "lanczos_iterations": 10, "tol_split": 0.0, "dtype": "c128", "form": "pair form chosen by the engine (merged pair tensor > 2^28 entries)"}
+        try:
+            rec["b200"] = molecular_sweep_seconds(lib, n, D, None, sweeps=1)
+            if rec["b200"] is not None:
+                rec["b200"]["phases_s"] = phases(lib)
+        except Exception as exc:
+            rec["b200"] = {"failed": str(exc)}
         out.append(rec)
     return out
 

@@ -367,7 +367,7 @@ static constexpr size_t SVD_SMEM_LIMIT = 220 * 1024;
 
 template <typename T>
 __global__ void __launch_bounds__(SVD_SMEM_THREADS) svd_smem_kernel(const SvdMat* __restrict__ mats, const int* __restrict__ sel, double tol, int max_sweeps,
-	const T* __restrict__ A, T* __restrict__ U, T* __restrict__ Vh, double* __restrict__ S)
+	const T* __restrict__ A, T* __restrict__ U, T* __restrict__ Vh, double* __restrict__ S, int* __restrict__ status)
 {
 	extern __shared__ __align__(16) unsigned char svd_smem_raw[];
 	const SvdMat mt = mats[sel[blockIdx.x]];
@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(SVD_SMEM_THREADS) svd_smem_kernel(const SvdMat
 
 	const int N = R + (R & 1);
 	const double thresh = tol * sqrt((double)C);
+	bool conv = (R < 2);
 	for (int sweep = 0; sweep < max_sweeps && R >= 2; sweep++)
 	{
 		if (tid == 0) { s_rot = 0; }
@@ -444,8 +445,11 @@ __global__ void __launch_bounds__(SVD_SMEM_THREADS) svd_smem_kernel(const SvdMat
 		}
 		const int nrot = s_rot;
 		__syncthreads();
-		if (nrot == 0) { break; }
+		if (nrot == 0) { conv = true; break; }
 	}
+	/* rotations still pending after the last sweep: the factors are not an SVD to working precision -- reported to the host, which
+	 * returns < 0 like the reference does when LAPACK ?gesvd fails to converge (dense_tensor.c:3636-3671) */
+	if (!conv && tid == 0) { atomicExch(status, 1); }
 
 	/* singular values = exact final row norms, sorted descending (ties by index); the accumulated-rotation rows are re-normalised */
 	for (int i = warp; i < R; i += nwarp) {
@@ -639,6 +643,7 @@ static int svd_big_iterate(SvdBig<T>* st)
 			int h_pending = 0;
 			if (ctbd_d2h(&h_pending, pending, sizeof(int)) < 0) { rc = -1; break; }
 			if (h_pending == 0) { break; }
+			if (sweep == max_sweeps - 1) { rc = fail_msg("batched SVD: tournament did not converge within 40 sweeps"); }
 		}
 	}
 	return rc;
@@ -664,6 +669,7 @@ static int svd_batched_impl(int nmat_all, const ctbd_mat_desc* descs_all, const 
 	std::vector<SvdMat> small_mats;
 	std::vector<ctbd_mat_desc> big;
 	size_t smem_max = 0;
+	void* d_status = nullptr;
 	/* test knobs: CTB_SVD_NO_SMEM=1 / CTB_SVD_SMEM_LIMIT=<bytes> send smaller blocks down the big-block path */
 	size_t smem_limit = SVD_SMEM_LIMIT;
 	if (getenv("CTB_SVD_NO_SMEM") != nullptr) { smem_limit = 0; }
@@ -696,22 +702,36 @@ static int svd_batched_impl(int nmat_all, const ctbd_mat_desc* descs_all, const 
 			CTBD_CUDA(cudaFuncSetAttribute(svd_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVD_SMEM_LIMIT));
 			attr_done = true;
 		}
+		if (ctbd_malloc(&d_status, sizeof(int)) < 0) { ctbd_free(d_sel); ctbd_free(d_small); return -1; }
 		svd_smem_kernel<T><<<(int)small_mats.size(), SVD_SMEM_THREADS, smem_max, rt().stream>>>((const SvdMat*)d_small, (const int*)d_sel, DBL_EPSILON, 40,
-			(const T*)A, (T*)U, (T*)Vh, S);
+			(const T*)A, (T*)U, (T*)Vh, S, (int*)d_status);
 		CTBD_LAUNCH_CHECK();
 		ctbd_free(d_sel); ctbd_free(d_small);
 	}
-	if (big.empty()) { return 0; }
-	/* default: QR-preconditioned block Jacobi on the tensor pipe (ctbd_svd_bj.cu); CTB_SVD_BJ=0 keeps the scalar tournament below */
+	int rc = 0;
+	if (!big.empty())
 	{
+		/* default: QR-preconditioned block Jacobi on the tensor pipe (ctbd_svd_bj.cu); CTB_SVD_BJ=0 keeps the scalar tournament below */
 		const char* env = getenv("CTB_SVD_BJ");
-		if (env == nullptr || atoi(env) != 0) { return svd_bj_impl<T>((int)big.size(), big.data(), A, U, Vh, S); }
+		if (env == nullptr || atoi(env) != 0) { rc = svd_bj_impl<T>((int)big.size(), big.data(), A, U, Vh, S); }
+		else {
+			SvdBig<T>* st = svd_big_setup<T>((int)big.size(), big.data(), A);
+			if (st == nullptr) { rc = -1; }
+			else {
+				rc = svd_big_iterate<T>(st);
+				if (rc == 0) { rc = svd_big_finish<T>(st, U, Vh, S); }
+				svd_big_free<T>(st);
+			}
+		}
 	}
-	SvdBig<T>* st = svd_big_setup<T>((int)big.size(), big.data(), A);
-	if (st == nullptr) { return -1; }
-	int rc = svd_big_iterate<T>(st);
-	if (rc == 0) { rc = svd_big_finish<T>(st, U, Vh, S); }
-	svd_big_free<T>(st);
+	if (d_status != nullptr)
+	{
+		/* convergence word of the single-CTA path (one 4-byte copy; the split that follows synchronises anyway) */
+		int h_status = 0;
+		if (ctbd_d2h(&h_status, d_status, sizeof(int)) < 0) { rc = -1; }
+		ctbd_free(d_status);
+		if (rc == 0 && h_status != 0) { rc = fail_msg("batched SVD: one-sided Jacobi did not converge within 40 sweeps"); }
+	}
 	return rc;
 }
 

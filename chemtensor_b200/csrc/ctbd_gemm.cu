@@ -777,6 +777,13 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 		for (int s = o.seg_begin; s < o.seg_end; s++) { const int k = h->segs[s].k; s8 += (double)((k + 7) >> 3); s16 += (double)((k + 15) >> 4); s32 += (double)((k + 31) >> 5); }
 		steps_bk[0][b] = s8; steps_bk[1][b] = s16; steps_bk[2][b] = s32;
 	}
+	/* pass 1: per class the (weight, count) groups of its tiles and a lower bound of the launch cost (perfect split of the padded
+	 * work, or the heaviest tile); pass 2: the exact longest-processing-time-first packing only for classes whose lower bound can
+	 * still beat the best exact cost found so far -- the exact packing of all eight classes was more than half of the time spent
+	 * in this function on the thousand small plans of a D = 1024 sweep */
+	struct ClassEval { int c, grid, per_sm; int64_t ntl; double total, wmax, lb; std::vector<std::pair<double, int64_t>> grp; };
+	std::vector<ClassEval> evals;
+	evals.reserve((size_t)nshapes);
 	for (int c = 0; c < nshapes; c++)
 	{
 		if (occ_cache[cplx][c] == 0) {
@@ -786,40 +793,51 @@ int ctbd_gemm_plan_create(const struct ctbd_gemm_plan_host* h, void** plan_out)
 			occ_cache[cplx][c] = occ < 1 ? 1 : occ;
 		}
 		const int slots = rt().sm_count * occ_cache[cplx][c];
+		ClassEval ev;
+		ev.c = c; ev.total = 0; ev.wmax = 0; ev.ntl = 0;
 		/* all tiles of one output block weigh the same: keep (weight, count) groups instead of one entry per tile */
-		std::vector<std::pair<double, int64_t>> grp;
-		grp.reserve((size_t)h->nouts);
-		double total = 0, wmax = 0;
-		int64_t ntl = 0;
+		ev.grp.reserve((size_t)h->nouts);
+		const std::vector<double>& stp = steps_bk[shapes[c].bk == 8 ? 0 : (shapes[c].bk == 16 ? 1 : 2)];
 		for (int b = 0; b < h->nouts; b++) {
 			const ctbd_gemm_out& o = h->outs[b];
 			if (o.m <= 0 || o.n <= 0) { continue; }
-			const double steps = steps_bk[shapes[c].bk == 8 ? 0 : (shapes[c].bk == 16 ? 1 : 2)][b];
 			const int64_t nt = ceil_div(o.m, shapes[c].bm) * ceil_div(o.n, shapes[c].bn);
-			const double w = steps + 32.0 / shapes[c].bk;
-			total += w * (double)nt; wmax = std::max(wmax, w); ntl += nt;
-			grp.push_back(std::make_pair(w, nt));
+			const double w = stp[b] + 32.0 / shapes[c].bk;
+			ev.total += w * (double)nt; ev.wmax = std::max(ev.wmax, w); ev.ntl += nt;
+			ev.grp.push_back(std::make_pair(w, nt));
 		}
-		if (ntl == 0) { continue; }
-		const int grid = (int)std::min<int64_t>(ntl, slots);
+		if (ev.ntl == 0) { continue; }
+		ev.grid = (int)std::min<int64_t>(ev.ntl, slots);
+		ev.per_sm = (int)ceil_div(ev.grid, rt().sm_count);      /* CTAs sharing the tensor pipe of one SM */
+		const double unit = (double)shapes[c].bk * shapes[c].bm * shapes[c].bn * shapes[c].eff * ev.per_sm;
+		ev.lb = std::max(ev.total / ev.grid, ev.wmax) * unit;
+		evals.push_back(std::move(ev));
+	}
+	std::stable_sort(evals.begin(), evals.end(), [](const ClassEval& x, const ClassEval& y) { return x.lb < y.lb; });
+	bool have_best = false;
+	for (ClassEval& ev : evals)
+	{
+		if (have_best && ev.lb >= best_cost) { break; }      /* sorted by lower bound: none of the remaining classes can win */
+		const int c = ev.c;
+		const int grid = ev.grid;
 		double makespan;
-		if (ntl <= 8 * (int64_t)slots) {
+		if (ev.ntl <= 8 * (int64_t)(rt().sm_count * occ_cache[cplx][c])) {
 			/* few tiles per slot: the exact longest-processing-time-first packing (wave quantisation matters here) */
-			std::sort(grp.begin(), grp.end(), [](const std::pair<double, int64_t>& a, const std::pair<double, int64_t>& b) { return a.first > b.first; });
+			std::sort(ev.grp.begin(), ev.grp.end(), [](const std::pair<double, int64_t>& a, const std::pair<double, int64_t>& b) { return a.first > b.first; });
 			std::vector<double> heap(grid, 0.0);     /* min-heap of slot loads */
 			auto cmpd = [](double a, double b) { return a > b; };
-			for (const auto& g : grp) {
+			for (const auto& g : ev.grp) {
 				for (int64_t i = 0; i < g.second; i++) { std::pop_heap(heap.begin(), heap.end(), cmpd); heap.back() += g.first; std::push_heap(heap.begin(), heap.end(), cmpd); }
 			}
 			makespan = *std::max_element(heap.begin(), heap.end());
 		}
 		else {
 			/* many tiles per slot: the packing ends within about half a (mean) tile of the perfect split */
-			makespan = std::max(total / grid + 0.5 * total / (double)ntl, wmax);
+			makespan = std::max(ev.total / grid + 0.5 * ev.total / (double)ev.ntl, ev.wmax);
 		}
-		const int per_sm = (int)ceil_div(grid, rt().sm_count);      /* CTAs sharing the tensor pipe of one SM */
-		const double cost = makespan * shapes[c].bk * shapes[c].bm * shapes[c].bn * shapes[c].eff * per_sm;
-		if (c == 0 || cost < best_cost) { best = c; best_cost = cost; }
+		const double cost = makespan * shapes[c].bk * shapes[c].bm * shapes[c].bn * shapes[c].eff * ev.per_sm;
+		/* ties go to the lower class index, as with the former scan in class order */
+		if (!have_best || cost < best_cost || (cost == best_cost && c < best)) { best = c; best_cost = cost; have_best = true; }
 	}
 	const char* force = getenv("CTB_GEMM_CLASS");   /* tuning knob: force one tile class */
 	if (force != nullptr && atoi(force) >= 0 && atoi(force) < nshapes) { best = atoi(force); }

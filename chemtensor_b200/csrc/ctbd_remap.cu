@@ -341,6 +341,8 @@ struct Probe
 	int b;              /* destination block */
 	uint32_t row;       /* destination row inside the block (outer positions) */
 	int ll;             /* logical index on the innermost destination axis */
+	int pos, bl;        /* position in the destination row, length of the row */
+	int srem;           /* positions left in the source block along axis jstar, this one included */
 	int sidx;           /* index into the scale vector */
 	int64_t scell;      /* source grid cell */
 	int64_t sbase;      /* element offset of the source block, < 0: not stored */
@@ -355,7 +357,7 @@ __device__ __forceinline__ void remap_decode(const LayoutDev& D, const LayoutDev
 {
 	const int dn = D.ndim, sn = S.ndim;
 	while (e >= D.blk_off[b + 1]) { b++; }
-	o.b = b; o.row = 0; o.ll = 0;
+	o.b = b; o.row = 0; o.ll = 0; o.pos = 0; o.bl = 1;
 	uint32_t r = (uint32_t)(e - D.blk_off[b]);
 	int64_t cell = D.blk_grid[b];
 	int ld[ND];
@@ -378,7 +380,7 @@ __device__ __forceinline__ void remap_decode(const LayoutDev& D, const LayoutDev
 		if (i < dn) {
 			const uint32_t q = r / (uint32_t)bd[i];
 			ld[i] = D.log_of[i][s0[i] + (int)(r - q * (uint32_t)bd[i])];
-			if (i == dn - 1) { bd_last = (uint32_t)bd[i]; o.row = q; o.ll = ld[i]; }
+			if (i == dn - 1) { bd_last = (uint32_t)bd[i]; o.row = q; o.ll = ld[i]; o.pos = (int)(r - q * (uint32_t)bd[i]); o.bl = bd[i]; }
 			r = q;
 		}
 	}
@@ -431,7 +433,7 @@ __device__ __forceinline__ void remap_decode(const LayoutDev& D, const LayoutDev
 	}
 	int64_t scell = 0;
 	uint32_t soff = 0, srest = 0, sstr = 1;
-	int spos = 0;
+	int spos = 0, srem = 1;
 	#pragma unroll
 	for (int j = 0; j < ND; j++) {
 		if (j < sn) {
@@ -442,16 +444,16 @@ __device__ __forceinline__ void remap_decode(const LayoutDev& D, const LayoutDev
 			soff = soff * sb + (uint32_t)ps;
 			srest = srest * sb + (j == jstar ? 0u : (uint32_t)ps);
 			sstr = (j == jstar) ? 1u : sstr * sb;
-			if (j == jstar) { spos = ps; }
+			if (j == jstar) { spos = ps; srem = (int)sb - ps; }
 		}
 	}
 	/* sstr so far = product of the block extents of the axes behind jstar (reset to 1 at jstar, multiplied afterwards) */
-	o.scell = scell; o.soff = soff; o.srest = srest; o.spos = spos; o.sstr = sstr;
+	o.scell = scell; o.soff = soff; o.srest = srest; o.spos = spos; o.sstr = sstr; o.srem = srem;
 	o.sbase = S.grid_off[scell];
 }
 
 template <typename T, int ND>
-__global__ void __launch_bounds__(256) remap_run_kernel(const LayoutDev D, const LayoutDev S, const RemapParams p, const int jstar, const int lin_ok,
+__global__ void __launch_bounds__(256, 2) remap_run_kernel(const LayoutDev D, const LayoutDev S, const RemapParams p, const int jstar, const int lin_ok,
 	T* __restrict__ dst, const T* __restrict__ src)
 {
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -469,7 +471,7 @@ __global__ void __launch_bounds__(256) remap_run_kernel(const LayoutDev D, const
 		if (pe > D.nstore - 1) { pe = D.nstore - 1; }
 		const bool sub_valid = (sub0 < D.nstore);
 		Probe pr;
-		pr.b = 0; pr.row = 0; pr.ll = 0; pr.sidx = 0; pr.scell = -1; pr.sbase = -1; pr.soff = 0; pr.srest = 0; pr.spos = 0; pr.sstr = 1;
+		pr.b = 0; pr.row = 0; pr.ll = 0; pr.sidx = 0; pr.pos = 0; pr.bl = 1; pr.srem = 1; pr.scell = -1; pr.sbase = -1; pr.soff = 0; pr.srest = 0; pr.spos = 0; pr.sstr = 1;
 		if (sub_valid)
 		{
 			int lo = 0, hi = D.nblk - 1;
@@ -479,7 +481,10 @@ __global__ void __launch_bounds__(256) remap_run_kernel(const LayoutDev D, const
 			}
 			remap_decode<ND>(D, S, p, jstar, pe, lo, pr);
 		}
-		/* exchange with the partner probe: even lanes judge their sub-chunk */
+		/* exchange with the partner probe.  Every sub-chunk is described by two PIECES, piece 0 held by the even lane (entries
+		 * [0, n0) of the sub-chunk) and piece 1 by the odd lane (entries [n0, n)): a sub-chunk that is one run has n0 = n; one that
+		 * crosses into the NEXT row of the same block is cut at the row end and both pieces are judged on their own (second probe
+		 * pass: last entry of the first row, first entry of the second); anything else is decoded entry by entry */
 		const int     o_b     = __shfl_xor_sync(FULL, pr.b, 1);
 		const uint32_t o_row  = __shfl_xor_sync(FULL, pr.row, 1);
 		const int     o_ll    = __shfl_xor_sync(FULL, pr.ll, 1);
@@ -487,27 +492,60 @@ __global__ void __launch_bounds__(256) remap_run_kernel(const LayoutDev D, const
 		const uint32_t o_rest = __shfl_xor_sync(FULL, pr.srest, 1);
 		const int     o_spos  = __shfl_xor_sync(FULL, pr.spos, 1);
 		const int64_t o_pe    = __shfl_xor_sync(FULL, pe, 1);
-		const int nn = (int)(o_pe - pe);          /* even lanes: entries of the sub-chunk - 1 */
-		int is_run = 0;
-		if (sub_valid && (lane & 1) == 0) {
-			is_run = (lin_ok != 0) && (o_b == pr.b) && (o_row == pr.row) && (o_ll - pr.ll == nn) && (o_scell == pr.scell) && (pr.sbase >= 0)
+		const bool even = (lane & 1) == 0;
+		const int nn = (int)(even ? o_pe - pe : pe - o_pe);      /* entries of the sub-chunk - 1 (both lanes) */
+		int p_run = 0, p_n = 0, p_si = pr.sidx, p_b = pr.b;
+		int64_t p_a0 = pr.sbase + (int64_t)pr.soff, p_st = (int64_t)pr.sstr;
+		int cand = 0, n0 = 0;
+		if (sub_valid && even) {
+			p_n = nn + 1;
+			p_run = (lin_ok != 0) && (o_b == pr.b) && (o_row == pr.row) && (o_ll - pr.ll == nn) && (o_scell == pr.scell) && (pr.sbase >= 0)
 				&& (o_rest == pr.srest) && (o_spos - pr.spos == nn);
-			if (nn == 0 && pr.sbase >= 0) { is_run = 1; }
+			if (nn == 0 && pr.sbase >= 0) { p_run = 1; }
+			/* longest run the first probe can start: to the end of its destination row or of its source block along jstar */
+			n0 = min(pr.bl - pr.pos, pr.srem);
+			cand = (!p_run) && (lin_ok != 0) && (pr.sbase >= 0) && (n0 >= 1) && (n0 <= nn);
 		}
-		/* four sub-chunks per pass: when all four are runs their eight loads per lane are in flight together */
+		const int cand_pair = __shfl_sync(FULL, cand, lane & ~1);
+		const int n0_pair = __shfl_sync(FULL, n0, lane & ~1);
+		if (__any_sync(FULL, cand_pair))
+		{
+			if (cand_pair)
+			{
+				Probe pz;
+				const int64_t e2 = sub0 + n0_pair - 1 + (even ? 0 : 1);
+				remap_decode<ND>(D, S, p, jstar, e2, even ? pr.b : o_b, pz);
+				if (even) {
+					/* piece 0 = [first probe, end of its row] */
+					const int c1 = n0_pair - 1;
+					p_n = n0_pair;
+					p_run = (pz.b == pr.b) && (pz.row == pr.row) && (pz.ll - pr.ll == c1) && (pz.scell == pr.scell) && (pr.sbase >= 0)
+						&& (pz.srest == pr.srest) && (pz.spos - pr.spos == c1);
+				}
+				else {
+					/* piece 1 = [start of the next row, last probe] */
+					const int c1 = nn - n0_pair;
+					p_n = nn + 1 - n0_pair;
+					p_run = (pz.b == pr.b) && (pz.row == pr.row) && (pr.ll - pz.ll == c1) && (pz.scell == pr.scell) && (pz.sbase >= 0)
+						&& (pz.srest == pr.srest) && (pr.spos - pz.spos == c1);
+					p_a0 = pz.sbase + (int64_t)pz.soff; p_st = (int64_t)pz.sstr; p_si = pz.sidx; p_b = pz.b;
+				}
+			}
+		}
+		const int inner = (p.scale_ax == D.ndim - 1);
+		/* four sub-chunks per pass: when all their pieces are runs the eight loads of a lane are in flight together */
 		#pragma unroll 1
 		for (int q4 = 0; q4 < NSUB; q4 += 4)
 		{
 			if (wbase + (int64_t)q4 * SUB >= D.nstore) { break; }
-			int run[4], n[4];
+			int c0[4], c1[4];
 			bool all_runs = true;
 			#pragma unroll
 			for (int u = 0; u < 4; u++) {
-				run[u] = __shfl_sync(FULL, is_run, 2 * (q4 + u));
-				n[u] = __shfl_sync(FULL, nn, 2 * (q4 + u)) + 1;
-				const bool present = (wbase + (int64_t)(q4 + u) * SUB < D.nstore);
-				if (!present) { n[u] = 0; run[u] = 1; }
-				all_runs = all_runs && (run[u] != 0);
+				c0[u] = __shfl_sync(FULL, p_n, 2 * (q4 + u));
+				c1[u] = __shfl_sync(FULL, p_n, 2 * (q4 + u) + 1);
+				const int r0 = __shfl_sync(FULL, p_run, 2 * (q4 + u)), r1 = __shfl_sync(FULL, p_run, 2 * (q4 + u) + 1);
+				all_runs = all_runs && (c0[u] == 0 || r0) && (c1[u] == 0 || r1);
 			}
 			if (all_runs)
 			{
@@ -515,17 +553,18 @@ __global__ void __launch_bounds__(256) remap_run_kernel(const LayoutDev D, const
 				double sc[4][2];
 				#pragma unroll
 				for (int u = 0; u < 4; u++) {
-					const int64_t a0 = __shfl_sync(FULL, pr.sbase, 2 * (q4 + u)) + (int64_t)__shfl_sync(FULL, pr.soff, 2 * (q4 + u));
-					const int64_t st = (int64_t)__shfl_sync(FULL, pr.sstr, 2 * (q4 + u));
-					const int si = __shfl_sync(FULL, pr.sidx, 2 * (q4 + u));
-					const int inner = (p.scale_ax == D.ndim - 1);
 					#pragma unroll
 					for (int t = 0; t < 2; t++) {
 						const int i = lane + 32 * t;
+						const int from = 2 * (q4 + u) + (i < c0[u] ? 0 : 1);      /* lane that holds the piece of entry i */
+						const int64_t a0 = __shfl_sync(FULL, p_a0, from);
+						const int64_t st = __shfl_sync(FULL, p_st, from);
+						const int si = __shfl_sync(FULL, p_si, from);
+						const int ip = (i < c0[u]) ? i : i - c0[u];
 						v[u][t] = zero_of<T>(); sc[u][t] = 1.0;
-						if (i < n[u]) {
-							v[u][t] = src[a0 + (int64_t)i * st];
-							if (p.scale_ax >= 0) { sc[u][t] = p.scale[si + (inner ? i : 0)]; }
+						if (i < c0[u] + c1[u]) {
+							v[u][t] = src[a0 + (int64_t)ip * st];
+							if (p.scale_ax >= 0) { sc[u][t] = p.scale[si + (inner ? ip : 0)]; }
 						}
 					}
 				}
@@ -535,7 +574,7 @@ __global__ void __launch_bounds__(256) remap_run_kernel(const LayoutDev D, const
 					#pragma unroll
 					for (int t = 0; t < 2; t++) {
 						const int i = lane + 32 * t;
-						if (i < n[u]) {
+						if (i < c0[u] + c1[u]) {
 							T x = conj_if<T>(v[u][t], p.conj);
 							if (p.scale_ax >= 0) { x = scale_by(x, sc[u][t]); }
 							dst[first + i] = x;
@@ -550,37 +589,43 @@ __global__ void __launch_bounds__(256) remap_run_kernel(const LayoutDev D, const
 				const int q = q4 + u;
 				const int64_t first = wbase + (int64_t)q * SUB;
 				if (first >= D.nstore) { break; }
-				const int nq = __shfl_sync(FULL, nn, 2 * q) + 1;
-				if (__shfl_sync(FULL, is_run, 2 * q))
+				#pragma unroll 1
+				for (int pc = 0; pc < 2; pc++)
 				{
-					const int64_t a0 = __shfl_sync(FULL, pr.sbase, 2 * q) + (int64_t)__shfl_sync(FULL, pr.soff, 2 * q);
-					const int64_t st = (int64_t)__shfl_sync(FULL, pr.sstr, 2 * q);
-					const int si = __shfl_sync(FULL, pr.sidx, 2 * q);
-					const int inner = (p.scale_ax == D.ndim - 1);
-					#pragma unroll
-					for (int t = 0; t < 2; t++) {
-						const int i = lane + 32 * t;
-						if (i < nq) {
-							T x = conj_if<T>(src[a0 + (int64_t)i * st], p.conj);
-							if (p.scale_ax >= 0) { x = scale_by(x, p.scale[si + (inner ? i : 0)]); }
-							dst[first + i] = x;
+					const int from = 2 * q + pc;
+					const int cnt = __shfl_sync(FULL, p_n, from);
+					if (cnt == 0) { continue; }
+					const int off = (pc == 0) ? 0 : __shfl_sync(FULL, p_n, 2 * q);
+					if (__shfl_sync(FULL, p_run, from))
+					{
+						const int64_t a0 = __shfl_sync(FULL, p_a0, from);
+						const int64_t st = __shfl_sync(FULL, p_st, from);
+						const int si = __shfl_sync(FULL, p_si, from);
+						#pragma unroll
+						for (int t = 0; t < 2; t++) {
+							const int i = lane + 32 * t;
+							if (i < cnt) {
+								T x = conj_if<T>(src[a0 + (int64_t)i * st], p.conj);
+								if (p.scale_ax >= 0) { x = scale_by(x, p.scale[si + (inner ? i : 0)]); }
+								dst[first + off + i] = x;
+							}
 						}
 					}
-				}
-				else
-				{
-					/* entry by entry */
-					const int bh = __shfl_sync(FULL, pr.b, 2 * q);
-					#pragma unroll 1
-					for (int t = 0; t < 2; t++) {
-						const int i = lane + 32 * t;
-						if (i < nq) {
-							Probe z;
-							remap_decode<ND>(D, S, p, jstar, first + i, bh, z);
-							T x = (z.sbase >= 0) ? src[z.sbase + (int64_t)z.soff] : zero_of<T>();
-							x = conj_if<T>(x, p.conj);
-							if (p.scale_ax >= 0) { x = scale_by(x, p.scale[z.sidx]); }
-							dst[first + i] = x;
+					else
+					{
+						/* entry by entry */
+						const int bh = __shfl_sync(FULL, p_b, 2 * q);
+						#pragma unroll 1
+						for (int t = 0; t < 2; t++) {
+							const int i = lane + 32 * t;
+							if (i < cnt) {
+								Probe z;
+								remap_decode<ND>(D, S, p, jstar, first + off + i, bh, z);
+								T x = (z.sbase >= 0) ? src[z.sbase + (int64_t)z.soff] : zero_of<T>();
+								x = conj_if<T>(x, p.conj);
+								if (p.scale_ax >= 0) { x = scale_by(x, p.scale[z.sidx]); }
+								dst[first + off + i] = x;
+							}
 						}
 					}
 				}

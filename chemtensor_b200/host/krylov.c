@@ -106,9 +106,10 @@ int ctb_lanczos_min(struct ctb_heff* h, const struct ctb_tensor* a_start, int ma
 	double *alpha = NULL, *beta = NULL, *host_scal = NULL;
 	int rc = 0, numiter = maxiter;
 #define LZ(call) do { rc = (call); if (rc < 0) { goto done; } } while (0)
-	/* zero-filled: the alignment padding between the blocks of a packed vector takes part in the level-1 kernels */
-	LZ(ctbd_malloc(&V, (size_t)maxiter * (size_t)ns * esize));
-	LZ(ctbd_malloc(&w_own, (size_t)ns * esize));
+	/* not zero-filled: every Krylov vector and the matvec result are written completely before they are read (the packed layout has
+	 * no padding between blocks, CTB_BLOCK_ALIGN == 1) -- at D = 4096 the fill was a 1.4 GB memset per bond */
+	LZ(ctbd_malloc_noinit(&V, (size_t)maxiter * (size_t)ns * esize));
+	LZ(ctbd_malloc_noinit(&w_own, (size_t)ns * esize));
 	/* scal: [0..maxiter) alpha (2 doubles each), [..] beta, then scratch */
 	LZ(ctbd_malloc((void**)&scal, (size_t)(3 * maxiter + 4) * sizeof(double)));
 	double* d_alpha = scal;                 /* stride 2 (re, im) */
