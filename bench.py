@@ -533,10 +533,18 @@ MOLECULAR_SWEEP_CASES = [
 ]
 
 
+def _sweep_selected(name: str) -> bool:
+    """CTB_BENCH_SWEEP_ONLY=substr[,substr...] restricts the sweep block to the matching configs (profiling aid; default: all)."""
+    only = os.environ.get("CTB_BENCH_SWEEP_ONLY")
+    return only is None or any(tok and tok in name for tok in only.split(","))
+
+
 def sweep_report(lib):
     """Two-site sweep seconds of the engine (and of the unmodified reference on the small case) -- reported, not the headline."""
     out = []
     for name, model, L, params, sector, D, nsw, with_ref in SWEEP_CASES:
+        if not _sweep_selected(name):
+            continue
         rec = {"config": name, "sweeps": nsw, "lanczos_iterations": 10, "tol_split": 0.0, "start": "seeded random MPS (construct_random_mps rule), bonds saturate at max_vdim"}
         ours = sweep_seconds(lib, model, L, params, sector, D, sweeps=nsw)
         rec["b200"] = ours
@@ -561,35 +569,40 @@ def sweep_report(lib):
                 rec["reference_cpu"] = {"failed": str(exc)}
         out.append(rec)
     # BASELINE.json configs[0]: perf/perf_dmrg.c as shipped, engine and reference side by side
-    rec = {"config": "perf_dmrg_c1", "what": "perf/perf_dmrg.c as shipped: 9 orbitals, sector (9, 1), max_vdim 512, 2 sweeps x 25 Lanczos iterations, tol_split 1e-8",
-           "expected_energy": -51.2777797066802}
-    rec["b200"] = perf_dmrg_c1(lib)
-    if rec["b200"] is not None:
-        rec["b200_repeat_wall_s"] = (perf_dmrg_c1(lib) or {}).get("wall_s")      # second call: plans' device allocations come from the warm pool
-        rec["energy_error_vs_expected"] = abs(rec["b200"]["energies"][-1] - rec["expected_energy"])
-    if os.path.exists(REF_SO):
-        code = (
-            "import sys, json\n"
-            f"sys.path.insert(0, {ROOT!r})\n"
-            f"sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
-            "import bench, helpers\n"
-            "print(json.dumps(bench.perf_dmrg_c1(helpers.load('ref'))))\n"
-        )
-        env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
-        try:
-            r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
-            rec["reference_cpu"] = json.loads(r.stdout.strip().splitlines()[-1])
-            rec["reference_cpu"]["cores"] = os.cpu_count()
-            if rec["b200"] is not None:
-                rec["max_energy_diff_vs_reference"] = float(np.max(np.abs(np.array(rec["b200"]["energies"]) - np.array(rec["reference_cpu"]["energies"]))))
-                rec["energy_parity_1e-10"] = bool(rec["max_energy_diff_vs_reference"] <= 1e-10)
-        except Exception as exc:
-            rec["reference_cpu"] = {"failed": str(exc)}
-    out.append(rec)
+    if _sweep_selected("perf_dmrg_c1"):
+        rec = {"config": "perf_dmrg_c1", "what": "perf/perf_dmrg.c as shipped: 9 orbitals, sector (9, 1), max_vdim 512, 2 sweeps x 25 Lanczos iterations, tol_split 1e-8",
+               "expected_energy": -51.2777797066802}
+        rec["b200"] = perf_dmrg_c1(lib)
+        if rec["b200"] is not None:
+            rec["b200_repeat_wall_s"] = (perf_dmrg_c1(lib) or {}).get("wall_s")      # second call: plans' device allocations come from the warm pool
+            rec["energy_error_vs_expected"] = abs(rec["b200"]["energies"][-1] - rec["expected_energy"])
+        if os.path.exists(REF_SO):
+            code = (
+                "import sys, json\n"
+                f"sys.path.insert(0, {ROOT!r})\n"
+                f"sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+                "import bench, helpers\n"
+                "print(json.dumps(bench.perf_dmrg_c1(helpers.load('ref'))))\n"
+            )
+            env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+            try:
+                r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
+                rec["reference_cpu"] = json.loads(r.stdout.strip().splitlines()[-1])
+                rec["reference_cpu"]["cores"] = os.cpu_count()
+                if rec["b200"] is not None:
+                    rec["max_energy_diff_vs_reference"] = float(np.max(np.abs(np.array(rec["b200"]["energies"]) - np.array(rec["reference_cpu"]["energies"]))))
+                    rec["energy_parity_1e-10"] = bool(rec["max_energy_diff_vs_reference"] <= 1e-10)
+            except Exception as exc:
+                rec["reference_cpu"] = {"failed": str(exc)}
+        out.append(rec)
     # BASELINE.json configs[1]: XXZ L=100, D=1024, two-site and single-site
-    out.append({"config": "xxz_L100_D1024_twosite", "sweeps": 1, "lanczos_iterations": 10, "tol_split": 0.0, "b200": xxz_c2(lib, False)})
-    out.append({"config": "xxz_L100_D1024_singlesite", "sweeps": 1, "lanczos_iterations": 10, "b200": xxz_c2(lib, True)})
+    if _sweep_selected("xxz_L100_D1024_twosite"):
+        out.append({"config": "xxz_L100_D1024_twosite", "sweeps": 1, "lanczos_iterations": 10, "tol_split": 0.0, "b200": xxz_c2(lib, False)})
+    if _sweep_selected("xxz_L100_D1024_singlesite"):
+        out.append({"config": "xxz_L100_D1024_singlesite", "sweeps": 1, "lanczos_iterations": 10, "b200": xxz_c2(lib, True)})
     for name, n, D, with_ref in MOLECULAR_SWEEP_CASES:
+        if not _sweep_selected(name):
+            continue
         rec = {"config": name, "sweeps": 2, "lanczos_iterations": 10, "tol_split": 0.0, "dtype": "c128"}
         rec["b200_merged_pair_tensor"] = molecular_sweep_seconds(lib, n, D, False)
         rec["b200_pair_form"] = molecular_sweep_seconds(lib, n, D, True)
@@ -614,6 +627,8 @@ def sweep_report(lib):
     # D = 1024, ONE sweep from the seeded random MPS.  The merged pair tensor of the reference would have 1226 x 256 x 1226 entries
     # per bond; the engine switches to the pair form (two site MPO tensors applied one after the other) by itself.
     for name, n, D in MOLECULAR_LARGE_CASES:
+        if not _sweep_selected(name):
+            continue
         rec = {"config": name, "sweeps": 1, "lanczos_iterations": 10, "tol_split": 0.0, "dtype": "c128", "form": "pair form chosen by the engine (merged pair tensor > 2^28 entries)"}
         try:
             rec["b200"] = molecular_sweep_seconds(lib, n, D, None, sweeps=1)

@@ -446,10 +446,10 @@ double mps_orthonormalize_qr(struct mps* mps, const enum mps_orthonormalization_
 		CTB_CHECK_ABORT(ctb_mps_local_rq(&A[0], &cap));
 	}
 	double norm = 0;
-	if (cap->grid_off[0] >= 0)
+	if (ctb_grid_offset(cap, 0) >= 0)
 	{
 		double v[2] = { 0, 0 };
-		CTB_CHECK_ABORT(ctbd_d2h(v, (char*)cap->d + (size_t)cap->grid_off[0] * ctb_sizeof_dtype(dtype), ctb_sizeof_dtype(dtype)));
+		CTB_CHECK_ABORT(ctbd_d2h(v, (char*)cap->d + (size_t)ctb_grid_offset(cap, 0) * ctb_sizeof_dtype(dtype), ctb_sizeof_dtype(dtype)));
 		norm = v[0];
 		if (norm < 0) {
 			CTB_CHECK_ABORT(ctbd_scale_host(dtype, A[edge]->nstore, A[edge]->d, -1.0));

@@ -20,7 +20,7 @@ static ct_long packed_offset(const struct ctb_tensor* t, const ct_long* index)
 {
 	int sec[CTB_MAXDIM];
 	for (int i = 0; i < t->ndim; i++) { sec[i] = t->ax[i].sec_of[index[i]]; }
-	const ct_long base = t->grid_off[ctb_grid_ravel(t, sec)];
+	const ct_long base = ctb_grid_offset(t, ctb_grid_ravel(t, sec));
 	if (base < 0) { return -1; }
 	ct_long off = 0;
 	for (int i = 0; i < t->ndim; i++) { off = off * t->ax[i].secdim[sec[i]] + t->ax[i].pos_of[index[i]]; }

@@ -586,7 +586,7 @@ static int heff_prepare_any(const struct ctb_tensor* a, const struct ctb_tensor*
 						int rows = 1;
 						for (int i = 0; i < kb; i++) { ifull[i] = idx[i]; rows *= pc->ax[i].secdim[idx[i]]; }
 						ifull[kb] = sfull;
-						const ct_long dst_blk = a->grid_off[ctb_grid_ravel(a, ifull)];
+						const ct_long dst_blk = ctb_grid_offset(a, ctb_grid_ravel(a, ifull));
 						CTB_REQUIRE(dst_blk >= 0);
 						const int np = pc->ax[kb].secdim[idx[kb]], nfull = a->ax[kb].secdim[sfull];
 						int j = 0;

@@ -90,7 +90,10 @@ struct ctb_tensor
 	int ndim;
 	struct ctb_axis ax[CTB_MAXDIM];
 	ct_long ngrid;       /* cells of the sector grid */
-	ct_long* grid_off;   /* [ngrid] element offset of the block or -1 */
+	ct_long* grid_off;   /* [ngrid] element offset of the block or -1; NULL for a large grid, which keeps the hash index below instead */
+	ct_long* gh_key;     /* large grids (ngrid > CTB_GRID_DENSE_MAX): open-addressing index cell -> element offset over the stored blocks */
+	ct_long* gh_val;
+	ct_long  gh_cap;     /* power of two, 0 when the dense table is used */
 	int nblk;            /* stored blocks */
 	ct_long* blk_grid;   /* [nblk] grid cell per stored block, ascending */
 	ct_long* blk_off;    /* [nblk+1] */
@@ -117,6 +120,22 @@ void ctb_tensor_free(struct ctb_tensor* t);
 void* ctb_tensor_layout(struct ctb_tensor* t);
 void ctb_grid_unravel(const struct ctb_tensor* t, ct_long cell, int* idx);
 ct_long ctb_grid_ravel(const struct ctb_tensor* t, const int* idx);
+/* sector grids beyond this many cells are not tabulated: the 6-leg intermediates of a molecular bond have 10^7 cells and 10^3 - 10^4
+ * stored blocks (allocating and clearing a dense table per plan was a third of the plan-building time at 24 orbitals) */
+#define CTB_GRID_DENSE_MAX ((ct_long)1 << 20)
+/* element offset of the stored block of grid cell 'cell', or -1 */
+static inline ct_long ctb_grid_offset(const struct ctb_tensor* t, ct_long cell)
+{
+	if (t->grid_off != NULL) { return t->grid_off[cell]; }
+	if (t->gh_cap == 0) { return -1; }
+	uint64_t h = (uint64_t)cell * 0x9E3779B97F4A7C15ull;
+	ct_long q = (ct_long)(h >> 20) & (t->gh_cap - 1);
+	while (t->gh_key[q] >= 0) {
+		if (t->gh_key[q] == cell) { return t->gh_val[q]; }
+		q = (q + 1) & (t->gh_cap - 1);
+	}
+	return -1;
+}
 bool ctb_tensor_same_structure(const struct ctb_tensor* a, const struct ctb_tensor* b);
 
 /* host struct <-> device tensor */

@@ -35,10 +35,10 @@ static int orthonormalize_right(struct ctb_tensor** A, int nsites, double* norm_
 	int rc = ctb_mps_local_rq(&A[0], &head);
 	if (rc < 0) { ctb_tensor_free(head); return rc; }
 	double norm = 0;
-	if (head->ngrid > 0 && head->grid_off[0] >= 0)
+	if (head->ngrid > 0 && ctb_grid_offset(head, 0) >= 0)
 	{
 		double v[2] = { 0, 0 };
-		CTB_CHECK(ctbd_d2h(v, (char*)head->d + (size_t)head->grid_off[0] * ctb_sizeof_dtype(head->dtype), ctb_sizeof_dtype(head->dtype)));
+		CTB_CHECK(ctbd_d2h(v, (char*)head->d + (size_t)ctb_grid_offset(head, 0) * ctb_sizeof_dtype(head->dtype), ctb_sizeof_dtype(head->dtype)));
 		norm = v[0];
 		if (norm < 0)
 		{

@@ -85,6 +85,8 @@ void ctb_axis_free(struct ctb_axis* ax)
 	memset(ax, 0, sizeof(*ax));
 }
 
+static int cmp_ct_long(const void* a, const void* b) { const ct_long x = *(const ct_long*)a, y = *(const ct_long*)b; return (x > y) - (x < y); }
+
 /* binary search in the sorted sector list; -1 if absent */
 int ctb_axis_find_sector(const struct ctb_axis* ax, qnumber q)
 {
@@ -133,15 +135,19 @@ struct ctb_tensor* ctb_tensor_from_axes(int dtype, int ndim, struct ctb_axis* ax
 	}
 	t->ngrid = 1;
 	for (int i = 0; i < ndim; i++) { t->ngrid *= t->ax[i].nsec; }
-	t->grid_off = ctb_malloc(t->ngrid * sizeof(ct_long));
-
 	/* stored blocks = the charge-conserving cells of the sector grid (reference block_sparse_tensor.c:126-133), in row-major grid order.
-	 * Only the leading ndim - 1 axes are enumerated: the sector of the last axis follows from sum dir q = 0 (binary search in its
-	 * sorted sector list), so the cost is ngrid / nsec_last lookups instead of a scan of the whole grid -- the grids of the
-	 * intermediate 5-leg tensors of a bond with ~100 sectors per leg have 10^5 - 10^6 cells. */
-	memset(t->grid_off, 0xFF, (size_t)t->ngrid * sizeof(ct_long));      /* -1 everywhere */
-	const int last = ndim - 1;
-	const ct_long nlead = (ndim > 0 && t->ax[last].nsec > 0) ? t->ngrid / t->ax[last].nsec : (ndim == 0 ? 1 : 0);
+	 * The axis with the MOST sectors is not enumerated: its sector follows from sum dir q = 0 (binary search in its sorted sector
+	 * list), so the cost is ngrid / max_i nsec_i lookups instead of a scan of the whole grid -- the 5- and 6-leg intermediates of a
+	 * bond have 10^5 - 10^7 cells (with a dummy last leg the former "solve the last axis" rule still walked all of them).  The cells
+	 * come out of order when the solved axis is not the last one and are sorted afterwards. */
+	int solved = ndim - 1;
+	for (int i = 0; i < ndim; i++) { if (t->ax[i].nsec > t->ax[solved].nsec) { solved = i; } }
+	ct_long cell_stride[CTB_MAXDIM];
+	{
+		ct_long st = 1;
+		for (int i = ndim - 1; i >= 0; i--) { cell_stride[i] = st; st *= t->ax[i].nsec; }
+	}
+	const ct_long nlead = (ndim > 0 && t->ax[solved].nsec > 0) ? t->ngrid / t->ax[solved].nsec : (ndim == 0 ? 1 : 0);
 	int idx[CTB_MAXDIM] = { 0 };
 	size_t cap = 256;
 	int nblk = 0;
@@ -149,21 +155,40 @@ struct ctb_tensor* ctb_tensor_from_axes(int dtype, int ndim, struct ctb_axis* ax
 	for (ct_long cl = 0; cl < nlead; cl++)
 	{
 		qnumber qsum = 0;
-		for (int i = 0; i < last; i++) { qsum += t->ax[i].dir * t->ax[i].qsec[idx[i]]; }
-		ct_long cell = -1;
+		ct_long cell = 0;
+		for (int i = 0; i < ndim; i++) { if (i != solved) { qsum += t->ax[i].dir * t->ax[i].qsec[idx[i]]; cell += idx[i] * cell_stride[i]; } }
 		if (ndim == 0) { cell = 0; }
 		else {
-			const int sl = ctb_axis_find_sector(&t->ax[last], -t->ax[last].dir * qsum);
-			if (sl >= 0) { cell = cl * t->ax[last].nsec + sl; }
+			const int sl = ctb_axis_find_sector(&t->ax[solved], -t->ax[solved].dir * qsum);
+			cell = (sl >= 0) ? cell + sl * cell_stride[solved] : -1;
 		}
 		if (cell >= 0) {
 			if ((size_t)nblk == cap) { cap *= 2; t->blk_grid = realloc(t->blk_grid, cap * sizeof(ct_long)); }      /* glibc: realloc keeps the 16-byte alignment */
 			t->blk_grid[nblk++] = cell;
 		}
-		for (int i = last - 1; i >= 0; i--) {
+		/* next combination of the enumerated axes, row-major (the last enumerated axis runs fastest) */
+		for (int i = ndim - 1; i >= 0; i--) {
+			if (i == solved) { continue; }
 			if (++idx[i] < t->ax[i].nsec) { break; }
 			idx[i] = 0;
 		}
+	}
+	if (solved != ndim - 1 && nblk > 1) { qsort(t->blk_grid, (size_t)nblk, sizeof(ct_long), cmp_ct_long); }
+	/* cell -> offset: a dense table for ordinary grids, a hash index over the stored blocks for large ones */
+	const char* dense_env = getenv("CTB_GRID_DENSE_MAX");      /* test knob: force the hash index on small grids */
+	const ct_long dense_max = (dense_env != NULL) ? (ct_long)atoll(dense_env) : CTB_GRID_DENSE_MAX;
+	t->grid_off = NULL; t->gh_key = NULL; t->gh_val = NULL; t->gh_cap = 0;
+	if (t->ngrid <= dense_max) {
+		t->grid_off = ctb_malloc((t->ngrid > 0 ? t->ngrid : 1) * sizeof(ct_long));
+		memset(t->grid_off, 0xFF, (size_t)t->ngrid * sizeof(ct_long));      /* -1 everywhere */
+	}
+	else {
+		ct_long hc = 16;
+		while (hc < 2 * (ct_long)nblk) { hc *= 2; }
+		t->gh_cap = hc;
+		t->gh_key = ctb_malloc(hc * sizeof(ct_long));
+		t->gh_val = ctb_malloc(hc * sizeof(ct_long));
+		memset(t->gh_key, 0xFF, (size_t)hc * sizeof(ct_long));
 	}
 	t->nblk = nblk;
 	t->blk_off  = ctb_malloc((nblk + 1) * sizeof(ct_long));
@@ -172,7 +197,13 @@ struct ctb_tensor* ctb_tensor_from_axes(int dtype, int ndim, struct ctb_axis* ax
 	{
 		ct_long rem = t->blk_grid[b], numel = 1;
 		for (int i = ndim - 1; i >= 0; i--) { numel *= t->ax[i].secdim[rem % t->ax[i].nsec]; rem /= t->ax[i].nsec; }
-		t->grid_off[t->blk_grid[b]] = off;
+		if (t->grid_off != NULL) { t->grid_off[t->blk_grid[b]] = off; }
+		else {
+			const ct_long cell = t->blk_grid[b];
+			ct_long q = (ct_long)(((uint64_t)cell * 0x9E3779B97F4A7C15ull) >> 20) & (t->gh_cap - 1);
+			while (t->gh_key[q] >= 0) { q = (q + 1) & (t->gh_cap - 1); }
+			t->gh_key[q] = cell; t->gh_val[q] = off;
+		}
 		t->blk_off[b] = off;
 		nelem += numel;
 		off += numel;
@@ -220,7 +251,7 @@ void ctb_tensor_free(struct ctb_tensor* t)
 {
 	if (t == NULL) { return; }
 	for (int i = 0; i < t->ndim; i++) { ctb_axis_free(&t->ax[i]); }
-	ctb_free(t->grid_off);
+	ctb_free(t->grid_off); ctb_free(t->gh_key); ctb_free(t->gh_val);
 	ctb_free(t->blk_grid);
 	ctb_free(t->blk_off);
 	if (t->layout != NULL) { ctbd_layout_destroy(t->layout); }
@@ -255,12 +286,20 @@ void* ctb_tensor_layout(struct ctb_tensor* t)
 			h.log_of[i]   = t->ax[i].log_of;
 		}
 		h.ngrid = t->ngrid;
-		h.grid_off = t->grid_off;
+		ct_long* dense_tmp = NULL;
+		if (t->grid_off == NULL) {
+			/* a re-blocking kernel wants the dense table of a large grid (rare: the large grids belong to plan intermediates) */
+			dense_tmp = ctb_malloc((t->ngrid > 0 ? t->ngrid : 1) * sizeof(ct_long));
+			memset(dense_tmp, 0xFF, (size_t)t->ngrid * sizeof(ct_long));
+			for (int b = 0; b < t->nblk; b++) { dense_tmp[t->blk_grid[b]] = t->blk_off[b]; }
+		}
+		h.grid_off = (t->grid_off != NULL) ? t->grid_off : dense_tmp;
 		h.nblk = t->nblk;
 		h.blk_grid = t->blk_grid;
 		h.blk_off = t->blk_off;
 		h.nstore = t->nstore;
 		CTB_CHECK_ABORT(ctbd_layout_create(&h, &t->layout));
+		ctb_free(dense_tmp);
 	}
 	return t->layout;
 }

@@ -279,7 +279,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 				for (int i = 0; i < ndimr; i++) { idx_full[i] = idx_r[i]; }
 				idx_full[ea] = ctb_axis_find_sector(&full->ax[ea], r->ax[ea].qsec[idx_r[ea]]);
 				CTB_REQUIRE(idx_full[ea] >= 0);
-				const ct_long off_full = full->grid_off[ctb_grid_ravel(full, idx_full)];
+				const ct_long off_full = ctb_grid_offset(full, ctb_grid_ravel(full, idx_full));
 				CTB_REQUIRE(off_full >= 0);
 				o->c_off = off_full;
 				const int np = r->ax[ea].secdim[idx_r[ea]];
@@ -303,10 +303,10 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 				kap[ndim_mult - 1] = conserved_sector(s, idx_s, shift_s + ndim_mult - 1);
 				const bool present = (kap[ndim_mult - 1] >= 0);
 				if (present) { for (int i = 0; i < ndim_mult; i++) { idx_s[shift_s + i] = kap[i]; idx_t[shift_t + i] = kap[i]; } }
-				const ct_long a_off = present ? s->grid_off[ctb_grid_ravel(s, idx_s)] : -1;
+				const ct_long a_off = present ? ctb_grid_offset(s, ctb_grid_ravel(s, idx_s)) : -1;
 				if (a_off >= 0)
 				{
-					const ct_long b_off = t->grid_off[ctb_grid_ravel(t, idx_t)];
+					const ct_long b_off = ctb_grid_offset(t, ctb_grid_ravel(t, idx_t));
 					CTB_REQUIRE(b_off >= 0);   /* conservation in t follows from s and r (reference :1976-1984) */
 					ct_long K = 1;
 					for (int i = 0; i < ndim_mult; i++) { K *= s->ax[shift_s + i].secdim[kap[i]]; }
@@ -353,7 +353,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 				kap[ndim_mult - 1] = conserved_sector(t, idx_t, shift_t + ndim_mult - 1);
 				const bool present = (kap[ndim_mult - 1] >= 0);
 				if (present) { idx_t[shift_t + ndim_mult - 1] = kap[ndim_mult - 1]; }
-				const ct_long b_off = present ? t->grid_off[ctb_grid_ravel(t, idx_t)] : -1;
+				const ct_long b_off = present ? ctb_grid_offset(t, ctb_grid_ravel(t, idx_t)) : -1;
 				const ct_long c = cl * s->ax[shift_s + ndim_mult - 1].nsec + (present ? kap[ndim_mult - 1] : 0);      /* contracted grid cell */
 				if (b_off >= 0)
 				{
@@ -461,7 +461,7 @@ struct ctb_tensor* ctb_dot_prepare_ex(const struct ctb_tensor* s, int axrange_s,
 				{
 					ct_long cell = segs[sg].pad_;
 					for (int i = ndim_mult - 1; i >= 0; i--) { idx_s[shift_s + i] = (int)(cell % s->ax[shift_s + i].nsec); cell /= s->ax[shift_s + i].nsec; }
-					const ct_long a_off = s->grid_off[ctb_grid_ravel(s, idx_s)];
+					const ct_long a_off = ctb_grid_offset(s, ctb_grid_ravel(s, idx_s));
 					CTB_REQUIRE(a_off >= 0);   /* conservation in s follows from r and t */
 					sig[nsig++] = a_off;
 				}
@@ -827,7 +827,7 @@ struct ctb_tensor* ctb_cyclic_partial_trace(struct ctb_tensor* t, int ntrace)
 			int sec[CTB_MAXDIM];
 			for (int i = 0; i < ntrace; i++) { idx[ntrace + i] = idx[i]; }
 			for (int i = 0; i < 2 * ntrace; i++) { sec[i] = delta->ax[i].sec_of[idx[i]]; }
-			const ct_long base = delta->grid_off[ctb_grid_ravel(delta, sec)];
+			const ct_long base = ctb_grid_offset(delta, ctb_grid_ravel(delta, sec));
 			CTB_REQUIRE(base >= 0);      /* equal quantum numbers with opposite directions always conserve */
 			ct_long off = 0;
 			for (int i = 0; i < 2 * ntrace; i++) { off = off * delta->ax[i].secdim[sec[i]] + delta->ax[i].pos_of[idx[i]]; }
@@ -885,8 +885,8 @@ static int build_mat_descs(const struct ctb_tensor* a, const struct ctb_tensor* 
 		d->n = a->ax[1].secdim[idx[1]];
 		const int i0[2] = { idx[0], kk };
 		const int i1[2] = { kk, idx[1] };
-		d->o0_off = o0->grid_off[ctb_grid_ravel(o0, i0)];
-		d->o1_off = o1->grid_off[ctb_grid_ravel(o1, i1)];
+		d->o0_off = ctb_grid_offset(o0, ctb_grid_ravel(o0, i0));
+		d->o1_off = ctb_grid_offset(o1, ctb_grid_ravel(o1, i1));
 		CTB_REQUIRE(d->o0_off >= 0 && d->o1_off >= 0);
 		const int kmin = d->m < d->n ? d->m : d->n;
 		CTB_REQUIRE(o0->ax[1].secdim[kk] == kmin);
@@ -1003,7 +1003,7 @@ static int svd_direct(struct ctb_tensor* a, struct ctb_tensor** u, double** s_de
 	if (dummy)
 	{
 		const int iu[2] = { 0, ctb_axis_find_sector(&(*u)->ax[1], (*u)->ax[1].qlog[0]) };
-		const ct_long off = (*u)->grid_off[ctb_grid_ravel(*u, iu)];
+		const ct_long off = ctb_grid_offset((*u), ctb_grid_ravel(*u, iu));
 		CTB_REQUIRE(off >= 0);
 		CTB_CHECK(ctb_set_entry(*u, off, 1.0, 0.0));
 		return 0;
@@ -1099,13 +1099,13 @@ static int qr_common(struct ctb_tensor* a, int rq, struct ctb_tensor** o0, struc
 		/* the isometry gets a single entry 1, the triangular factor stays zero */
 		if (!rq) {
 			const int iq[2] = { 0, ctb_axis_find_sector(&(*o0)->ax[1], q0) };
-			const ct_long off = (*o0)->grid_off[ctb_grid_ravel(*o0, iq)];
+			const ct_long off = ctb_grid_offset((*o0), ctb_grid_ravel(*o0, iq));
 			CTB_REQUIRE(off >= 0);
 			CTB_CHECK(ctb_set_entry(*o0, off, 1.0, 0.0));
 		}
 		else {
 			const int iq[2] = { ctb_axis_find_sector(&(*o1)->ax[0], q0), 0 };
-			const ct_long off = (*o1)->grid_off[ctb_grid_ravel(*o1, iq)];
+			const ct_long off = ctb_grid_offset((*o1), ctb_grid_ravel(*o1, iq));
 			CTB_REQUIRE(off >= 0);
 			CTB_CHECK(ctb_set_entry(*o1, off, 1.0, 0.0));
 		}
