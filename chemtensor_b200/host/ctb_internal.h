@@ -121,8 +121,9 @@ void* ctb_tensor_layout(struct ctb_tensor* t);
 void ctb_grid_unravel(const struct ctb_tensor* t, ct_long cell, int* idx);
 ct_long ctb_grid_ravel(const struct ctb_tensor* t, const int* idx);
 /* sector grids beyond this many cells are not tabulated: the 6-leg intermediates of a molecular bond have 10^7 cells and 10^3 - 10^4
- * stored blocks (allocating and clearing a dense table per plan was a third of the plan-building time at 24 orbitals) */
-#define CTB_GRID_DENSE_MAX ((ct_long)1 << 20)
+ * stored blocks (allocating and clearing a dense table per plan was a third of the plan-building time at 24 orbitals).  The 5-leg
+ * intermediates of the D = 4096 Fermi-Hubbard sweep (1.2 M cells) stay below the bound and keep the table. */
+#define CTB_GRID_DENSE_MAX ((ct_long)1 << 22)
 /* element offset of the stored block of grid cell 'cell', or -1 */
 static inline ct_long ctb_grid_offset(const struct ctb_tensor* t, ct_long cell)
 {
