@@ -150,7 +150,7 @@ _EXT_SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES) + tuple(_EXT_SIGNATURES) + ("allocate_zero_dense_tensor", "allocate_block_sparse_tensor_like",
-    "copy_block_sparse_tensor", "allocate_mps", "delete_mps", "allocate_mpo", "delete_mpo")
+    "copy_block_sparse_tensor", "allocate_mps", "delete_mps", "allocate_mpo", "delete_mpo", "save_mps", "load_mps")
 
 
 class CLibrary:

@@ -34,6 +34,10 @@ void copy_block_sparse_tensor(const struct block_sparse_tensor* src, struct bloc
 /* include/state/mps.h:28-31, include/operator/mpo.h:46-49 */
 void allocate_mps(const enum numeric_type dtype, const int nsites, const ct_long d, const qnumber* qsite, const ct_long* dim_bonds, const qnumber** qbonds, struct mps* mps);
 void delete_mps(struct mps* mps);
+/* reference include/state/mps.h:129-131, src/state/mps.c:1219 / :1309: the MPS in the reference's HDF5 layout (attributes nsites, qsite,
+ * qbond_<i>; dense datasets tensor_<i>); written and parsed without libhdf5 (chemtensor_b200/host/mps_io.c); 0 on success, < 0 otherwise */
+int save_mps(const char* filename, const struct mps* mps);
+int load_mps(const char* filename, struct mps* mps);
 void allocate_mpo(const enum numeric_type dtype, const int nsites, const ct_long d, const qnumber* qsite, const ct_long* dim_bonds, const qnumber** qbonds, struct mpo* mpo);
 void delete_mpo(struct mpo* mpo);
 /* include/algorithm/truncation.h:38 */
