@@ -265,6 +265,35 @@ int ctbd_copy_plan_run_multi(void* plan, int nsrc, const void* const* srcs, int6
 int ctbd_copy_plan_run_push(void* plan, const void* src, int ndst, void* const* dsts);
 int ctbd_copy_plan_destroy(void* plan);
 
+/* ---- batched strided block linear combinations ------------------------------------------------
+ * The data movement of the SU(2) layer (host/su2.c): F-moves (a result degeneracy tensor is a recoupling-coefficient weighted sum
+ * of source degeneracy tensors of the same shape, reference src/tensor/su2_tensor.c:770-886), axis permutations of degeneracy tensors
+ * (:647), the per-sector scalings of axis reversals and swaps (:916, :467), stacking of sector blocks into the matrices the batched
+ * QR / SVD kernels factorise, and the (de)normalisation of Lanczos vectors (:4725).  For every block and every multi-index i over
+ * dim[] (row-major enumeration):
+ *     dst[dst_off + sum_a i_a * dstride[a]]  =  sum_{t in [term_begin, term_end)}  coef_t * op(src[src_off_t + sum_a i_a * sstride[a]])
+ * op = complex conjugation when the plan was created with conj != 0.  A block without terms is zero-filled.  src may equal dst
+ * only when both index maps are the same (in-place scaling).  HBM-bound: (terms + 1) x block bytes. */
+#define CTBD_LC_MAXDIM 8
+struct ctbd_lc_term
+{
+	int64_t src_off;
+	double coef;
+};
+struct ctbd_lc_block
+{
+	int64_t dst_off;
+	int32_t term_begin, term_end;
+	int32_t ndim;                        /* 1 .. CTBD_LC_MAXDIM */
+	int32_t pad_;
+	int32_t dim[CTBD_LC_MAXDIM];
+	int64_t dstride[CTBD_LC_MAXDIM];
+	int64_t sstride[CTBD_LC_MAXDIM];
+};
+int ctbd_lc_plan_create(int dtype, int conj, int nblk, const struct ctbd_lc_block* blocks_host, int nterm, const struct ctbd_lc_term* terms_host, void** plan);
+int ctbd_lc_plan_run(void* plan, const void* src, void* dst);
+int ctbd_lc_plan_destroy(void* plan);
+
 /* ---- level-1 kernels for the Lanczos iteration (scalars stay on the device) ----------------- */
 
 /* out[0] = Re sum conj(x_i) y_i, out[1] = Im (0 for real) */

@@ -816,3 +816,48 @@ int ctbd_truncate_select(int64_t n, const double* S, double tol, int relative, i
 	*nret = num; info3[0] = norm_sigma; info3[1] = entropy;
 	return 0;
 }
+
+/* ---- batched strided block linear combinations (twin of csrc/ctbd_blocklc.cu) ---- */
+struct emu_lc_plan { int dtype, conj, nblk, nterm; struct ctbd_lc_block* blocks; struct ctbd_lc_term* terms; };
+int ctbd_lc_plan_create(int dtype, int conj, int nblk, const struct ctbd_lc_block* blocks, int nterm, const struct ctbd_lc_term* terms, void** plan)
+{
+	if (dtype != CTBD_F64 && dtype != CTBD_C128) { snprintf(g_err, sizeof g_err, "emu: lc plan dtype"); return -1; }
+	struct emu_lc_plan* p = calloc(1, sizeof *p);
+	p->dtype = dtype; p->conj = conj; p->nblk = nblk; p->nterm = nterm;
+	p->blocks = dup_mem(blocks, (size_t)nblk * sizeof *blocks);
+	p->terms = dup_mem(terms, (size_t)nterm * sizeof *terms);
+	*plan = p;
+	return 0;
+}
+int ctbd_lc_plan_run(void* plan, const void* src, void* dst)
+{
+	const struct emu_lc_plan* p = plan;
+	const int cplx = (p->dtype == CTBD_C128);
+	g_launches++;
+	for (int ib = 0; ib < p->nblk; ib++)
+	{
+		const struct ctbd_lc_block* b = &p->blocks[ib];
+		int64_t n = 1;
+		for (int a = 0; a < b->ndim; a++) { n *= b->dim[a]; }
+		for (int64_t e = 0; e < n; e++)
+		{
+			int64_t r = e, doff = b->dst_off, soff = 0;
+			for (int a = b->ndim - 1; a >= 0; a--) {
+				const int64_t i = r % b->dim[a]; r /= b->dim[a];
+				doff += i * b->dstride[a]; soff += i * b->sstride[a];
+			}
+			if (cplx) {
+				double complex acc = 0;
+				for (int t = b->term_begin; t < b->term_end; t++) { acc += p->terms[t].coef * ((const double complex*)src)[p->terms[t].src_off + soff]; }
+				((double complex*)dst)[doff] = p->conj ? conj(acc) : acc;
+			}
+			else {
+				double acc = 0;
+				for (int t = b->term_begin; t < b->term_end; t++) { acc += p->terms[t].coef * ((const double*)src)[p->terms[t].src_off + soff]; }
+				((double*)dst)[doff] = acc;
+			}
+		}
+	}
+	return 0;
+}
+int ctbd_lc_plan_destroy(void* plan) { struct emu_lc_plan* p = plan; if (p) { free(p->blocks); free(p->terms); free(p); } return 0; }

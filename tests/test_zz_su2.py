@@ -1,0 +1,231 @@
+"""SU(2)-symmetric path (SURVEY 8(a) last row, 8(f) rank 2, BASELINE configs[4]) against the unmodified reference (oracle/_ref).
+
+Mirrors the reference's own fixture-free SU(2) tests (test/algorithm/test_su2_chain_ops.c, test_su2_dmrg.c, test/tensor/test_su2_tensor.c):
+inputs from the reference's generators, the same host structs through the engine's C entry points.  Bars: trees, irreducible lists,
+degeneracy dimensions and charge-sector tables bit-exact; degeneracy-tensor entries 1e-12 relative; sweep energies 1e-10
+(the tests assert tighter), entropies 1e-10.  'emu' = host logic on the CPU test double (runs without a GPU), 'cuda' = the product.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers
+import su2_helpers as S
+
+KINDS = ["emu", pytest.param("cuda", marks=pytest.mark.gpu)]
+T = S.SU2Tensor
+
+
+def _envs(r, psi, mpo, L):
+    rl = (T * L)()
+    r.su2_compute_right_operator_blocks(C.byref(psi), C.byref(psi), C.byref(mpo), rl)
+    lb = T()
+    r.su2_create_dummy_operator_block_left(1, C.byref(lb))
+    lbs = [lb]
+    for i in range(L - 1):
+        nr = T()
+        r.su2_contraction_operator_step_left(C.byref(psi.a[i]), C.byref(psi.a[i]), C.byref(mpo.a[i]), C.byref(lbs[-1]), C.byref(nr))
+        lbs.append(nr)
+    return lbs, rl
+
+
+def test_recoupling_coefficients_equal_reference_tables():
+    """Racah-formula evaluation against the reference's generated tables over their whole range (ja, jb, jc <= 5), incl. the zero pattern"""
+    r, e = S.ref(), S.engine("emu")
+    worst = 0.0
+    for ja in range(6):
+        for jb in range(6):
+            for jc in range(6):
+                for js in range((ja + jb + jc) % 2, ja + jb + jc + 1, 2):
+                    for je in range(abs(ja - jb), ja + jb + 1, 2):
+                        for jf in range(abs(jb - jc), jb + jc + 1, 2):
+                            a = r.su2_recoupling_coefficient(ja, jb, jc, js, je, jf)
+                            b = e.su2_recoupling_coefficient(ja, jb, jc, js, je, jf)
+                            assert (a == 0) == (b == 0), (ja, jb, jc, js, je, jf, a, b)
+                            worst = max(worst, abs(a - b))
+    assert worst < 5e-16
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_contract_simple_and_fmove(kind):
+    r, e = S.ref(), S.engine(kind)
+    psi = S.random_mps(6, [1], [0, 1], 0, 5, 11, 41, scale=2.0)
+    mpo = S.heisenberg_mpo(6, 0.7)
+    for i in range(5):
+        x, y = T(), T()
+        ia, ib = (C.c_int * 1)(2), (C.c_int * 1)(0)
+        r.su2_tensor_contract_simple(C.byref(psi.a[i]), ia, C.byref(psi.a[i + 1]), ib, 1, C.byref(x))
+        e.su2_tensor_contract_simple(C.byref(psi.a[i]), ia, C.byref(psi.a[i + 1]), ib, 1, C.byref(y))
+        S.assert_same_su2(y, x, 1e-13)
+        ax = x.tree.tree_split.contents.c[0].contents.i_ax
+        fx, fy = T(), T()
+        r.su2_tensor_fmove(C.byref(x), ax, C.byref(fx))
+        e.su2_tensor_fmove(C.byref(x), ax, C.byref(fy))
+        S.assert_same_su2(fy, fx, 1e-13)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("model", ["heisenberg", "fermi_hubbard"])
+def test_environment_steps_and_local_hamiltonian(kind, model):
+    r, e = S.ref(), S.engine(kind)
+    L = 6
+    if model == "heisenberg":
+        mpo = S.heisenberg_mpo(L, 1.3)
+        psi = S.random_mps(L, [1], [0, 1], 0, 5, 9, 83, scale=3.0)
+    else:
+        mpo = S.fermi_hubbard_mpo(L, 1.0, 4.0, 0.3)
+        # site: j = 0 twice (empty, doubly occupied), j = 1/2 once
+        psi = S.random_mps(L, [0, 1], [2, 1], 0, 3, 7, 87, scale=2.0)
+    rl_ref, rl_eng = (T * L)(), (T * L)()
+    r.su2_compute_right_operator_blocks(C.byref(psi), C.byref(psi), C.byref(mpo), rl_ref)
+    e.su2_compute_right_operator_blocks(C.byref(psi), C.byref(psi), C.byref(mpo), rl_eng)
+    for i in range(L):
+        S.assert_same_su2(rl_eng[i], rl_ref[i], 1e-12)
+    lb_ref, lb_eng = T(), T()
+    r.su2_create_dummy_operator_block_left(1, C.byref(lb_ref))
+    e.su2_create_dummy_operator_block_left(1, C.byref(lb_eng))
+    S.assert_same_su2(lb_eng, lb_ref, 0.0)
+    rb_ref, rb_eng = T(), T()
+    r.su2_create_dummy_operator_block_right(1, 3, C.byref(rb_ref))
+    e.su2_create_dummy_operator_block_right(1, 3, C.byref(rb_eng))
+    S.assert_same_su2(rb_eng, rb_ref, 0.0)
+    lbs = [lb_ref]
+    for i in range(L - 1):
+        nr, ne = T(), T()
+        r.su2_contraction_operator_step_left(C.byref(psi.a[i]), C.byref(psi.a[i]), C.byref(mpo.a[i]), C.byref(lbs[-1]), C.byref(nr))
+        e.su2_contraction_operator_step_left(C.byref(psi.a[i]), C.byref(psi.a[i]), C.byref(mpo.a[i]), C.byref(lbs[-1]), C.byref(ne))
+        S.assert_same_su2(ne, nr, 1e-12)
+        lbs.append(nr)
+    for i in range(L):
+        br, be = T(), T()
+        r.su2_apply_local_hamiltonian(C.byref(psi.a[i]), C.byref(mpo.a[i]), C.byref(lbs[i]), C.byref(rl_ref[i]), C.byref(br))
+        e.su2_apply_local_hamiltonian(C.byref(psi.a[i]), C.byref(mpo.a[i]), C.byref(lbs[i]), C.byref(rl_ref[i]), C.byref(be))
+        S.assert_same_su2(be, br, 1e-12)
+    a, b = C.c_double(), C.c_double()
+    r.su2_mpo_inner_product(C.byref(psi), C.byref(mpo), C.byref(psi), C.byref(a))
+    e.su2_mpo_inner_product(C.byref(psi), C.byref(mpo), C.byref(psi), C.byref(b))
+    assert abs(a.value - b.value) <= 1e-12 * max(1.0, abs(a.value))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_pair_form_equals_merged_reference(kind):
+    """two site operators one after the other on the 4-leg tensor == the reference's merged pair tensor on the fused 3-leg tensor"""
+    r, e = S.ref(), S.engine(kind)
+    e.ctb_su2_apply_local_hamiltonian_pair.restype = None
+    e.ctb_su2_apply_local_hamiltonian_pair.argtypes = [C.POINTER(T)] * 6
+    L = 6
+    mpo = S.heisenberg_mpo(L, 1.1)
+    psi = S.random_mps(L, [1], [0, 1], 0, 5, 9, 85, scale=3.0)
+    lbs, rl = _envs(r, psi, mpo, L)
+    for i in range(L - 1):
+        a2, am, h2, bm, b2, bf = T(), T(), T(), T(), T(), T()
+        r.su2_mps_contract_tensor_pair(C.byref(psi.a[i]), C.byref(psi.a[i + 1]), C.byref(a2))
+        r.su2_mps_merge_tensor_pair(C.byref(psi.a[i]), C.byref(psi.a[i + 1]), C.byref(am))
+        r.su2_mpo_merge_tensor_pair(C.byref(mpo.a[i]), C.byref(mpo.a[i + 1]), C.byref(h2))
+        r.su2_apply_local_hamiltonian(C.byref(am), C.byref(h2), C.byref(lbs[i]), C.byref(rl[i + 1]), C.byref(bm))
+        e.ctb_su2_apply_local_hamiltonian_pair(C.byref(a2), C.byref(mpo.a[i]), C.byref(mpo.a[i + 1]), C.byref(lbs[i]), C.byref(rl[i + 1]), C.byref(b2))
+        r.su2_tensor_fuse_axes(C.byref(b2), 1, 2, C.byref(bf))
+        S.assert_same_su2(bf, bm, 1e-12)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_mps_orthonormalize(kind, mode):
+    r, e = S.ref(), S.engine(kind)
+    L = 7
+    mpo = S.heisenberg_mpo(L, 1.3)
+    psi = S.random_mps(L, [1], [0, 1], 1, 5, 27, 81, scale=14.0)
+    p1, p2 = S.copy_mps(psi), S.copy_mps(psi)
+    n1 = r.su2_mps_orthonormalize_qr(C.byref(p1), mode)
+    n2 = e.su2_mps_orthonormalize_qr(C.byref(p2), mode)
+    assert abs(n1 - n2) <= 1e-12 * n1
+    assert r.su2_mps_is_consistent(C.byref(p2))
+    a, b = C.c_double(), C.c_double()
+    r.su2_mpo_inner_product(C.byref(p1), C.byref(mpo), C.byref(p1), C.byref(a))
+    r.su2_mpo_inner_product(C.byref(p2), C.byref(mpo), C.byref(p2), C.byref(b))
+    assert abs(a.value - b.value) <= 1e-12 * abs(a.value)
+    # same bond structure
+    for i in range(L):
+        for ax in (0, 2):
+            ja = [p1.a[i].outer_irreps[ax].jlist[k] for k in range(p1.a[i].outer_irreps[ax].num)]
+            jb = [p2.a[i].outer_irreps[ax].jlist[k] for k in range(p2.a[i].outer_irreps[ax].num)]
+            assert ja == jb
+            assert [p1.a[i].dim_degen[ax][j] for j in ja] == [p2.a[i].dim_degen[ax][j] for j in jb]
+    # the state itself: same vector (the gauge of the isometries drops out)
+    v1, v2 = T(), T()
+    r.su2_mps_to_statevector(C.byref(p1), C.byref(v1))
+    r.su2_mps_to_statevector(C.byref(p2), C.byref(v2))
+    assert r.su2_tensor_allclose(C.byref(v1), C.byref(v2), 1e-11)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_su2_dmrg_singlesite(kind):
+    """the reference's test_su2_dmrg_singlesite (test/algorithm/test_su2_dmrg.c:15-125): same inputs, energies against the reference's run"""
+    r, e = S.ref(), S.engine(kind)
+    L, ns = 7, 3
+    mpo = S.heisenberg_mpo(L, 1.3)
+    psi = S.random_mps(L, [1], [0, 1], 1, 5, 27, 81, scale=14.0)
+    p1, p2 = S.copy_mps(psi), S.copy_mps(psi)
+    e1, e2 = (C.c_double * ns)(), (C.c_double * ns)()
+    assert r.su2_dmrg_singlesite(C.byref(mpo), ns, 5, C.byref(p1), e1) == 0
+    assert e.su2_dmrg_singlesite(C.byref(mpo), ns, 5, C.byref(p2), e2) == 0
+    assert np.allclose(list(e1), list(e2), rtol=0, atol=1e-11)
+    assert r.su2_mps_is_consistent(C.byref(p2))
+    b = C.c_double()
+    r.su2_mpo_inner_product(C.byref(p2), C.byref(mpo), C.byref(p2), C.byref(b))
+    assert abs(b.value - e2[ns - 1]) <= 1e-12 * abs(b.value)
+    # exact ground state of the 7-site chain (dense diagonalisation of the spin-1/2 Heisenberg Hamiltonian)
+    assert abs(e2[ns - 1] - _heisenberg_ground_state(L, 1.3)) < 1e-11
+
+
+def _heisenberg_ground_state(L: int, J: float) -> float:
+    sx = np.array([[0, 0.5], [0.5, 0]]); sy = np.array([[0, -0.5j], [0.5j, 0]]); sz = np.diag([0.5, -0.5])
+    H = np.zeros((2 ** L, 2 ** L), dtype=complex)
+    for i in range(L - 1):
+        for s in (sx, sy, sz):
+            H += J * np.kron(np.kron(np.eye(2 ** i), np.kron(s, s)), np.eye(2 ** (L - i - 2)))
+    return float(np.linalg.eigvalsh(H)[0])
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("tol,max_vdim", [(1e-5, 1000), (0.0, 12), (1e-3, 16)])
+def test_su2_dmrg_twosite(kind, tol, max_vdim):
+    """the reference's test_su2_dmrg_twosite (test/algorithm/test_su2_dmrg.c:128-): energies, entropies and bond structure against the reference"""
+    r, e = S.ref(), S.engine(kind)
+    L, ns = 7, 2
+    mpo = S.heisenberg_mpo(L, 1.1)
+    psi = S.random_mps(L, [1], [0, 1], 1, 5, 27, 82, scale=14.0)
+    p1, p2 = S.copy_mps(psi), S.copy_mps(psi)
+    e1, e2 = (C.c_double * ns)(), (C.c_double * ns)()
+    s1, s2 = (C.c_double * (L - 1))(), (C.c_double * (L - 1))()
+    assert r.su2_dmrg_twosite(C.byref(mpo), ns, 5, tol, max_vdim, C.byref(p1), e1, s1) == 0
+    assert e.su2_dmrg_twosite(C.byref(mpo), ns, 5, tol, max_vdim, C.byref(p2), e2, s2) == 0
+    assert np.allclose(list(e1), list(e2), rtol=0, atol=1e-10), (list(e1), list(e2))
+    assert np.allclose(list(s1), list(s2), rtol=0, atol=1e-9), (list(s1), list(s2))
+    assert r.su2_mps_is_consistent(C.byref(p2))
+    for i in range(L):
+        ja = [p1.a[i].outer_irreps[2].jlist[k] for k in range(p1.a[i].outer_irreps[2].num)]
+        jb = [p2.a[i].outer_irreps[2].jlist[k] for k in range(p2.a[i].outer_irreps[2].num)]
+        assert ja == jb
+        assert [p1.a[i].dim_degen[2][j] for j in ja] == [p2.a[i].dim_degen[2][j] for j in jb]
+    b = C.c_double()
+    r.su2_mpo_inner_product(C.byref(p2), C.byref(mpo), C.byref(p2), C.byref(b))
+    assert abs(b.value - e2[ns - 1]) <= 1e-11 * abs(b.value)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_su2_dmrg_twosite_fermi_hubbard_longer_chain(kind):
+    """a chain whose bonds grow through the split (L = 12, two physical irreducible sectors), against the reference"""
+    r, e = S.ref(), S.engine(kind)
+    L, ns = 10, 2
+    mpo = S.fermi_hubbard_mpo(L, 1.0, 4.0, 1.5)
+    psi = S.random_mps(L, [0, 1], [2, 1], 0, 3, 6, 91, scale=3.0)
+    p1, p2 = S.copy_mps(psi), S.copy_mps(psi)
+    e1, e2 = (C.c_double * ns)(), (C.c_double * ns)()
+    s1, s2 = (C.c_double * (L - 1))(), (C.c_double * (L - 1))()
+    assert r.su2_dmrg_twosite(C.byref(mpo), ns, 8, 1e-8, 60, C.byref(p1), e1, s1) == 0
+    assert e.su2_dmrg_twosite(C.byref(mpo), ns, 8, 1e-8, 60, C.byref(p2), e2, s2) == 0
+    assert np.allclose(list(e1), list(e2), rtol=0, atol=1e-10), (list(e1), list(e2))
+    assert np.allclose(list(s1), list(s2), rtol=0, atol=1e-8)
+    assert r.su2_mps_is_consistent(C.byref(p2))
