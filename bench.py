@@ -525,6 +525,11 @@ MOLECULAR_LARGE_CASES = [
     # (name, spatial orbitals, bond dimension)
     ("mol_n24_D1024_c128", 24, 1024),
 ]
+# (name, arguments of tools/su2_run.py, time the reference too)
+SU2_CASES = [
+    ("su2_heisenberg_L24_parity", "24 60 --sweeps 2 --lanczos 6 --degen 3 --max-irrep 2 --tol 1e-5", True),
+    ("su2_heisenberg_L200_D2048", "200 2048 --sweeps 3 --lanczos 10 --degen 8", False),
+]
 
 MOLECULAR_SWEEP_CASES = [
     # (name, spatial orbitals, bond dimension, time the reference too?)
@@ -634,6 +639,30 @@ def sweep_report(lib):
             rec["b200"] = molecular_sweep_seconds(lib, n, D, None, sweeps=1)
             if rec["b200"] is not None:
                 rec["b200"]["phases_s"] = phases(lib)
+        except Exception as exc:
+            rec["b200"] = {"failed": str(exc)}
+        out.append(rec)
+    # BASELINE.json configs[4]: SU(2)-symmetric Heisenberg chain, SU(2) DMRG variant (su2_dmrg_twosite behind the reference's symbol).
+    # (i) a chain the unmodified reference can run (its recoupling tables end at 2j = 5, src/tensor/su2_recoupling.c:959-963: start bonds
+    # up to 2j = 2, tol_split 1e-5) for energy parity and the CPU time beside it; (ii) L = 200 as named, logical bond dimension 2048.
+    for name, su2_args, with_ref in SU2_CASES:
+        if not _sweep_selected(name):
+            continue
+        rec = {"config": name, "args": su2_args, "driver": "tools/su2_run.py (one su2_dmrg_twosite call per sweep on host structs)"}
+        outp = f"/tmp/ctb_bench_su2_{name}_{os.getpid()}.json"
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "su2_run.py"), "cuda"] + su2_args.split() + ["--out", outp] + (["--ref"] if with_ref else [])
+        try:
+            env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+            subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+            src = outp if os.path.exists(outp) else outp + ".partial"     # a reference that dies leaves the engine's sweeps in the partial record
+            with open(src) as f:
+                got = json.load(f)
+            rec["b200"] = got.get("engine")
+            if with_ref:
+                rec["reference_cpu"] = got.get("reference", {"failed": "the reference did not finish"})
+                if "energy_diff" in got:
+                    rec["max_energy_diff_vs_reference"] = got["energy_diff"]
+                    rec["energy_parity_1e-10"] = bool(got["energy_diff"] <= 1e-10)
         except Exception as exc:
             rec["b200"] = {"failed": str(exc)}
         out.append(rec)

@@ -23,7 +23,7 @@ def declared_functions(header):
 def test_product_library_loads_and_exports_the_declared_abi():
     helpers._make("lib")
     lib = C.CDLL(helpers.CUDA_SO, mode=os.RTLD_NOW)      # every undefined symbol must resolve at load time
-    api = declared_functions("chemtensor_b200.h")
+    api = declared_functions("chemtensor_b200.h") | declared_functions("ctb_su2.h")
     dev = declared_functions("ctb_device.h")
     assert len(api) > 50 and len(dev) > 40
     missing = sorted(n for n in api | dev if not hasattr(lib, n))
@@ -34,7 +34,7 @@ def test_product_library_loads_and_exports_the_declared_abi():
 def test_test_double_exports_the_device_layer():
     helpers._make("emu")
     lib = C.CDLL(helpers.EMU_SO, mode=os.RTLD_NOW)
-    missing = sorted(n for n in declared_functions("ctb_device.h") | declared_functions("chemtensor_b200.h") if not hasattr(lib, n))
+    missing = sorted(n for n in declared_functions("ctb_device.h") | declared_functions("chemtensor_b200.h") | declared_functions("ctb_su2.h") if not hasattr(lib, n))
     assert not missing, f"test double lacks: {missing}"
     assert lib.ctbd_backend() == 2
 
