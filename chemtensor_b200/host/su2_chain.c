@@ -1155,3 +1155,46 @@ int su2_dmrg_twosite(const struct su2_mpo* hamiltonian, const int num_sweeps, co
 	ctb_free(a); ctb_free(w); ctb_free(rb); ctb_free(lb);
 	return rc;
 }
+
+/* ---- measurement aid: the block linear combination kernel alone against the HBM roofline ----
+ * nblk destination blocks of nelem entries, each the sum of nterm source blocks (the shape of an F-move on a large tensor);
+ * algorithmic bytes = (nterm + 1) x nblk x nelem x sizeof(T).  out = { best ms of 5 (L2 flushed before each), GB/s, bytes }. */
+int ctb_su2_lc_benchmark(ct_long nelem, int nblk, int nterm, int cplx, double* out)
+{
+	CTB_CHECK(ctbd_init(-1));
+	const size_t es = cplx ? 16 : 8;
+	void *src = NULL, *dst = NULL, *flush = NULL;
+	const size_t flush_bytes = (size_t)192 << 20;
+	CTB_CHECK(ctbd_malloc(&src, (size_t)nelem * nblk * nterm * es));
+	CTB_CHECK(ctbd_malloc(&dst, (size_t)nelem * nblk * es));
+	CTB_CHECK(ctbd_malloc(&flush, flush_bytes));
+	struct ctbd_lc_block* blocks = ctb_calloc((size_t)nblk, sizeof *blocks);
+	struct ctbd_lc_term* terms = ctb_calloc((size_t)nblk * nterm, sizeof *terms);
+	for (int b = 0; b < nblk; b++) {
+		blocks[b].dst_off = (int64_t)b * nelem; blocks[b].term_begin = b * nterm; blocks[b].term_end = (b + 1) * nterm;
+		blocks[b].ndim = 1; blocks[b].dim[0] = (int32_t)nelem; blocks[b].dstride[0] = 1; blocks[b].sstride[0] = 1;
+		for (int t = 0; t < nterm; t++) { terms[b * nterm + t].src_off = ((int64_t)t * nblk + b) * nelem; terms[b * nterm + t].coef = 0.5 + t; }
+	}
+	void* plan = NULL;
+	CTB_CHECK(ctbd_lc_plan_create(cplx ? CTBD_C128 : CTBD_F64, 0, nblk, blocks, nblk * nterm, terms, &plan));
+	void *e0 = NULL, *e1 = NULL;
+	CTB_CHECK(ctbd_event_create(&e0)); CTB_CHECK(ctbd_event_create(&e1));
+	double best = 1e30;
+	for (int rep = 0; rep < 6; rep++)
+	{
+		CTB_CHECK(ctbd_memset_zero(flush, flush_bytes));
+		CTB_CHECK(ctbd_event_record(e0));
+		CTB_CHECK(ctbd_lc_plan_run(plan, src, dst));
+		CTB_CHECK(ctbd_event_record(e1));
+		float ms = 0;
+		CTB_CHECK(ctbd_event_elapsed_ms(e0, e1, &ms));
+		if (rep > 0 && ms < best) { best = ms; }
+	}
+	const double bytes = (double)(nterm + 1) * (double)nblk * (double)nelem * (double)es;
+	out[0] = best; out[1] = bytes / (best * 1e-3) / 1e9; out[2] = bytes;
+	ctbd_event_destroy(e0); ctbd_event_destroy(e1);
+	ctbd_lc_plan_destroy(plan);
+	ctb_free(blocks); ctb_free(terms);
+	ctbd_free(src); ctbd_free(dst); ctbd_free(flush);
+	return 0;
+}

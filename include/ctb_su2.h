@@ -121,6 +121,8 @@ void ctb_su2_apply_local_hamiltonian_pair(const struct su2_tensor* a2, const str
 
 /* statistics of the last su2_dmrg_* call: { device launches of the SU(2) layer, Heff applications, seconds in local solves, seconds in splits / QR, seconds in environment steps } */
 void ctb_su2_get_stats(double* out5);
+/* measurement aid: the block linear combination kernel (csrc/ctbd_blocklc.cu) alone; out = { ms, GB/s, algorithmic bytes } */
+int ctb_su2_lc_benchmark(ct_long nelem, int nblk, int nterm, int cplx, double* out);
 
 #ifdef __cplusplus
 }
