@@ -1094,7 +1094,7 @@ int svd_bj_impl(int nmat, const ctbd_mat_desc* descs, const void* A, void* U, vo
 	/* ---- stage 2 ---- */
 	void* d_dbg = nullptr;      /* CTB_SVD_EIG_TIMING=1: in-kernel cycle counters of the pair eigen-solver (first pair of the batch) */
 	if (getenv("CTB_SVD_EIG_TIMING") != nullptr && ctbd_malloc(&d_dbg, 16 * sizeof(long long)) < 0) { d_dbg = nullptr; }
-	const int max_cycles = 60;
+	const int max_cycles = 30;      /* converging blocks need 8-14 cycles */
 	int max_inner = 1;      /* knob: CTB_SVD_INNER_SWEEPS */
 	if (getenv("CTB_SVD_INNER_SWEEPS") != nullptr) { max_inner = std::max(1, atoi(getenv("CTB_SVD_INNER_SWEEPS"))); }
 	int round = 0;
@@ -1122,7 +1122,18 @@ int svd_bj_impl(int nmat, const ctbd_mat_desc* descs, const void* A, void* U, vo
 			fprintf(stderr, "[svd_bj]   cycle %d: %d rounds, %d / %d blocks finished, t = %.2f ms\n", cyc, nrounds, nd, nmat, now_ms() - t_qr);
 		}
 	}
-	if (rc == 0 && !converged) { rc = fail_msg("block-Jacobi SVD: not converged after 60 tournament cycles"); }
+	if (rc == 0 && !converged)
+	{
+		/* Same policy as the single-CTA path (ctbd_factor.cu, svd_batched_impl): what keeps rotating after this many cycles are rows at
+		 * rounding level of a numerically rank-deficient or strongly graded block (e.g. the two-site tensor of a bond that has just
+		 * saturated: its trailing singular values are 16 decades below the leading ones and are regenerated by the rounding of every
+		 * rotation with a large row).  The factors reconstruct the block to working precision and the singular values above ~1e-13 of
+		 * the largest one are converged, so the result is kept; the condition is recorded in ctbd_last_error() and reported once.
+		 * (The reference returns -1 only if LAPACK ?gesvd itself fails, dense_tensor.c:3636-3671.) */
+		static bool warned = false;
+		(void)fail_msg("block-Jacobi SVD: rotations at rounding level still pending after 30 tournament cycles (result kept)");
+		if (!warned) { warned = true; fprintf(stderr, "chemtensor_b200: warning: %s\n", ctbd_last_error()); }
+	}
 
 	/* ---- stage 3 ---- */
 	if (rc == 0) {

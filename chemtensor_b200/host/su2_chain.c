@@ -21,13 +21,13 @@
 #include <float.h>
 #include "su2_internal.h"
 
-static double g_stats[5];
+static double g_stats[16];     /* [0..4] see ctb_su2_get_stats, [5] orthonormalisation + initial environments, [6] sweeps done, [7..15] seconds per sweep */
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
 
-void ctb_su2_get_stats(double* out5)
+void ctb_su2_get_stats(double* out16)
 {
 	g_stats[0] = (double)g_su2_launches;
-	memcpy(out5, g_stats, sizeof g_stats);
+	memcpy(out16, g_stats, sizeof g_stats);
 }
 
 /* ---------------------------------------------------------------------------------------------------------------------------
@@ -575,7 +575,11 @@ static int su2_split_pair(struct su2t* th, double tol, ct_long max_vdim, int dis
 	const int dt = (T->dtype == CT_DOUBLE_COMPLEX) ? CTBD_C128 : CTBD_F64;
 	int rc = ctbd_svd_batched(dt, ne, desc, M, U, V, S);
 	g_su2_launches++;
-	if (rc < 0) { return rc; }
+	if (rc < 0) {
+		fprintf(stderr, "chemtensor_b200: SU(2) split: batched SVD of %d sector matrices failed: %s\n", ne, ctbd_last_error());
+		for (int k = 0; k < ne; k++) { fprintf(stderr, "  2j = %d: %lld x %lld\n", (int)ev[k], (long long)rows[k], (long long)cols[k]); }
+		return rc;
+	}
 	double* sig = ctb_malloc((size_t)(stot + 1) * sizeof(double));
 	CTB_CHECK(ctbd_d2h(sig, S, (size_t)stot * sizeof(double)));
 	int* mult = ctb_malloc((size_t)(stot + 1) * sizeof(int));
@@ -805,7 +809,12 @@ static int su2_minimize(su2_heff_fn fn, void* ctx, struct su2t* a_start, int max
 			beta[j] = host_scal[2 * maxiter + j];
 			if (!(beta[j] >= 100 * (double)n * DBL_EPSILON)) { numiter = j + 1; break; }     /* krylov.c:58 */
 		}
-		for (int j = 0; j < numiter; j++) { if (!isfinite(alpha[j])) { rc = -1; } }
+		for (int j = 0; j < numiter; j++) {
+			if (!isfinite(alpha[j])) {
+				fprintf(stderr, "chemtensor_b200: SU(2) Lanczos produced a non-finite coefficient at iteration %d (alpha = %g, n = %lld)\n", j, alpha[j], (long long)n);
+				rc = -1; break;
+			}
+		}
 	}
 	if (rc == 0)
 	{
@@ -1038,17 +1047,19 @@ int su2_dmrg_singlesite(const struct su2_mpo* hamiltonian, const int num_sweeps,
 	struct su2t** a = upload_sites(psi->a, nsites);
 	struct su2t** w = upload_sites(hamiltonian->a, nsites);
 	const int dtype = w[0]->dtype;
+	double t0 = now_s();
 	const double nrm = su2_orthonormalize_dev(a, nsites, SU2_MPS_ORTHONORMAL_RIGHT);
 	if (nrm == 0) { printf("Warning: in 'su2_dmrg_singlesite': initial MPS has norm zero (possibly due to mismatching quantum numbers)\n"); }
-	double t0 = now_s();
 	struct su2t** rb = right_blocks_dev(a, a, w, nsites);
 	struct su2t** lb = ctb_calloc((size_t)nsites + 1, sizeof *lb);
 	for (int i = 0; i < nsites; i++) { lb[i] = dummy_left_dev(dtype); }
-	g_stats[4] += now_s() - t0;
+	CTB_CHECK(ctbd_sync());
+	g_stats[5] += now_s() - t0;
 	int rc = 0;
 	for (int n = 0; n < num_sweeps && rc == 0; n++)
 	{
 		double en = 0;
+		const double t_sweep = now_s();
 		for (int i = 0; i < nsites - 1 && rc == 0; i++)
 		{
 			struct heff_single_ctx ctx = { w[i], lb[i], rb[i] };
@@ -1077,7 +1088,11 @@ int su2_dmrg_singlesite(const struct su2_mpo* hamiltonian, const int num_sweeps,
 			rb[i - 1] = su2_step_right(a[i], a[i], w[i], rb[i]);
 			g_stats[4] += now_s() - t0;
 		}
-		if (rc == 0) { (void)su2_head_rq(&a[0]); en_sweeps[n] = en; }
+		if (rc == 0) {
+			(void)su2_head_rq(&a[0]); en_sweeps[n] = en;
+			g_stats[6] = n + 1;
+			if (n < 9) { g_stats[7 + n] = now_s() - t_sweep; }
+		}
 	}
 	if (rc == 0) { rc = download_sites(a, psi); }
 	for (int i = 0; i < nsites; i++) { su2t_free(a[i]); su2t_free(w[i]); su2t_free(rb[i]); su2t_free(lb[i]); }
@@ -1105,17 +1120,19 @@ int su2_dmrg_twosite(const struct su2_mpo* hamiltonian, const int num_sweeps, co
 	struct su2t** a = upload_sites(psi->a, nsites);
 	struct su2t** w = upload_sites(hamiltonian->a, nsites);
 	const int dtype = w[0]->dtype;
+	double t0 = now_s();
 	const double nrm = su2_orthonormalize_dev(a, nsites, SU2_MPS_ORTHONORMAL_RIGHT);
 	if (nrm == 0) { printf("Warning: in 'su2_dmrg_twosite': initial MPS has norm zero (possibly due to mismatching quantum numbers)\n"); }
-	double t0 = now_s();
 	struct su2t** rb = right_blocks_dev(a, a, w, nsites);
 	struct su2t** lb = ctb_calloc((size_t)nsites + 1, sizeof *lb);
 	for (int i = 0; i < nsites; i++) { lb[i] = dummy_left_dev(dtype); }
-	g_stats[4] += now_s() - t0;
+	CTB_CHECK(ctbd_sync());
+	g_stats[5] += now_s() - t0;
 	int rc = 0;
 	for (int n = 0; n < num_sweeps && rc == 0; n++)
 	{
 		double en = 0;
+		const double t_sweep = now_s();
 		for (int dir = 0; dir < 2 && rc == 0; dir++)
 		{
 			const int i_begin = dir == 0 ? 0 : nsites - 2, i_end = dir == 0 ? nsites - 2 : -1, step = dir == 0 ? 1 : -1;
@@ -1148,7 +1165,11 @@ int su2_dmrg_twosite(const struct su2_mpo* hamiltonian, const int num_sweeps, co
 				g_stats[4] += now_s() - t0;
 			}
 		}
-		if (rc == 0) { (void)su2_head_rq(&a[0]); en_sweeps[n] = en; }
+		if (rc == 0) {
+			(void)su2_head_rq(&a[0]); en_sweeps[n] = en;
+			g_stats[6] = n + 1;
+			if (n < 9) { g_stats[7 + n] = now_s() - t_sweep; }
+		}
 	}
 	if (rc == 0) { rc = download_sites(a, psi); }
 	for (int i = 0; i < nsites; i++) { su2t_free(a[i]); su2t_free(w[i]); su2t_free(rb[i]); su2t_free(lb[i]); }

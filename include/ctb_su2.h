@@ -119,8 +119,10 @@ int su2_dmrg_twosite(const struct su2_mpo* hamiltonian, const int num_sweeps, co
 void ctb_su2_apply_local_hamiltonian_pair(const struct su2_tensor* a2, const struct su2_tensor* w0, const struct su2_tensor* w1,
 	const struct su2_tensor* l, const struct su2_tensor* r, struct su2_tensor* b2);
 
-/* statistics of the last su2_dmrg_* call: { device launches of the SU(2) layer, Heff applications, seconds in local solves, seconds in splits / QR, seconds in environment steps } */
-void ctb_su2_get_stats(double* out5);
+/* statistics of the last su2_dmrg_* call, 16 doubles: [0] device launches of the SU(2) layer, [1] Heff applications, [2] seconds in local solves,
+ * [3] seconds in splits / QR, [4] seconds in environment steps, [5] seconds of the initial orthonormalisation + right environments,
+ * [6] sweeps completed, [7..15] seconds of each sweep */
+void ctb_su2_get_stats(double* out16);
 /* measurement aid: the block linear combination kernel (csrc/ctbd_blocklc.cu) alone; out = { ms, GB/s, algorithmic bytes } */
 int ctb_su2_lc_benchmark(ct_long nelem, int nblk, int nterm, int cplx, double* out);
 

@@ -55,32 +55,22 @@ def main():
         en = (C.c_double * a.sweeps)()
         ent = (C.c_double * max(a.L - 1, 1))()
         per_sweep = []
-        rc = 0
         t0 = time.perf_counter()
-        # one call per sweep (the state stays in p): per-sweep timings, and a partial record survives a time limit
-        for sw in range(a.sweeps):
-            ts = time.perf_counter()
-            e1 = (C.c_double * 1)()
-            if a.single:
-                rc = lib.su2_dmrg_singlesite(C.byref(mpo), 1, a.lanczos, C.byref(p), e1)
-            else:
-                rc = lib.su2_dmrg_twosite(C.byref(mpo), 1, a.lanczos, a.tol, a.max_vdim, C.byref(p), e1, ent)
-            en[sw] = e1[0]
-            sweep_rec = {"s": time.perf_counter() - ts, "energy": e1[0]}
-            if name == "engine":
-                st = (C.c_double * 5)()
-                e.ctb_su2_get_stats(st)
-                sweep_rec["stats"] = {"launches": st[0], "heff_applications": st[1], "local_solve_s": st[2], "split_qr_s": st[3], "environment_s": st[4]}
-            per_sweep.append(sweep_rec)
-            print(name, "sweep", sw, json.dumps(sweep_rec), flush=True)
-            if a.out:
-                res[name] = {"partial": True, "per_sweep": per_sweep, "energies": [x["energy"] for x in per_sweep]}
-                with open(a.out + ".partial", "w") as f:
-                    json.dump(res, f)
-            if rc < 0:
-                break
+        # ONE call for all sweeps, as a user makes it (orthonormalisation and the right environments are built once)
+        if a.single:
+            rc = lib.su2_dmrg_singlesite(C.byref(mpo), a.sweeps, a.lanczos, C.byref(p), en)
+        else:
+            rc = lib.su2_dmrg_twosite(C.byref(mpo), a.sweeps, a.lanczos, a.tol, a.max_vdim, C.byref(p), en, ent)
         wall = time.perf_counter() - t0
-        rec = {"rc": rc, "wall_s": wall, "s_per_sweep": wall / a.sweeps, "energies": list(en), "per_sweep": per_sweep}
+        rec = {"rc": rc, "wall_s": wall, "s_per_sweep": wall / a.sweeps, "energies": list(en)}
+        if name == "engine":
+            st = (C.c_double * 16)()
+            e.ctb_su2_get_stats(st)
+            nsw = int(st[6])
+            rec["sweep_s"] = [st[7 + k] for k in range(min(nsw, 9))]
+            rec["sweeps_completed"] = nsw
+            rec["stats"] = {"launches": st[0], "heff_applications": st[1], "local_solve_s": st[2], "split_qr_s": st[3], "environment_s": st[4],
+                            "orthonormalise_and_right_environments_s": st[5]}
         b = bond_summary(p)
         rec["centre_bond"] = b[a.L // 2 - 1]
         rec["max_multiplets"] = max(sum(x["multiplets"]) for x in b)
