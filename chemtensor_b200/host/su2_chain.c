@@ -1219,3 +1219,112 @@ int ctb_su2_lc_benchmark(ct_long nelem, int nblk, int nterm, int cplx, double* o
 	ctbd_free(src); ctbd_free(dst); ctbd_free(flush);
 	return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * remaining entry points of SURVEY 8(a)'s SU(2) row with the reference's signatures
+ * ------------------------------------------------------------------------------------------------------------------------- */
+
+/* su2_tensor_num_elements_degensors (src/tensor/su2_tensor.c:4663) */
+ct_long su2_tensor_num_elements_degensors(const struct su2_tensor* t)
+{
+	ct_long n = 0;
+	for (ct_long c = 0; c < t->charge_sectors.nsec; c++) {
+		ct_long m = 1;
+		for (int i = 0; i < t->degensors[c]->ndim; i++) { m *= t->degensors[c]->dim[i]; }
+		n += m;
+	}
+	return n;
+}
+
+/* su2_tensor_serialize_renormalized_entries / su2_tensor_deserialize_renormalized_entries (src/tensor/su2_tensor.c:4725-4942): the packed
+ * vector the Lanczos iteration works on, every sector weighted by sqrt(2 j_root + 1) so that the Euclidean norm is the norm of the logical
+ * tensor.  Host structs on both sides (inside the engine the same weights are folded into the first and last launch of the recorded matvec). */
+static void su2_renormalized_copy(const struct su2_tensor* t, void* entries, int to_entries)
+{
+	const int root = t->tree.tree_fuse->i_ax;
+	const int nd = t->charge_sectors.ndim;
+	const int cplx = (t->dtype == CT_DOUBLE_COMPLEX || t->dtype == CT_SINGLE_COMPLEX);
+	const int dbl = (t->dtype == CT_DOUBLE_REAL || t->dtype == CT_DOUBLE_COMPLEX);
+	ct_long pos = 0;
+	for (ct_long c = 0; c < t->charge_sectors.nsec; c++)
+	{
+		const qnumber j = t->charge_sectors.jlists[c * nd + root];
+		ct_long n = 1;
+		for (int i = 0; i < t->degensors[c]->ndim; i++) { n *= t->degensors[c]->dim[i]; }
+		n *= cplx ? 2 : 1;
+		if (dbl) {
+			const double f = to_entries ? sqrt((double)j + 1.0) : 1.0 / sqrt((double)j + 1.0);
+			double* d = t->degensors[c]->data; double* e = (double*)entries + pos;
+			if (to_entries) { for (ct_long i = 0; i < n; i++) { e[i] = f * d[i]; } } else { for (ct_long i = 0; i < n; i++) { d[i] = f * e[i]; } }
+		}
+		else {
+			const float f = to_entries ? sqrtf((float)j + 1.0f) : 1.0f / sqrtf((float)j + 1.0f);
+			float* d = t->degensors[c]->data; float* e = (float*)entries + pos;
+			if (to_entries) { for (ct_long i = 0; i < n; i++) { e[i] = f * d[i]; } } else { for (ct_long i = 0; i < n; i++) { d[i] = f * e[i]; } }
+		}
+		pos += n;
+	}
+}
+
+void su2_tensor_serialize_renormalized_entries(const struct su2_tensor* t, void* entries) { su2_renormalized_copy(t, entries, 1); }
+void su2_tensor_deserialize_renormalized_entries(struct su2_tensor* t, const void* entries) { su2_renormalized_copy(t, (void*)entries, 0); }
+
+/* su2_tensor_svd (src/tensor/su2_tensor.c:4300-4440): economical SVD of an SU(2) symmetric matrix (two logical axes and one trivial auxiliary
+ * axis): ONE batched launch over the degeneracy matrices of all charge sectors. */
+int su2_tensor_svd(const struct su2_tensor* a, const bool copy_tree_left, struct su2_tensor* u, struct dense_tensor* s, int** multiplicities, struct su2_tensor* vh)
+{
+	CTB_REQUIRE(a->ndim_logical == 2 && a->ndim_auxiliary == 1 && a->charge_sectors.nsec > 0);
+	struct su2t* ha = su2t_upload(a);
+	const ct_long ns = ha->nsec;
+	const size_t es = ctb_sizeof_dtype(ha->dtype);
+	struct ctbd_mat_desc* desc = ctb_calloc((size_t)ns + 1, sizeof *desc);
+	qnumber* js = ctb_malloc((size_t)(ns + 1) * sizeof(qnumber));
+	ct_long* kk = ctb_malloc((size_t)(ns + 1) * sizeof(ct_long));
+	ct_long utot = 0, vtot = 0, stot = 0;
+	for (ct_long c = 0; c < ns; c++)
+	{
+		const qnumber j = ha->jl[c * 3];
+		CTB_REQUIRE(ha->jl[c * 3 + 1] == j && ha->jl[c * 3 + 2] == 0);
+		const ct_long m = dd_at(ha, 0, j), n = dd_at(ha, 1, j);
+		js[c] = j; kk[c] = m < n ? m : n;
+		desc[c].a_off = ha->off[c]; desc[c].m = (int32_t)m; desc[c].n = (int32_t)n;
+		desc[c].o0_off = utot; utot += m * kk[c];
+		desc[c].o1_off = vtot; vtot += kk[c] * n;
+		desc[c].s_off = stot; stot += kk[c];
+	}
+	/* u and vh: structure of a with the shared bond in place of the second / first axis; the other factor carries the mirrored tree */
+	struct su2t* hu = su2t_clone_meta(ha); struct su2t* hv = su2t_clone_meta(ha);
+	hu->dev = hv->dev = NULL; hu->own = hv->own = 0;
+	set_axis_irreps(hu, 1, (int)ns, js, kk);
+	set_axis_irreps(hv, 0, (int)ns, js, kk);
+	{
+		struct su2t* flipped = copy_tree_left ? hv : hu;
+		su2t_flip_trees(flipped);
+		for (int i = 0; i < flipped->nn; i++) { if (flipped->node[i].ax == 0) { flipped->node[i].ax = 1; } else if (flipped->node[i].ax == 1) { flipped->node[i].ax = 0; } }
+	}
+	for (ct_long c = 0; c < ns; c++) {
+		hu->off[c] = desc[c].o0_off; hu->nel[c] = (ct_long)desc[c].m * kk[c];
+		hv->off[c] = desc[c].o1_off; hv->nel[c] = kk[c] * (ct_long)desc[c].n;
+	}
+	hu->nstore = utot; hv->nstore = vtot;
+	double* S = NULL;
+	CTB_CHECK(ctbd_malloc_noinit(&hu->dev, (size_t)(utot > 0 ? utot : 1) * es)); hu->own = 1;
+	CTB_CHECK(ctbd_malloc_noinit(&hv->dev, (size_t)(vtot > 0 ? vtot : 1) * es)); hv->own = 1;
+	CTB_CHECK(ctbd_malloc((void**)&S, (size_t)(stot > 0 ? stot : 1) * sizeof(double)));
+	int rc = ctbd_svd_batched(ha->dtype == CT_DOUBLE_COMPLEX ? CTBD_C128 : CTBD_F64, (int)ns, desc, ha->dev, hu->dev, hv->dev, S);
+	if (rc == 0)
+	{
+		s->dtype = CT_DOUBLE_REAL; s->ndim = 1;
+		s->dim = ctb_malloc(sizeof(ct_long)); s->dim[0] = stot;
+		s->data = ctb_malloc((size_t)(stot > 0 ? stot : 1) * sizeof(double));
+		rc = ctbd_d2h(s->data, S, (size_t)stot * sizeof(double));
+		*multiplicities = ctb_malloc((size_t)(stot > 0 ? stot : 1) * sizeof(int));
+		for (ct_long c = 0; c < ns; c++) { for (ct_long i = 0; i < kk[c]; i++) { (*multiplicities)[desc[c].s_off + i] = js[c] + 1; } }
+	}
+	if (rc == 0) { rc = su2t_download(hu, u); }
+	if (rc == 0) { rc = su2t_download(hv, vh); }
+	ctbd_free(S);
+	su2t_free(ha); su2t_free(hu); su2t_free(hv);
+	ctb_free(desc); ctb_free(js); ctb_free(kk);
+	return rc < 0 ? -1 : 0;
+}

@@ -21,6 +21,8 @@
  *   su2_create_dummy_operator_block_left / _right    (src/algorithm/su2_chain_ops.c:82, :16)
  *   su2_mpo_inner_product                            (src/algorithm/su2_chain_ops.c:399)
  *   su2_mps_orthonormalize_qr                        include/state/su2_mps.h:79        (src/state/su2_mps.c:450)
+ *   su2_tensor_svd                                   include/tensor/su2_tensor.h:197   (src/tensor/su2_tensor.c:4300)
+ *   su2_tensor_(de)serialize_renormalized_entries    include/tensor/su2_tensor.h:221   (src/tensor/su2_tensor.c:4725, :4837)
  *   su2_dmrg_singlesite / su2_dmrg_twosite           include/algorithm/su2_dmrg.h:10-13 (src/algorithm/su2_dmrg.c:155, :262)
  */
 #ifndef CTB_SU2_H
@@ -108,6 +110,12 @@ void su2_mpo_inner_product(const struct su2_mps* chi, const struct su2_mpo* op, 
 void su2_apply_local_hamiltonian(const struct su2_tensor* a, const struct su2_tensor* w, const struct su2_tensor* l, const struct su2_tensor* r, struct su2_tensor* b);
 
 double su2_mps_orthonormalize_qr(struct su2_mps* mps, const enum su2_mps_orthonormalization_mode mode);
+
+/* include/tensor/su2_tensor.h:197, :217-222 */
+int su2_tensor_svd(const struct su2_tensor* a, const bool copy_tree_left, struct su2_tensor* u, struct dense_tensor* s, int** multiplicities, struct su2_tensor* vh);
+ct_long su2_tensor_num_elements_degensors(const struct su2_tensor* t);
+void su2_tensor_serialize_renormalized_entries(const struct su2_tensor* t, void* entries);
+void su2_tensor_deserialize_renormalized_entries(struct su2_tensor* t, const void* entries);
 
 int su2_dmrg_singlesite(const struct su2_mpo* hamiltonian, const int num_sweeps, const int maxiter_lanczos, struct su2_mps* psi, double* en_sweeps);
 int su2_dmrg_twosite(const struct su2_mpo* hamiltonian, const int num_sweeps, const int maxiter_lanczos, const double tol_split, const ct_long max_vdim,

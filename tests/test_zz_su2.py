@@ -229,3 +229,91 @@ def test_su2_dmrg_twosite_fermi_hubbard_longer_chain(kind):
     assert np.allclose(list(e1), list(e2), rtol=0, atol=1e-10), (list(e1), list(e2))
     assert np.allclose(list(s1), list(s2), rtol=0, atol=1e-8)
     assert r.su2_mps_is_consistent(C.byref(p2))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("copy_tree_left", [True, False])
+def test_su2_tensor_svd_and_renormalized_entries(kind, copy_tree_left):
+    """su2_tensor_svd (reference test/tensor/test_su2_tensor.c, test_su2_tensor_svd): structure bit-exact, singular values, isometries, reconstruction"""
+    r, e = S.ref(), S.engine(kind)
+    r.su2_tensor_fuse_axes_add_auxiliary.restype = None
+    r.su2_tensor_fuse_axes_add_auxiliary.argtypes = [C.POINTER(T), C.c_int, C.c_int, C.POINTER(T)]
+    r.su2_tensor_svd.restype = C.c_int
+    r.su2_tensor_is_isometry.restype = C.c_bool
+    r.su2_tensor_is_isometry.argtypes = [C.POINTER(T), C.c_double, C.c_bool]
+    from chemtensor_b200 import cabi
+    sig = [C.POINTER(T), C.c_bool, C.POINTER(T), C.POINTER(cabi.DenseTensor), C.POINTER(C.POINTER(C.c_int)), C.POINTER(T)]
+    r.su2_tensor_svd.argtypes = sig
+    e.su2_tensor_svd.restype = C.c_int
+    e.su2_tensor_svd.argtypes = sig
+    psi = S.random_mps(6, [1], [0, 1], 0, 5, 13, 57, scale=2.0)
+    for i in (1, 2, 3):
+        a = T()
+        r.su2_tensor_fuse_axes_add_auxiliary(C.byref(psi.a[i]), 0, 1, C.byref(a))
+        ur, vr, ue, ve = T(), T(), T(), T()
+        sr, se = cabi.DenseTensor(), cabi.DenseTensor()
+        mr, me = C.POINTER(C.c_int)(), C.POINTER(C.c_int)()
+        assert r.su2_tensor_svd(C.byref(a), copy_tree_left, C.byref(ur), C.byref(sr), C.byref(mr), C.byref(vr)) == 0
+        assert e.su2_tensor_svd(C.byref(a), copy_tree_left, C.byref(ue), C.byref(se), C.byref(me), C.byref(ve)) == 0
+        n = sr.dim[0]
+        assert se.dim[0] == n
+        s1 = np.ctypeslib.as_array(C.cast(sr.data, C.POINTER(C.c_double)), shape=(n,)).copy()
+        s2 = np.ctypeslib.as_array(C.cast(se.data, C.POINTER(C.c_double)), shape=(n,)).copy()
+        assert np.allclose(s1, s2, rtol=0, atol=1e-13 * s1.max())
+        assert [mr[k] for k in range(n)] == [me[k] for k in range(n)]
+        S.assert_same_su2(ue, ur, 1e300)      # structure only: the factors are unique up to signs
+        S.assert_same_su2(ve, vr, 1e300)
+        assert r.su2_tensor_is_isometry(C.byref(ue), 1e-12, False)
+        assert r.su2_tensor_is_isometry(C.byref(ve), 1e-12, True)
+        off = 0
+        for c in range(S.sectors(a).shape[0]):
+            U, V, A = S.degensor(ue, c), S.degensor(ve, c), S.degensor(a, c)
+            k = U.shape[1]
+            assert np.allclose((U * s2[off:off + k]) @ V, A, rtol=0, atol=1e-12 * max(1.0, np.abs(A).max()))
+            off += k
+    # renormalised (de)serialisation: same packed vector as the reference, round trip
+    e.su2_tensor_num_elements_degensors.restype = C.c_int64
+    e.su2_tensor_num_elements_degensors.argtypes = [C.POINTER(T)]
+    for lib in (r, e):
+        lib.su2_tensor_serialize_renormalized_entries.restype = None
+        lib.su2_tensor_serialize_renormalized_entries.argtypes = [C.POINTER(T), C.c_void_p]
+        lib.su2_tensor_deserialize_renormalized_entries.restype = None
+        lib.su2_tensor_deserialize_renormalized_entries.argtypes = [C.POINTER(T), C.c_void_p]
+    t = psi.a[2]
+    n = e.su2_tensor_num_elements_degensors(C.byref(t))
+    v1, v2 = np.zeros(n), np.zeros(n)
+    r.su2_tensor_serialize_renormalized_entries(C.byref(t), v1.ctypes.data)
+    e.su2_tensor_serialize_renormalized_entries(C.byref(t), v2.ctypes.data)
+    assert np.array_equal(v1, v2)
+    t2 = T()
+    r.copy_su2_tensor(C.byref(t), C.byref(t2))
+    e.su2_tensor_deserialize_renormalized_entries(C.byref(t2), v2.ctypes.data)
+    S.assert_same_su2(t2, t, 1e-15)
+
+
+def _heisenberg_ground_state_sparse(L: int, J: float) -> float:
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    sx = sp.csr_matrix(np.array([[0, 0.5], [0.5, 0]])); sz = sp.csr_matrix(np.diag([0.5, -0.5]))
+    sy = sp.csr_matrix(np.array([[0, -0.5j], [0.5j, 0]]))
+    H = sp.csr_matrix((2 ** L, 2 ** L), dtype=complex)
+    for i in range(L - 1):
+        for s in (sx, sy, sz):
+            H = H + J * sp.kron(sp.kron(sp.identity(2 ** i), sp.kron(s, s)), sp.identity(2 ** (L - i - 2)))
+    return float(spl.eigsh(H.real.astype(float), k=1, which="SA")[0][0])
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_su2_dmrg_beyond_the_reference_table_range(kind):
+    """Bond quantum numbers above 2j = 5 (L = 14 chain, start bonds up to 2j = 5, no truncation): the reference reads past its recoupling
+    tables there (src/tensor/su2_recoupling.c:959-963), so the check is the exact ground-state energy of the chain (sparse diagonalisation)."""
+    e = S.engine(kind)
+    L, ns = 14, 4
+    mpo = S.heisenberg_mpo(L, 1.0)
+    psi = S.random_mps(L, [1], [0, 1], 0, 5, 4, 77, scale=2.0)
+    en = (C.c_double * ns)()
+    ent = (C.c_double * (L - 1))()
+    assert e.su2_dmrg_twosite(C.byref(mpo), ns, 12, 0.0, 1 << 20, C.byref(psi), en, ent) == 0
+    top = max(psi.a[i].outer_irreps[2].jlist[k] for i in range(L) for k in range(psi.a[i].outer_irreps[2].num))
+    assert top >= 6, top
+    assert abs(en[ns - 1] - _heisenberg_ground_state_sparse(L, 1.0)) < 1e-9
