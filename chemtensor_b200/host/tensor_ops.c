@@ -30,9 +30,9 @@ static void i32vec_reserve(struct i32vec* t, size_t extra)
  * result block inside the permuted result block */
 /* optional embedding of the result into a larger tensor along one result axis (sharded effective Hamiltonian: the rank's column
  * slice is written straight into the packed layout of the full tensor); set by ctb_dot_prepare_embed for the duration of one call */
-static const struct ctb_embed* g_embed = NULL;
-static int g_map_nat = -1;              /* natural axis the position map applies to, -1: none */
-static const int32_t* g_map_pos = NULL; /* position inside the piece sector -> position inside the full sector */
+static _Thread_local const struct ctb_embed* g_embed = NULL;     /* per calling thread: set for the duration of one plan build */
+static _Thread_local int g_map_nat = -1;              /* natural axis the position map applies to, -1: none */
+static _Thread_local const int32_t* g_map_pos = NULL; /* position inside the piece sector -> position inside the full sector */
 
 static void append_offset_table(struct i32vec* tab, int first, int count, const struct ctb_axis* const* nat, const int* nat_sec,
 	const int* pos_of_nat, const ct_long* stride_r, ct_long base)
