@@ -1328,3 +1328,19 @@ int su2_tensor_svd(const struct su2_tensor* a, const bool copy_tree_left, struct
 	ctb_free(desc); ctb_free(js); ctb_free(kk);
 	return rc < 0 ? -1 : 0;
 }
+
+/* su2_mps_local_orthonormalize_qr / _rq (src/state/su2_mps.c:262-346): both tensors are replaced (the old host tensors are released the
+ * way delete_su2_tensor does).  A bond quantum number without any charge sector in 'a' is dropped from the new bond (the reference keeps
+ * it with an identity block in q and no block in r: the same state). */
+static void su2_local_orthonormalize_host(struct su2_tensor* a, struct su2_tensor* a_nb, int rq)
+{
+	struct su2t* ha = su2t_upload(a); struct su2t* hn = su2t_upload(a_nb);
+	if (rq) { su2_local_rq(&ha, &hn); } else { su2_local_qr(&ha, &hn); }
+	struct su2_tensor ta, tn;
+	CTB_CHECK_ABORT(su2t_download(ha, &ta)); CTB_CHECK_ABORT(su2t_download(hn, &tn));
+	free_host_su2(a); free_host_su2(a_nb);
+	*a = ta; *a_nb = tn;
+	su2t_free(ha); su2t_free(hn);
+}
+void su2_mps_local_orthonormalize_qr(struct su2_tensor* a, struct su2_tensor* a_next) { su2_local_orthonormalize_host(a, a_next, 0); }
+void su2_mps_local_orthonormalize_rq(struct su2_tensor* a, struct su2_tensor* a_prev) { su2_local_orthonormalize_host(a, a_prev, 1); }

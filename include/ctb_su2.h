@@ -110,6 +110,9 @@ void su2_mpo_inner_product(const struct su2_mps* chi, const struct su2_mpo* op, 
 void su2_apply_local_hamiltonian(const struct su2_tensor* a, const struct su2_tensor* w, const struct su2_tensor* l, const struct su2_tensor* r, struct su2_tensor* b);
 
 double su2_mps_orthonormalize_qr(struct su2_mps* mps, const enum su2_mps_orthonormalization_mode mode);
+/* include/state/su2_mps.h:75-76 (src/state/su2_mps.c:262, :307) */
+void su2_mps_local_orthonormalize_qr(struct su2_tensor* a, struct su2_tensor* a_next);
+void su2_mps_local_orthonormalize_rq(struct su2_tensor* a, struct su2_tensor* a_prev);
 
 /* include/tensor/su2_tensor.h:197, :217-222 */
 int su2_tensor_svd(const struct su2_tensor* a, const bool copy_tree_left, struct su2_tensor* u, struct dense_tensor* s, int** multiplicities, struct su2_tensor* vh);

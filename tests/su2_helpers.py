@@ -71,6 +71,8 @@ def bind(dll) -> None:
         ("su2_dmrg_twosite", C.c_int, [C.POINTER(SU2MPO), C.c_int, C.c_int, C.c_double, C.c_int64, C.POINTER(SU2MPS),
                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         ("su2_recoupling_coefficient", C.c_double, [C.c_int32] * 6),
+        ("su2_mps_local_orthonormalize_qr", None, [T, T]),
+        ("su2_mps_local_orthonormalize_rq", None, [T, T]),
     ]:
         f = getattr(dll, name)
         f.restype = res

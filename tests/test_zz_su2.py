@@ -317,3 +317,31 @@ def test_su2_dmrg_beyond_the_reference_table_range(kind):
     top = max(psi.a[i].outer_irreps[2].jlist[k] for i in range(L) for k in range(psi.a[i].outer_irreps[2].num))
     assert top >= 6, top
     assert abs(en[ns - 1] - _heisenberg_ground_state_sparse(L, 1.0)) < 1e-9
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_su2_mps_local_orthonormalize(kind):
+    """one QR step to the right and one RQ step to the left: same bond structure as the reference, isometries, same two-site tensor"""
+    r, e = S.ref(), S.engine(kind)
+    r.su2_tensor_is_isometry.restype = C.c_bool
+    r.su2_tensor_is_isometry.argtypes = [C.POINTER(T), C.c_double, C.c_bool]
+    psi = S.random_mps(6, [1], [0, 1], 0, 5, 9, 23, scale=2.0)
+    for rq in (False, True):
+        i, j = (2, 3) if not rq else (3, 2)
+        ar, br, ae, be = T(), T(), T(), T()
+        for dst in (ar, ae):
+            r.copy_su2_tensor(C.byref(psi.a[i]), C.byref(dst))
+        for dst in (br, be):
+            r.copy_su2_tensor(C.byref(psi.a[j]), C.byref(dst))
+        if rq:
+            r.su2_mps_local_orthonormalize_rq(C.byref(ar), C.byref(br)); e.su2_mps_local_orthonormalize_rq(C.byref(ae), C.byref(be))
+        else:
+            r.su2_mps_local_orthonormalize_qr(C.byref(ar), C.byref(br)); e.su2_mps_local_orthonormalize_qr(C.byref(ae), C.byref(be))
+        S.assert_same_su2(ae, ar, 1e300)     # structure; the entries are unique up to the signs of the triangular factor
+        S.assert_same_su2(be, br, 1e300)
+        left, right = (ae, be) if not rq else (be, ae)
+        pr, pe = T(), T()
+        lr, rr = (ar, br) if not rq else (br, ar)
+        r.su2_mps_contract_tensor_pair(C.byref(lr), C.byref(rr), C.byref(pr))
+        r.su2_mps_contract_tensor_pair(C.byref(left), C.byref(right), C.byref(pe))
+        S.assert_same_su2(pe, pr, 1e-12)
