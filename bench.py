@@ -528,7 +528,7 @@ MOLECULAR_LARGE_CASES = [
 # (name, arguments of tools/su2_run.py, time the reference too)
 SU2_CASES = [
     ("su2_heisenberg_L24_parity", "24 60 --sweeps 2 --lanczos 6 --degen 3 --max-irrep 2 --tol 1e-5", True),
-    ("su2_heisenberg_L200_D2048", "200 2048 --sweeps 3 --lanczos 10 --degen 8", False),
+    ("su2_heisenberg_L200_2048multiplets", "200 8192 --sweeps 4 --lanczos 10 --degen 8", False),
 ]
 
 MOLECULAR_SWEEP_CASES = [
@@ -644,13 +644,14 @@ def sweep_report(lib):
         out.append(rec)
     # BASELINE.json configs[4]: SU(2)-symmetric Heisenberg chain, SU(2) DMRG variant (su2_dmrg_twosite behind the reference's symbol).
     # (i) a chain the unmodified reference can run (its recoupling tables end at 2j = 5, src/tensor/su2_recoupling.c:959-963: start bonds
-    # up to 2j = 2, tol_split 1e-5) for energy parity and the CPU time beside it; (ii) L = 200 as named, logical bond dimension 2048.
+    # up to 2j = 2, tol_split 1e-5) for energy parity and the CPU time beside it; (ii) L = 200 as named: logical bond dimension 8192 = about 2000 multiplets once the bond
+    # has saturated in the fourth sweep (the first three sweeps grow it from 8 multiplets per sector).
     for name, su2_args, with_ref in SU2_CASES:
         if not _sweep_selected(name):
             continue
-        rec = {"config": name, "args": su2_args, "driver": "tools/su2_run.py (one su2_dmrg_twosite call per sweep on host structs)"}
+        rec = {"config": name, "args": su2_args, "driver": "tools/su2_run.py (one su2_dmrg_twosite call on host structs; max_vdim is the logical bond dimension)"}
         outp = f"/tmp/ctb_bench_su2_{name}_{os.getpid()}.json"
-        cmd = [sys.executable, os.path.join(ROOT, "tools", "su2_run.py"), "cuda"] + su2_args.split() + ["--out", outp] + (["--ref"] if with_ref else [])
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "su2_run.py"), os.environ.get("CTB_BENCH_SU2_ENGINE", "cuda")] + su2_args.split() + ["--out", outp] + (["--ref"] if with_ref else [])
         try:
             env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
             subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
