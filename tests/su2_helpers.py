@@ -233,3 +233,22 @@ def assert_same_su2(x: SU2Tensor, y: SU2Tensor, tol: float) -> float:
         ref_mag = max(ref_mag, float(np.max(np.abs(b))) if b.size else 0.0)
     assert err <= tol * max(ref_mag, 1e-300), (err, ref_mag)
     return err / max(ref_mag, 1e-300)
+
+
+def complexify(t: SU2Tensor) -> None:
+    """in place: real double SU(2) tensor -> complex double with zero imaginary parts (the reference has no complex SU(2) Hamiltonian)"""
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    for c in range(t.charge_sectors.nsec):
+        d = t.degensors[c].contents
+        n = 1
+        for i in range(d.ndim):
+            n *= d.dim[i]
+        old = np.ctypeslib.as_array(C.cast(d.data, C.POINTER(C.c_double)), shape=(n,)).copy()
+        buf = libc.malloc(16 * max(n, 1))
+        arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double)), shape=(2 * n,))
+        arr[0::2] = old
+        arr[1::2] = 0.0
+        d.data = buf
+        d.dtype = 3
+    t.dtype = 3

@@ -345,3 +345,46 @@ def test_su2_mps_local_orthonormalize(kind):
         r.su2_mps_contract_tensor_pair(C.byref(lr), C.byref(rr), C.byref(pr))
         r.su2_mps_contract_tensor_pair(C.byref(left), C.byref(right), C.byref(pe))
         S.assert_same_su2(pe, pr, 1e-12)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_su2_complex128(kind):
+    """complex128 through the same kernels (conjugation of the bra tensor fused into the launches): a complex random SU(2) MPS against the
+    Heisenberg MPO converted to complex entries, environments entry-wise and both DMRG variants against the reference"""
+    r, e = S.ref(), S.engine(kind)
+    L = 6
+    mpo = S.heisenberg_mpo(L, 1.3)
+    for i in range(L):
+        S.complexify(mpo.a[i])
+    psi = S.random_mps(L, [1], [0, 1], 0, 5, 7, 19, dtype=3, scale=3.0)
+    rl_ref, rl_eng = (T * L)(), (T * L)()
+    r.su2_compute_right_operator_blocks(C.byref(psi), C.byref(psi), C.byref(mpo), rl_ref)
+    e.su2_compute_right_operator_blocks(C.byref(psi), C.byref(psi), C.byref(mpo), rl_eng)
+    for i in range(L):
+        S.assert_same_su2(rl_eng[i], rl_ref[i], 1e-12)
+    lb = T()
+    r.su2_create_dummy_operator_block_left(3, C.byref(lb))
+    lbs = [lb]
+    for i in range(L - 1):
+        nr, ne = T(), T()
+        r.su2_contraction_operator_step_left(C.byref(psi.a[i]), C.byref(psi.a[i]), C.byref(mpo.a[i]), C.byref(lbs[-1]), C.byref(nr))
+        e.su2_contraction_operator_step_left(C.byref(psi.a[i]), C.byref(psi.a[i]), C.byref(mpo.a[i]), C.byref(lbs[-1]), C.byref(ne))
+        S.assert_same_su2(ne, nr, 1e-12)
+        lbs.append(nr)
+    for i in range(L):
+        br, be = T(), T()
+        r.su2_apply_local_hamiltonian(C.byref(psi.a[i]), C.byref(mpo.a[i]), C.byref(lbs[i]), C.byref(rl_ref[i]), C.byref(br))
+        e.su2_apply_local_hamiltonian(C.byref(psi.a[i]), C.byref(mpo.a[i]), C.byref(lbs[i]), C.byref(rl_ref[i]), C.byref(be))
+        S.assert_same_su2(be, br, 1e-12)
+    for two in (True, False):
+        p1, p2 = S.copy_mps(psi), S.copy_mps(psi)
+        e1, e2 = (C.c_double * 2)(), (C.c_double * 2)()
+        s1, s2 = (C.c_double * L)(), (C.c_double * L)()
+        if two:
+            assert r.su2_dmrg_twosite(C.byref(mpo), 2, 5, 1e-8, 100, C.byref(p1), e1, s1) == 0
+            assert e.su2_dmrg_twosite(C.byref(mpo), 2, 5, 1e-8, 100, C.byref(p2), e2, s2) == 0
+        else:
+            assert r.su2_dmrg_singlesite(C.byref(mpo), 2, 5, C.byref(p1), e1) == 0
+            assert e.su2_dmrg_singlesite(C.byref(mpo), 2, 5, C.byref(p2), e2) == 0
+        assert np.allclose(list(e1), list(e2), rtol=0, atol=1e-11)
+        assert r.su2_mps_is_consistent(C.byref(p2))
