@@ -55,3 +55,33 @@ def test_reference_callers_reach_the_engine(kind):
     assert bd_d == bd_r
     assert np.max(np.abs(ent_d - ent_r)) <= 1e-8
     assert abs(nrm_d - 1) <= 1e-12 and abs(nrm_r - 1) <= 1e-12
+
+
+@pytest.mark.parametrize("kind", VARIANTS)
+def test_su2_callers_reach_the_engine(kind):
+    """su2_dmrg.c / su2_chain_ops.c dropped, the overlapping functions of su2_tensor.c, su2_mps.c and
+    su2_recoupling.c renamed away; the reference's SU(2) generators feed the engine's su2_dmrg_twosite inside the combined library."""
+    import su2_helpers as S
+    lib = load_dropin(kind)
+    d = lib.dll
+    S.bind_ref(d)
+    eng = C.CDLL(helpers.EMU_SO if kind == "emu" else helpers.CUDA_SO)
+    for name in ("su2_dmrg_twosite", "su2_dmrg_singlesite", "su2_apply_local_hamiltonian", "su2_tensor_contract_simple", "su2_tensor_fmove", "su2_tensor_svd"):
+        assert C.cast(getattr(d, name), C.c_void_p).value == C.cast(getattr(eng, name), C.c_void_p).value, name
+    assert hasattr(d, "ref_su2_tensor_fmove") and hasattr(d, "construct_heisenberg_1d_su2_mpo")
+    if kind == "cuda":
+        assert lib.ctb_init(-1) == 0
+    r = S.ref()
+    L, ns = 7, 2
+    res = {}
+    for name, x in (("dropin", d), ("reference", r)):
+        mpo = S.SU2MPO()
+        x.construct_heisenberg_1d_su2_mpo(L, 1.1, C.byref(mpo))
+        psi = S.random_mps(L, [1], [0, 1], 1, 5, 27, 82, scale=14.0)      # same seeded input for both
+        en = (C.c_double * ns)()
+        ent = (C.c_double * (L - 1))()
+        assert x.su2_dmrg_twosite(C.byref(mpo), ns, 5, 1e-8, 200, C.byref(psi), en, ent) == 0
+        assert x.su2_mps_is_consistent(C.byref(psi))
+        res[name] = (list(en), list(ent))
+    assert np.allclose(res["dropin"][0], res["reference"][0], rtol=0, atol=1e-10)
+    assert np.allclose(res["dropin"][1], res["reference"][1], rtol=0, atol=1e-8)
