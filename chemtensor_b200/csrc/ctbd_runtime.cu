@@ -829,3 +829,40 @@ int ctbd_host_free(void* hptr) { CTBD_CUDA(cudaFreeHost(hptr)); return 0; }
 long long ctbd_bytes_in_use(void) { return rt().bytes_in_use; }
 
 } // extern "C"
+
+/* ---- CUDA graphs of launch sequences (include/ctb_device.h) ---- */
+extern "C" int ctbd_graph_capture_begin(void)
+{
+	CTBD_REQUIRE_INIT();
+	if (getenv("CTB_NO_GRAPH") != nullptr) { return 1; }
+	const cudaError_t e = cudaStreamBeginCapture(rt().stream, cudaStreamCaptureModeThreadLocal);
+	if (e != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+	return 0;
+}
+
+extern "C" int ctbd_graph_capture_end(void** graph)
+{
+	*graph = nullptr;
+	cudaGraph_t g = nullptr;
+	cudaError_t e = cudaStreamEndCapture(rt().stream, &g);
+	if (e != cudaSuccess || g == nullptr) { (void)cudaGetLastError(); if (g != nullptr) { cudaGraphDestroy(g); } return 1; }
+	cudaGraphExec_t ex = nullptr;
+	e = cudaGraphInstantiate(&ex, g, 0);
+	cudaGraphDestroy(g);
+	if (e != cudaSuccess || ex == nullptr) { (void)cudaGetLastError(); return 1; }
+	*graph = (void*)ex;
+	return 0;
+}
+
+extern "C" int ctbd_graph_launch(void* graph)
+{
+	CTBD_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph, rt().stream));
+	rt().launches++;
+	return 0;
+}
+
+extern "C" int ctbd_graph_destroy(void* graph)
+{
+	if (graph != nullptr) { cudaGraphExecDestroy((cudaGraphExec_t)graph); }
+	return 0;
+}

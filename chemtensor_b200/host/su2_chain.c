@@ -784,6 +784,7 @@ static int su2_minimize(su2_heff_fn fn, void* ctx, struct su2t* a_start, int max
 	su2t_free(aten); su2t_free(ain);
 	su2_prog_end();
 	g_stats[1] += 1;
+	if (rc == 0 && maxiter > 2) { su2_prog_capture(&prog); }
 
 	int numiter = maxiter;
 	double* host_scal = ctb_calloc((size_t)(3 * maxiter + 4), sizeof(double));

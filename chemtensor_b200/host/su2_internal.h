@@ -53,6 +53,7 @@ struct su2_prog
 	void** keep; int nkeep, keepcap;     /* device buffers of the intermediates, released with the program */
 	void* in;                            /* device buffer the recorded launches read the input from */
 	void* out;                           /* device buffer of the result */
+	void* graph;                         /* the launches captured as ONE CUDA graph (NULL: replay launch by launch) */
 	ct_long n;                           /* vector length */
 };
 
@@ -81,6 +82,7 @@ int su2t_child_axis(const struct su2t* h, int split_tree, int k);      /* axis o
 void su2_prog_begin(struct su2_prog* p);
 void su2_prog_end(void);
 int su2_prog_run(struct su2_prog* p);
+void su2_prog_capture(struct su2_prog* p);      /* after recording: capture the launches into a CUDA graph where the device layer offers it */
 void su2_prog_free(struct su2_prog* p);
 int su2_dev_lc(int dtype, int conj, int nblk, struct ctbd_lc_block* blocks, int nterm, struct ctbd_lc_term* terms, const void* src, void* dst, int varies);
 int su2_dev_gemm(const struct ctbd_gemm_plan_host* ph, const void* A, const void* B, void* C, int varies);

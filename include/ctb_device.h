@@ -294,6 +294,16 @@ int ctbd_lc_plan_create(int dtype, int conj, int nblk, const struct ctbd_lc_bloc
 int ctbd_lc_plan_run(void* plan, const void* src, void* dst);
 int ctbd_lc_plan_destroy(void* plan);
 
+/* ---- CUDA graph of a launch sequence ---------------------------------------------------------
+ * The recorded effective-Hamiltonian program of the SU(2) layer (host/su2_core.c) is ~15 launches of a few microseconds each in the
+ * small-bond regime; captured once per local solve it is replayed with ONE graph launch per Lanczos iteration.  Only kernel launches
+ * of this layer may be issued between begin and end (ctbd_gemm_run, ctbd_lc_plan_run): no allocation, copy to the host or synchronisation.
+ * Return value > 0 means "not available / capture discarded": the caller then replays launch by launch (the same kernels). */
+int ctbd_graph_capture_begin(void);
+int ctbd_graph_capture_end(void** graph);
+int ctbd_graph_launch(void* graph);
+int ctbd_graph_destroy(void* graph);
+
 /* ---- level-1 kernels for the Lanczos iteration (scalars stay on the device) ----------------- */
 
 /* out[0] = Re sum conj(x_i) y_i, out[1] = Im (0 for real) */

@@ -861,3 +861,9 @@ int ctbd_lc_plan_run(void* plan, const void* src, void* dst)
 	return 0;
 }
 int ctbd_lc_plan_destroy(void* plan) { struct emu_lc_plan* p = plan; if (p) { free(p->blocks); free(p->terms); free(p); } return 0; }
+
+/* CUDA graphs: not available on the test double (the caller replays launch by launch) */
+int ctbd_graph_capture_begin(void) { return 1; }
+int ctbd_graph_capture_end(void** graph) { *graph = NULL; return 1; }
+int ctbd_graph_launch(void* graph) { (void)graph; snprintf(g_err, sizeof g_err, "emu: no graphs"); return -1; }
+int ctbd_graph_destroy(void* graph) { (void)graph; return 0; }
