@@ -150,7 +150,14 @@ _EXT_SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES) + tuple(_EXT_SIGNATURES) + ("allocate_zero_dense_tensor", "allocate_block_sparse_tensor_like",
-    "copy_block_sparse_tensor", "allocate_mps", "delete_mps", "allocate_mpo", "delete_mpo", "save_mps", "load_mps")
+    "copy_block_sparse_tensor", "allocate_mps", "delete_mps", "allocate_mpo", "delete_mpo", "save_mps", "load_mps",
+    # SU(2)-symmetric variant (include/ctb_su2.h; ctypes structures and bindings in tests/su2_helpers.py)
+    "su2_dmrg_twosite", "su2_dmrg_singlesite", "su2_apply_local_hamiltonian", "su2_contraction_operator_step_left",
+    "su2_contraction_operator_step_right", "su2_compute_right_operator_blocks", "su2_create_dummy_operator_block_left",
+    "su2_create_dummy_operator_block_right", "su2_mpo_inner_product", "su2_mps_orthonormalize_qr", "su2_mps_local_orthonormalize_qr",
+    "su2_mps_local_orthonormalize_rq", "su2_tensor_contract_simple", "su2_tensor_fmove", "su2_tensor_svd", "su2_recoupling_coefficient",
+    "su2_tensor_num_elements_degensors", "su2_tensor_serialize_renormalized_entries", "su2_tensor_deserialize_renormalized_entries",
+    "ctb_su2_apply_local_hamiltonian_pair", "ctb_su2_get_stats")
 
 
 class CLibrary:
