@@ -163,10 +163,28 @@ extern "C" int ctbd_lc_plan_create(int dtype, int conj, int nblk, const struct c
 		}
 	}
 	p->nchunk = nchunk;
+	/* ONE device allocation and ONE copy for the three tables (a local solve of the SU(2) layer creates ~14 of these plans;
+	 * with three uploads each the plan creation was a fifth of a small-bond local solve) */
+	const size_t nb = ((size_t)nblk * sizeof(ctbd_lc_block) + 15) & ~(size_t)15;
+	const size_t nt = ((size_t)nterm * sizeof(ctbd_lc_term) + 15) & ~(size_t)15;
+	const size_t nc = (size_t)nchunk * sizeof(LcChunk);
+	const size_t total = nb + nt + nc;
 	int rc = 0;
-	if (nblk > 0)   { rc = upload(blocks_host, (size_t)nblk * sizeof(ctbd_lc_block), (void**)&p->blocks); }
-	if (rc == 0 && nterm > 0)  { rc = upload(terms_host, (size_t)nterm * sizeof(ctbd_lc_term), (void**)&p->terms); }
-	if (rc == 0 && nchunk > 0) { rc = upload(ch, (size_t)nchunk * sizeof(LcChunk), (void**)&p->chunks); }
+	if (total > 0)
+	{
+		char* host = (char*)malloc(total);
+		if (nblk > 0)  { memcpy(host, blocks_host, (size_t)nblk * sizeof(ctbd_lc_block)); }
+		if (nterm > 0) { memcpy(host + nb, terms_host, (size_t)nterm * sizeof(ctbd_lc_term)); }
+		if (nchunk > 0) { memcpy(host + nb + nt, ch, nc); }
+		void* dev = nullptr;
+		rc = upload(host, total, &dev);
+		free(host);
+		if (rc == 0) {
+			p->blocks = (ctbd_lc_block*)dev;
+			p->terms = (ctbd_lc_term*)((char*)dev + nb);
+			p->chunks = (LcChunk*)((char*)dev + nb + nt);
+		}
+	}
 	free(ch);
 	if (rc < 0) { ctbd_lc_plan_destroy(p); return rc; }
 	*plan = p;
@@ -193,9 +211,7 @@ extern "C" int ctbd_lc_plan_destroy(void* plan)
 {
 	LcPlan* p = (LcPlan*)plan;
 	if (p == nullptr) { return 0; }
-	if (p->blocks) { ctbd_free(p->blocks); }
-	if (p->terms)  { ctbd_free(p->terms); }
-	if (p->chunks) { ctbd_free(p->chunks); }
+	if (p->blocks) { ctbd_free(p->blocks); }      /* terms and chunks live in the same allocation */
 	delete p;
 	return 0;
 }
