@@ -388,3 +388,42 @@ def test_su2_complex128(kind):
             assert e.su2_dmrg_singlesite(C.byref(mpo), 2, 5, C.byref(p2), e2) == 0
         assert np.allclose(list(e1), list(e2), rtol=0, atol=1e-11)
         assert r.su2_mps_is_consistent(C.byref(p2))
+
+
+def test_su2_missing_charge_sectors():
+    """A site tensor that lacks every charge sector of one bond quantum number (removed with the reference's
+    su2_tensor_delete_charge_sector_by_index): orthonormalisation and both DMRG variants give the reference's norm, expectation value and energies.
+    The engine drops the empty quantum number from the bond where the reference keeps it with an identity block: same state."""
+    r, e = S.ref(), S.engine("emu")
+    r.su2_tensor_delete_charge_sector_by_index.restype = None
+    r.su2_tensor_delete_charge_sector_by_index.argtypes = [C.POINTER(T), C.c_int64]
+    L = 6
+    mpo = S.heisenberg_mpo(L, 1.0)
+    psi = S.random_mps(L, [1], [0, 1], 0, 3, 4, 5, scale=3.0)
+    secs = S.sectors(psi.a[2])
+    assert any(s[2] == 3 for s in secs)
+    for c in reversed(range(secs.shape[0])):
+        if secs[c][2] == 3:
+            r.su2_tensor_delete_charge_sector_by_index(C.byref(psi.a[2]), c)
+    assert r.su2_mps_is_consistent(C.byref(psi))
+    for mode in (0, 1):
+        p1, p2 = S.copy_mps(psi), S.copy_mps(psi)
+        n1 = r.su2_mps_orthonormalize_qr(C.byref(p1), mode)
+        n2 = e.su2_mps_orthonormalize_qr(C.byref(p2), mode)
+        assert abs(n1 - n2) <= 1e-12 * n1 and r.su2_mps_is_consistent(C.byref(p2))
+        a, b = C.c_double(), C.c_double()
+        r.su2_mpo_inner_product(C.byref(p1), C.byref(mpo), C.byref(p1), C.byref(a))
+        r.su2_mpo_inner_product(C.byref(p2), C.byref(mpo), C.byref(p2), C.byref(b))
+        assert abs(a.value - b.value) <= 1e-12 * abs(a.value)
+    for two in (True, False):
+        p1, p2 = S.copy_mps(psi), S.copy_mps(psi)
+        e1, e2 = (C.c_double * 2)(), (C.c_double * 2)()
+        s1, s2 = (C.c_double * L)(), (C.c_double * L)()
+        if two:
+            assert r.su2_dmrg_twosite(C.byref(mpo), 2, 5, 1e-8, 100, C.byref(p1), e1, s1) == 0
+            assert e.su2_dmrg_twosite(C.byref(mpo), 2, 5, 1e-8, 100, C.byref(p2), e2, s2) == 0
+        else:
+            assert r.su2_dmrg_singlesite(C.byref(mpo), 2, 5, C.byref(p1), e1) == 0
+            assert e.su2_dmrg_singlesite(C.byref(mpo), 2, 5, C.byref(p2), e2) == 0
+        assert np.allclose(list(e1), list(e2), rtol=0, atol=1e-11)
+        assert r.su2_mps_is_consistent(C.byref(p2))
