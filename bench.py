@@ -528,7 +528,9 @@ MOLECULAR_LARGE_CASES = [
 # (name, arguments of tools/su2_run.py, time the reference too)
 SU2_CASES = [
     ("su2_heisenberg_L24_parity", "24 60 --sweeps 2 --lanczos 6 --degen 3 --max-irrep 2 --tol 1e-5", True),
-    ("su2_heisenberg_L200_2048multiplets", "200 8192 --sweeps 4 --lanczos 10 --degen 8", False),
+    # three growth sweeps by default (about 18 s: the bond reaches ~1200 multiplets / logical 6144); CTB_BENCH_SU2_FULL=1 adds the fourth,
+    # saturated sweep (~2000 multiplets, logical 8192, about 70 s more) -- recorded in profiles/r2_bench_1gpu_su2_sweep_block.json
+    ("su2_heisenberg_L200_2048multiplets", "200 8192 --sweeps %d --lanczos 10 --degen 8" % (4 if os.environ.get("CTB_BENCH_SU2_FULL") else 3), False),
 ]
 
 MOLECULAR_SWEEP_CASES = [
