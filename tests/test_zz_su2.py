@@ -427,3 +427,30 @@ def test_su2_missing_charge_sectors():
             assert e.su2_dmrg_singlesite(C.byref(mpo), 2, 5, C.byref(p2), e2) == 0
         assert np.allclose(list(e1), list(e2), rtol=0, atol=1e-11)
         assert r.su2_mps_is_consistent(C.byref(p2))
+
+
+def test_su2_and_u1_engines_agree_on_a_longer_chain():
+    """Two independent code paths of the engine on the same physics at a size the SU(2) reference cannot run (L = 24, bonds up to 2j >= 6):
+    the SU(2) two-site sweep on the Heisenberg chain against the U(1) two-site sweep on the XXZ chain with Delta = 1, h = 0, both from
+    seeded random states with generous bonds; the converged energies agree to the truncation level."""
+    e = S.engine("emu")
+    eng = helpers.load("emu")
+    ref = helpers.load("ref")
+    L = 24
+    mpo2 = S.heisenberg_mpo(L, 1.0)
+    psi2 = S.random_mps(L, [1], [0, 1], 0, 5, 3, 11, scale=2.0)
+    ns = 4
+    en2 = (C.c_double * ns)()
+    ent2 = (C.c_double * (L - 1))()
+    assert e.su2_dmrg_twosite(C.byref(mpo2), ns, 8, 1e-10, 400, C.byref(psi2), en2, ent2) == 0
+    top = max(psi2.a[i].outer_irreps[2].jlist[k] for i in range(L) for k in range(psi2.a[i].outer_irreps[2].num))
+    assert top >= 4
+    mpo1_r = helpers.ref_mpo(ref, "xxz", L, 1.0, 1.0, 0.0)
+    psi1_r = helpers.ref_random_mps(ref, np.float64, L, mpo1_r.qsite, 0, 60, seed=7)
+    mpo1, psi1 = helpers.clone_chain(eng, mpo1_r), helpers.clone_chain(eng, psi1_r)
+    en1 = np.zeros(ns)
+    ent1 = np.zeros(L - 1)
+    assert eng.dmrg_twosite(mpo1.ptr, ns, 8, 1e-10, 120, psi1.ptr, en1.ctypes.data_as(C.POINTER(C.c_double)), ent1.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    assert abs(en2[ns - 1] - en1[ns - 1]) < 2e-6, (en2[ns - 1], en1[ns - 1])
+    # entanglement entropy of the centre bond: the SU(2) value counts every multiplet with its dimension
+    assert abs(ent2[L // 2 - 1] - ent1[L // 2 - 1]) < 1e-3
