@@ -451,6 +451,28 @@ def test_su2_and_u1_engines_agree_on_a_longer_chain():
     en1 = np.zeros(ns)
     ent1 = np.zeros(L - 1)
     assert eng.dmrg_twosite(mpo1.ptr, ns, 8, 1e-10, 120, psi1.ptr, en1.ctypes.data_as(C.POINTER(C.c_double)), ent1.ctypes.data_as(C.POINTER(C.c_double))) == 0
-    assert abs(en2[ns - 1] - en1[ns - 1]) < 2e-6, (en2[ns - 1], en1[ns - 1])
+    assert abs(en2[ns - 1] - en1[ns - 1]) < 1e-7, (en2[ns - 1], en1[ns - 1])      # measured: 2e-9 (the U(1) state is the less converged one)
     # entanglement entropy of the centre bond: the SU(2) value counts every multiplet with its dimension
-    assert abs(ent2[L // 2 - 1] - ent1[L // 2 - 1]) < 1e-3
+    assert abs(ent2[L // 2 - 1] - ent1[L // 2 - 1]) < 1e-5
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_su2_dmrg_longer_chains_inside_the_reference_range(kind):
+    """L = 32 single-site (start bonds up to 2j = 3) and L = 24 two-site (start bonds up to 2j = 2, tol_split 1e-5): the largest chains the
+    unmodified reference runs without leaving its recoupling tables; energies against it"""
+    r, e = S.ref(), S.engine(kind)
+    mpo = S.heisenberg_mpo(32, 1.0)
+    psi = S.random_mps(32, [1], [0, 1], 0, 3, 12, 42, scale=1.0)
+    p1, p2 = S.copy_mps(psi), S.copy_mps(psi)
+    e1, e2 = (C.c_double * 2)(), (C.c_double * 2)()
+    assert r.su2_dmrg_singlesite(C.byref(mpo), 2, 6, C.byref(p1), e1) == 0
+    assert e.su2_dmrg_singlesite(C.byref(mpo), 2, 6, C.byref(p2), e2) == 0
+    assert np.allclose(list(e1), list(e2), rtol=0, atol=1e-10)
+    mpo = S.heisenberg_mpo(24, 1.0)
+    psi = S.random_mps(24, [1], [0, 1], 0, 2, 3, 42, scale=1.0)
+    p1, p2 = S.copy_mps(psi), S.copy_mps(psi)
+    s1, s2 = (C.c_double * 23)(), (C.c_double * 23)()
+    assert r.su2_dmrg_twosite(C.byref(mpo), 2, 6, 1e-5, 60, C.byref(p1), e1, s1) == 0
+    assert e.su2_dmrg_twosite(C.byref(mpo), 2, 6, 1e-5, 60, C.byref(p2), e2, s2) == 0
+    assert np.allclose(list(e1), list(e2), rtol=0, atol=1e-10)
+    assert np.allclose(list(s1), list(s2), rtol=0, atol=1e-8)
