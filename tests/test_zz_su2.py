@@ -476,3 +476,39 @@ def test_su2_dmrg_longer_chains_inside_the_reference_range(kind):
     assert e.su2_dmrg_twosite(C.byref(mpo), 2, 6, 1e-5, 60, C.byref(p2), e2, s2) == 0
     assert np.allclose(list(e1), list(e2), rtol=0, atol=1e-10)
     assert np.allclose(list(s1), list(s2), rtol=0, atol=1e-6)      # truncated at 1e-5: measured 1.5e-8
+
+
+def _dense(r, t):
+    """logical dense tensor (Clebsch-Gordan structure included) by the reference's su2_to_dense_tensor"""
+    from chemtensor_b200 import cabi
+    d = cabi.DenseTensor()
+    r.su2_to_dense_tensor(C.byref(t), C.byref(d))
+    shape = tuple(d.dim[i] for i in range(d.ndim))
+    n = int(np.prod(shape))
+    return np.ctypeslib.as_array(C.cast(d.data, C.POINTER(C.c_double)), shape=(n,)).reshape(shape).copy()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_su2_local_hamiltonian_equals_the_dense_contraction(kind):
+    """Pinned to the physics rather than to another SU(2) implementation (as the reference's test_su2_chain_ops.c does): the logical dense
+    tensors of a, w, l, r contracted with einsum against the dense tensor of the engine's result, single-site and pair form"""
+    r, e = S.ref(), S.engine(kind)
+    e.ctb_su2_apply_local_hamiltonian_pair.restype = None
+    e.ctb_su2_apply_local_hamiltonian_pair.argtypes = [C.POINTER(T)] * 6
+    L = 5
+    mpo = S.heisenberg_mpo(L, 1.3)
+    psi = S.random_mps(L, [1], [0, 1], 1, 3, 3, 9, scale=2.0)
+    lbs, rl = _envs(r, psi, mpo, L)
+    for i in range(L):
+        be = T()
+        e.su2_apply_local_hamiltonian(C.byref(psi.a[i]), C.byref(mpo.a[i]), C.byref(lbs[i]), C.byref(rl[i]), C.byref(be))
+        a, w, l, rr, b = (_dense(r, x) for x in (psi.a[i], mpo.a[i], lbs[i], rl[i], be))
+        want = np.einsum('olwk,lpr,wqps,rsmt->kqm', l, a, w, rr)
+        assert np.max(np.abs(want - b)) <= 1e-13 * max(1.0, np.max(np.abs(want)))
+    for i in range(L - 1):
+        a2, b2 = T(), T()
+        r.su2_mps_contract_tensor_pair(C.byref(psi.a[i]), C.byref(psi.a[i + 1]), C.byref(a2))
+        e.ctb_su2_apply_local_hamiltonian_pair(C.byref(a2), C.byref(mpo.a[i]), C.byref(mpo.a[i + 1]), C.byref(lbs[i]), C.byref(rl[i + 1]), C.byref(b2))
+        a, w0, w1, l, rr, b = (_dense(r, x) for x in (a2, mpo.a[i], mpo.a[i + 1], lbs[i], rl[i + 1], b2))
+        want = np.einsum('olwk,lpqr,wxpu,uyqs,rsmt->kxym', l, a, w0, w1, rr)
+        assert np.max(np.abs(want - b)) <= 1e-13 * max(1.0, np.max(np.abs(want)))
