@@ -512,3 +512,25 @@ def test_su2_local_hamiltonian_equals_the_dense_contraction(kind):
         a, w0, w1, l, rr, b = (_dense(r, x) for x in (a2, mpo.a[i], mpo.a[i + 1], lbs[i], rl[i + 1], b2))
         want = np.einsum('olwk,lpqr,wxpu,uyqs,rsmt->kxym', l, a, w0, w1, rr)
         assert np.max(np.abs(want - b)) <= 1e-13 * max(1.0, np.max(np.abs(want)))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_su2_environment_steps_equal_the_dense_contraction(kind):
+    """environment updates as dense einsum contractions of the logical tensors (real entries: no conjugation)"""
+    r, e = S.ref(), S.engine(kind)
+    L = 5
+    mpo = S.heisenberg_mpo(L, 1.3)
+    psi = S.random_mps(L, [1], [0, 1], 1, 3, 3, 9, scale=2.0)
+    lbs, rl = _envs(r, psi, mpo, L)
+    for i in range(L - 1, 0, -1):
+        rn = T()
+        e.su2_contraction_operator_step_right(C.byref(psi.a[i]), C.byref(psi.a[i]), C.byref(mpo.a[i]), C.byref(rl[i]), C.byref(rn))
+        a, w, rr, out = (_dense(r, x) for x in (psi.a[i], mpo.a[i], rl[i], rn))
+        want = np.einsum('lpr,rsmt,wqps,kqm->lwkt', a, rr, w, a)
+        assert np.max(np.abs(want - out)) <= 1e-13 * max(1.0, np.max(np.abs(want)))
+    for i in range(L - 1):
+        ln = T()
+        e.su2_contraction_operator_step_left(C.byref(psi.a[i]), C.byref(psi.a[i]), C.byref(mpo.a[i]), C.byref(lbs[i]), C.byref(ln))
+        a, w, l, out = (_dense(r, x) for x in (psi.a[i], mpo.a[i], lbs[i], ln))
+        want = np.einsum('olwk,lpr,wqps,kqm->orsm', l, a, w, a)
+        assert np.max(np.abs(want - out)) <= 1e-13 * max(1.0, np.max(np.abs(want)))
